@@ -1,0 +1,70 @@
+# starway_b200 build (sm_100a only).  `make` builds everything __graft_entry__.build() needs.
+NVCC      ?= /usr/local/cuda/bin/nvcc
+CXX       ?= g++
+CC        ?= gcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -cudart static
+CXXFLAGS  := -O2 -g -std=c++17 -fPIC -Wall -Wextra -Wno-unused-parameter -pthread
+CFLAGS    := -O2 -g -std=c11 -fPIC -Wall -Wextra
+
+CSRC      := starway_b200/csrc
+LIB       := starway_b200/libstarway_b200.so
+ORACLE    := oracle/liboracle_tagmatch.so
+CPUENG    := oracle/libstarway_cpu.so
+HOSTSIM   := tests/hostsim/libstarway_hostsim.so
+PROBE     := tests/gpu_probe/sw_probe
+
+ENGINE_SRCS := $(CSRC)/engine.cpp
+ENGINE_HDRS := $(CSRC)/gpu.h $(CSRC)/sw_device.h include/starway_b200.h
+
+all: lib oracle hostsim probe
+
+lib: $(LIB)
+oracle: $(ORACLE) $(CPUENG)
+hostsim: $(HOSTSIM)
+probe: $(PROBE)
+
+build/gpu_cuda.o: $(CSRC)/gpu_cuda.cu $(CSRC)/kernels.cuh $(CSRC)/gpu.h $(CSRC)/sw_device.h
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+build/engine.o: $(ENGINE_SRCS) $(ENGINE_HDRS)
+	@mkdir -p build
+	$(CXX) $(CXXFLAGS) -Iinclude -c $< -o $@
+
+# The product library: host progress engine + CUDA kernels.  No CPU fallback is linked in.
+$(LIB): build/engine.o build/gpu_cuda.o
+	$(NVCC) $(ARCH) -shared -cudart static -o $@ $^ -lpthread -lrt -ldl
+
+# Test infrastructure -------------------------------------------------------------
+build/tagmatch.o: oracle/tagmatch.c oracle/tagmatch.h
+	@mkdir -p build
+	$(CC) $(CFLAGS) -c $< -o $@
+
+$(ORACLE): build/tagmatch.o
+	$(CC) -shared -o $@ $^
+
+$(CPUENG): oracle/cpu_engine.cpp oracle/tagmatch.c oracle/tagmatch.h
+	$(CXX) $(CXXFLAGS) -shared -o $@ oracle/cpu_engine.cpp build/tagmatch.o -lpthread -lrt
+
+build/engine_sim.o: $(ENGINE_SRCS) $(ENGINE_HDRS)
+	@mkdir -p build
+	$(CXX) $(CXXFLAGS) -Iinclude -c $< -o $@
+
+build/gpu_sim.o: tests/hostsim/gpu_sim.cpp $(CSRC)/gpu.h $(CSRC)/sw_device.h oracle/tagmatch.h
+	@mkdir -p build
+	$(CXX) $(CXXFLAGS) -c $< -o $@
+
+# Host-logic simulator: the SAME engine.cpp linked against a CPU stand-in for the device
+# backend, used only by `pytest -m "not gpu"` to exercise connection/protocol/flush/close
+# logic (world_size 2 on CPU).  Never loaded by the starway_b200 package.
+$(HOSTSIM): build/engine_sim.o build/gpu_sim.o build/tagmatch.o
+	$(CXX) -shared -o $@ $^ -lpthread -lrt -ldl
+
+$(PROBE): tests/gpu_probe/probe.cu build/gpu_cuda.o build/tagmatch.o
+	$(NVCC) $(NVFLAGS) -o $@ tests/gpu_probe/probe.cu build/gpu_cuda.o build/tagmatch.o
+
+clean:
+	rm -rf build $(LIB) $(ORACLE) $(CPUENG) $(HOSTSIM) $(PROBE)
+
+.PHONY: all lib oracle hostsim probe clean

@@ -1,0 +1,2244 @@
+// starway_b200 — host progress engine behind the C ABI in include/starway_b200.h.
+//
+// Replaces the reference's per-object UCX worker thread
+// (Client::start_working / Server::start_working, reference src/bindings/main.cpp:234-550,
+// 1063-1373) with ONE progress thread per context that
+//   * drains a submission queue filled by sw_post_* (reference Channel<T> mailboxes, chan.hpp:84-120),
+//   * batches sends into sw_put_kernel launches (eager payloads / RTS descriptors stored straight
+//     into the peer's device-resident inbound ring through a CUDA-IPC mapping),
+//   * feeds new receives and ring arrivals to sw_match_kernel + sw_deliver_kernel
+//     (device-resident posted/unexpected queues),
+//   * turns rendezvous matches into sw_bulk_*_kernel launches that PULL the payload from the
+//     sender's buffer (IPC mapping) into the caller's receive buffer,
+//   * resolves operations by polling CUDA events (replaces ucp_worker_progress + UCX callbacks).
+// Host<->host signalling (doorbells, credits, FIN/CLOSE) uses a small POSIX shared-memory
+// control block per connection; the worker-address handshake (main.cpp:292-317, 912-985)
+// becomes an exchange of CUDA IPC handles over a TCP / abstract-unix bootstrap socket.
+//
+// This file contains no CUDA: the device is reached through gpu.h only.
+#include "starway_b200.h"
+
+#include <arpa/inet.h>
+#include <errno.h>
+#include <fcntl.h>
+#include <netinet/in.h>
+#include <netinet/tcp.h>
+#include <poll.h>
+#include <signal.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/eventfd.h>
+#include <sys/mman.h>
+#include <sys/socket.h>
+#include <sys/stat.h>
+#include <sys/un.h>
+#include <time.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <random>
+#include <set>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "gpu.h"
+#include "sw_device.h"
+
+namespace {
+
+// ============================================================================ utilities
+thread_local std::string g_last_error;
+void set_error(const std::string& s) { g_last_error = s; }
+
+double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+uint64_t rand64() {
+  static std::mutex mu;
+  static std::mt19937_64 rng(std::random_device{}() ^ ((uint64_t)getpid() << 32) ^
+                             (uint64_t)std::chrono::steady_clock::now().time_since_epoch().count());
+  std::lock_guard<std::mutex> lk(mu);
+  return rng();
+}
+bool pid_alive(uint32_t pid) { return pid == 0 || kill((pid_t)pid, 0) == 0 || errno == EPERM; }
+
+// ============================================================================ shared control block
+constexpr uint32_t SHM_MAGIC = 0x53574332u;  // "SWC2"
+constexpr uint32_t CTL_RING = 256;
+enum : uint32_t { CTL_FIN = 1, CTL_CLOSE = 2, CTL_CLOSE_ACK = 3, CTL_CANCEL_RTS = 4, CTL_CANCEL_ACK = 5 };
+
+struct CtlMsg {
+  uint32_t type;
+  int32_t status;
+  uint64_t a;
+  uint64_t b;
+  uint64_t pad;
+};
+
+struct alignas(64) ShmDir {  // one direction: sender side X -> receiver side Y
+  alignas(64) std::atomic<uint64_t> produced;  // ring slots completely written by X (after put kernels finished)
+  alignas(64) std::atomic<uint64_t> consumed;  // ring slots released by Y (credits)
+  alignas(64) std::atomic<uint64_t> ctl_head;  // control messages written by X
+  alignas(64) std::atomic<uint64_t> ctl_tail;  // control messages consumed by Y
+  alignas(64) CtlMsg ctl[CTL_RING];
+};
+
+struct ShmCtl {
+  uint32_t magic;
+  uint32_t version;
+  uint32_t pid[2];  // [0] client, [1] server
+  ShmDir dir[2];    // [0] client -> server, [1] server -> client
+};
+
+// ============================================================================ wire format (bootstrap socket)
+constexpr uint32_t WIRE_MAGIC = 0x53574231u;  // "SWB1"
+constexpr uint32_t ADDR_MAGIC = 0x53574144u;  // "SWAD"
+
+struct WireHello {
+  uint32_t magic, version;
+  uint32_t pid;
+  int32_t device;
+  uint64_t ctx_uuid;
+  uint64_t worker_id;
+  uint8_t ring_handle[64];
+  uint64_t ring_ptr;
+  uint32_t ring_slots;
+  uint32_t pad;
+  char shm_name[64];
+};
+struct WireWelcome {
+  uint32_t magic;
+  int32_t status;
+  uint32_t pid;
+  int32_t device;
+  uint64_t ctx_uuid;
+  uint64_t worker_id;
+  uint8_t ring_handle[64];
+  uint64_t ring_ptr;
+  uint32_t ring_slots;
+  uint32_t ep_index;
+};
+struct AddrBlob {  // what listen_address()/get_worker_address() return (reference: UCX worker address bytes)
+  uint32_t magic, version;
+  uint32_t pid;
+  int32_t device;
+  uint64_t ctx_uuid;
+  uint64_t worker_id;
+  char unix_name[64];  // abstract-namespace bootstrap socket ("" for clients)
+  char host[32];
+};
+
+bool write_all(int fd, const void* p, size_t n) {
+  const char* c = (const char*)p;
+  while (n) {
+    ssize_t r = ::send(fd, c, n, MSG_NOSIGNAL);
+    if (r < 0) {
+      if (errno == EINTR) continue;
+      return false;
+    }
+    c += r;
+    n -= (size_t)r;
+  }
+  return true;
+}
+bool read_all(int fd, void* p, size_t n) {
+  char* c = (char*)p;
+  while (n) {
+    ssize_t r = ::recv(fd, c, n, 0);
+    if (r == 0) return false;
+    if (r < 0) {
+      if (errno == EINTR) continue;
+      return false;
+    }
+    c += r;
+    n -= (size_t)r;
+  }
+  return true;
+}
+void set_sock_timeout(int fd, double sec) {
+  struct timeval tv;
+  tv.tv_sec = (long)sec;
+  tv.tv_usec = (long)((sec - (long)sec) * 1e6);
+  setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
+  setsockopt(fd, SOL_SOCKET, SO_SNDTIMEO, &tv, sizeof(tv));
+}
+
+// ============================================================================ pinned bounce pool (host receive buffers)
+struct HostPool {
+  static constexpr int NCLS = 3;
+  const size_t cls_bytes[NCLS] = {256, 4096, 65536};
+  const size_t chunk_blocks[NCLS] = {4096, 512, 64};
+  std::vector<void*> free_list[NCLS];
+  std::vector<void*> chunks;
+  int cls_of(size_t n) const {
+    for (int i = 0; i < NCLS; i++)
+      if (n <= cls_bytes[i]) return i;
+    return -1;
+  }
+  void* get(size_t n) {
+    int c = cls_of(n ? n : 1);
+    if (c < 0) return nullptr;
+    if (free_list[c].empty()) {
+      uint8_t* chunk = (uint8_t*)swgpu::host_alloc(cls_bytes[c] * chunk_blocks[c]);
+      if (!chunk) return nullptr;
+      chunks.push_back(chunk);
+      for (size_t i = 0; i < chunk_blocks[c]; i++) free_list[c].push_back(chunk + i * cls_bytes[c]);
+    }
+    void* p = free_list[c].back();
+    free_list[c].pop_back();
+    return p;
+  }
+  void put(void* p, size_t n) {
+    int c = cls_of(n ? n : 1);
+    if (c >= 0 && p) free_list[c].push_back(p);
+  }
+  void destroy() {
+    for (void* c : chunks) swgpu::host_free(c);
+    chunks.clear();
+  }
+};
+
+// ============================================================================ engine objects
+struct Worker;
+struct Ctx;
+
+struct SendOp {
+  uint64_t op_id = 0;
+  Worker* w = nullptr;
+  struct Ep* ep = nullptr;
+  const uint8_t* ptr = nullptr;
+  size_t len = 0;
+  uint64_t tag = 0;
+  int mem = SW_MEM_AUTO;
+  uint64_t sseq = 0;        // per-endpoint send sequence, for flush
+  bool user_done = false;   // user-visible completion already delivered
+  void* dev_staging = nullptr;
+  uint64_t rndv_seq = 0;
+};
+
+struct RecvOp {
+  uint64_t op_id = 0;
+  Worker* w = nullptr;
+  uint8_t* ptr = nullptr;
+  size_t cap = 0;
+  uint64_t tag = 0, mask = 0;
+  int mem = SW_MEM_AUTO;
+  void* pinned_bounce = nullptr;  // small host receives land here (device-mapped pinned memory)
+  void* dev_staging = nullptr;    // large host receives land here, then D2H
+};
+
+struct FlushOp {
+  uint64_t op_id = 0;
+  struct Ep* ep = nullptr;               // nullptr: every endpoint of the worker
+  std::map<struct Ep*, uint64_t> marks;  // per-endpoint: sends with sseq < mark must be complete
+};
+
+struct BulkJob {
+  Worker* w = nullptr;
+  struct Ep* ep = nullptr;
+  uint64_t recv_op = 0;
+  uint64_t dst = 0, cap = 0, tag = 0, len = 0;
+  SwRts rts;
+  uint64_t src = 0;
+  void* mapping = nullptr;
+  bool failed = false;
+  int32_t fail_status = 0;
+};
+
+struct Ep {
+  uint64_t id = 0;
+  Worker* owner = nullptr;
+  uint32_t index = 0;  // index of the inbound ring in the owner's match state
+  bool is_client_side = false;
+  // peer identity
+  uint32_t peer_pid = 0;
+  int32_t peer_device = -1;
+  uint64_t peer_ctx_uuid = 0;
+  uint64_t peer_worker_id = 0;
+  bool in_process = false;
+  // our inbound ring (owned) and the peer's inbound ring (mapped)
+  uint8_t* ring = nullptr;
+  uint32_t ring_slots = 0;
+  uint8_t* peer_ring = nullptr;
+  void* peer_ring_mapping = nullptr;  // base returned by ipc_open (nullptr when in-process)
+  uint32_t peer_ring_slots = 0;
+  // control block
+  ShmCtl* shm = nullptr;
+  size_t shm_size = 0;
+  ShmDir* out = nullptr;  // we are the sender side of this direction
+  ShmDir* in = nullptr;   // we are the receiver side of this direction
+  std::deque<CtlMsg> ctl_backlog;
+  // send side
+  std::deque<SendOp*> sendq;
+  uint64_t out_sent = 0;       // slots handed to put kernels
+  uint64_t out_published = 0;  // slots published in out->produced
+  uint64_t next_sseq = 1;
+  std::set<uint64_t> out_seqs;  // outstanding sends (sseq)
+  uint64_t rndv_next = 1;
+  std::map<uint64_t, SendOp*> rndv_wait;  // rendezvous sends waiting for FIN
+  std::set<uint64_t> cancel_wait;          // CANCEL_RTS sent, waiting for ack / FIN
+  uint32_t puts_inflight = 0;
+  // receive side
+  std::set<uint64_t> canceled_rts;  // sender cancelled these rendezvous ids
+  // lifecycle
+  bool peer_closed = false;
+  bool close_ack_owed = false;
+  bool close_sent = false;
+  bool close_acked = false;
+  // metadata (reference ServerEndpoint, main.hpp:292-304)
+  sw_ep_info info;
+};
+
+struct Worker {
+  uint64_t id = 0;
+  int kind = 0;
+  Ctx* ctx = nullptr;
+  std::atomic<int> status{SW_ST_VOID};
+  // device-resident queues
+  SwMatchState* mstate = nullptr;
+  SwMatchIn* min = nullptr;
+  SwMatchOut* mout = nullptr;
+  swgpu::event_t mev = nullptr, mev_start = nullptr;
+  bool match_inflight = false;
+  uint32_t match_posts_inflight = 0;
+  std::vector<Ep*> eps;  // index == Ep::index
+  // receives
+  std::deque<RecvOp*> new_posts;
+  std::unordered_map<uint64_t, RecvOp*> recvs;  // handed to the device, not completed
+  uint32_t posted_est = 0;
+  // flush
+  std::vector<FlushOp*> flushes;
+  // listeners
+  int tcp_fd = -1, unix_fd = -1;
+  std::string unix_name;
+  AddrBlob blob;
+  std::atomic<bool> blob_ready{false};
+  // close
+  uint64_t close_op = 0;
+  int close_phase = 0;
+  double close_deadline = 0;
+  bool registered = false;
+  std::thread connector;
+  uint32_t bulk_inflight = 0;
+};
+
+enum : int { SQ_SEND = 1, SQ_RECV = 2, SQ_FLUSH = 3, SQ_CLOSE = 4, SQ_NEW_EP = 5, SQ_REGISTER = 6 };
+struct SqItem {
+  int kind;
+  Worker* w;
+  void* p;
+};
+
+struct PutItem {
+  Ep* ep;
+  SendOp* op;
+  bool rndv;
+};
+struct PutBlock {
+  SwPutDesc* descs = nullptr;
+  SwRts* rts = nullptr;
+  uint8_t* stage = nullptr;
+  swgpu::event_t ev = nullptr, ev_start = nullptr;
+  bool busy = false;
+  std::vector<PutItem> items;
+};
+struct BulkBlock {
+  SwSeg* segs = nullptr;
+  swgpu::event_t ev = nullptr, ev_start = nullptr;
+  bool busy = false;
+  std::vector<BulkJob> jobs;
+  uint64_t bytes = 0;
+};
+struct PostCopy {  // device staging -> host user buffer after delivery
+  swgpu::event_t ev;
+  RecvOp* op;
+  uint64_t tag, len;
+  int32_t status;
+};
+struct Mapping {
+  void* base;
+  uint32_t refs;
+  double last_use;
+};
+
+constexpr uint32_t PUT_BATCH = 512;
+constexpr int N_PUT_BLOCKS = 4;
+constexpr int N_BULK_BLOCKS = 3;
+constexpr uint32_t MAX_SEGS = 8192;
+constexpr size_t HOST_BOUNCE_MAX = 65536;
+
+struct Ctx {
+  int device = 0;
+  uint64_t uuid = 0;
+  std::atomic<uint64_t> next_id{1};
+  // handle tables
+  std::mutex mu;
+  std::unordered_map<uint64_t, Worker*> workers;
+  std::unordered_map<uint64_t, Ep*> eps;
+  // submission queue
+  std::mutex sq_mu;
+  std::vector<SqItem> sq;
+  std::atomic<uint32_t> sq_count{0};
+  // completion queue
+  std::mutex cq_mu;
+  std::condition_variable cq_cv;
+  std::deque<sw_completion> cq;
+  int efd = -1;
+  // progress thread
+  std::thread thr;
+  std::atomic<bool> stop{false};
+  std::vector<Worker*> active;  // progress-thread private
+  // device resources
+  swgpu::stream_t s_put = nullptr, s_match = nullptr, s_bulk = nullptr;
+  PutBlock put_blocks[N_PUT_BLOCKS];
+  uint32_t put_head = 0, put_tail = 0;  // ring of in-flight put blocks
+  BulkBlock bulk_blocks[N_BULK_BLOCKS];
+  uint32_t bulk_head = 0, bulk_tail = 0;
+  std::deque<BulkJob> pending_bulk;
+  std::deque<PostCopy> post_copies;
+  HostPool host_pool;
+  std::map<std::string, Mapping> mappings;  // key: pid + ipc handle bytes
+  // options
+  std::atomic<int64_t> opt_eager_max{SW_EAGER_MAX};
+  std::atomic<int64_t> opt_ring_slots{SW_RING_SLOTS_DEFAULT};
+  std::atomic<int64_t> opt_bulk_mode{0}, opt_bulk_stages{4}, opt_bulk_stage_bytes{32768}, opt_bulk_ctas{2};
+  std::atomic<int64_t> opt_heap_small{4096}, opt_heap_big{512};
+  std::atomic<int64_t> opt_profile{0};
+  // stats
+  std::mutex st_mu;
+  sw_stats stats;
+};
+
+std::mutex g_ctx_mu;
+std::vector<Ctx*> g_ctxs;
+
+// ============================================================================ completions
+void push_completion(Ctx* c, const sw_completion& comp) {
+  {
+    std::lock_guard<std::mutex> lk(c->cq_mu);
+    c->cq.push_back(comp);
+  }
+  c->cq_cv.notify_one();
+  if (c->efd >= 0) {
+    uint64_t one = 1;
+    ssize_t r = write(c->efd, &one, sizeof(one));
+    (void)r;
+  }
+  std::lock_guard<std::mutex> lk(c->st_mu);
+  c->stats.completions++;
+}
+void complete(Ctx* c, Worker* w, uint64_t op_id, uint32_t kind, int32_t status, uint64_t tag = 0, uint64_t len = 0,
+              uint64_t ep = 0) {
+  sw_completion comp;
+  memset(&comp, 0, sizeof(comp));
+  comp.op_id = op_id;
+  comp.status = status;
+  comp.kind = kind;
+  comp.sender_tag = tag;
+  comp.length = len;
+  comp.worker = w ? w->id : 0;
+  comp.ep = ep;
+  push_completion(c, comp);
+}
+
+// ============================================================================ control messages
+bool ctl_try_send(Ep* ep, const CtlMsg& m) {
+  ShmDir* d = ep->out;
+  uint64_t head = d->ctl_head.load(std::memory_order_relaxed);
+  uint64_t tail = d->ctl_tail.load(std::memory_order_acquire);
+  if (head - tail >= CTL_RING) return false;
+  d->ctl[head % CTL_RING] = m;
+  d->ctl_head.store(head + 1, std::memory_order_release);
+  return true;
+}
+void ctl_send(Ep* ep, uint32_t type, int32_t status, uint64_t a, uint64_t b = 0) {
+  if (!ep->shm) return;
+  CtlMsg m;
+  m.type = type;
+  m.status = status;
+  m.a = a;
+  m.b = b;
+  m.pad = 0;
+  if (!ep->ctl_backlog.empty() || !ctl_try_send(ep, m)) ep->ctl_backlog.push_back(m);
+}
+void ctl_flush_backlog(Ep* ep) {
+  while (!ep->ctl_backlog.empty() && ctl_try_send(ep, ep->ctl_backlog.front())) ep->ctl_backlog.pop_front();
+}
+
+// ============================================================================ send-op bookkeeping
+void send_finished(Ctx* c, SendOp* op, int32_t status) {
+  if (!op->user_done) {
+    complete(c, op->w, op->op_id, SW_OP_SEND, status);
+    op->user_done = true;
+  }
+  if (op->dev_staging) swgpu::dev_free(op->dev_staging);
+  op->ep->out_seqs.erase(op->sseq);
+  delete op;
+}
+
+void recv_release(Ctx* c, RecvOp* r) {
+  if (r->pinned_bounce) c->host_pool.put(r->pinned_bounce, r->cap);
+  if (r->dev_staging) swgpu::dev_free(r->dev_staging);
+  delete r;
+}
+
+// finish a receive whose payload (if any) already sits in its landing buffer
+void recv_finish(Ctx* c, Worker* w, uint64_t op_id, int32_t status, uint64_t tag, uint64_t len) {
+  auto it = w->recvs.find(op_id);
+  if (it == w->recvs.end()) return;
+  RecvOp* r = it->second;
+  if (status == SW_OK && len && r->pinned_bounce) {
+    memcpy(r->ptr, r->pinned_bounce, (size_t)std::min<uint64_t>(len, r->cap));
+    std::lock_guard<std::mutex> lk(c->st_mu);
+    c->stats.d2h_bytes += len;
+  }
+  if (status == SW_OK && len && r->dev_staging) {
+    // large host receive: bring the bytes down, complete when the copy has finished
+    w->recvs.erase(it);
+    swgpu::event_t ev = swgpu::event_create(0);
+    swgpu::memcpy_d2h(r->ptr, r->dev_staging, (size_t)len, c->s_bulk);
+    swgpu::event_record(ev, c->s_bulk);
+    c->post_copies.push_back(PostCopy{ev, r, tag, len, status});
+    std::lock_guard<std::mutex> lk(c->st_mu);
+    c->stats.d2h_bytes += len;
+    return;
+  }
+  w->recvs.erase(it);
+  complete(c, w, op_id, SW_OP_RECV, status, tag, len);
+  recv_release(c, r);
+}
+
+// ============================================================================ worker resources
+bool worker_alloc_device(Ctx* c, Worker* w) {
+  w->mstate = swgpu::match_state_create((uint32_t)c->opt_heap_small.load(), (uint32_t)c->opt_heap_big.load());
+  if (!w->mstate) {
+    set_error(std::string("match_state_create: ") + swgpu::last_error());
+    return false;
+  }
+  w->min = (SwMatchIn*)swgpu::host_alloc(sizeof(SwMatchIn));
+  w->mout = (SwMatchOut*)swgpu::host_alloc(sizeof(SwMatchOut));
+  w->mev = swgpu::event_create(0);
+  w->mev_start = swgpu::event_create(1);
+  if (!w->min || !w->mout || !w->mev) {
+    set_error(std::string("worker pinned alloc: ") + swgpu::last_error());
+    return false;
+  }
+  return true;
+}
+
+void fill_blob(Ctx* c, Worker* w) {
+  memset(&w->blob, 0, sizeof(w->blob));
+  w->blob.magic = ADDR_MAGIC;
+  w->blob.version = SW_ABI_VERSION;
+  w->blob.pid = (uint32_t)getpid();
+  w->blob.device = c->device;
+  w->blob.ctx_uuid = c->uuid;
+  w->blob.worker_id = w->id;
+  snprintf(w->blob.unix_name, sizeof(w->blob.unix_name), "%s", w->unix_name.c_str());
+  gethostname(w->blob.host, sizeof(w->blob.host) - 1);
+  w->blob_ready.store(true, std::memory_order_release);
+}
+
+Ep* ep_new(Ctx* c, Worker* w) {
+  Ep* ep = new Ep();
+  ep->id = c->next_id.fetch_add(1);
+  ep->owner = w;
+  memset(&ep->info, 0, sizeof(ep->info));
+  return ep;
+}
+
+bool ep_alloc_ring(Ctx* c, Ep* ep) {
+  uint32_t slots = (uint32_t)c->opt_ring_slots.load();
+  uint32_t p2 = 1;
+  while (p2 < slots) p2 <<= 1;
+  ep->ring_slots = p2;
+  ep->ring = (uint8_t*)swgpu::dev_alloc((size_t)p2 * SW_SLOT_BYTES);
+  if (!ep->ring) {
+    set_error(std::string("ring alloc: ") + swgpu::last_error());
+    return false;
+  }
+  return true;
+}
+
+ShmCtl* shm_create(std::string& name_out, size_t& size_out) {
+  char name[64];
+  snprintf(name, sizeof(name), "/swb200-%d-%llx", (int)getpid(), (unsigned long long)rand64());
+  int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+  if (fd < 0) return nullptr;
+  size_t sz = (sizeof(ShmCtl) + 4095) & ~(size_t)4095;
+  if (ftruncate(fd, (off_t)sz) != 0) {
+    close(fd);
+    shm_unlink(name);
+    return nullptr;
+  }
+  void* p = mmap(nullptr, sz, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (p == MAP_FAILED) {
+    shm_unlink(name);
+    return nullptr;
+  }
+  memset(p, 0, sz);
+  ShmCtl* s = (ShmCtl*)p;
+  s->magic = SHM_MAGIC;
+  s->version = SW_ABI_VERSION;
+  name_out = name;
+  size_out = sz;
+  return s;
+}
+ShmCtl* shm_attach(const char* name, size_t& size_out) {
+  int fd = shm_open(name, O_RDWR, 0600);
+  if (fd < 0) return nullptr;
+  size_t sz = (sizeof(ShmCtl) + 4095) & ~(size_t)4095;
+  void* p = mmap(nullptr, sz, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (p == MAP_FAILED) return nullptr;
+  ShmCtl* s = (ShmCtl*)p;
+  if (s->magic != SHM_MAGIC) {
+    munmap(p, sz);
+    return nullptr;
+  }
+  size_out = sz;
+  return s;
+}
+
+void sq_push(Ctx* c, int kind, Worker* w, void* p) {
+  std::lock_guard<std::mutex> lk(c->sq_mu);
+  c->sq.push_back(SqItem{kind, w, p});
+  c->sq_count.fetch_add(1, std::memory_order_release);
+}
+
+// ============================================================================ connection: server side
+int make_unix_listener(std::string& name_out) {
+  int fd = socket(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0);
+  if (fd < 0) return -1;
+  char name[64];
+  snprintf(name, sizeof(name), "starway-b200-%d-%llx", (int)getpid(), (unsigned long long)rand64());
+  struct sockaddr_un sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.sun_family = AF_UNIX;
+  size_t n = strlen(name);
+  memcpy(sa.sun_path + 1, name, n);  // abstract namespace
+  if (bind(fd, (struct sockaddr*)&sa, (socklen_t)(offsetof(struct sockaddr_un, sun_path) + 1 + n)) != 0 ||
+      listen(fd, 128) != 0) {
+    close(fd);
+    return -1;
+  }
+  fcntl(fd, F_SETFL, fcntl(fd, F_GETFL) | O_NONBLOCK);
+  name_out = name;
+  return fd;
+}
+int make_tcp_listener(const char* addr, uint16_t port) {
+  int fd = socket(AF_INET, SOCK_STREAM | SOCK_CLOEXEC, 0);
+  if (fd < 0) return -1;
+  int one = 1;
+  setsockopt(fd, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
+  struct sockaddr_in sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.sin_family = AF_INET;
+  sa.sin_port = htons(port);
+  if (inet_pton(AF_INET, addr, &sa.sin_addr) != 1) {
+    close(fd);
+    errno = EINVAL;
+    return -1;
+  }
+  if (bind(fd, (struct sockaddr*)&sa, sizeof(sa)) != 0 || listen(fd, 128) != 0) {
+    int e = errno;
+    close(fd);
+    errno = e;
+    return -1;
+  }
+  fcntl(fd, F_SETFL, fcntl(fd, F_GETFL) | O_NONBLOCK);
+  return fd;
+}
+
+void describe_transport(Ctx* c, Ep* ep) {
+  ep->info.num_transports = 1;
+  snprintf(ep->info.transport_device[0], 32, "cuda:%d", c->device);
+  if (ep->in_process)
+    snprintf(ep->info.transport_name[0], 32, "cuda_loopback");
+  else if (ep->peer_device == c->device)
+    snprintf(ep->info.transport_name[0], 32, "cuda_ipc");
+  else
+    snprintf(ep->info.transport_name[0], 32, "nvlink_ipc");
+}
+
+// Runs on the progress thread: accept one bootstrap connection and perform the handshake.
+void server_handshake(Ctx* c, Worker* w, int fd, bool tcp) {
+  set_sock_timeout(fd, 2.0);
+  WireHello h;
+  WireWelcome wl;
+  memset(&wl, 0, sizeof(wl));
+  wl.magic = WIRE_MAGIC;
+  wl.status = SW_ERR_INVALID_PARAM;
+  Ep* ep = nullptr;
+  do {
+    if (!read_all(fd, &h, sizeof(h)) || h.magic != WIRE_MAGIC) break;
+    h.shm_name[sizeof(h.shm_name) - 1] = 0;
+    if (w->eps.size() >= SW_MAX_EPS) {
+      wl.status = SW_ERR_NO_MEMORY;
+      break;
+    }
+    ep = ep_new(c, w);
+    ep->index = (uint32_t)w->eps.size();
+    ep->peer_pid = h.pid;
+    ep->peer_device = h.device;
+    ep->peer_ctx_uuid = h.ctx_uuid;
+    ep->peer_worker_id = h.worker_id;
+    ep->in_process = (h.pid == (uint32_t)getpid() && h.ctx_uuid == c->uuid);
+    ep->shm = shm_attach(h.shm_name, ep->shm_size);
+    if (!ep->shm) {
+      wl.status = SW_ERR_IO_ERROR;
+      break;
+    }
+    ep->shm->pid[1] = (uint32_t)getpid();
+    ep->out = &ep->shm->dir[1];
+    ep->in = &ep->shm->dir[0];
+    if (!ep_alloc_ring(c, ep)) {
+      wl.status = SW_ERR_NO_MEMORY;
+      break;
+    }
+    if (ep->in_process) {
+      ep->peer_ring = (uint8_t*)(uintptr_t)h.ring_ptr;
+    } else {
+      void* base = nullptr;
+      if (swgpu::ipc_open(h.ring_handle, &base) != 0) {
+        fprintf(stderr, "starway_b200: cannot map the client's inbound ring: %s\n", swgpu::last_error());
+        wl.status = SW_ERR_UNREACHABLE;
+        break;
+      }
+      ep->peer_ring_mapping = base;
+      ep->peer_ring = (uint8_t*)base;
+      if (swgpu::ipc_get(ep->ring, wl.ring_handle) != 0) {
+        wl.status = SW_ERR_IO_ERROR;
+        break;
+      }
+    }
+    ep->peer_ring_slots = h.ring_slots;
+    if (swgpu::match_state_set_ring(w->mstate, ep->index, ep->ring, ep->ring_slots) != 0) {
+      wl.status = SW_ERR_IO_ERROR;
+      break;
+    }
+    // endpoint metadata (reference handle_new_endpoint, main.cpp:867-910)
+    snprintf(ep->info.name, sizeof(ep->info.name), "starway-ep-%u[pid %u gpu %d]", ep->index, h.pid, h.device);
+    if (tcp) {
+      struct sockaddr_in la, ra;
+      socklen_t ll = sizeof(la), rl = sizeof(ra);
+      if (getsockname(fd, (struct sockaddr*)&la, &ll) == 0) {
+        inet_ntop(AF_INET, &la.sin_addr, ep->info.local_addr, sizeof(ep->info.local_addr));
+        ep->info.local_port = ntohs(la.sin_port);
+      }
+      if (getpeername(fd, (struct sockaddr*)&ra, &rl) == 0) {
+        inet_ntop(AF_INET, &ra.sin_addr, ep->info.remote_addr, sizeof(ep->info.remote_addr));
+        ep->info.remote_port = ntohs(ra.sin_port);
+      }
+    }
+    describe_transport(c, ep);
+    wl.status = SW_OK;
+    wl.pid = (uint32_t)getpid();
+    wl.device = c->device;
+    wl.ctx_uuid = c->uuid;
+    wl.worker_id = w->id;
+    wl.ring_ptr = (uint64_t)(uintptr_t)ep->ring;
+    wl.ring_slots = ep->ring_slots;
+    wl.ep_index = ep->index;
+  } while (0);
+
+  if (wl.status == SW_OK) {
+    // the endpoint is visible (list_clients) before the client learns the connect succeeded
+    w->eps.push_back(ep);
+    {
+      std::lock_guard<std::mutex> lk(c->mu);
+      c->eps[ep->id] = ep;
+    }
+    if (!write_all(fd, &wl, sizeof(wl))) ep->peer_closed = true;
+    complete(c, w, 0, SW_OP_ACCEPT, SW_OK, 0, 0, ep->id);
+  } else {
+    write_all(fd, &wl, sizeof(wl));
+    if (ep) {
+      if (ep->peer_ring_mapping) swgpu::ipc_close(ep->peer_ring_mapping);
+      if (ep->ring) swgpu::dev_free(ep->ring);
+      if (ep->shm) munmap(ep->shm, ep->shm_size);
+      delete ep;
+    }
+  }
+  close(fd);
+}
+
+void poll_listeners(Ctx* c, Worker* w) {
+  if (w->status.load(std::memory_order_acquire) != SW_ST_RUNNING) return;
+  for (int k = 0; k < 2; k++) {
+    int lfd = k == 0 ? w->unix_fd : w->tcp_fd;
+    if (lfd < 0) continue;
+    for (int n = 0; n < 8; n++) {
+      int fd = accept4(lfd, nullptr, nullptr, SOCK_CLOEXEC);
+      if (fd < 0) break;
+      server_handshake(c, w, fd, k == 1);
+    }
+  }
+}
+
+// ============================================================================ connection: client side
+struct ConnectReq {
+  int mode;  // 0 tcp, 1 address blob
+  std::string addr;
+  uint16_t port;
+  AddrBlob blob;
+  uint64_t op_id;
+};
+
+void client_connect_thread(Ctx* c, Worker* w, ConnectReq req) {
+  swgpu::bind_thread(c->device);
+  int32_t status = SW_ERR_NOT_CONNECTED;
+  int fd = -1;
+  Ep* ep = nullptr;
+  std::string shm_name;
+  do {
+    // ---- bootstrap socket
+    if (req.mode == 0) {
+      fd = socket(AF_INET, SOCK_STREAM | SOCK_CLOEXEC, 0);
+      if (fd < 0) break;
+      struct sockaddr_in sa;
+      memset(&sa, 0, sizeof(sa));
+      sa.sin_family = AF_INET;
+      sa.sin_port = htons(req.port);
+      if (inet_pton(AF_INET, req.addr.c_str(), &sa.sin_addr) != 1) {
+        status = SW_ERR_INVALID_PARAM;
+        break;
+      }
+      set_sock_timeout(fd, 5.0);
+      if (connect(fd, (struct sockaddr*)&sa, sizeof(sa)) != 0) {
+        status = (errno == ETIMEDOUT || errno == EINPROGRESS) ? SW_ERR_TIMED_OUT : SW_ERR_NOT_CONNECTED;
+        break;
+      }
+      int one = 1;
+      setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));
+    } else {
+      if (req.blob.magic != ADDR_MAGIC || req.blob.unix_name[0] == 0) {
+        status = SW_ERR_INVALID_PARAM;
+        break;
+      }
+      fd = socket(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0);
+      if (fd < 0) break;
+      struct sockaddr_un sa;
+      memset(&sa, 0, sizeof(sa));
+      sa.sun_family = AF_UNIX;
+      req.blob.unix_name[sizeof(req.blob.unix_name) - 1] = 0;
+      size_t n = strlen(req.blob.unix_name);
+      memcpy(sa.sun_path + 1, req.blob.unix_name, n);
+      set_sock_timeout(fd, 5.0);
+      if (connect(fd, (struct sockaddr*)&sa, (socklen_t)(offsetof(struct sockaddr_un, sun_path) + 1 + n)) != 0) {
+        status = SW_ERR_NOT_CONNECTED;
+        break;
+      }
+    }
+    // ---- local resources: device queues, inbound ring, control block
+    status = SW_ERR_NO_MEMORY;
+    if (!worker_alloc_device(c, w)) break;
+    ep = ep_new(c, w);
+    ep->index = 0;
+    ep->is_client_side = true;
+    if (!ep_alloc_ring(c, ep)) break;
+    if (swgpu::match_state_set_ring(w->mstate, 0, ep->ring, ep->ring_slots) != 0) break;
+    ep->shm = shm_create(shm_name, ep->shm_size);
+    if (!ep->shm) {
+      status = SW_ERR_IO_ERROR;
+      break;
+    }
+    ep->shm->pid[0] = (uint32_t)getpid();
+    ep->out = &ep->shm->dir[0];
+    ep->in = &ep->shm->dir[1];
+    // ---- handshake
+    WireHello h;
+    memset(&h, 0, sizeof(h));
+    h.magic = WIRE_MAGIC;
+    h.version = SW_ABI_VERSION;
+    h.pid = (uint32_t)getpid();
+    h.device = c->device;
+    h.ctx_uuid = c->uuid;
+    h.worker_id = w->id;
+    h.ring_ptr = (uint64_t)(uintptr_t)ep->ring;
+    h.ring_slots = ep->ring_slots;
+    snprintf(h.shm_name, sizeof(h.shm_name), "%s", shm_name.c_str());
+    if (swgpu::ipc_get(ep->ring, h.ring_handle) != 0) {
+      // not fatal for an in-process peer; a remote peer will fail to map and refuse
+      memset(h.ring_handle, 0, sizeof(h.ring_handle));
+    }
+    status = SW_ERR_NOT_CONNECTED;
+    if (!write_all(fd, &h, sizeof(h))) break;
+    WireWelcome wl;
+    if (!read_all(fd, &wl, sizeof(wl)) || wl.magic != WIRE_MAGIC) break;
+    if (wl.status != SW_OK) {
+      status = wl.status;
+      break;
+    }
+    ep->peer_pid = wl.pid;
+    ep->peer_device = wl.device;
+    ep->peer_ctx_uuid = wl.ctx_uuid;
+    ep->peer_worker_id = wl.worker_id;
+    ep->in_process = (wl.pid == (uint32_t)getpid() && wl.ctx_uuid == c->uuid);
+    ep->peer_ring_slots = wl.ring_slots;
+    if (ep->in_process) {
+      ep->peer_ring = (uint8_t*)(uintptr_t)wl.ring_ptr;
+    } else {
+      void* base = nullptr;
+      if (swgpu::ipc_open(wl.ring_handle, &base) != 0) {
+        fprintf(stderr, "starway_b200: cannot map the server's inbound ring: %s\n", swgpu::last_error());
+        status = SW_ERR_UNREACHABLE;
+        break;
+      }
+      ep->peer_ring_mapping = base;
+      ep->peer_ring = (uint8_t*)base;
+    }
+    snprintf(ep->info.name, sizeof(ep->info.name), "starway-server[pid %u gpu %d]", wl.pid, wl.device);
+    describe_transport(c, ep);
+    status = SW_OK;
+  } while (0);
+  if (fd >= 0) close(fd);
+  if (!shm_name.empty()) shm_unlink(shm_name.c_str());  // both sides have it mapped (or the attempt failed)
+
+  if (status == SW_OK) {
+    w->eps.push_back(ep);
+    {
+      std::lock_guard<std::mutex> lk(c->mu);
+      c->eps[ep->id] = ep;
+    }
+    w->status.store(SW_ST_INIT, std::memory_order_release);
+    sq_push(c, SQ_REGISTER, w, (void*)(uintptr_t)req.op_id);
+  } else {
+    if (ep) {
+      if (ep->peer_ring_mapping) swgpu::ipc_close(ep->peer_ring_mapping);
+      if (ep->ring) swgpu::dev_free(ep->ring);
+      if (ep->shm) munmap(ep->shm, ep->shm_size);
+      delete ep;
+    }
+    if (w->mstate) {
+      swgpu::match_state_destroy(w->mstate);
+      w->mstate = nullptr;
+    }
+    w->status.store(SW_ST_CLOSED, std::memory_order_release);
+    complete(c, w, req.op_id, SW_OP_CONNECT, status);
+  }
+}
+
+// ============================================================================ progress: sends
+bool pump_sends(Ctx* c) {
+  if ((c->put_tail - c->put_head) >= (uint32_t)N_PUT_BLOCKS) return false;
+  PutBlock& b = c->put_blocks[c->put_tail % N_PUT_BLOCKS];
+  uint32_t n = 0;
+  uint64_t bytes = 0, h2d = 0;
+  const uint64_t eager_max = (uint64_t)std::min<int64_t>(c->opt_eager_max.load(), SW_EAGER_MAX);
+  b.items.clear();
+  for (Worker* w : c->active) {
+    for (Ep* ep : w->eps) {
+      while (!ep->sendq.empty() && n < PUT_BATCH) {
+        SendOp* op = ep->sendq.front();
+        if (ep->peer_closed) {
+          ep->sendq.pop_front();
+          send_finished(c, op, SW_ERR_CONNECTION_RESET);
+          continue;
+        }
+        uint64_t consumed = ep->out->consumed.load(std::memory_order_acquire);
+        if (ep->out_sent - consumed >= ep->peer_ring_slots) break;  // no credit
+        SwPutDesc& d = b.descs[n];
+        d.tag = op->tag;
+        d.msg_len = op->len;
+        bool rndv = false;
+        if (op->len <= eager_max) {
+          if (op->mem == SW_MEM_HOST) {
+            memcpy(b.stage + (size_t)n * SW_SLOT_BYTES, op->ptr, op->len);
+            d.src = (uint64_t)(uintptr_t)(b.stage + (size_t)n * SW_SLOT_BYTES);
+            h2d += op->len;
+          } else {
+            d.src = (uint64_t)(uintptr_t)op->ptr;
+          }
+          d.len = (uint32_t)op->len;
+          d.kind = SW_KIND_EAGER;
+        } else {
+          // ---- rendezvous: publish a descriptor of the source, the receiver pulls
+          rndv = true;
+          SwRts& r = b.rts[n];
+          memset(&r, 0, sizeof(r));
+          uint64_t base = 0, size = 0;
+          int srcdev = c->device;
+          if (op->mem == SW_MEM_HOST) {
+            if (!op->dev_staging) {
+              op->dev_staging = swgpu::dev_alloc_raw(op->len);
+              if (!op->dev_staging) {
+                ep->sendq.pop_front();
+                send_finished(c, op, SW_ERR_NO_MEMORY);
+                continue;
+              }
+              swgpu::memcpy_h2d(op->dev_staging, op->ptr, op->len, c->s_put);
+              h2d += op->len;
+            }
+            base = (uint64_t)(uintptr_t)op->dev_staging;
+            size = op->len;
+            r.src_ptr = base;
+          } else {
+            swgpu::PtrInfo pi;
+            swgpu::ptr_info(op->ptr, &pi);
+            base = pi.base;
+            size = pi.size;
+            srcdev = pi.device;
+            r.src_ptr = (uint64_t)(uintptr_t)op->ptr;
+            if (!ep->in_process && (!pi.is_device || base == 0)) {
+              ep->sendq.pop_front();
+              set_error("rendezvous source is not a CUDA device allocation");
+              send_finished(c, op, SW_ERR_INVALID_PARAM);
+              continue;
+            }
+          }
+          if (!ep->in_process && swgpu::ipc_get((void*)(uintptr_t)base, r.ipc_handle) != 0) {
+            fprintf(stderr, "starway_b200: cudaIpcGetMemHandle failed: %s\n", swgpu::last_error());
+            ep->sendq.pop_front();
+            send_finished(c, op, SW_ERR_INVALID_PARAM);
+            continue;
+          }
+          r.alloc_base = base;
+          r.alloc_size = size;
+          r.ctx_uuid = c->uuid;
+          r.src_pid = (uint32_t)getpid();
+          r.src_dev = srcdev;
+          op->rndv_seq = ep->rndv_next++;
+          r.send_seq = op->rndv_seq;
+          d.src = (uint64_t)(uintptr_t)&r;
+          d.len = (uint32_t)sizeof(SwRts);
+          d.kind = SW_KIND_RTS;
+        }
+        d.dst = (uint64_t)(uintptr_t)(ep->peer_ring + (size_t)(ep->out_sent % ep->peer_ring_slots) * SW_SLOT_BYTES);
+        d.seq = ep->out_sent + 1;
+        ep->out_sent++;
+        ep->puts_inflight++;
+        ep->sendq.pop_front();
+        if (rndv) ep->rndv_wait[op->rndv_seq] = op;
+        b.items.push_back(PutItem{ep, op, rndv});
+        bytes += d.len;
+        n++;
+      }
+      if (n >= PUT_BATCH) break;
+    }
+    if (n >= PUT_BATCH) break;
+  }
+  if (!n) return false;
+  const bool prof = c->opt_profile.load() != 0;
+  if (prof) swgpu::event_record(b.ev_start, c->s_put);
+  if (swgpu::launch_put(c->s_put, b.descs, n) != 0)
+    fprintf(stderr, "starway_b200: put launch failed: %s\n", swgpu::last_error());
+  swgpu::event_record(b.ev, c->s_put);
+  b.busy = true;
+  c->put_tail++;
+  std::lock_guard<std::mutex> lk(c->st_mu);
+  c->stats.put_launches++;
+  c->stats.put_msgs += n;
+  c->stats.put_bytes += bytes;
+  c->stats.h2d_bytes += h2d;
+  return true;
+}
+
+bool poll_puts(Ctx* c) {
+  bool any = false;
+  while (c->put_head != c->put_tail) {
+    PutBlock& b = c->put_blocks[c->put_head % N_PUT_BLOCKS];
+    int q = swgpu::event_query(b.ev);
+    if (q == 1) break;
+    if (q < 0) fprintf(stderr, "starway_b200: put kernel failed: %s\n", swgpu::last_error());
+    if (c->opt_profile.load()) {
+      float ms = swgpu::event_elapsed_ms(b.ev_start, b.ev);
+      if (ms >= 0) {
+        std::lock_guard<std::mutex> lk(c->st_mu);
+        c->stats.put_event_ms += ms;
+        c->stats.put_event_launches++;
+      }
+    }
+    // publish the slots (doorbell), then complete the eager sends
+    for (PutItem& it : b.items) {
+      it.ep->out_published++;
+      it.ep->puts_inflight--;
+    }
+    for (PutItem& it : b.items) {
+      Ep* ep = it.ep;
+      if (ep->out->produced.load(std::memory_order_relaxed) != ep->out_published)
+        ep->out->produced.store(ep->out_published, std::memory_order_release);
+    }
+    for (PutItem& it : b.items) {
+      SendOp* op = it.op;
+      if (!it.rndv) {
+        send_finished(c, op, q < 0 ? SW_ERR_IO_ERROR : SW_OK);
+      } else if (op->dev_staging && !op->user_done) {
+        // host buffer has been staged on the device: the caller may reuse it (UCX eager-bcopy semantics)
+        complete(c, op->w, op->op_id, SW_OP_SEND, SW_OK);
+        op->user_done = true;
+      }
+    }
+    b.items.clear();
+    b.busy = false;
+    c->put_head++;
+    any = true;
+  }
+  return any;
+}
+
+// ============================================================================ progress: matching
+bool pump_match(Ctx* c, Worker* w) {
+  if (w->match_inflight || !w->mstate) return false;
+  int st = w->status.load(std::memory_order_acquire);
+  if (st != SW_ST_RUNNING && st != SW_ST_CLOSING) return false;
+  SwMatchIn* in = w->min;
+  uint32_t np = 0;
+  uint64_t new_arrivals = 0;
+  for (Ep* ep : w->eps) {
+    uint64_t p = ep->in->produced.load(std::memory_order_acquire);
+    in->produced[ep->index] = p;
+    uint64_t consumed = ep->in->consumed.load(std::memory_order_relaxed);
+    if (p > consumed) new_arrivals += p - consumed;
+  }
+  if (w->close_phase == 0) {
+    while (!w->new_posts.empty() && np < SW_MAX_POSTS && w->posted_est + np < SW_PQ_CAP / 2) {
+      RecvOp* r = w->new_posts.front();
+      uint64_t buf = (uint64_t)(uintptr_t)r->ptr;
+      if (r->mem == SW_MEM_HOST) {
+        if (r->cap <= HOST_BOUNCE_MAX) {
+          r->pinned_bounce = c->host_pool.get(r->cap);
+          buf = (uint64_t)(uintptr_t)r->pinned_bounce;
+        } else {
+          r->dev_staging = swgpu::dev_alloc_raw(r->cap);
+          buf = (uint64_t)(uintptr_t)r->dev_staging;
+        }
+        if (!buf) {
+          w->new_posts.pop_front();
+          complete(c, w, r->op_id, SW_OP_RECV, SW_ERR_NO_MEMORY);
+          delete r;
+          continue;
+        }
+      }
+      SwPost& p = in->posts[np++];
+      p.tag = r->tag;
+      p.mask = r->mask;
+      p.buf = buf;
+      p.cap = r->cap;
+      p.op_id = r->op_id;
+      w->recvs[r->op_id] = r;
+      w->new_posts.pop_front();
+    }
+  }
+  // arrivals can only make progress when something new happened: new slots, or new
+  // receives that may unblock a ring stalled on the unexpected heap
+  static thread_local std::unordered_map<Worker*, uint64_t> dummy;
+  (void)dummy;
+  bool stalled_retry = np > 0;
+  uint64_t unseen = 0;
+  for (Ep* ep : w->eps) {
+    uint64_t p = in->produced[ep->index];
+    uint64_t seen = ep->in->consumed.load(std::memory_order_relaxed);
+    if (p > seen) unseen += p - seen;
+  }
+  if (np == 0 && (unseen == 0 || (w->match_posts_inflight == 0xFFFFFFFFu && !stalled_retry))) return false;
+  in->n_posts = np;
+  in->n_eps = (uint32_t)w->eps.size();
+  in->max_arrivals = SW_MAX_ARRIVALS;
+  const bool prof = c->opt_profile.load() != 0;
+  if (prof) swgpu::event_record(w->mev_start, c->s_match);
+  if (swgpu::launch_match(c->s_match, w->mstate, in, w->mout) != 0)
+    fprintf(stderr, "starway_b200: match launch failed: %s\n", swgpu::last_error());
+  uint32_t max_jobs = np + (uint32_t)std::min<uint64_t>(unseen, SW_MAX_ARRIVALS);
+  if (swgpu::launch_deliver(c->s_match, w->mstate, w->mout, max_jobs) != 0)
+    fprintf(stderr, "starway_b200: deliver launch failed: %s\n", swgpu::last_error());
+  swgpu::event_record(w->mev, c->s_match);
+  w->match_inflight = true;
+  w->match_posts_inflight = np;
+  w->posted_est += np;
+  std::lock_guard<std::mutex> lk(c->st_mu);
+  c->stats.match_launches++;
+  c->stats.deliver_launches += max_jobs ? 1 : 0;
+  c->stats.match_posts += np;
+  return true;
+}
+
+bool poll_match(Ctx* c, Worker* w) {
+  if (!w->match_inflight) return false;
+  int q = swgpu::event_query(w->mev);
+  if (q == 1) return false;
+  if (q < 0) fprintf(stderr, "starway_b200: match/deliver kernel failed: %s\n", swgpu::last_error());
+  w->match_inflight = false;
+  SwMatchOut* out = w->mout;
+  if (c->opt_profile.load()) {
+    float ms = swgpu::event_elapsed_ms(w->mev_start, w->mev);
+    if (ms >= 0) {
+      std::lock_guard<std::mutex> lk(c->st_mu);
+      c->stats.match_event_ms += ms;
+      c->stats.match_event_launches++;
+    }
+  }
+  if (out->err) fprintf(stderr, "starway_b200: device matcher reported inconsistency 0x%x\n", out->err);
+  // credits first: the slots are free again
+  bool stalled = false;
+  for (Ep* ep : w->eps) {
+    uint64_t cns = out->consumed[ep->index];
+    if (cns != ep->in->consumed.load(std::memory_order_relaxed)) ep->in->consumed.store(cns, std::memory_order_release);
+    if (cns < w->min->produced[ep->index]) stalled = true;
+  }
+  // remember a heap-stall so that we do not spin relaunching until new receives arrive
+  w->match_posts_inflight = (stalled && out->n_arrivals == 0 && w->min->n_posts == 0) ? 0xFFFFFFFFu : 0;
+  {
+    std::lock_guard<std::mutex> lk(c->st_mu);
+    c->stats.match_arrivals += out->n_arrivals;
+  }
+  w->posted_est = out->n_posted;
+  uint32_t nj = std::min<uint32_t>(out->n_jobs, SW_MAX_JOBS);
+  for (uint32_t i = 0; i < nj; i++) {
+    const SwCqe& e = out->cq[i];
+    if (e.kind != SW_JOB_DELIVER) continue;
+    recv_finish(c, w, e.op_id, e.status, e.tag, e.len);
+  }
+  uint32_t nr = std::min<uint32_t>(out->n_rndv, SW_MAX_JOBS);
+  for (uint32_t i = 0; i < nr; i++) {
+    const SwRndvRec& r = out->rndv[i];
+    BulkJob j;
+    j.w = w;
+    j.ep = r.ep < w->eps.size() ? w->eps[r.ep] : nullptr;
+    j.recv_op = r.op_id;
+    j.dst = r.dst;
+    j.cap = r.cap;
+    j.tag = r.tag;
+    j.len = r.len;
+    j.rts = r.rts;
+    if (r.status != SW_OK) {
+      j.failed = true;
+      j.fail_status = r.status;
+    }
+    c->pending_bulk.push_back(j);
+  }
+  return true;
+}
+
+// ============================================================================ progress: rendezvous pulls
+void* resolve_mapping(Ctx* c, BulkJob& j) {
+  std::string key((const char*)j.rts.ipc_handle, 64);
+  key.append((const char*)&j.rts.src_pid, sizeof(j.rts.src_pid));
+  auto it = c->mappings.find(key);
+  if (it == c->mappings.end()) {
+    // bound the cache: drop idle mappings
+    if (c->mappings.size() >= 64) {
+      for (auto m = c->mappings.begin(); m != c->mappings.end();) {
+        if (m->second.refs == 0) {
+          swgpu::ipc_close(m->second.base);
+          m = c->mappings.erase(m);
+        } else {
+          ++m;
+        }
+      }
+    }
+    void* base = nullptr;
+    if (swgpu::ipc_open(j.rts.ipc_handle, &base) != 0) {
+      fprintf(stderr, "starway_b200: cannot map the sender's buffer: %s\n", swgpu::last_error());
+      return nullptr;
+    }
+    it = c->mappings.emplace(key, Mapping{base, 0, now_s()}).first;
+  }
+  it->second.refs++;
+  it->second.last_use = now_s();
+  j.mapping = it->second.base;
+  return it->second.base;
+}
+void release_mapping(Ctx* c, BulkJob& j) {
+  if (!j.mapping) return;
+  for (auto& kv : c->mappings)
+    if (kv.second.base == j.mapping) {
+      if (kv.second.refs) kv.second.refs--;
+      break;
+    }
+  j.mapping = nullptr;
+}
+
+void bulk_job_done(Ctx* c, BulkJob& j, int32_t status) {
+  recv_finish(c, j.w, j.recv_op, status, j.tag, j.len);
+  if (j.ep) {
+    bool was_cancelled = j.ep->canceled_rts.erase(j.rts.send_seq) > 0;
+    (void)was_cancelled;
+    // FIN: the sender's buffer is no longer needed (UCX: rendezvous ATS)
+    ctl_send(j.ep, CTL_FIN, status == SW_ERR_MESSAGE_TRUNCATED ? SW_OK : status, j.rts.send_seq);
+  }
+  release_mapping(c, j);
+  if (j.w->bulk_inflight) j.w->bulk_inflight--;
+}
+
+bool pump_bulk(Ctx* c) {
+  if (c->pending_bulk.empty()) return false;
+  if ((c->bulk_tail - c->bulk_head) >= (uint32_t)N_BULK_BLOCKS) return false;
+  BulkBlock& b = c->bulk_blocks[c->bulk_tail % N_BULK_BLOCKS];
+  b.jobs.clear();
+  b.bytes = 0;
+  const uint64_t MAX_BYTES = 8ull << 30;
+  // ---- choose the jobs of this launch
+  while (!c->pending_bulk.empty() && b.jobs.size() < 2048 && b.bytes < MAX_BYTES) {
+    BulkJob j = c->pending_bulk.front();
+    c->pending_bulk.pop_front();
+    j.w->bulk_inflight++;
+    if (!j.failed && j.ep && j.ep->canceled_rts.count(j.rts.send_seq)) {
+      j.failed = true;
+      j.fail_status = SW_ERR_CONNECTION_RESET;
+    }
+    if (!j.failed) {
+      if (j.rts.ctx_uuid == c->uuid && j.rts.src_pid == (uint32_t)getpid()) {
+        j.src = j.rts.src_ptr;
+      } else {
+        void* base = resolve_mapping(c, j);
+        if (!base) {
+          j.failed = true;
+          j.fail_status = SW_ERR_UNREACHABLE;
+        } else {
+          j.src = (uint64_t)(uintptr_t)base + (j.rts.src_ptr - j.rts.alloc_base);
+        }
+      }
+    }
+    if (j.failed) {
+      if (j.fail_status == SW_ERR_CONNECTION_RESET) {
+        // cancelled by the sender: no FIN, the CANCEL_ACK was already sent
+        recv_finish(c, j.w, j.recv_op, j.fail_status, j.tag, j.len);
+        if (j.ep) j.ep->canceled_rts.erase(j.rts.send_seq);
+        j.w->bulk_inflight--;
+      } else {
+        bulk_job_done(c, j, j.fail_status);
+      }
+      continue;
+    }
+    b.bytes += j.len;
+    b.jobs.push_back(j);
+  }
+  if (b.jobs.empty()) return true;
+  // ---- segment list: [0, ntma) TMA-eligible pieces, [ntma, nseg) generic pieces
+  swgpu::BulkTuning tune;
+  tune.mode = (int)c->opt_bulk_mode.load();
+  tune.stages = (int)c->opt_bulk_stages.load();
+  tune.stage_bytes = (int)c->opt_bulk_stage_bytes.load();
+  tune.ctas_per_sm = (int)c->opt_bulk_ctas.load();
+  const uint64_t sms = (uint64_t)swgpu::sm_count();
+  uint64_t target = sms * (uint64_t)std::max(1, tune.ctas_per_sm) * 4;
+  uint64_t seg = (b.bytes + target - 1) / target;
+  const uint64_t unit = tune.mode == 0 ? (uint64_t)std::max(1024, tune.stage_bytes & ~15) : 65536;
+  seg = ((seg + unit - 1) / unit) * unit;
+  seg = std::max<uint64_t>(seg, std::max<uint64_t>(unit, 65536 / unit * unit));
+  seg = std::min<uint64_t>(seg, 4u << 20);
+  while ((b.bytes / seg) + 2 * b.jobs.size() + 2 > MAX_SEGS) seg *= 2;
+  std::vector<SwSeg> tma, simt;
+  for (BulkJob& j : b.jobs) {
+    uint64_t src = j.src, dst = j.dst, len = j.len;
+    // receives into host memory were redirected to device staging at post time
+    if (tune.mode == 0 && ((src | dst) & 15) == 0 && len >= 16) {
+      uint64_t body = len & ~15ull;
+      for (uint64_t off = 0; off < body; off += seg) tma.push_back(SwSeg{src + off, dst + off, std::min(seg, body - off), 0});
+      if (len > body) simt.push_back(SwSeg{src + body, dst + body, len - body, 0});
+    } else {
+      for (uint64_t off = 0; off < len; off += seg) simt.push_back(SwSeg{src + off, dst + off, std::min(seg, len - off), 0});
+    }
+  }
+  uint32_t ntma = (uint32_t)tma.size(), nsimt = (uint32_t)simt.size();
+  if (ntma) memcpy(b.segs, tma.data(), sizeof(SwSeg) * ntma);
+  if (nsimt) memcpy(b.segs + ntma, simt.data(), sizeof(SwSeg) * nsimt);
+  const bool prof = c->opt_profile.load() != 0;
+  if (prof) swgpu::event_record(b.ev_start, c->s_bulk);
+  int rc = 0;
+  if (ntma) rc |= swgpu::launch_bulk(c->s_bulk, b.segs, ntma, &tune);
+  if (nsimt) {
+    swgpu::BulkTuning t2 = tune;
+    t2.mode = 1;
+    t2.ctas_per_sm = 8;
+    rc |= swgpu::launch_bulk(c->s_bulk, b.segs + ntma, nsimt, &t2);
+  }
+  if (rc) fprintf(stderr, "starway_b200: bulk launch failed: %s\n", swgpu::last_error());
+  swgpu::event_record(b.ev, c->s_bulk);
+  b.busy = true;
+  c->bulk_tail++;
+  std::lock_guard<std::mutex> lk(c->st_mu);
+  if (ntma) c->stats.bulk_tma_launches++;
+  if (nsimt) c->stats.bulk_simt_launches++;
+  c->stats.bulk_jobs += b.jobs.size();
+  c->stats.bulk_bytes += b.bytes;
+  return true;
+}
+
+bool poll_bulk(Ctx* c) {
+  bool any = false;
+  while (c->bulk_head != c->bulk_tail) {
+    BulkBlock& b = c->bulk_blocks[c->bulk_head % N_BULK_BLOCKS];
+    int q = swgpu::event_query(b.ev);
+    if (q == 1) break;
+    if (q < 0) fprintf(stderr, "starway_b200: bulk kernel failed: %s\n", swgpu::last_error());
+    if (c->opt_profile.load()) {
+      float ms = swgpu::event_elapsed_ms(b.ev_start, b.ev);
+      if (ms >= 0) {
+        std::lock_guard<std::mutex> lk(c->st_mu);
+        c->stats.bulk_event_ms += ms;
+        c->stats.bulk_event_launches++;
+        c->stats.bulk_event_bytes += b.bytes;
+      }
+    }
+    for (BulkJob& j : b.jobs) bulk_job_done(c, j, q < 0 ? SW_ERR_IO_ERROR : SW_OK);
+    b.jobs.clear();
+    b.busy = false;
+    c->bulk_head++;
+    any = true;
+  }
+  while (!c->post_copies.empty()) {
+    PostCopy& pc = c->post_copies.front();
+    int q = swgpu::event_query(pc.ev);
+    if (q == 1) break;
+    complete(c, pc.op->w, pc.op->op_id, SW_OP_RECV, q < 0 ? SW_ERR_IO_ERROR : pc.status, pc.tag, pc.len);
+    swgpu::event_destroy(pc.ev);
+    recv_release(c, pc.op);
+    c->post_copies.pop_front();
+    any = true;
+  }
+  return any;
+}
+
+// ============================================================================ progress: control ring, flush, close
+void fail_ep_sends(Ctx* c, Ep* ep, int32_t status) {
+  while (!ep->sendq.empty()) {
+    SendOp* op = ep->sendq.front();
+    ep->sendq.pop_front();
+    send_finished(c, op, status);
+  }
+  for (auto& kv : ep->rndv_wait) send_finished(c, kv.second, status);
+  ep->rndv_wait.clear();
+  ep->cancel_wait.clear();
+}
+
+bool poll_ctl(Ctx* c, Ep* ep) {
+  if (!ep->shm) return false;
+  ctl_flush_backlog(ep);
+  ShmDir* d = ep->in;
+  bool any = false;
+  for (;;) {
+    uint64_t tail = d->ctl_tail.load(std::memory_order_relaxed);
+    uint64_t head = d->ctl_head.load(std::memory_order_acquire);
+    if (tail == head) break;
+    CtlMsg m = d->ctl[tail % CTL_RING];
+    d->ctl_tail.store(tail + 1, std::memory_order_release);
+    any = true;
+    switch (m.type) {
+      case CTL_FIN: {
+        ep->cancel_wait.erase(m.a);
+        auto it = ep->rndv_wait.find(m.a);
+        if (it != ep->rndv_wait.end()) {
+          SendOp* op = it->second;
+          ep->rndv_wait.erase(it);
+          send_finished(c, op, m.status);
+        }
+        break;
+      }
+      case CTL_CANCEL_ACK:
+        ep->cancel_wait.erase(m.a);
+        break;
+      case CTL_CANCEL_RTS: {
+        // the sender is closing and withdraws rendezvous m.a
+        bool in_flight = false;
+        for (uint32_t k = c->bulk_head; k != c->bulk_tail; k++)
+          for (BulkJob& j : c->bulk_blocks[k % N_BULK_BLOCKS].jobs)
+            if (j.ep == ep && j.rts.send_seq == m.a) in_flight = true;
+        if (!in_flight) {
+          ep->canceled_rts.insert(m.a);
+          ctl_send(ep, CTL_CANCEL_ACK, SW_OK, m.a);
+        }  // else: the FIN of the running pull acknowledges it
+        break;
+      }
+      case CTL_CLOSE:
+        ep->peer_closed = true;
+        ep->close_ack_owed = true;
+        fail_ep_sends(c, ep, SW_ERR_CONNECTION_RESET);
+        break;
+      case CTL_CLOSE_ACK:
+        ep->close_acked = true;
+        break;
+      default:
+        break;
+    }
+  }
+  if (ep->close_ack_owed && ep->puts_inflight == 0) {
+    // nothing of ours targets the peer's ring any more: it may free it
+    ctl_send(ep, CTL_CLOSE_ACK, SW_OK, 0);
+    ep->close_ack_owed = false;
+  }
+  return any;
+}
+
+void check_flushes(Ctx* c, Worker* w) {
+  for (size_t i = 0; i < w->flushes.size();) {
+    FlushOp* f = w->flushes[i];
+    bool done = true;
+    for (auto& kv : f->marks) {
+      Ep* ep = kv.first;
+      if (!ep->out_seqs.empty() && *ep->out_seqs.begin() < kv.second) {
+        done = false;
+        break;
+      }
+    }
+    if (done) {
+      complete(c, w, f->op_id, f->ep ? SW_OP_FLUSH_EP : SW_OP_FLUSH, SW_OK);
+      delete f;
+      w->flushes.erase(w->flushes.begin() + (long)i);
+    } else {
+      i++;
+    }
+  }
+}
+
+void worker_release(Ctx* c, Worker* w, bool leak_rings) {
+  for (Ep* ep : w->eps) {
+    if (ep->peer_ring_mapping) {
+      swgpu::ipc_close(ep->peer_ring_mapping);
+      ep->peer_ring_mapping = nullptr;
+    }
+    ep->peer_ring = nullptr;
+    bool safe = ep->close_acked || ep->in_process || !pid_alive(ep->peer_pid) || !leak_rings;
+    if (ep->ring && safe) swgpu::dev_free(ep->ring);
+    ep->ring = nullptr;
+    if (ep->shm) {
+      munmap(ep->shm, ep->shm_size);
+      ep->shm = nullptr;
+      ep->in = ep->out = nullptr;
+    }
+  }
+  if (w->mstate) {
+    swgpu::match_state_destroy(w->mstate);
+    w->mstate = nullptr;
+  }
+  if (w->min) swgpu::host_free(w->min);
+  if (w->mout) swgpu::host_free(w->mout);
+  w->min = nullptr;
+  w->mout = nullptr;
+  if (w->mev) swgpu::event_destroy(w->mev);
+  if (w->mev_start) swgpu::event_destroy(w->mev_start);
+  w->mev = w->mev_start = nullptr;
+  if (w->tcp_fd >= 0) close(w->tcp_fd);
+  if (w->unix_fd >= 0) close(w->unix_fd);
+  w->tcp_fd = w->unix_fd = -1;
+}
+
+// reference shutdown sequence: main.cpp:469-550 (client), 1269-1373 (server)
+bool progress_close(Ctx* c, Worker* w) {
+  if (w->close_phase == 0) return false;
+  if (w->close_phase == 1) {
+    // ---- cancel everything that has not reached the device / the wire
+    while (!w->new_posts.empty()) {
+      RecvOp* r = w->new_posts.front();
+      w->new_posts.pop_front();
+      complete(c, w, r->op_id, SW_OP_RECV, SW_ERR_CANCELED);
+      delete r;
+    }
+    for (FlushOp* f : w->flushes) {
+      complete(c, w, f->op_id, f->ep ? SW_OP_FLUSH_EP : SW_OP_FLUSH, SW_ERR_CANCELED);
+      delete f;
+    }
+    w->flushes.clear();
+    for (Ep* ep : w->eps) {
+      while (!ep->sendq.empty()) {
+        SendOp* op = ep->sendq.front();
+        ep->sendq.pop_front();
+        send_finished(c, op, SW_ERR_CANCELED);
+      }
+      // withdraw unmatched rendezvous sends; their buffers stay valid until the peer acknowledges
+      for (auto& kv : ep->rndv_wait) {
+        if (!ep->peer_closed) {
+          ctl_send(ep, CTL_CANCEL_RTS, SW_OK, kv.first);
+          ep->cancel_wait.insert(kv.first);
+        }
+      }
+    }
+    w->close_phase = 2;
+    w->close_deadline = now_s() + 3.0;
+    return true;
+  }
+  if (w->close_phase == 2) {
+    // ---- wait for in-flight device work and for the cancel acknowledgements
+    bool busy = w->match_inflight || w->bulk_inflight > 0;
+    for (Ep* ep : w->eps) {
+      if (ep->puts_inflight) busy = true;
+      if (!ep->cancel_wait.empty() && !ep->peer_closed && pid_alive(ep->peer_pid) && now_s() < w->close_deadline)
+        busy = true;
+    }
+    for (auto& j : c->pending_bulk)
+      if (j.w == w) busy = true;
+    for (auto& pc : c->post_copies)
+      if (pc.op->w == w) busy = true;
+    if (busy) return false;
+    for (Ep* ep : w->eps) {
+      for (auto& kv : ep->rndv_wait) send_finished(c, kv.second, SW_ERR_CANCELED);
+      ep->rndv_wait.clear();
+      ep->cancel_wait.clear();
+    }
+    // pending receives fail with "Request canceled" (reference main.cpp:498-502)
+    std::vector<uint64_t> ids;
+    for (auto& kv : w->recvs) ids.push_back(kv.first);
+    for (uint64_t id : ids) recv_finish(c, w, id, SW_ERR_CANCELED, 0, 0);
+    for (Ep* ep : w->eps) {
+      if (!ep->peer_closed && ep->shm) {
+        ctl_send(ep, CTL_CLOSE, SW_OK, 0);
+        ep->close_sent = true;
+      }
+    }
+    w->close_phase = 3;
+    w->close_deadline = now_s() + 2.0;
+    return true;
+  }
+  if (w->close_phase == 3) {
+    // ---- wait until no peer can still be writing into our rings
+    bool waiting = false;
+    for (Ep* ep : w->eps) {
+      ctl_flush_backlog(ep);
+      if (ep->close_sent && !ep->close_acked && pid_alive(ep->peer_pid) && now_s() < w->close_deadline) waiting = true;
+      if (ep->close_ack_owed || !ep->ctl_backlog.empty()) {
+        if (now_s() < w->close_deadline) waiting = true;
+      }
+    }
+    if (waiting) return false;
+    worker_release(c, w, true);
+    w->close_phase = 4;
+    w->status.store(SW_ST_CLOSED, std::memory_order_release);
+    if (w->close_op) complete(c, w, w->close_op, SW_OP_CLOSE, SW_OK);
+    return true;
+  }
+  return false;
+}
+
+// ============================================================================ progress thread
+void drain_sq(Ctx* c) {
+  if (c->sq_count.load(std::memory_order_acquire) == 0) return;
+  std::vector<SqItem> items;
+  {
+    std::lock_guard<std::mutex> lk(c->sq_mu);
+    items.swap(c->sq);
+    c->sq_count.store(0, std::memory_order_release);
+  }
+  for (SqItem& it : items) {
+    Worker* w = it.w;
+    switch (it.kind) {
+      case SQ_REGISTER: {
+        if (!w->registered) {
+          c->active.push_back(w);
+          w->registered = true;
+        }
+        if (w->kind == SW_WORKER_CLIENT) {
+          w->status.store(SW_ST_RUNNING, std::memory_order_release);
+          complete(c, w, (uint64_t)(uintptr_t)it.p, SW_OP_CONNECT, SW_OK);
+        }
+        break;
+      }
+      case SQ_SEND: {
+        SendOp* op = (SendOp*)it.p;
+        int st = w->status.load(std::memory_order_acquire);
+        if (st != SW_ST_RUNNING || w->close_phase != 0) {
+          // reference: submitted after close began -> UCS_ERR_NOT_CONNECTED (main.cpp:619-622)
+          complete(c, w, op->op_id, SW_OP_SEND, st == SW_ST_RUNNING ? SW_ERR_CANCELED : SW_ERR_NOT_CONNECTED);
+          delete op;
+          break;
+        }
+        op->sseq = op->ep->next_sseq++;
+        op->ep->out_seqs.insert(op->sseq);
+        op->ep->sendq.push_back(op);
+        break;
+      }
+      case SQ_RECV: {
+        RecvOp* r = (RecvOp*)it.p;
+        int st = w->status.load(std::memory_order_acquire);
+        if (st != SW_ST_RUNNING || w->close_phase != 0) {
+          complete(c, w, r->op_id, SW_OP_RECV, st == SW_ST_RUNNING ? SW_ERR_CANCELED : SW_ERR_NOT_CONNECTED);
+          delete r;
+          break;
+        }
+        w->new_posts.push_back(r);
+        break;
+      }
+      case SQ_FLUSH: {
+        FlushOp* f = (FlushOp*)it.p;
+        int st = w->status.load(std::memory_order_acquire);
+        if (st != SW_ST_RUNNING || w->close_phase != 0) {
+          complete(c, w, f->op_id, f->ep ? SW_OP_FLUSH_EP : SW_OP_FLUSH,
+                   st == SW_ST_RUNNING ? SW_ERR_CANCELED : SW_ERR_NOT_CONNECTED);
+          delete f;
+          break;
+        }
+        if (f->ep)
+          f->marks[f->ep] = f->ep->next_sseq;
+        else
+          for (Ep* ep : w->eps) f->marks[ep] = ep->next_sseq;
+        w->flushes.push_back(f);
+        break;
+      }
+      case SQ_CLOSE: {
+        w->close_op = (uint64_t)(uintptr_t)it.p;
+        if (w->close_phase == 0) w->close_phase = 1;
+        if (!w->registered) {
+          c->active.push_back(w);
+          w->registered = true;
+        }
+        break;
+      }
+      default:
+        break;
+    }
+  }
+}
+
+void progress_main(Ctx* c) {
+  swgpu::bind_thread(c->device);
+  uint64_t iter = 0;
+  double last_active = now_s();
+  while (!c->stop.load(std::memory_order_acquire)) {
+    bool active = false;
+    drain_sq(c);
+    active |= poll_puts(c);
+    active |= pump_sends(c);
+    for (Worker* w : c->active) {
+      if (w->close_phase >= 4) continue;
+      for (Ep* ep : w->eps) active |= poll_ctl(c, ep);
+      active |= poll_match(c, w);
+      active |= pump_match(c, w);
+      check_flushes(c, w);
+      active |= progress_close(c, w);
+      if ((iter & 31) == 0 && w->kind == SW_WORKER_SERVER) poll_listeners(c, w);
+    }
+    active |= poll_bulk(c);
+    active |= pump_bulk(c);
+    // forget fully closed workers
+    if ((iter & 1023) == 0) {
+      c->active.erase(std::remove_if(c->active.begin(), c->active.end(), [](Worker* w) { return w->close_phase >= 4; }),
+                      c->active.end());
+    }
+    iter++;
+    bool inflight = (c->put_head != c->put_tail) || (c->bulk_head != c->bulk_tail) || !c->post_copies.empty();
+    for (Worker* w : c->active) inflight |= w->match_inflight;
+    if (active || inflight) {
+      last_active = now_s();
+    } else {
+      double idle = now_s() - last_active;
+      if (idle > 0.02) {
+        struct timespec ts = {0, 200000};
+        nanosleep(&ts, nullptr);
+      } else if (idle > 0.001) {
+        struct timespec ts = {0, 20000};
+        nanosleep(&ts, nullptr);
+      } else if (idle > 0.0001) {
+        sched_yield();
+      }
+    }
+  }
+}
+
+Worker* find_worker(Ctx* c, sw_worker_t id) {
+  std::lock_guard<std::mutex> lk(c->mu);
+  auto it = c->workers.find(id);
+  return it == c->workers.end() ? nullptr : it->second;
+}
+Ep* find_ep(Ctx* c, sw_ep_t id) {
+  std::lock_guard<std::mutex> lk(c->mu);
+  auto it = c->eps.find(id);
+  return it == c->eps.end() ? nullptr : it->second;
+}
+
+int classify_mem(const void* ptr, int mem_kind) {
+  if (mem_kind == SW_MEM_HOST || mem_kind == SW_MEM_DEVICE) return mem_kind;
+  swgpu::PtrInfo pi;
+  swgpu::ptr_info(ptr, &pi);
+  return pi.is_device ? SW_MEM_DEVICE : SW_MEM_HOST;
+}
+
+}  // namespace
+
+// ================================================================================== C ABI
+extern "C" {
+
+int sw_abi_version(void) { return SW_ABI_VERSION; }
+const char* sw_backend_name(void) { return swgpu::backend_name(); }
+const char* sw_last_error(void) { return g_last_error.c_str(); }
+int sw_device_count(void) { return swgpu::device_count(); }
+
+const char* sw_status_string(int32_t status) {
+  switch (status) {
+    case SW_STATUS_OK: return "Success";
+    case SW_STATUS_IO_ERROR: return "Input/output error";
+    case SW_STATUS_NO_MEMORY: return "Out of memory";
+    case SW_STATUS_INVALID_PARAM: return "Invalid parameter";
+    case SW_STATUS_UNREACHABLE: return "Destination is unreachable";
+    case SW_STATUS_MESSAGE_TRUNCATED: return "Message truncated";
+    case SW_STATUS_BUSY: return "Device is busy";
+    case SW_STATUS_CANCELED: return "Request canceled";
+    case SW_STATUS_TIMED_OUT: return "Operation timed out";
+    case SW_STATUS_NOT_CONNECTED: return "Endpoint is not connected";
+    case SW_STATUS_CONNECTION_RESET: return "Connection reset by remote peer";
+    default: return "Unknown error";
+  }
+}
+
+sw_ctx* sw_ctx_create(int device) {
+  if (swgpu::init(device) != 0) {
+    set_error(std::string("sw_ctx_create: ") + swgpu::last_error());
+    return nullptr;
+  }
+  Ctx* c = new Ctx();
+  c->device = device;
+  c->uuid = rand64() | 1;
+  memset(&c->stats, 0, sizeof(c->stats));
+  c->efd = eventfd(0, EFD_NONBLOCK | EFD_CLOEXEC);
+  c->s_put = swgpu::stream_create();
+  c->s_match = swgpu::stream_create();
+  c->s_bulk = swgpu::stream_create();
+  bool ok = c->s_put && c->s_match && c->s_bulk;
+  for (int i = 0; ok && i < N_PUT_BLOCKS; i++) {
+    PutBlock& b = c->put_blocks[i];
+    b.descs = (SwPutDesc*)swgpu::host_alloc(sizeof(SwPutDesc) * PUT_BATCH);
+    b.rts = (SwRts*)swgpu::host_alloc(sizeof(SwRts) * PUT_BATCH);
+    b.stage = (uint8_t*)swgpu::host_alloc((size_t)PUT_BATCH * SW_SLOT_BYTES);
+    b.ev = swgpu::event_create(1);
+    b.ev_start = swgpu::event_create(1);
+    ok = b.descs && b.rts && b.stage && b.ev && b.ev_start;
+  }
+  for (int i = 0; ok && i < N_BULK_BLOCKS; i++) {
+    BulkBlock& b = c->bulk_blocks[i];
+    b.segs = (SwSeg*)swgpu::host_alloc(sizeof(SwSeg) * MAX_SEGS);
+    b.ev = swgpu::event_create(1);
+    b.ev_start = swgpu::event_create(1);
+    ok = b.segs && b.ev && b.ev_start;
+  }
+  if (!ok) {
+    set_error(std::string("sw_ctx_create: ") + swgpu::last_error());
+    delete c;
+    return nullptr;
+  }
+  // environment knobs
+  if (const char* e = getenv("STARWAY_EAGER_MAX")) c->opt_eager_max = std::min<int64_t>(atoll(e), SW_EAGER_MAX);
+  if (const char* e = getenv("STARWAY_RING_SLOTS")) c->opt_ring_slots = std::max<int64_t>(atoll(e), 4);
+  if (const char* e = getenv("STARWAY_BULK_MODE")) c->opt_bulk_mode = atoll(e);
+  if (const char* e = getenv("STARWAY_BULK_STAGES")) c->opt_bulk_stages = atoll(e);
+  if (const char* e = getenv("STARWAY_BULK_STAGE_BYTES")) c->opt_bulk_stage_bytes = atoll(e);
+  if (const char* e = getenv("STARWAY_BULK_CTAS")) c->opt_bulk_ctas = atoll(e);
+  c->thr = std::thread(progress_main, c);
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  g_ctxs.push_back(c);
+  return (sw_ctx*)c;
+}
+
+int sw_ctx_device(sw_ctx* ctx) { return ((Ctx*)ctx)->device; }
+
+void sw_ctx_destroy(sw_ctx* ctx) {
+  Ctx* c = (Ctx*)ctx;
+  if (!c) return;
+  // close every running worker first (reference ~Client/~Server force status 3 and join)
+  std::vector<Worker*> ws;
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (auto& kv : c->workers) ws.push_back(kv.second);
+  }
+  for (Worker* w : ws) sw_worker_destroy(ctx, w->id);
+  c->stop.store(true, std::memory_order_release);
+  if (c->thr.joinable()) c->thr.join();
+  swgpu::bind_thread(c->device);
+  for (int i = 0; i < N_PUT_BLOCKS; i++) {
+    PutBlock& b = c->put_blocks[i];
+    swgpu::host_free(b.descs);
+    swgpu::host_free(b.rts);
+    swgpu::host_free(b.stage);
+    if (b.ev) swgpu::event_destroy(b.ev);
+    if (b.ev_start) swgpu::event_destroy(b.ev_start);
+  }
+  for (int i = 0; i < N_BULK_BLOCKS; i++) {
+    BulkBlock& b = c->bulk_blocks[i];
+    swgpu::host_free(b.segs);
+    if (b.ev) swgpu::event_destroy(b.ev);
+    if (b.ev_start) swgpu::event_destroy(b.ev_start);
+  }
+  for (auto& kv : c->mappings) swgpu::ipc_close(kv.second.base);
+  c->host_pool.destroy();
+  swgpu::stream_destroy(c->s_put);
+  swgpu::stream_destroy(c->s_match);
+  swgpu::stream_destroy(c->s_bulk);
+  if (c->efd >= 0) close(c->efd);
+  {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    g_ctxs.erase(std::remove(g_ctxs.begin(), g_ctxs.end(), c), g_ctxs.end());
+  }
+  for (Worker* w : ws) {
+    if (w->connector.joinable()) w->connector.join();
+    for (Ep* ep : w->eps) delete ep;
+    delete w;
+  }
+  delete c;
+}
+
+int sw_set_option(sw_ctx* ctx, const char* key, int64_t value) {
+  Ctx* c = (Ctx*)ctx;
+  std::string k(key);
+  if (k == "eager_max") c->opt_eager_max = std::max<int64_t>(0, std::min<int64_t>(value, SW_EAGER_MAX));
+  else if (k == "ring_slots") c->opt_ring_slots = std::max<int64_t>(4, value);
+  else if (k == "bulk_mode") c->opt_bulk_mode = value;
+  else if (k == "bulk_stages") c->opt_bulk_stages = value;
+  else if (k == "bulk_stage_bytes") c->opt_bulk_stage_bytes = value;
+  else if (k == "bulk_ctas_per_sm") c->opt_bulk_ctas = value;
+  else if (k == "heap_small_blocks") c->opt_heap_small = std::max<int64_t>(1, value);
+  else if (k == "heap_big_blocks") c->opt_heap_big = std::max<int64_t>(1, value);
+  else if (k == "profile") c->opt_profile = value;
+  else {
+    set_error("unknown option " + k);
+    return -1;
+  }
+  return 0;
+}
+int64_t sw_get_option(sw_ctx* ctx, const char* key) {
+  Ctx* c = (Ctx*)ctx;
+  std::string k(key);
+  if (k == "eager_max") return c->opt_eager_max;
+  if (k == "ring_slots") return c->opt_ring_slots;
+  if (k == "bulk_mode") return c->opt_bulk_mode;
+  if (k == "bulk_stages") return c->opt_bulk_stages;
+  if (k == "bulk_stage_bytes") return c->opt_bulk_stage_bytes;
+  if (k == "bulk_ctas_per_sm") return c->opt_bulk_ctas;
+  if (k == "heap_small_blocks") return c->opt_heap_small;
+  if (k == "heap_big_blocks") return c->opt_heap_big;
+  if (k == "profile") return c->opt_profile;
+  if (k == "sm_count") return swgpu::sm_count();
+  return -1;
+}
+
+sw_worker_t sw_worker_create(sw_ctx* ctx, int kind) {
+  Ctx* c = (Ctx*)ctx;
+  if (kind != SW_WORKER_SERVER && kind != SW_WORKER_CLIENT) {
+    set_error("bad worker kind");
+    return 0;
+  }
+  Worker* w = new Worker();
+  w->id = c->next_id.fetch_add(1);
+  w->kind = kind;
+  w->ctx = c;
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->workers[w->id] = w;
+  return w->id;
+}
+
+int sw_worker_status(sw_ctx* ctx, sw_worker_t wid) {
+  Worker* w = find_worker((Ctx*)ctx, wid);
+  return w ? w->status.load(std::memory_order_acquire) : -1;
+}
+
+static int server_start(Ctx* c, Worker* w, const char* addr, uint16_t port, bool tcp) {
+  int expected = SW_ST_VOID;
+  if (w->kind != SW_WORKER_SERVER || !w->status.compare_exchange_strong(expected, SW_ST_INIT)) {
+    // reference main.cpp:818-820
+    set_error("Server: already listening. You can only listen once, and cannot listen again after close.");
+    return -1;
+  }
+  swgpu::bind_thread(c->device);
+  if (!worker_alloc_device(c, w)) {
+    w->status.store(SW_ST_VOID);
+    return -1;
+  }
+  w->unix_fd = make_unix_listener(w->unix_name);
+  if (w->unix_fd < 0) {
+    set_error("Server: failed to create the bootstrap socket");
+    worker_release(c, w, false);
+    w->status.store(SW_ST_VOID);
+    return -1;
+  }
+  if (tcp) {
+    w->tcp_fd = make_tcp_listener(addr, port);
+    if (w->tcp_fd < 0) {
+      set_error(std::string("UCP error: failed to create listener - ") + strerror(errno));
+      worker_release(c, w, false);
+      w->status.store(SW_ST_VOID);
+      return -1;
+    }
+  }
+  fill_blob(c, w);
+  w->status.store(SW_ST_RUNNING, std::memory_order_release);
+  sq_push(c, SQ_REGISTER, w, nullptr);
+  return 0;
+}
+
+int sw_listen(sw_ctx* ctx, sw_worker_t wid, const char* addr, uint16_t port) {
+  Ctx* c = (Ctx*)ctx;
+  Worker* w = find_worker(c, wid);
+  if (!w) {
+    set_error("bad worker handle");
+    return -1;
+  }
+  return server_start(c, w, addr, port, true);
+}
+int sw_listen_address(sw_ctx* ctx, sw_worker_t wid) {
+  Ctx* c = (Ctx*)ctx;
+  Worker* w = find_worker(c, wid);
+  if (!w) {
+    set_error("bad worker handle");
+    return -1;
+  }
+  return server_start(c, w, nullptr, 0, false);
+}
+
+int64_t sw_get_address(sw_ctx* ctx, sw_worker_t wid, void* out, size_t cap) {
+  Worker* w = find_worker((Ctx*)ctx, wid);
+  if (!w || !w->blob_ready.load(std::memory_order_acquire) || w->status.load() == SW_ST_CLOSED) {
+    // reference main.cpp:587-590, 854-857
+    set_error(w && w->kind == SW_WORKER_CLIENT ? "Client: worker address not ready. Connect first before querying."
+                                               : "Server: worker address not ready. Start listening first.");
+    return -1;
+  }
+  if (cap < sizeof(AddrBlob)) return (int64_t)sizeof(AddrBlob);
+  memcpy(out, &w->blob, sizeof(AddrBlob));
+  return (int64_t)sizeof(AddrBlob);
+}
+
+static uint64_t client_start(Ctx* c, Worker* w, ConnectReq req) {
+  int expected = SW_ST_VOID;
+  if (w->kind != SW_WORKER_CLIENT || !w->status.compare_exchange_strong(expected, SW_ST_INIT)) {
+    // reference main.cpp:554-555
+    set_error("Client: already connected. You can only connect once, and cannot reconnect after close.");
+    return 0;
+  }
+  req.op_id = c->next_id.fetch_add(1);
+  fill_blob(c, w);
+  w->connector = std::thread(client_connect_thread, c, w, req);
+  return req.op_id;
+}
+
+uint64_t sw_connect(sw_ctx* ctx, sw_worker_t wid, const char* addr, uint16_t port) {
+  Ctx* c = (Ctx*)ctx;
+  Worker* w = find_worker(c, wid);
+  if (!w) {
+    set_error("bad worker handle");
+    return 0;
+  }
+  ConnectReq req;
+  req.mode = 0;
+  req.addr = addr ? addr : "";
+  req.port = port;
+  memset(&req.blob, 0, sizeof(req.blob));
+  return client_start(c, w, req);
+}
+uint64_t sw_connect_address(sw_ctx* ctx, sw_worker_t wid, const void* blob, size_t len) {
+  Ctx* c = (Ctx*)ctx;
+  Worker* w = find_worker(c, wid);
+  if (!w) {
+    set_error("bad worker handle");
+    return 0;
+  }
+  ConnectReq req;
+  req.mode = 1;
+  req.port = 0;
+  memset(&req.blob, 0, sizeof(req.blob));
+  if (blob && len >= sizeof(AddrBlob)) memcpy(&req.blob, blob, sizeof(AddrBlob));
+  return client_start(c, w, req);
+}
+
+uint64_t sw_close(sw_ctx* ctx, sw_worker_t wid) {
+  Ctx* c = (Ctx*)ctx;
+  Worker* w = find_worker(c, wid);
+  int expected = SW_ST_RUNNING;
+  if (!w || !w->status.compare_exchange_strong(expected, SW_ST_CLOSING)) {
+    // reference main.cpp:596-597, 1377-1378
+    set_error(w && w->kind == SW_WORKER_SERVER ? "Server: not running. You can only close once, after listen."
+                                               : "Client: not running. You can only close once, after connect done.");
+    return 0;
+  }
+  uint64_t op = c->next_id.fetch_add(1);
+  sq_push(c, SQ_CLOSE, w, (void*)(uintptr_t)op);
+  return op;
+}
+
+int sw_worker_destroy(sw_ctx* ctx, sw_worker_t wid) {
+  Ctx* c = (Ctx*)ctx;
+  Worker* w = find_worker(c, wid);
+  if (!w) return -1;
+  // a connect may still be running
+  if (w->connector.joinable()) w->connector.join();
+  double deadline = now_s() + 2.0;
+  while (w->status.load() == SW_ST_INIT && now_s() < deadline) sched_yield();
+  int expected = SW_ST_RUNNING;
+  if (w->status.compare_exchange_strong(expected, SW_ST_CLOSING)) sq_push(c, SQ_CLOSE, w, nullptr);
+  deadline = now_s() + 10.0;
+  while (w->status.load() == SW_ST_CLOSING && now_s() < deadline) {
+    struct timespec ts = {0, 100000};
+    nanosleep(&ts, nullptr);
+  }
+  return 0;
+}
+
+static uint64_t not_running(Worker* w, const char* verb) {
+  // reference main.cpp:607-608, 629-630, 651-652, 1389-1390, 1413-1414, 1435-1436, 1455-1456
+  bool server = w && w->kind == SW_WORKER_SERVER;
+  set_error(std::string(server ? "Server" : "Client") + ": not running. You can only " + verb + ", after " +
+            (server ? "listen." : "connect."));
+  return 0;
+}
+
+uint64_t sw_post_send(sw_ctx* ctx, sw_worker_t wid, sw_ep_t epid, const void* ptr, size_t len, uint64_t tag,
+                      int mem_kind) {
+  Ctx* c = (Ctx*)ctx;
+  Worker* w = find_worker(c, wid);
+  if (!w || w->status.load(std::memory_order_acquire) != SW_ST_RUNNING) return not_running(w, "send");
+  Ep* ep = nullptr;
+  if (w->kind == SW_WORKER_CLIENT) {
+    ep = w->eps.empty() ? nullptr : w->eps[0];
+  } else {
+    ep = find_ep(c, epid);
+    if (ep && ep->owner != w) ep = nullptr;
+  }
+  if (!ep) {
+    set_error("send: unknown endpoint");
+    return 0;
+  }
+  SendOp* op = new SendOp();
+  op->op_id = c->next_id.fetch_add(1);
+  op->w = w;
+  op->ep = ep;
+  op->ptr = (const uint8_t*)ptr;
+  op->len = len;
+  op->tag = tag;
+  op->mem = len ? classify_mem(ptr, mem_kind) : SW_MEM_DEVICE;
+  uint64_t id = op->op_id;
+  sq_push(c, SQ_SEND, w, op);
+  return id;
+}
+
+uint64_t sw_post_recv(sw_ctx* ctx, sw_worker_t wid, void* ptr, size_t cap, uint64_t tag, uint64_t tag_mask,
+                      int mem_kind) {
+  Ctx* c = (Ctx*)ctx;
+  Worker* w = find_worker(c, wid);
+  if (!w || w->status.load(std::memory_order_acquire) != SW_ST_RUNNING) return not_running(w, "recv");
+  RecvOp* r = new RecvOp();
+  r->op_id = c->next_id.fetch_add(1);
+  r->w = w;
+  r->ptr = (uint8_t*)ptr;
+  r->cap = cap;
+  r->tag = tag;
+  r->mask = tag_mask;
+  r->mem = cap ? classify_mem(ptr, mem_kind) : SW_MEM_DEVICE;
+  uint64_t id = r->op_id;
+  sq_push(c, SQ_RECV, w, r);
+  return id;
+}
+
+uint64_t sw_post_flush(sw_ctx* ctx, sw_worker_t wid) {
+  Ctx* c = (Ctx*)ctx;
+  Worker* w = find_worker(c, wid);
+  if (!w || w->status.load(std::memory_order_acquire) != SW_ST_RUNNING) return not_running(w, "flush");
+  FlushOp* f = new FlushOp();
+  f->op_id = c->next_id.fetch_add(1);
+  uint64_t id = f->op_id;
+  sq_push(c, SQ_FLUSH, w, f);
+  return id;
+}
+uint64_t sw_post_flush_ep(sw_ctx* ctx, sw_worker_t wid, sw_ep_t epid) {
+  Ctx* c = (Ctx*)ctx;
+  Worker* w = find_worker(c, wid);
+  if (!w || w->status.load(std::memory_order_acquire) != SW_ST_RUNNING) return not_running(w, "flush");
+  Ep* ep = find_ep(c, epid);
+  if (!ep || ep->owner != w) {
+    set_error("flush_ep: unknown endpoint");
+    return 0;
+  }
+  FlushOp* f = new FlushOp();
+  f->op_id = c->next_id.fetch_add(1);
+  f->ep = ep;
+  uint64_t id = f->op_id;
+  sq_push(c, SQ_FLUSH, w, f);
+  return id;
+}
+
+int sw_poll(sw_ctx* ctx, sw_completion* out, int max) {
+  Ctx* c = (Ctx*)ctx;
+  std::lock_guard<std::mutex> lk(c->cq_mu);
+  int n = 0;
+  while (n < max && !c->cq.empty()) {
+    out[n++] = c->cq.front();
+    c->cq.pop_front();
+  }
+  if (c->cq.empty() && c->efd >= 0) {
+    uint64_t v;
+    ssize_t r = read(c->efd, &v, sizeof(v));
+    (void)r;
+  }
+  return n;
+}
+
+int sw_wait(sw_ctx* ctx, sw_completion* out, int max, int timeout_ms) {
+  Ctx* c = (Ctx*)ctx;
+  std::unique_lock<std::mutex> lk(c->cq_mu);
+  if (c->cq.empty()) c->cq_cv.wait_for(lk, std::chrono::milliseconds(timeout_ms), [&] { return !c->cq.empty(); });
+  int n = 0;
+  while (n < max && !c->cq.empty()) {
+    out[n++] = c->cq.front();
+    c->cq.pop_front();
+  }
+  if (c->cq.empty() && c->efd >= 0) {
+    uint64_t v;
+    ssize_t r = read(c->efd, &v, sizeof(v));
+    (void)r;
+  }
+  return n;
+}
+
+int sw_event_fd(sw_ctx* ctx) { return ((Ctx*)ctx)->efd; }
+
+int sw_list_eps(sw_ctx* ctx, sw_worker_t wid, sw_ep_t* out, int max) {
+  Ctx* c = (Ctx*)ctx;
+  std::lock_guard<std::mutex> lk(c->mu);
+  auto it = c->workers.find(wid);
+  if (it == c->workers.end()) return -1;
+  int n = 0;
+  // endpoints are never removed (reference: tests/test_basic.py:53-56)
+  std::vector<uint64_t> ids;
+  for (auto& kv : c->eps)
+    if (kv.second->owner == it->second) ids.push_back(kv.first);
+  std::sort(ids.begin(), ids.end());
+  for (uint64_t id : ids) {
+    if (n < max) out[n] = id;
+    n++;
+  }
+  return n;
+}
+
+int sw_ep_info_get(sw_ctx* ctx, sw_worker_t wid, sw_ep_t epid, sw_ep_info* out) {
+  Ep* ep = find_ep((Ctx*)ctx, epid);
+  if (!ep || ep->owner->id != wid) return -1;
+  *out = ep->info;
+  return 0;
+}
+
+// reference evaluate_perf (main.cpp:452-467, 666-678): UCX's analytic estimate; here a
+// latency + size/bandwidth model from the measured curves (seconds)
+double sw_evaluate_perf(sw_ctx* ctx, sw_worker_t wid, sw_ep_t epid, size_t msg_size) {
+  Ctx* c = (Ctx*)ctx;
+  Worker* w = find_worker(c, wid);
+  if (!w || w->status.load() != SW_ST_RUNNING) {
+    set_error("Server: not running. You can only evaluate perf, after listen.");
+    return -1.0;
+  }
+  Ep* ep = epid ? find_ep(c, epid) : (w->eps.empty() ? nullptr : w->eps[0]);
+  bool local = !ep || ep->in_process || ep->peer_device == c->device;
+  double lat = msg_size <= SW_EAGER_MAX ? 12e-6 : 30e-6;
+  double bw = local ? 2.8e12 : 7.0e11;
+  return lat + (double)msg_size / bw;
+}
+
+int sw_stats_get(sw_ctx* ctx, sw_stats* out) {
+  Ctx* c = (Ctx*)ctx;
+  std::lock_guard<std::mutex> lk(c->st_mu);
+  *out = c->stats;
+  return 0;
+}
+int sw_stats_reset(sw_ctx* ctx) {
+  Ctx* c = (Ctx*)ctx;
+  std::lock_guard<std::mutex> lk(c->st_mu);
+  memset(&c->stats, 0, sizeof(c->stats));
+  return 0;
+}
+
+}  // extern "C"

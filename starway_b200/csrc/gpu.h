@@ -1,0 +1,76 @@
+// starway_b200 — the narrow interface between the host progress engine
+// (engine.cpp) and the device backend.  The product backend is gpu_cuda.cu
+// (hand-written sm_100a kernels).  tests/hostsim/gpu_sim.cpp is a test-only
+// stand-in that lets the CPU test-suite exercise the host protocol logic
+// without a GPU; it is never linked into the product library.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include "sw_device.h"
+
+namespace swgpu {
+
+typedef void* stream_t;
+typedef void* event_t;
+
+struct PtrInfo {
+  int is_device;      // 1: device memory, 0: host (pageable or pinned)
+  int is_pinned;      // host memory registered/pinned with CUDA (device accessible)
+  int device;         // ordinal for device memory
+  uint64_t base;      // allocation base (device memory)
+  uint64_t size;      // allocation size (device memory)
+};
+
+struct BulkTuning {
+  int mode;           // 0: TMA-staged (cp.async.bulk), 1: SIMT vectorised
+  int stages;         // TMA smem stages per CTA (2..8)
+  int stage_bytes;    // bytes per stage (multiple of 16)
+  int ctas_per_sm;    // resident CTAs per SM targeted
+};
+
+const char* backend_name();
+const char* last_error();
+
+int device_count();
+int init(int device);                 // binds the calling thread to `device`
+int bind_thread(int device);          // cudaSetDevice for helper threads
+int sm_count();
+
+void* dev_alloc(size_t bytes);        // IPC-shareable device allocation, zeroed
+int dev_free(void* p);
+void* host_alloc(size_t bytes);       // pinned, device-mapped host memory, zeroed
+int host_free(void* p);
+
+int ipc_get(const void* alloc_base, uint8_t handle[64]);
+int ipc_open(const uint8_t handle[64], void** out);
+int ipc_close(void* p);
+int ptr_info(const void* p, PtrInfo* out);
+
+stream_t stream_create();
+int stream_destroy(stream_t s);
+int stream_sync(stream_t s);
+event_t event_create(int timing);
+int event_destroy(event_t e);
+int event_record(event_t e, stream_t s);
+int event_query(event_t e);           // 0: complete, 1: not ready, <0: error
+int event_sync(event_t e);
+float event_elapsed_ms(event_t a, event_t b);
+
+int memcpy_h2d(void* dst, const void* src, size_t n, stream_t s);
+int memcpy_d2h(void* dst, const void* src, size_t n, stream_t s);
+int memcpy_d2d(void* dst, const void* src, size_t n, stream_t s);
+int memset_dev(void* dst, int v, size_t n, stream_t s);
+int upload(void* dst_dev, const void* src_host, size_t n);   // synchronous small upload
+
+// Build/destroy the device-resident queues of one worker.
+SwMatchState* match_state_create(uint32_t heap_small_blocks, uint32_t heap_big_blocks);
+int match_state_destroy(SwMatchState* st);
+int match_state_set_ring(SwMatchState* st, uint32_t ep, void* ring_base, uint32_t slots);
+
+// Kernel launches (asynchronous on `s`).
+int launch_put(stream_t s, const SwPutDesc* descs, uint32_t n);
+int launch_match(stream_t s, SwMatchState* st, const SwMatchIn* in, SwMatchOut* out);
+int launch_deliver(stream_t s, SwMatchState* st, SwMatchOut* out, uint32_t max_jobs);
+int launch_bulk(stream_t s, const SwSeg* segs, uint32_t nseg, const BulkTuning* tune);
+
+}  // namespace swgpu

@@ -1,0 +1,372 @@
+// starway_b200 — CUDA (sm_100a) implementation of the swgpu backend interface.
+// Compiled with: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "gpu.h"
+#include "kernels.cuh"
+
+namespace swgpu {
+
+static thread_local std::string g_err;
+static int g_sms = 148;
+static int g_max_smem_optin = 0;
+
+static int fail(cudaError_t e, const char* what) {
+  char buf[256];
+  snprintf(buf, sizeof(buf), "%s: %s (%d)", what, cudaGetErrorString(e), (int)e);
+  g_err = buf;
+  cudaGetLastError();  // clear sticky-less errors
+  return -1;
+}
+#define SW_CUDA(call)                            \
+  do {                                           \
+    cudaError_t e__ = (call);                    \
+    if (e__ != cudaSuccess) return fail(e__, #call); \
+  } while (0)
+
+const char* backend_name() { return "cuda-sm_100a"; }
+const char* last_error() { return g_err.c_str(); }
+
+int device_count() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int init(int device) {
+  int n = device_count();
+  if (n <= 0) {
+    g_err = "no CUDA device visible: starway_b200 has no CPU fallback";
+    return -1;
+  }
+  if (device < 0 || device >= n) {
+    g_err = "CUDA device ordinal out of range";
+    return -1;
+  }
+  SW_CUDA(cudaSetDevice(device));
+  SW_CUDA(cudaFree(0));
+  cudaDeviceProp prop;
+  SW_CUDA(cudaGetDeviceProperties(&prop, device));
+  g_sms = prop.multiProcessorCount;
+  g_max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  cudaFuncAttributes fa;
+  SW_CUDA(cudaFuncGetAttributes(&fa, sw_bulk_tma_kernel));
+  g_max_smem_optin -= (int)fa.sharedSizeBytes;   // static mbarrier storage counts against the opt-in limit
+  SW_CUDA(cudaFuncSetAttribute(sw_bulk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem_optin));
+  return 0;
+}
+int bind_thread(int device) {
+  SW_CUDA(cudaSetDevice(device));
+  return 0;
+}
+int sm_count() { return g_sms; }
+
+void* dev_alloc(size_t bytes) {
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+  if (e != cudaSuccess) {
+    fail(e, "cudaMalloc");
+    return nullptr;
+  }
+  e = cudaMemset(p, 0, bytes);
+  if (e != cudaSuccess) {
+    fail(e, "cudaMemset");
+    cudaFree(p);
+    return nullptr;
+  }
+  return p;
+}
+int dev_free(void* p) {
+  if (p) SW_CUDA(cudaFree(p));
+  return 0;
+}
+void* host_alloc(size_t bytes) {
+  void* p = nullptr;
+  cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocPortable | cudaHostAllocMapped);
+  if (e != cudaSuccess) {
+    fail(e, "cudaHostAlloc");
+    return nullptr;
+  }
+  memset(p, 0, bytes);
+  return p;
+}
+int host_free(void* p) {
+  if (p) SW_CUDA(cudaFreeHost(p));
+  return 0;
+}
+
+int ipc_get(const void* alloc_base, uint8_t handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+  cudaIpcMemHandle_t h;
+  SW_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(alloc_base)));
+  memcpy(handle, &h, 64);
+  return 0;
+}
+int ipc_open(const uint8_t handle[64], void** out) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  SW_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+int ipc_close(void* p) {
+  SW_CUDA(cudaIpcCloseMemHandle(p));
+  return 0;
+}
+
+int ptr_info(const void* p, PtrInfo* out) {
+  memset(out, 0, sizeof(*out));
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return 0;  // plain host memory unknown to CUDA
+  }
+  if (a.type == cudaMemoryTypeDevice) {
+    out->is_device = 1;
+    out->device = a.device;
+    // allocation range through the driver entry point (no link-time libcuda dependency)
+    typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
+    static range_fn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+      void* f = nullptr;
+      cudaDriverEntryPointQueryResult qr;
+      if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &qr) == cudaSuccess &&
+          qr == cudaDriverEntryPointSuccess)
+        fn = reinterpret_cast<range_fn>(f);
+      else
+        cudaGetLastError();
+    });
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (fn && fn(&base, &size, (unsigned long long)(uintptr_t)p) == 0) {
+      out->base = base;
+      out->size = size;
+    }
+  } else if (a.type == cudaMemoryTypeHost) {
+    out->is_pinned = 1;
+  } else if (a.type == cudaMemoryTypeManaged) {
+    out->is_device = 1;
+    out->device = a.device;
+  }
+  return 0;
+}
+
+stream_t stream_create() {
+  cudaStream_t s;
+  cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    fail(e, "cudaStreamCreate");
+    return nullptr;
+  }
+  return (stream_t)s;
+}
+int stream_destroy(stream_t s) {
+  SW_CUDA(cudaStreamDestroy((cudaStream_t)s));
+  return 0;
+}
+int stream_sync(stream_t s) {
+  SW_CUDA(cudaStreamSynchronize((cudaStream_t)s));
+  return 0;
+}
+event_t event_create(int timing) {
+  cudaEvent_t e;
+  cudaError_t r = cudaEventCreateWithFlags(&e, timing ? cudaEventDefault : cudaEventDisableTiming);
+  if (r != cudaSuccess) {
+    fail(r, "cudaEventCreate");
+    return nullptr;
+  }
+  return (event_t)e;
+}
+int event_destroy(event_t e) {
+  SW_CUDA(cudaEventDestroy((cudaEvent_t)e));
+  return 0;
+}
+int event_record(event_t e, stream_t s) {
+  SW_CUDA(cudaEventRecord((cudaEvent_t)e, (cudaStream_t)s));
+  return 0;
+}
+int event_query(event_t e) {
+  cudaError_t r = cudaEventQuery((cudaEvent_t)e);
+  if (r == cudaSuccess) return 0;
+  if (r == cudaErrorNotReady) return 1;
+  return fail(r, "cudaEventQuery");
+}
+int event_sync(event_t e) {
+  SW_CUDA(cudaEventSynchronize((cudaEvent_t)e));
+  return 0;
+}
+float event_elapsed_ms(event_t a, event_t b) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, (cudaEvent_t)a, (cudaEvent_t)b) != cudaSuccess) {
+    cudaGetLastError();
+    return -1.f;
+  }
+  return ms;
+}
+
+int memcpy_h2d(void* dst, const void* src, size_t n, stream_t s) {
+  SW_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, (cudaStream_t)s));
+  return 0;
+}
+int memcpy_d2h(void* dst, const void* src, size_t n, stream_t s) {
+  SW_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, (cudaStream_t)s));
+  return 0;
+}
+int memcpy_d2d(void* dst, const void* src, size_t n, stream_t s) {
+  SW_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, (cudaStream_t)s));
+  return 0;
+}
+int memset_dev(void* dst, int v, size_t n, stream_t s) {
+  SW_CUDA(cudaMemsetAsync(dst, v, n, (cudaStream_t)s));
+  return 0;
+}
+int upload(void* dst_dev, const void* src_host, size_t n) {
+  SW_CUDA(cudaMemcpy(dst_dev, src_host, n, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// ---------------------------------------------------------------- match state
+struct StateOwner {   // host-side bookkeeping so destroy can free every array
+  SwMatchState host;
+  SwMatchState* dev;
+};
+static std::mutex g_states_mu;
+static std::vector<StateOwner*> g_states;
+
+SwMatchState* match_state_create(uint32_t heap_small_blocks, uint32_t heap_big_blocks) {
+  StateOwner* o = new StateOwner();
+  SwMatchState& h = o->host;
+  memset(&h, 0, sizeof(h));
+#define SW_ALLOC(field, type, count)                       \
+  h.field = (type*)dev_alloc(sizeof(type) * (size_t)(count)); \
+  if (!h.field) return nullptr;
+  SW_ALLOC(p_tag, uint64_t, SW_PQ_CAP);
+  SW_ALLOC(p_mask, uint64_t, SW_PQ_CAP);
+  SW_ALLOC(p_buf, uint64_t, SW_PQ_CAP);
+  SW_ALLOC(p_cap, uint64_t, SW_PQ_CAP);
+  SW_ALLOC(p_op, uint64_t, SW_PQ_CAP);
+  SW_ALLOC(p_valid, uint32_t, SW_PQ_CAP);
+  SW_ALLOC(u_tag, uint64_t, SW_UQ_CAP);
+  SW_ALLOC(u_len, uint64_t, SW_UQ_CAP);
+  SW_ALLOC(u_data, uint64_t, SW_UQ_CAP);
+  SW_ALLOC(u_meta, uint32_t, SW_UQ_CAP);
+  SW_ALLOC(u_blk, uint32_t, SW_UQ_CAP);
+  h.cap_small = heap_small_blocks;
+  h.cap_big = heap_big_blocks;
+  SW_ALLOC(heap_small, uint8_t, (size_t)heap_small_blocks * SW_HEAP_SMALL_BYTES);
+  SW_ALLOC(heap_big, uint8_t, (size_t)heap_big_blocks * SW_HEAP_BIG_BYTES);
+  SW_ALLOC(free_small, uint32_t, heap_small_blocks);
+  SW_ALLOC(free_big, uint32_t, heap_big_blocks);
+  SW_ALLOC(pend_small, uint32_t, heap_small_blocks);
+  SW_ALLOC(pend_big, uint32_t, heap_big_blocks);
+  SW_ALLOC(jobs, SwJob, SW_MAX_JOBS);
+#undef SW_ALLOC
+  {
+    std::vector<uint32_t> idx(heap_small_blocks > heap_big_blocks ? heap_small_blocks : heap_big_blocks);
+    for (size_t i = 0; i < idx.size(); i++) idx[i] = (uint32_t)i;
+    if (heap_small_blocks && upload(h.free_small, idx.data(), sizeof(uint32_t) * heap_small_blocks)) return nullptr;
+    if (heap_big_blocks && upload(h.free_big, idx.data(), sizeof(uint32_t) * heap_big_blocks)) return nullptr;
+  }
+  h.n_free_small = heap_small_blocks;
+  h.n_free_big = heap_big_blocks;
+  o->dev = (SwMatchState*)dev_alloc(sizeof(SwMatchState));
+  if (!o->dev) return nullptr;
+  if (upload(o->dev, &h, sizeof(h))) return nullptr;
+  std::lock_guard<std::mutex> lk(g_states_mu);
+  g_states.push_back(o);
+  return o->dev;
+}
+
+int match_state_destroy(SwMatchState* st) {
+  StateOwner* o = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_states_mu);
+    for (size_t i = 0; i < g_states.size(); i++)
+      if (g_states[i]->dev == st) {
+        o = g_states[i];
+        g_states.erase(g_states.begin() + i);
+        break;
+      }
+  }
+  if (!o) return -1;
+  SwMatchState& h = o->host;
+  void* ptrs[] = {h.p_tag,  h.p_mask, h.p_buf,      h.p_cap,    h.p_op,     h.p_valid,  h.u_tag,   h.u_len, h.u_data,
+                  h.u_meta, h.u_blk,  h.heap_small, h.heap_big, h.free_small, h.free_big, h.pend_small, h.pend_big,
+                  h.jobs,   o->dev};
+  for (void* p : ptrs) dev_free(p);
+  delete o;
+  return 0;
+}
+
+int match_state_set_ring(SwMatchState* st, uint32_t ep, void* ring_base, uint32_t slots) {
+  if (ep >= SW_MAX_EPS) return -1;
+  uint64_t base = (uint64_t)(uintptr_t)ring_base;
+  uint64_t zero = 0;
+  SW_CUDA(cudaMemcpy(&st->ring_base[ep], &base, sizeof(base), cudaMemcpyHostToDevice));
+  SW_CUDA(cudaMemcpy(&st->ring_slots[ep], &slots, sizeof(slots), cudaMemcpyHostToDevice));
+  SW_CUDA(cudaMemcpy(&st->ring_cons[ep], &zero, sizeof(zero), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// ---------------------------------------------------------------- launches
+int launch_put(stream_t s, const SwPutDesc* descs, uint32_t n) {
+  if (!n) return 0;
+  const uint32_t warps_per_cta = 8;
+  uint32_t grid = (n + warps_per_cta - 1) / warps_per_cta;
+  const uint32_t cap = (uint32_t)g_sms * 8;
+  if (grid > cap) grid = cap;
+  sw_put_kernel<<<grid, warps_per_cta * 32, 0, (cudaStream_t)s>>>(descs, n);
+  SW_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_match(stream_t s, SwMatchState* st, const SwMatchIn* in, SwMatchOut* out) {
+  sw_match_kernel<<<1, 32, 0, (cudaStream_t)s>>>(st, in, out);
+  SW_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_deliver(stream_t s, SwMatchState* st, SwMatchOut* out, uint32_t max_jobs) {
+  if (!max_jobs) return 0;
+  const uint32_t warps_per_cta = 8;
+  uint32_t grid = (max_jobs + warps_per_cta - 1) / warps_per_cta;
+  const uint32_t cap = (uint32_t)g_sms * 4;
+  if (grid > cap) grid = cap;
+  sw_deliver_kernel<<<grid, warps_per_cta * 32, 0, (cudaStream_t)s>>>(st, out);
+  SW_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_bulk(stream_t s, const SwSeg* segs, uint32_t nseg, const BulkTuning* t) {
+  if (!nseg) return 0;
+  if (t->mode == 0) {
+    int stages = t->stages < 2 ? 2 : (t->stages > SW_BULK_MAX_STAGES ? SW_BULK_MAX_STAGES : t->stages);
+    int sb = t->stage_bytes & ~15;
+    if (sb < 1024) sb = 1024;
+    size_t smem = (size_t)stages * sb;
+    if ((int)smem > g_max_smem_optin) {
+      g_err = "bulk tuning exceeds shared memory";
+      return -1;
+    }
+    uint32_t grid = (uint32_t)(g_sms * (t->ctas_per_sm > 0 ? t->ctas_per_sm : 1));
+    if (grid > nseg) grid = nseg;
+    sw_bulk_tma_kernel<<<grid, 32, smem, (cudaStream_t)s>>>(segs, nseg, (uint32_t)sb, (uint32_t)stages);
+  } else {
+    uint32_t grid = (uint32_t)(g_sms * (t->ctas_per_sm > 0 ? t->ctas_per_sm : 4));
+    if (grid > nseg) grid = nseg;
+    sw_bulk_simt_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(segs, nseg);
+  }
+  SW_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace swgpu
