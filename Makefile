@@ -21,6 +21,7 @@ all: lib oracle hostsim probe
 
 lib: $(LIB)
 oracle: $(ORACLE) $(CPUENG)
+oracle-core: $(ORACLE)
 hostsim: $(HOSTSIM)
 probe: $(PROBE)
 
@@ -34,7 +35,7 @@ build/engine.o: $(ENGINE_SRCS) $(ENGINE_HDRS)
 
 # The product library: host progress engine + CUDA kernels.  No CPU fallback is linked in.
 $(LIB): build/engine.o build/gpu_cuda.o
-	$(NVCC) $(ARCH) -shared -cudart static -o $@ $^ -lpthread -lrt -ldl
+	$(NVCC) $(ARCH) -shared -cudart static -Xlinker -Bsymbolic -Xlinker --version-script=$(CSRC)/exports.map -o $@ $^ -lpthread -lrt -ldl
 
 # Test infrastructure -------------------------------------------------------------
 build/tagmatch.o: oracle/tagmatch.c oracle/tagmatch.h
@@ -59,7 +60,7 @@ build/gpu_sim.o: tests/hostsim/gpu_sim.cpp $(CSRC)/gpu.h $(CSRC)/sw_device.h ora
 # backend, used only by `pytest -m "not gpu"` to exercise connection/protocol/flush/close
 # logic (world_size 2 on CPU).  Never loaded by the starway_b200 package.
 $(HOSTSIM): build/engine_sim.o build/gpu_sim.o build/tagmatch.o
-	$(CXX) -shared -o $@ $^ -lpthread -lrt -ldl
+	$(CXX) -shared -Wl,-Bsymbolic -Wl,--version-script=$(CSRC)/exports.map -o $@ $^ -lpthread -lrt -ldl
 
 $(PROBE): tests/gpu_probe/probe.cu build/gpu_cuda.o build/tagmatch.o
 	$(NVCC) $(NVFLAGS) -o $@ tests/gpu_probe/probe.cu build/gpu_cuda.o build/tagmatch.o
@@ -67,4 +68,4 @@ $(PROBE): tests/gpu_probe/probe.cu build/gpu_cuda.o build/tagmatch.o
 clean:
 	rm -rf build $(LIB) $(ORACLE) $(CPUENG) $(HOSTSIM) $(PROBE)
 
-.PHONY: all lib oracle hostsim probe clean
+.PHONY: all lib oracle oracle-core hostsim probe clean

@@ -1,0 +1,584 @@
+"""ctypes shim + asyncio API over the starway_b200 C ABI (include/starway_b200.h).
+
+Mirrors the reference's public surface — ``Server`` / ``Client`` /
+``ServerEndpoint`` with ``asend / arecv / aflush / aflush_ep / aconnect /
+aconnect_address / aclose / listen / listen_address`` (reference
+``src/starway/__init__.py:71-345``) — over the drop-in replacement for its
+``_bindings`` extension (reference ``src/starway/_bindings.pyi:7-88``).
+
+Differences that are deliberate:
+  * buffers may live on the GPU (torch CUDA tensors, ``__cuda_array_interface__``)
+    as well as on the host (NumPy); the reference accepts CPU arrays only;
+  * futures are resolved from ONE completion-poller thread per context, one
+    ``call_soon_threadsafe`` per batch, instead of one UCX callback + GIL
+    acquisition + ``call_soon_threadsafe`` per operation
+    (reference ``src/bindings/main.cpp:172-232`` and ``__init__.py:124-128``);
+  * the buffer object is kept alive until the operation completes (the
+    reference keeps only the raw pointer, ``main.cpp:610-611``).
+
+``bind(lib)`` builds the API classes on top of an already loaded ctypes
+library.  The package binds it to ``libstarway_b200.so`` (CUDA, no fallback);
+the CPU test-suite binds it to the host-logic simulator under ``tests/hostsim``.
+"""
+from __future__ import annotations
+
+import asyncio
+import atexit
+import ctypes
+import threading
+from collections.abc import Callable
+from types import SimpleNamespace
+from typing import Any
+
+import numpy as np
+
+# ----------------------------------------------------------------------------- C structs
+SW_WORKER_SERVER = 1
+SW_WORKER_CLIENT = 2
+SW_MEM_HOST = 1
+SW_MEM_DEVICE = 2
+SW_OP_SEND, SW_OP_RECV, SW_OP_FLUSH, SW_OP_FLUSH_EP, SW_OP_CONNECT, SW_OP_CLOSE, SW_OP_ACCEPT = 1, 2, 3, 4, 5, 6, 7
+
+
+class SwCompletion(ctypes.Structure):
+    _fields_ = [
+        ("op_id", ctypes.c_uint64),
+        ("status", ctypes.c_int32),
+        ("kind", ctypes.c_uint32),
+        ("sender_tag", ctypes.c_uint64),
+        ("length", ctypes.c_uint64),
+        ("worker", ctypes.c_uint64),
+        ("ep", ctypes.c_uint64),
+    ]
+
+
+class SwEpInfo(ctypes.Structure):
+    _fields_ = [
+        ("name", ctypes.c_char * 64),
+        ("local_addr", ctypes.c_char * 48),
+        ("remote_addr", ctypes.c_char * 48),
+        ("local_port", ctypes.c_uint16),
+        ("remote_port", ctypes.c_uint16),
+        ("num_transports", ctypes.c_uint32),
+        ("transport_device", (ctypes.c_char * 32) * 4),
+        ("transport_name", (ctypes.c_char * 32) * 4),
+    ]
+
+
+class SwStats(ctypes.Structure):
+    _fields_ = [
+        ("put_launches", ctypes.c_uint64),
+        ("put_msgs", ctypes.c_uint64),
+        ("put_bytes", ctypes.c_uint64),
+        ("match_launches", ctypes.c_uint64),
+        ("deliver_launches", ctypes.c_uint64),
+        ("match_posts", ctypes.c_uint64),
+        ("match_arrivals", ctypes.c_uint64),
+        ("bulk_tma_launches", ctypes.c_uint64),
+        ("bulk_simt_launches", ctypes.c_uint64),
+        ("bulk_jobs", ctypes.c_uint64),
+        ("bulk_bytes", ctypes.c_uint64),
+        ("h2d_bytes", ctypes.c_uint64),
+        ("d2h_bytes", ctypes.c_uint64),
+        ("completions", ctypes.c_uint64),
+        ("bulk_event_ms", ctypes.c_double),
+        ("bulk_event_launches", ctypes.c_uint64),
+        ("bulk_event_bytes", ctypes.c_uint64),
+        ("put_event_ms", ctypes.c_double),
+        ("put_event_launches", ctypes.c_uint64),
+        ("match_event_ms", ctypes.c_double),
+        ("match_event_launches", ctypes.c_uint64),
+    ]
+
+
+# every symbol include/starway_b200.h declares: name -> (restype, argtypes)
+_u64, _i64, _i32, _int, _vp, _cp, _sz = (
+    ctypes.c_uint64,
+    ctypes.c_int64,
+    ctypes.c_int32,
+    ctypes.c_int,
+    ctypes.c_void_p,
+    ctypes.c_char_p,
+    ctypes.c_size_t,
+)
+C_ABI = {
+    "sw_abi_version": (_int, []),
+    "sw_backend_name": (_cp, []),
+    "sw_last_error": (_cp, []),
+    "sw_status_string": (_cp, [_i32]),
+    "sw_device_count": (_int, []),
+    "sw_ctx_create": (_vp, [_int]),
+    "sw_ctx_destroy": (None, [_vp]),
+    "sw_ctx_device": (_int, [_vp]),
+    "sw_set_option": (_int, [_vp, _cp, _i64]),
+    "sw_get_option": (_i64, [_vp, _cp]),
+    "sw_worker_create": (_u64, [_vp, _int]),
+    "sw_worker_destroy": (_int, [_vp, _u64]),
+    "sw_worker_status": (_int, [_vp, _u64]),
+    "sw_listen": (_int, [_vp, _u64, _cp, ctypes.c_uint16]),
+    "sw_listen_address": (_int, [_vp, _u64]),
+    "sw_get_address": (_i64, [_vp, _u64, _vp, _sz]),
+    "sw_connect": (_u64, [_vp, _u64, _cp, ctypes.c_uint16]),
+    "sw_connect_address": (_u64, [_vp, _u64, _vp, _sz]),
+    "sw_close": (_u64, [_vp, _u64]),
+    "sw_post_send": (_u64, [_vp, _u64, _u64, _vp, _sz, _u64, _int]),
+    "sw_post_recv": (_u64, [_vp, _u64, _vp, _sz, _u64, _u64, _int]),
+    "sw_post_flush": (_u64, [_vp, _u64]),
+    "sw_post_flush_ep": (_u64, [_vp, _u64, _u64]),
+    "sw_poll": (_int, [_vp, ctypes.POINTER(SwCompletion), _int]),
+    "sw_wait": (_int, [_vp, ctypes.POINTER(SwCompletion), _int, _int]),
+    "sw_event_fd": (_int, [_vp]),
+    "sw_list_eps": (_int, [_vp, _u64, ctypes.POINTER(_u64), _int]),
+    "sw_ep_info_get": (_int, [_vp, _u64, _u64, ctypes.POINTER(SwEpInfo)]),
+    "sw_evaluate_perf": (ctypes.c_double, [_vp, _u64, _u64, _sz]),
+    "sw_stats_get": (_int, [_vp, ctypes.POINTER(SwStats)]),
+    "sw_stats_reset": (_int, [_vp]),
+}
+
+
+def declare(lib: ctypes.CDLL) -> ctypes.CDLL:
+    """Attach restype/argtypes for every C-ABI entry point; raises if one is missing."""
+    for name, (res, args) in C_ABI.items():
+        fn = getattr(lib, name)  # AttributeError => the library does not export the ABI
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+# ----------------------------------------------------------------------------- buffers
+def _is_torch_tensor(obj: Any) -> bool:
+    mod = type(obj).__module__
+    return mod == "torch" or mod.startswith("torch.")
+
+
+def as_buffer(obj: Any, writable: bool):
+    """-> (ptr, nbytes, mem_kind, keepalive).  1-D contiguous uint8, host or device."""
+    if isinstance(obj, np.ndarray):
+        arr = obj
+        if writable:
+            if arr.dtype != np.uint8 or arr.ndim != 1 or not arr.flags.c_contiguous or not arr.flags.writeable:
+                raise TypeError("recv buffer must be a writable, contiguous 1-D uint8 array")
+        else:
+            if arr.ndim != 1:
+                raise TypeError("send buffer must be 1-D")
+            if arr.dtype != np.uint8:
+                # nanobind's ndarray caster converts implicitly (reference tests pass int64 arrays,
+                # tests/test_basic.py:562); the temporary is kept alive until completion
+                arr = arr.astype(np.uint8)
+            if not arr.flags.c_contiguous:
+                arr = np.ascontiguousarray(arr)
+        return arr.ctypes.data, arr.nbytes, SW_MEM_HOST, arr
+    if _is_torch_tensor(obj):
+        t = obj
+        if t.dim() != 1 or not t.is_contiguous():
+            raise TypeError("tensor buffers must be 1-D and contiguous")
+        if t.element_size() != 1:
+            if writable:
+                raise TypeError("recv buffer must be a uint8 tensor")
+            t = t.view(-1).contiguous().view(dtype=__import__("torch").uint8)
+        nbytes = t.numel() * t.element_size()
+        return t.data_ptr(), nbytes, (SW_MEM_DEVICE if t.is_cuda else SW_MEM_HOST), t
+    cai = getattr(obj, "__cuda_array_interface__", None)
+    if cai is not None:
+        shape = cai["shape"]
+        if len(shape) != 1 or cai.get("strides") not in (None, (np.dtype(cai["typestr"]).itemsize,)):
+            raise TypeError("device buffers must be 1-D and contiguous")
+        ptr, readonly = cai["data"]
+        if writable and readonly:
+            raise TypeError("recv buffer is read-only")
+        return int(ptr), int(shape[0]) * np.dtype(cai["typestr"]).itemsize, SW_MEM_DEVICE, obj
+    raise TypeError(f"unsupported buffer type {type(obj)!r}: expected numpy.ndarray, torch.Tensor or a CUDA array")
+
+
+# ----------------------------------------------------------------------------- API factory
+def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None) -> SimpleNamespace:
+    """Build Context/Server/Client/ServerEndpoint classes on top of a loaded C-ABI library."""
+    declare(lib)
+
+    def _err() -> str:
+        s = lib.sw_last_error()
+        return s.decode() if s else "unknown error"
+
+    def status_string(code: int) -> str:
+        return lib.sw_status_string(code).decode()
+
+    class Context:
+        """One per (process, device): owns the native context and the completion poller.
+
+        Replaces the reference's global ``Context()`` (``__init__.py:68``) plus the
+        per-object UCX progress threads."""
+
+        def __init__(self, device: int | None = None):
+            if device is None:
+                device = default_device() if default_device else 0
+            self.device = device
+            self._h = lib.sw_ctx_create(device)
+            if not self._h:
+                raise RuntimeError(_err())
+            self._lock = threading.Lock()
+            self._ops: dict[int, tuple] = {}
+            self._servers: dict[int, Any] = {}
+            self._stop = False
+            self._thread = threading.Thread(target=self._poll_loop, name="starway-b200-poller", daemon=True)
+            self._thread.start()
+
+        # -- submission helpers ------------------------------------------------
+        def submit(self, post: Callable[[], int], entry: tuple) -> int:
+            with self._lock:
+                op = post()
+                if not op:
+                    raise RuntimeError(_err())
+                self._ops[op] = entry
+            return op
+
+        # -- completion side ---------------------------------------------------
+        def _poll_loop(self):
+            buf = (SwCompletion * 512)()
+            while not self._stop:
+                n = lib.sw_wait(self._h, buf, 512, 50)
+                if n <= 0:
+                    continue
+                batches: dict[Any, list] = {}
+                with self._lock:
+                    items = []
+                    for i in range(n):
+                        c = buf[i]
+                        if c.kind == SW_OP_ACCEPT:
+                            items.append((None, c.kind, c.status, c.worker, c.ep))
+                        else:
+                            items.append((self._ops.pop(c.op_id, None), c.kind, c.status, c.sender_tag, c.length))
+                for entry, kind, status, a, b in items:
+                    if kind == SW_OP_ACCEPT:
+                        srv = self._servers.get(a)
+                        if srv is not None:
+                            srv._on_accept(b)
+                        continue
+                    if entry is None:
+                        continue
+                    if entry[0] == "fut":
+                        _, loop, fut, _keep, post_ok = entry
+                        if status == 0:
+                            if post_ok is not None:
+                                post_ok()
+                            val = (a, b) if kind == SW_OP_RECV else None
+                            batches.setdefault(loop, []).append((fut, True, val))
+                        else:
+                            batches.setdefault(loop, []).append((fut, False, status_string(status)))
+                    else:  # raw callbacks, invoked on the poller thread (reference: on the worker thread)
+                        _, done, fail, _keep = entry
+                        try:
+                            if status == 0:
+                                if kind == SW_OP_RECV:
+                                    done(a, b)
+                                elif kind == SW_OP_CONNECT:
+                                    done("")
+                                else:
+                                    done()
+                            else:
+                                if kind == SW_OP_CONNECT:
+                                    done(status_string(status))
+                                elif fail is not None:
+                                    fail(status_string(status))
+                        except Exception as exc:  # never kill the poller
+                            print(f"starway_b200: exception in user callback: {exc!r}")
+                for loop, lst in batches.items():
+                    try:
+                        loop.call_soon_threadsafe(_resolve_batch, lst)
+                    except RuntimeError:
+                        pass  # loop already closed
+
+        def stats(self) -> dict:
+            s = SwStats()
+            lib.sw_stats_get(self._h, ctypes.byref(s))
+            return {name: getattr(s, name) for name, _ in SwStats._fields_}
+
+        def reset_stats(self) -> None:
+            lib.sw_stats_reset(self._h)
+
+        def set_option(self, key: str, value: int) -> None:
+            if lib.sw_set_option(self._h, key.encode(), int(value)) != 0:
+                raise ValueError(_err())
+
+        def get_option(self, key: str) -> int:
+            return int(lib.sw_get_option(self._h, key.encode()))
+
+        def close(self):
+            if self._h:
+                self._stop = True
+                self._thread.join(timeout=2.0)
+                h, self._h = self._h, None
+                lib.sw_ctx_destroy(h)
+
+    def _resolve_batch(lst):
+        for fut, ok, val in lst:
+            if fut.done():
+                continue
+            if ok:
+                fut.set_result(val)
+            else:
+                fut.set_exception(Exception(val))
+
+    _state = SimpleNamespace(ctx=None)
+    _state_lock = threading.Lock()
+
+    def get_context() -> Context:
+        with _state_lock:
+            if _state.ctx is None:
+                _state.ctx = Context()
+                atexit.register(shutdown)
+            return _state.ctx
+
+    def shutdown():
+        with _state_lock:
+            ctx, _state.ctx = _state.ctx, None
+        if ctx is not None:
+            ctx.close()
+
+    class ServerEndpoint:
+        """Reference ``ServerEndpoint`` (``main.hpp:292-304``, ``_bindings.pyi:10-21``)."""
+
+        __slots__ = ("_ctx", "_worker", "_id", "_info")
+
+        def __init__(self, ctx: Context, worker: int, ep_id: int):
+            self._ctx = ctx
+            self._worker = worker
+            self._id = ep_id
+            info = SwEpInfo()
+            lib.sw_ep_info_get(ctx._h, worker, ep_id, ctypes.byref(info))
+            self._info = info
+
+        name = property(lambda self: self._info.name.decode())
+        local_addr = property(lambda self: self._info.local_addr.decode())
+        local_port = property(lambda self: int(self._info.local_port))
+        remote_addr = property(lambda self: self._info.remote_addr.decode())
+        remote_port = property(lambda self: int(self._info.remote_port))
+
+        def view_transports(self) -> list[tuple[str, str]]:
+            n = self._info.num_transports
+            return [
+                (self._info.transport_device[i].value.decode(), self._info.transport_name[i].value.decode())
+                for i in range(n)
+            ]
+
+        def __hash__(self):
+            return hash(self._id)
+
+        def __eq__(self, other):
+            return isinstance(other, ServerEndpoint) and other._id == self._id
+
+        def __repr__(self):
+            return f"<ServerEndpoint {self.name!r}>"
+
+    class _Base:
+        _kind = 0
+
+        def __init__(self, ctx: Context | None = None):
+            self._ctx = ctx if ctx is not None else get_context()
+            self._w = lib.sw_worker_create(self._ctx._h, self._kind)
+            if not self._w:
+                raise RuntimeError(_err())
+
+        def __del__(self):
+            # reference ~Client/~Server: implicit close + join (main.cpp:703-719, 1519-1536)
+            try:
+                ctx = self._ctx
+                if ctx._h:
+                    lib.sw_worker_destroy(ctx._h, self._w)
+                    ctx._servers.pop(self._w, None)
+            except Exception:
+                pass
+
+        # -- helpers -------------------------------------------------------------
+        def _future(self, loop):
+            if loop is None:
+                loop = asyncio.get_running_loop()
+            return loop, asyncio.Future(loop=loop)
+
+        def _post_recv(self, buffer, tag, tag_mask, entry_of):
+            ptr, n, mem, keep = as_buffer(buffer, writable=True)
+            h, w = self._ctx._h, self._w
+            return self._ctx.submit(
+                lambda: lib.sw_post_recv(h, w, ptr, n, tag & 0xFFFFFFFFFFFFFFFF, tag_mask & 0xFFFFFFFFFFFFFFFF, mem),
+                entry_of(keep),
+            )
+
+        def recv(self, buffer, tag: int, tag_mask: int, done_callback, fail_callback):
+            self._post_recv(buffer, tag, tag_mask, lambda keep: ("cb", done_callback, fail_callback, keep))
+
+        def arecv(self, buffer, tag: int, tag_mask: int, loop: asyncio.AbstractEventLoop | None = None):
+            loop, fut = self._future(loop)
+            self._post_recv(buffer, tag, tag_mask, lambda keep: ("fut", loop, fut, keep, None))
+            return fut
+
+        def flush(self, done_callback, fail_callback):
+            h, w = self._ctx._h, self._w
+            self._ctx.submit(lambda: lib.sw_post_flush(h, w), ("cb", done_callback, fail_callback, None))
+
+        def aflush(self, loop: asyncio.AbstractEventLoop | None = None):
+            loop, fut = self._future(loop)
+            h, w = self._ctx._h, self._w
+            self._ctx.submit(lambda: lib.sw_post_flush(h, w), ("fut", loop, fut, None, None))
+            return fut
+
+        def get_worker_address(self) -> bytes:
+            buf = ctypes.create_string_buffer(512)
+            n = lib.sw_get_address(self._ctx._h, self._w, buf, 512)
+            if n < 0:
+                raise RuntimeError(_err())
+            return buf.raw[:n]
+
+        def _aclose(self, loop, banner):
+            loop, fut = self._future(loop)
+            h, w = self._ctx._h, self._w
+            self._ctx.submit(lambda: lib.sw_close(h, w), ("fut", loop, fut, None, lambda: print(banner)))
+            return fut
+
+    class Server(_Base):
+        """Reference ``Server`` (``src/starway/__init__.py:71-209``)."""
+
+        _kind = SW_WORKER_SERVER
+
+        def __init__(self, ctx: Context | None = None):
+            super().__init__(ctx)
+            self._accept_cb = None
+            self._eps: dict[int, ServerEndpoint] = {}
+            self._ctx._servers[self._w] = self
+
+        def _ep(self, ep_id: int) -> ServerEndpoint:
+            ep = self._eps.get(ep_id)
+            if ep is None:
+                ep = self._eps[ep_id] = ServerEndpoint(self._ctx, self._w, ep_id)
+            return ep
+
+        def _on_accept(self, ep_id: int):
+            ep = self._ep(ep_id)
+            cb = self._accept_cb
+            if cb is not None:
+                try:
+                    cb(ep)
+                except Exception as exc:
+                    print(f"starway_b200: exception in accept callback: {exc!r}")
+
+        def listen(self, addr: str, port: int):
+            if lib.sw_listen(self._ctx._h, self._w, addr.encode(), port) != 0:
+                raise RuntimeError(_err())
+
+        def listen_address(self) -> bytes:
+            if lib.sw_listen_address(self._ctx._h, self._w) != 0:
+                raise RuntimeError(_err())
+            return self.get_worker_address()
+
+        def set_accept_cb(self, on_accept: Callable[[ServerEndpoint], None]):
+            self._accept_cb = on_accept
+
+        set_accept_callback = set_accept_cb
+
+        def aclose(self, loop: asyncio.AbstractEventLoop | None = None):
+            return self._aclose(loop, "Server closed!")
+
+        def list_clients(self) -> set[ServerEndpoint]:
+            arr = (ctypes.c_uint64 * 256)()
+            n = lib.sw_list_eps(self._ctx._h, self._w, arr, 256)
+            return {self._ep(arr[i]) for i in range(max(0, min(n, 256)))}
+
+        def _post_send(self, client_ep, buffer, tag, entry_of):
+            if not isinstance(client_ep, ServerEndpoint):
+                raise TypeError("client_ep must be a ServerEndpoint")
+            ptr, n, mem, keep = as_buffer(buffer, writable=False)
+            h, w, e = self._ctx._h, self._w, client_ep._id
+            return self._ctx.submit(
+                lambda: lib.sw_post_send(h, w, e, ptr, n, tag & 0xFFFFFFFFFFFFFFFF, mem), entry_of(keep)
+            )
+
+        def send(self, client_ep, buffer, tag: int, done_callback, fail_callback):
+            self._post_send(client_ep, buffer, tag, lambda keep: ("cb", done_callback, fail_callback, keep))
+
+        def asend(self, client_ep, buffer, tag: int, loop: asyncio.AbstractEventLoop | None = None):
+            loop, fut = self._future(loop)
+            self._post_send(client_ep, buffer, tag, lambda keep: ("fut", loop, fut, keep, None))
+            return fut
+
+        def flush_ep(self, client_ep, done_callback, fail_callback):
+            h, w, e = self._ctx._h, self._w, client_ep._id
+            self._ctx.submit(lambda: lib.sw_post_flush_ep(h, w, e), ("cb", done_callback, fail_callback, None))
+
+        def aflush_ep(self, client_ep, loop: asyncio.AbstractEventLoop | None = None):
+            loop, fut = self._future(loop)
+            h, w, e = self._ctx._h, self._w, client_ep._id
+            self._ctx.submit(lambda: lib.sw_post_flush_ep(h, w, e), ("fut", loop, fut, None, None))
+            return fut
+
+        def evaluate_perf(self, client_ep, msg_size: int) -> float:
+            t = lib.sw_evaluate_perf(self._ctx._h, self._w, client_ep._id, msg_size)
+            if t < 0:
+                raise RuntimeError(_err())
+            return t
+
+    class Client(_Base):
+        """Reference ``Client`` (``src/starway/__init__.py:212-345``)."""
+
+        _kind = SW_WORKER_CLIENT
+
+        def connect(self, addr: str, port: int, callback: Callable[[str], None]):
+            h, w = self._ctx._h, self._w
+            self._ctx.submit(lambda: lib.sw_connect(h, w, addr.encode(), port), ("cb", callback, None, None))
+
+        def connect_address(self, remote_address: bytes, callback: Callable[[str], None]):
+            h, w = self._ctx._h, self._w
+            blob = bytes(remote_address)
+            self._ctx.submit(lambda: lib.sw_connect_address(h, w, blob, len(blob)), ("cb", callback, None, blob))
+
+        def aconnect(self, addr: str, port: int, loop: asyncio.AbstractEventLoop | None = None):
+            loop, fut = self._future(loop)
+            h, w = self._ctx._h, self._w
+            self._ctx.submit(
+                lambda: lib.sw_connect(h, w, addr.encode(), port), ("fut", loop, fut, None, lambda: print("Connected!"))
+            )
+            return fut
+
+        def aconnect_address(self, remote_address: bytes, loop: asyncio.AbstractEventLoop | None = None):
+            loop, fut = self._future(loop)
+            h, w = self._ctx._h, self._w
+            blob = bytes(remote_address)
+            self._ctx.submit(
+                lambda: lib.sw_connect_address(h, w, blob, len(blob)),
+                ("fut", loop, fut, blob, lambda: print("Connected!")),
+            )
+            return fut
+
+        def aclose(self, loop: asyncio.AbstractEventLoop | None = None):
+            return self._aclose(loop, "Client closed!")
+
+        def _post_send(self, buffer, tag, entry_of):
+            ptr, n, mem, keep = as_buffer(buffer, writable=False)
+            h, w = self._ctx._h, self._w
+            return self._ctx.submit(
+                lambda: lib.sw_post_send(h, w, 0, ptr, n, tag & 0xFFFFFFFFFFFFFFFF, mem), entry_of(keep)
+            )
+
+        def send(self, buffer, tag: int, done_callback, fail_callback):
+            self._post_send(buffer, tag, lambda keep: ("cb", done_callback, fail_callback, keep))
+
+        def asend(self, buffer, tag: int, loop: asyncio.AbstractEventLoop | None = None):
+            loop, fut = self._future(loop)
+            self._post_send(buffer, tag, lambda keep: ("fut", loop, fut, keep, None))
+            return fut
+
+        def evaluate_perf(self, msg_size: int) -> float:
+            t = lib.sw_evaluate_perf(self._ctx._h, self._w, 0, msg_size)
+            if t < 0:
+                raise RuntimeError(_err())
+            return t
+
+    return SimpleNamespace(
+        lib=lib,
+        Context=Context,
+        Server=Server,
+        Client=Client,
+        ServerEndpoint=ServerEndpoint,
+        get_context=get_context,
+        shutdown=shutdown,
+        status_string=status_string,
+        backend_name=lambda: lib.sw_backend_name().decode(),
+        device_count=lambda: lib.sw_device_count(),
+    )

@@ -208,6 +208,47 @@ struct HostPool {
   }
 };
 
+// ============================================================================ device staging pool
+// Large host-memory sends/receives are staged through device buffers.  cudaMalloc/cudaFree
+// per message would serialise the device (cudaFree synchronises), so freed blocks are kept.
+struct StagingPool {
+  std::multimap<size_t, void*> free_blocks;
+  size_t cached = 0;
+  static constexpr size_t MAX_CACHED = 6ull << 30;
+  void* get(size_t n, size_t* got) {
+    auto it = free_blocks.lower_bound(n);
+    if (it != free_blocks.end() && it->first <= 2 * n + 4096) {
+      void* p = it->second;
+      *got = it->first;
+      cached -= it->first;
+      free_blocks.erase(it);
+      return p;
+    }
+    size_t sz = (n + 0xFFFFF) & ~(size_t)0xFFFFF;  // 1 MiB granules
+    void* p = swgpu::dev_alloc_raw(sz);
+    if (!p && !free_blocks.empty()) {
+      destroy();
+      p = swgpu::dev_alloc_raw(sz);
+    }
+    *got = sz;
+    return p;
+  }
+  void put(void* p, size_t sz) {
+    if (!p) return;
+    if (cached + sz > MAX_CACHED) {
+      swgpu::dev_free(p);
+      return;
+    }
+    free_blocks.emplace(sz, p);
+    cached += sz;
+  }
+  void destroy() {
+    for (auto& kv : free_blocks) swgpu::dev_free(kv.second);
+    free_blocks.clear();
+    cached = 0;
+  }
+};
+
 // ============================================================================ engine objects
 struct Worker;
 struct Ctx;
@@ -223,6 +264,7 @@ struct SendOp {
   uint64_t sseq = 0;        // per-endpoint send sequence, for flush
   bool user_done = false;   // user-visible completion already delivered
   void* dev_staging = nullptr;
+  size_t staging_size = 0;
   uint64_t rndv_seq = 0;
 };
 
@@ -235,6 +277,7 @@ struct RecvOp {
   int mem = SW_MEM_AUTO;
   void* pinned_bounce = nullptr;  // small host receives land here (device-mapped pinned memory)
   void* dev_staging = nullptr;    // large host receives land here, then D2H
+  size_t staging_size = 0;
 };
 
 struct FlushOp {
@@ -407,6 +450,7 @@ struct Ctx {
   std::deque<BulkJob> pending_bulk;
   std::deque<PostCopy> post_copies;
   HostPool host_pool;
+  StagingPool staging;
   std::map<std::string, Mapping> mappings;  // key: pid + ipc handle bytes
   // options
   std::atomic<int64_t> opt_eager_max{SW_EAGER_MAX};
@@ -481,14 +525,14 @@ void send_finished(Ctx* c, SendOp* op, int32_t status) {
     complete(c, op->w, op->op_id, SW_OP_SEND, status);
     op->user_done = true;
   }
-  if (op->dev_staging) swgpu::dev_free(op->dev_staging);
+  if (op->dev_staging) c->staging.put(op->dev_staging, op->staging_size);
   op->ep->out_seqs.erase(op->sseq);
   delete op;
 }
 
 void recv_release(Ctx* c, RecvOp* r) {
   if (r->pinned_bounce) c->host_pool.put(r->pinned_bounce, r->cap);
-  if (r->dev_staging) swgpu::dev_free(r->dev_staging);
+  if (r->dev_staging) c->staging.put(r->dev_staging, r->staging_size);
   delete r;
 }
 
@@ -972,7 +1016,7 @@ bool pump_sends(Ctx* c) {
           int srcdev = c->device;
           if (op->mem == SW_MEM_HOST) {
             if (!op->dev_staging) {
-              op->dev_staging = swgpu::dev_alloc_raw(op->len);
+              op->dev_staging = c->staging.get(op->len, &op->staging_size);
               if (!op->dev_staging) {
                 ep->sendq.pop_front();
                 send_finished(c, op, SW_ERR_NO_MEMORY);
@@ -982,7 +1026,7 @@ bool pump_sends(Ctx* c) {
               h2d += op->len;
             }
             base = (uint64_t)(uintptr_t)op->dev_staging;
-            size = op->len;
+            size = op->staging_size;
             r.src_ptr = base;
           } else {
             swgpu::PtrInfo pi;
@@ -1111,7 +1155,7 @@ bool pump_match(Ctx* c, Worker* w) {
           r->pinned_bounce = c->host_pool.get(r->cap);
           buf = (uint64_t)(uintptr_t)r->pinned_bounce;
         } else {
-          r->dev_staging = swgpu::dev_alloc_raw(r->cap);
+          r->dev_staging = c->staging.get(r->cap, &r->staging_size);
           buf = (uint64_t)(uintptr_t)r->dev_staging;
         }
         if (!buf) {
@@ -1859,6 +1903,7 @@ void sw_ctx_destroy(sw_ctx* ctx) {
   }
   for (auto& kv : c->mappings) swgpu::ipc_close(kv.second.base);
   c->host_pool.destroy();
+  c->staging.destroy();
   swgpu::stream_destroy(c->s_put);
   swgpu::stream_destroy(c->s_match);
   swgpu::stream_destroy(c->s_bulk);

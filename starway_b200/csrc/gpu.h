@@ -37,6 +37,7 @@ int bind_thread(int device);          // cudaSetDevice for helper threads
 int sm_count();
 
 void* dev_alloc(size_t bytes);        // IPC-shareable device allocation, zeroed
+void* dev_alloc_raw(size_t bytes);    // same, contents undefined (large staging buffers)
 int dev_free(void* p);
 void* host_alloc(size_t bytes);       // pinned, device-mapped host memory, zeroed
 int host_free(void* p);

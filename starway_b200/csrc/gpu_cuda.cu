@@ -84,6 +84,15 @@ void* dev_alloc(size_t bytes) {
   }
   return p;
 }
+void* dev_alloc_raw(size_t bytes) {
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+  if (e != cudaSuccess) {
+    fail(e, "cudaMalloc");
+    return nullptr;
+  }
+  return p;
+}
 int dev_free(void* p) {
   if (p) SW_CUDA(cudaFree(p));
   return 0;

@@ -1,0 +1,418 @@
+// tests/hostsim/gpu_sim.cpp — TEST INFRASTRUCTURE, never part of the product library.
+//
+// A CPU stand-in for the swgpu device backend (starway_b200/csrc/gpu.h) so that the
+// `pytest -m "not gpu"` suite can drive the REAL host progress engine (engine.cpp:
+// connection handshake, credits, rendezvous protocol, flush, close, cancellation,
+// 2-process operation) on a machine without a GPU.  "Device memory" is POSIX shared
+// memory (so the CUDA-IPC exchange has something real to exercise), "kernels" run
+// synchronously on the calling thread, and the match step is a plain sequential
+// restatement of the semantics in oracle/tagmatch.c over the same queue layout the
+// CUDA kernels use.  libstarway_hostsim.so is only ever loaded by tests/.
+#include <fcntl.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../starway_b200/csrc/gpu.h"
+
+namespace swgpu {
+
+static thread_local std::string g_err;
+static std::mutex g_mu;
+struct DevAlloc {
+  size_t size;
+  std::string name;
+};
+static std::map<uintptr_t, DevAlloc> g_allocs;       // our "device" allocations (shm backed)
+static std::map<uintptr_t, size_t> g_opened;         // mappings opened through ipc_open
+static int g_counter = 0;
+static int g_device = 0;
+
+const char* backend_name() { return "hostsim (test only)"; }
+const char* last_error() { return g_err.c_str(); }
+int device_count() {
+  const char* e = getenv("SW_SIM_DEVICES");
+  return e ? atoi(e) : 2;
+}
+int init(int device) {
+  if (device < 0 || device >= device_count()) {
+    g_err = "CUDA device ordinal out of range";
+    return -1;
+  }
+  g_device = device;
+  return 0;
+}
+int bind_thread(int) { return 0; }
+int sm_count() { return 8; }
+
+static void cleanup_all() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto& kv : g_allocs) shm_unlink(kv.second.name.c_str());
+}
+
+void* dev_alloc_raw(size_t bytes) {
+  static bool registered = false;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!registered) {
+    atexit(cleanup_all);
+    registered = true;
+  }
+  char name[64];
+  snprintf(name, sizeof(name), "/swsim-%d-%d", (int)getpid(), g_counter++);
+  int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+  if (fd < 0) {
+    g_err = "shm_open failed";
+    return nullptr;
+  }
+  size_t sz = ((bytes ? bytes : 16) + 4095) & ~(size_t)4095;
+  if (ftruncate(fd, (off_t)sz) != 0) {
+    close(fd);
+    shm_unlink(name);
+    g_err = "ftruncate failed";
+    return nullptr;
+  }
+  void* p = mmap(nullptr, sz, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (p == MAP_FAILED) {
+    shm_unlink(name);
+    g_err = "mmap failed";
+    return nullptr;
+  }
+  g_allocs[(uintptr_t)p] = DevAlloc{sz, name};
+  return p;
+}
+void* dev_alloc(size_t bytes) { return dev_alloc_raw(bytes); }  // fresh shm is zero-filled
+int dev_free(void* p) {
+  if (!p) return 0;
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_allocs.find((uintptr_t)p);
+  if (it == g_allocs.end()) {
+    g_err = "dev_free: unknown pointer";
+    return -1;
+  }
+  shm_unlink(it->second.name.c_str());
+  munmap(p, it->second.size);
+  g_allocs.erase(it);
+  return 0;
+}
+void* host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (posix_memalign(&p, 4096, bytes ? bytes : 16) != 0) return nullptr;
+  memset(p, 0, bytes);
+  return p;
+}
+int host_free(void* p) {
+  free(p);
+  return 0;
+}
+
+int ipc_get(const void* alloc_base, uint8_t handle[64]) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_allocs.find((uintptr_t)alloc_base);
+  if (it == g_allocs.end()) {
+    g_err = "ipc_get: not the base of a device allocation";
+    return -1;
+  }
+  memset(handle, 0, 64);
+  snprintf((char*)handle, 48, "%s", it->second.name.c_str());
+  uint64_t sz = it->second.size;
+  memcpy(handle + 48, &sz, 8);
+  uint32_t pid = (uint32_t)getpid();
+  memcpy(handle + 56, &pid, 4);
+  return 0;
+}
+int ipc_open(const uint8_t handle[64], void** out) {
+  uint32_t pid;
+  memcpy(&pid, handle + 56, 4);
+  if (pid == (uint32_t)getpid()) {
+    // CUDA refuses to open a handle in the process that exported it
+    g_err = "ipc_open: invalid device context (same process)";
+    return -1;
+  }
+  char name[49];
+  memcpy(name, handle, 48);
+  name[48] = 0;
+  uint64_t sz;
+  memcpy(&sz, handle + 48, 8);
+  int fd = shm_open(name, O_RDWR, 0600);
+  if (fd < 0) {
+    g_err = "ipc_open: shm_open failed";
+    return -1;
+  }
+  void* p = mmap(nullptr, sz, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (p == MAP_FAILED) {
+    g_err = "ipc_open: mmap failed";
+    return -1;
+  }
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_opened[(uintptr_t)p] = sz;
+  *out = p;
+  return 0;
+}
+int ipc_close(void* p) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_opened.find((uintptr_t)p);
+  if (it == g_opened.end()) return -1;
+  munmap(p, it->second);
+  g_opened.erase(it);
+  return 0;
+}
+int ptr_info(const void* p, PtrInfo* out) {
+  memset(out, 0, sizeof(*out));
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_allocs.upper_bound((uintptr_t)p);
+  if (it != g_allocs.begin()) {
+    --it;
+    if ((uintptr_t)p < it->first + it->second.size) {
+      out->is_device = 1;
+      out->device = g_device;
+      out->base = it->first;
+      out->size = it->second.size;
+    }
+  }
+  return 0;
+}
+
+stream_t stream_create() { return (stream_t)(uintptr_t)1; }
+int stream_destroy(stream_t) { return 0; }
+int stream_sync(stream_t) { return 0; }
+event_t event_create(int) { return (event_t)(uintptr_t)1; }
+int event_destroy(event_t) { return 0; }
+int event_record(event_t, stream_t) { return 0; }
+int event_query(event_t) { return 0; }
+int event_sync(event_t) { return 0; }
+float event_elapsed_ms(event_t, event_t) { return 0.001f; }
+int memcpy_h2d(void* d, const void* s, size_t n, stream_t) { memcpy(d, s, n); return 0; }
+int memcpy_d2h(void* d, const void* s, size_t n, stream_t) { memcpy(d, s, n); return 0; }
+int memcpy_d2d(void* d, const void* s, size_t n, stream_t) { memmove(d, s, n); return 0; }
+int memset_dev(void* d, int v, size_t n, stream_t) { memset(d, v, n); return 0; }
+int upload(void* d, const void* s, size_t n) { memcpy(d, s, n); return 0; }
+
+// ---------------------------------------------------------------- match state (host memory)
+SwMatchState* match_state_create(uint32_t hs, uint32_t hb) {
+  SwMatchState* st = (SwMatchState*)calloc(1, sizeof(SwMatchState));
+  st->p_tag = (uint64_t*)calloc(SW_PQ_CAP, 8);
+  st->p_mask = (uint64_t*)calloc(SW_PQ_CAP, 8);
+  st->p_buf = (uint64_t*)calloc(SW_PQ_CAP, 8);
+  st->p_cap = (uint64_t*)calloc(SW_PQ_CAP, 8);
+  st->p_op = (uint64_t*)calloc(SW_PQ_CAP, 8);
+  st->p_valid = (uint32_t*)calloc(SW_PQ_CAP, 4);
+  st->u_tag = (uint64_t*)calloc(SW_UQ_CAP, 8);
+  st->u_len = (uint64_t*)calloc(SW_UQ_CAP, 8);
+  st->u_data = (uint64_t*)calloc(SW_UQ_CAP, 8);
+  st->u_meta = (uint32_t*)calloc(SW_UQ_CAP, 4);
+  st->u_blk = (uint32_t*)calloc(SW_UQ_CAP, 4);
+  st->cap_small = hs;
+  st->cap_big = hb;
+  st->heap_small = (uint8_t*)calloc((size_t)hs, SW_HEAP_SMALL_BYTES);
+  st->heap_big = (uint8_t*)calloc((size_t)hb, SW_HEAP_BIG_BYTES);
+  st->free_small = (uint32_t*)calloc(hs, 4);
+  st->free_big = (uint32_t*)calloc(hb, 4);
+  st->pend_small = (uint32_t*)calloc(hs, 4);
+  st->pend_big = (uint32_t*)calloc(hb, 4);
+  for (uint32_t i = 0; i < hs; i++) st->free_small[i] = i;
+  for (uint32_t i = 0; i < hb; i++) st->free_big[i] = i;
+  st->n_free_small = hs;
+  st->n_free_big = hb;
+  st->jobs = (SwJob*)calloc(SW_MAX_JOBS, sizeof(SwJob));
+  return st;
+}
+int match_state_destroy(SwMatchState* st) {
+  if (!st) return -1;
+  void* ptrs[] = {st->p_tag, st->p_mask, st->p_buf, st->p_cap, st->p_op, st->p_valid, st->u_tag, st->u_len, st->u_data,
+                  st->u_meta, st->u_blk, st->heap_small, st->heap_big, st->free_small, st->free_big, st->pend_small,
+                  st->pend_big, st->jobs};
+  for (void* p : ptrs) free(p);
+  free(st);
+  return 0;
+}
+int match_state_set_ring(SwMatchState* st, uint32_t ep, void* ring_base, uint32_t slots) {
+  if (ep >= SW_MAX_EPS) return -1;
+  st->ring_base[ep] = (uint64_t)(uintptr_t)ring_base;
+  st->ring_slots[ep] = slots;
+  st->ring_cons[ep] = 0;
+  return 0;
+}
+
+// ---------------------------------------------------------------- "kernels"
+int launch_put(stream_t, const SwPutDesc* descs, uint32_t n) {
+  for (uint32_t i = 0; i < n; i++) {
+    const SwPutDesc& d = descs[i];
+    uint8_t* slot = (uint8_t*)(uintptr_t)d.dst;
+    if (d.len) memcpy(slot + SW_SLOT_HDR, (const void*)(uintptr_t)d.src, d.len);
+    SwSlotHdr h;
+    memset(&h, 0, sizeof(h));
+    h.tag = d.tag;
+    h.len = d.msg_len;
+    h.seq = d.seq;
+    h.kind = d.kind;
+    h.magic = SW_SLOT_MAGIC;
+    __atomic_thread_fence(__ATOMIC_RELEASE);
+    memcpy(slot, &h, 32);
+  }
+  return 0;
+}
+
+static void emit_job(SwMatchState* st, uint64_t src, uint64_t dst, uint64_t len, uint64_t op, uint64_t tag,
+                     uint64_t msg_len, int32_t status, uint32_t kind) {
+  SwJob& j = st->jobs[st->n_jobs++];
+  j.src = src;
+  j.dst = dst;
+  j.len = len;
+  j.op_id = op;
+  j.tag = tag;
+  j.msg_len = msg_len;
+  j.status = status;
+  j.kind = kind;
+}
+static void emit_match(SwMatchState* st, SwMatchOut* out, bool is_rts, uint64_t payload, uint64_t stag,
+                       uint64_t msg_len, uint32_t ep, uint64_t buf, uint64_t cap, uint64_t op) {
+  const bool trunc = msg_len > cap;
+  if (!is_rts) {
+    emit_job(st, payload, buf, trunc ? 0 : msg_len, op, stag, msg_len, trunc ? SW_ERR_MESSAGE_TRUNCATED : SW_OK,
+             SW_JOB_DELIVER);
+  } else {
+    SwRndvRec& r = out->rndv[out->n_rndv++];
+    memcpy(&r.rts, (const void*)(uintptr_t)payload, sizeof(SwRts));
+    r.op_id = op;
+    r.dst = buf;
+    r.cap = cap;
+    r.tag = stag;
+    r.len = msg_len;
+    r.ep = ep;
+    r.status = trunc ? SW_ERR_MESSAGE_TRUNCATED : SW_OK;
+  }
+}
+
+int launch_match(stream_t, SwMatchState* st, const SwMatchIn* in, SwMatchOut* out) {
+  const uint64_t PQM = SW_PQ_CAP - 1, UQM = SW_UQ_CAP - 1;
+  st->n_jobs = 0;
+  out->n_rndv = 0;
+  out->err = 0;
+  // deferred frees become allocatable
+  for (uint32_t i = 0; i < st->n_pend_small; i++) st->free_small[st->n_free_small++] = st->pend_small[i];
+  for (uint32_t i = 0; i < st->n_pend_big; i++) st->free_big[st->n_free_big++] = st->pend_big[i];
+  st->n_pend_small = st->n_pend_big = 0;
+  // phase 1: new receives against the unexpected queue (earliest-arrived first)
+  for (uint32_t i = 0; i < in->n_posts; i++) {
+    const SwPost& p = in->posts[i];
+    bool found = false;
+    for (uint64_t idx = st->u_head; idx < st->u_tail; idx++) {
+      uint64_t s = idx & UQM;
+      uint32_t meta = st->u_meta[s];
+      if (!(meta & SW_UMETA_VALID) || !sw_tag_match(st->u_tag[s], p.tag, p.mask)) continue;
+      st->u_meta[s] = 0;
+      st->u_count--;
+      emit_match(st, out, (meta & SW_UMETA_RTS) != 0, st->u_data[s], st->u_tag[s], st->u_len[s],
+                 meta & SW_UMETA_EPMASK, p.buf, p.cap, p.op_id);
+      if (meta & SW_UMETA_BIG)
+        st->pend_big[st->n_pend_big++] = st->u_blk[s];
+      else
+        st->pend_small[st->n_pend_small++] = st->u_blk[s];
+      found = true;
+      break;
+    }
+    while (st->u_head < st->u_tail && !(st->u_meta[st->u_head & UQM] & SW_UMETA_VALID)) st->u_head++;
+    if (!found) {
+      uint64_t s = st->p_tail & PQM;
+      st->p_tag[s] = p.tag;
+      st->p_mask[s] = p.mask;
+      st->p_buf[s] = p.buf;
+      st->p_cap[s] = p.cap;
+      st->p_op[s] = p.op_id;
+      st->p_valid[s] = 1;
+      st->p_tail++;
+      st->p_count++;
+    }
+  }
+  // phase 2: arrivals against the posted queue (earliest-posted first), rings round-robin
+  uint32_t budget = in->max_arrivals < SW_MAX_ARRIVALS ? in->max_arrivals : SW_MAX_ARRIVALS;
+  uint32_t total = 0;
+  const uint32_t n_eps = in->n_eps;
+  const uint32_t rr = n_eps ? st->rr_ep % n_eps : 0;
+  for (uint32_t e = 0; e < n_eps; e++) {
+    const uint32_t ep = (rr + e) % n_eps;
+    uint64_t cons = st->ring_cons[ep];
+    const uint64_t prod = in->produced[ep];
+    while (cons < prod && budget > 0) {
+      const uint8_t* slot = (const uint8_t*)(uintptr_t)(st->ring_base[ep] + (cons & (st->ring_slots[ep] - 1)) * SW_SLOT_BYTES);
+      SwSlotHdr h;
+      memcpy(&h, slot, 32);
+      if (h.magic != SW_SLOT_MAGIC || h.seq != cons + 1) out->err |= 1;
+      const bool is_rts = h.kind == SW_KIND_RTS;
+      const uint64_t payload = (uint64_t)(uintptr_t)(slot + SW_SLOT_HDR);
+      bool found = false;
+      for (uint64_t idx = st->p_head; idx < st->p_tail; idx++) {
+        uint64_t s = idx & PQM;
+        if (!st->p_valid[s] || !sw_tag_match(h.tag, st->p_tag[s], st->p_mask[s])) continue;
+        st->p_valid[s] = 0;
+        st->p_count--;
+        emit_match(st, out, is_rts, payload, h.tag, h.len, ep, st->p_buf[s], st->p_cap[s], st->p_op[s]);
+        found = true;
+        break;
+      }
+      while (st->p_head < st->p_tail && !st->p_valid[st->p_head & PQM]) st->p_head++;
+      if (!found) {
+        const uint64_t need = is_rts ? sizeof(SwRts) : h.len;
+        const bool big = need > SW_HEAP_SMALL_BYTES;
+        if ((big ? st->n_free_big : st->n_free_small) == 0 || st->u_tail - st->u_head >= SW_UQ_CAP) break;
+        uint32_t blk = big ? st->free_big[--st->n_free_big] : st->free_small[--st->n_free_small];
+        uint64_t haddr = big ? (uint64_t)(uintptr_t)st->heap_big + (uint64_t)blk * SW_HEAP_BIG_BYTES
+                             : (uint64_t)(uintptr_t)st->heap_small + (uint64_t)blk * SW_HEAP_SMALL_BYTES;
+        emit_job(st, payload, haddr, need, 0, h.tag, h.len, SW_OK, SW_JOB_STASH);
+        uint64_t s = st->u_tail & UQM;
+        st->u_tag[s] = h.tag;
+        st->u_len[s] = h.len;
+        st->u_data[s] = haddr;
+        st->u_blk[s] = blk;
+        st->u_meta[s] = SW_UMETA_VALID | (big ? SW_UMETA_BIG : 0) | (is_rts ? SW_UMETA_RTS : 0) | (ep & SW_UMETA_EPMASK);
+        st->u_tail++;
+        st->u_count++;
+      }
+      cons++;
+      budget--;
+      total++;
+    }
+    st->ring_cons[ep] = cons;
+    out->consumed[ep] = cons;
+  }
+  st->rr_ep = rr + 1;
+  out->n_arrivals = total;
+  out->n_jobs = st->n_jobs;
+  out->n_posted = st->p_count;
+  out->n_unexp = st->u_count;
+  out->heap_small_free = st->n_free_small;
+  out->heap_big_free = st->n_free_big;
+  return 0;
+}
+
+int launch_deliver(stream_t, SwMatchState* st, SwMatchOut* out, uint32_t) {
+  for (uint32_t i = 0; i < st->n_jobs; i++) {
+    const SwJob& j = st->jobs[i];
+    if (j.len) memcpy((void*)(uintptr_t)j.dst, (const void*)(uintptr_t)j.src, j.len);
+    SwCqe& c = out->cq[i];
+    c.op_id = j.op_id;
+    c.tag = j.tag;
+    c.len = j.msg_len;
+    c.status = j.status;
+    c.kind = j.kind;
+  }
+  return 0;
+}
+
+int launch_bulk(stream_t, const SwSeg* segs, uint32_t nseg, const BulkTuning*) {
+  for (uint32_t i = 0; i < nseg; i++)
+    memcpy((void*)(uintptr_t)segs[i].dst, (const void*)(uintptr_t)segs[i].src, segs[i].len);
+  return 0;
+}
+
+}  // namespace swgpu

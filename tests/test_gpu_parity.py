@@ -1,0 +1,375 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Everything here goes through
+the C ABI of libstarway_b200.so (ctypes) into the sm_100a kernels; results are compared
+bit-exactly with the CPU oracle (oracle/tagmatch.*), with the golden vectors transcribed
+from the reference's tests, and through size-independent properties at full sizes."""
+import asyncio
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from tests import cases_basic as cb
+from tests.golden_util import load_cases, payload
+
+pytestmark = pytest.mark.gpu
+
+U64 = (1 << 64) - 1
+
+
+def run(coro, timeout=180):
+    return asyncio.run(asyncio.wait_for(coro, timeout=timeout))
+
+
+def torch_cuda():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def test_product_library_is_cuda(cuda_api):
+    # the product path must be the CUDA extension, never a CPU stand-in
+    assert cuda_api.backend_name() == "cuda-sm_100a"
+    torch_cuda()
+
+
+# ------------------------------------------------------------------ the reference's own tests, host (NumPy) buffers
+@pytest.mark.parametrize("case", cb.SINGLE_PROCESS_CASES, ids=lambda c: c.__name__)
+def test_reference_case(cuda_api, port, case):
+    run(case(cuda_api, port))
+
+
+@pytest.mark.parametrize("size", [1, 1024, 4096, 8128, 8129, 65536, 65537, 1 << 20, (1 << 24) + 13])
+def test_message_integrity_host_buffers(cuda_api, port, size):
+    run(cb.case_message_integrity(cuda_api, port, size))
+
+
+@pytest.mark.parametrize("mode", ["flush", "flush_ep"])
+def test_two_process_server_send_with_flush_good(cuda_api, port, mode):
+    run(cb.case_server_send_with_flush_good(cuda_api, port, "cuda", mode), timeout=300)
+
+
+def test_two_process_client_send_with_flush_good(cuda_api, port):
+    run(cb.case_client_send_with_flush_good(cuda_api, port, "cuda"), timeout=300)
+
+
+# ------------------------------------------------------------------ golden vectors through the CUDA path
+CASES = load_cases()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_golden_reference_cases(cuda_api, port, case):
+    async def go():
+        n_eps = 1 + max([ev[1] for ev in case["events"] if ev[0] == "send"], default=0)
+        server = cuda_api.Server()
+        server.listen("127.0.0.1", port)
+        clients = [cuda_api.Client() for _ in range(n_eps)]
+        for c in clients:
+            await c.aconnect("127.0.0.1", port)
+        bufs, futs, sends = {}, {}, []
+        for ev in case["events"]:
+            if ev[0] == "recv":
+                _, op, tag, mask, cap = ev
+                bufs[op] = np.full(cap, 0xEE, dtype=np.uint8)
+                futs[op] = server.arecv(bufs[op], tag, mask)
+            else:
+                _, ep, tag, spec = ev
+                sends.append(clients[ep].asend(payload(spec), tag))
+        await asyncio.gather(*sends)
+        pending = set(case.get("pending", []))
+        results = {}
+        for op, f in futs.items():
+            if op in pending:
+                continue
+            results[op] = await asyncio.wait_for(f, 30)
+        for op, (tag, length, spec) in case.get("complete", {}).items():
+            assert results[int(op)] == (tag, length)
+            if spec is not None:
+                np.testing.assert_array_equal(bufs[int(op)][:length], payload(spec))
+                assert (bufs[int(op)][length:] == 0xEE).all()
+        if "tagset" in case:
+            ops, tags = case["tagset"]
+            assert {results[o][0] for o in ops} == set(tags)
+        await asyncio.sleep(0.05)
+        for op in pending:
+            assert not futs[op].done()
+        for c in clients:
+            await c.aclose()
+        await server.aclose()
+        for op in pending:
+            with pytest.raises(Exception, match="cancel"):
+                await futs[op]
+
+    run(go())
+
+
+# ------------------------------------------------------------------ device buffers (the hot path proper)
+@pytest.mark.parametrize(
+    "size", [0, 1, 15, 16, 17, 64, 4096, 8128, 8129, 65536, (1 << 20), (1 << 20) + 5, 64 << 20, (256 << 20) + 16]
+)
+def test_device_buffers_bit_exact(cuda_api, port, size):
+    torch = torch_cuda()
+
+    async def go():
+        async with cb.gen_server_client(cuda_api, port) as (server, client):
+            ep = next(iter(server.list_clients()))
+            g = torch.Generator(device="cuda").manual_seed(size + 1)
+            src = torch.randint(0, 256, (size,), dtype=torch.uint8, device="cuda", generator=g)
+            dst = torch.full((size + 64,), 0xEE, dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            # client -> server, tag=1 tag_mask=0xFFFF (BASELINE config 2 shape)
+            fut = server.arecv(dst[:size], 1, 0xFFFF)
+            await client.asend(src, 0xABCD0001)
+            assert await fut == (0xABCD0001, size)
+            torch.cuda.synchronize()
+            assert torch.equal(dst[:size], src)
+            assert bool((dst[size:] == 0xEE).all())
+            # server -> client into an offset (misaligned when size is odd) destination
+            dst.fill_(0xEE)
+            torch.cuda.synchronize()
+            fut = client.arecv(dst[7 : 7 + size], 0, 0)
+            await server.asend(ep, src, 5)
+            assert await fut == (5, size)
+            torch.cuda.synchronize()
+            assert torch.equal(dst[7 : 7 + size], src)
+            assert bool((dst[:7] == 0xEE).all()) and bool((dst[7 + size :] == 0xEE).all())
+
+    run(go())
+
+
+@pytest.mark.parametrize("src_off,dst_off", [(1, 1), (3, 19), (4, 8), (5, 2), (16, 48), (0, 9)])
+@pytest.mark.parametrize("size", [100, 8000, 300000, (4 << 20) + 3])
+def test_device_misaligned(cuda_api, port, src_off, dst_off, size):
+    torch = torch_cuda()
+
+    async def go():
+        async with cb.gen_server_client(cuda_api, port) as (server, client):
+            base = torch.randint(0, 256, (size + 64,), dtype=torch.uint8, device="cuda")
+            dst = torch.zeros(size + 128, dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            fut = server.arecv(dst[dst_off : dst_off + size], 9, U64)
+            await client.asend(base[src_off : src_off + size], 9)
+            assert await fut == (9, size)
+            torch.cuda.synchronize()
+            assert torch.equal(dst[dst_off : dst_off + size], base[src_off : src_off + size])
+            assert int(dst[:dst_off].sum()) == 0 and int(dst[dst_off + size :].sum()) == 0
+
+    run(go())
+
+
+def test_truncation_and_short_message(cuda_api, port):
+    torch = torch_cuda()
+
+    async def go():
+        async with cb.gen_server_client(cuda_api, port) as (server, client):
+            for n, cap in [(100, 10), (70000, 4096), (9000, 8128)]:
+                buf = torch.full((cap,), 0xEE, dtype=torch.uint8, device="cuda")
+                fut = server.arecv(buf, 0, 0)
+                await asyncio.sleep(0.01)
+                send = asyncio.ensure_future(client.asend(torch.ones(n, dtype=torch.uint8, device="cuda"), 3))
+                with pytest.raises(Exception, match="truncated"):
+                    await fut
+                await send  # the sender completes (UCX: truncation is a receive-side error)
+                torch.cuda.synchronize()
+                assert bool((buf == 0xEE).all())
+            # short message into a larger buffer: only `length` bytes are written
+            buf = torch.full((4096,), 0xEE, dtype=torch.uint8, device="cuda")
+            fut = server.arecv(buf, 0, 0)
+            await client.asend(torch.arange(10, dtype=torch.uint8, device="cuda"), 8)
+            assert await fut == (8, 10)
+            torch.cuda.synchronize()
+            assert buf[:10].tolist() == list(range(10)) and bool((buf[10:] == 0xEE).all())
+
+    run(go())
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_random_schedules_vs_oracle(cuda_api, port, seed):
+    """Sequential (quiesced) random schedules on one endpoint must reproduce the oracle exactly:
+    same receive <-> message pairing, (sender_tag, length), status and bytes."""
+    torch = torch_cuda()
+
+    class Dev:
+        @staticmethod
+        def alloc(cap):
+            return torch.full((cap,), 0xEE, dtype=torch.uint8, device="cuda")
+
+        @staticmethod
+        def from_np(a):
+            return torch.from_numpy(a).cuda()
+
+        @staticmethod
+        def to_np(b):
+            return b.cpu().numpy()
+
+        sync = staticmethod(torch.cuda.synchronize)
+
+    run(cb.case_random_schedule_vs_oracle(cuda_api, port, seed, Dev))
+
+
+def test_unexpected_flood_out_of_order(cuda_api, port):
+    """More unexpected eager messages than ring slots (1024): the matcher parks them on the
+    device heap, credits flow back, and receives posted in REVERSE tag order still pair up."""
+    torch = torch_cuda()
+
+    async def go():
+        async with cb.gen_server_client(cuda_api, port) as (server, client):
+            n = 3000
+            payloads = [torch.full((1 + (i % 200),), i % 251, dtype=torch.uint8, device="cuda") for i in range(n)]
+            torch.cuda.synchronize()
+            await asyncio.gather(*[client.asend(payloads[i], 1000 + i) for i in range(n)])
+            await client.aflush()
+            bufs = [torch.zeros(256, dtype=torch.uint8, device="cuda") for _ in range(n)]
+            res = await asyncio.gather(*[server.arecv(bufs[i], 1000 + i, U64) for i in reversed(range(n))])
+            torch.cuda.synchronize()
+            for k, i in enumerate(reversed(range(n))):
+                assert res[k] == (1000 + i, 1 + (i % 200))
+                assert torch.equal(bufs[i][: 1 + (i % 200)], payloads[i])
+
+    run(go())
+
+
+def test_heap_backpressure_no_deadlock(cuda_api, port):
+    """Unexpected 4 KiB messages beyond heap (512 big blocks) + ring (1024 slots): senders stall on
+    credits instead of overwriting; everything is delivered once receives are posted."""
+    torch = torch_cuda()
+
+    async def go():
+        async with cb.gen_server_client(cuda_api, port) as (server, client):
+            n = 2500
+            src = torch.randint(0, 256, (n, 4096), dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            sends = [asyncio.ensure_future(client.asend(src[i], i)) for i in range(n)]
+            await asyncio.sleep(0.3)
+            assert sum(s.done() for s in sends) < n  # some are parked waiting for credits
+            dst = torch.zeros((n, 4096), dtype=torch.uint8, device="cuda")
+            res = await asyncio.gather(*[server.arecv(dst[i], 0, 0) for i in range(n)])
+            await asyncio.gather(*sends)
+            torch.cuda.synchronize()
+            assert [r[0] for r in res] == list(range(n))  # single sender: FIFO, non-overtaking
+            assert torch.equal(dst, src)
+
+    run(go())
+
+
+def test_mixed_eager_rendezvous_fifo(cuda_api, port):
+    """Per-sender FIFO holds across the eager / rendezvous boundary."""
+    torch = torch_cuda()
+
+    async def go():
+        async with cb.gen_server_client(cuda_api, port) as (server, client):
+            sizes = [10, 100000, 20, 8129, 8128, 3 << 20, 1, 50000, 0, 70000] * 6
+            srcs = [torch.randint(0, 256, (s,), dtype=torch.uint8, device="cuda") for s in sizes]
+            dsts = [torch.zeros(max(sizes), dtype=torch.uint8, device="cuda") for _ in sizes]
+            torch.cuda.synchronize()
+            recvs = [server.arecv(d, 0, 0) for d in dsts]
+            await asyncio.gather(*[client.asend(s, i) for i, s in enumerate(srcs)])
+            res = await asyncio.gather(*recvs)
+            torch.cuda.synchronize()
+            for i, (tag, length) in enumerate(res):
+                assert (tag, length) == (i, sizes[i])
+                assert torch.equal(dsts[i][:length], srcs[i])
+
+    run(go())
+
+
+def test_full_size_roundtrip_properties(cuda_api, port):
+    """BASELINE sweep upper end (1 GiB): checksum equality and send->recv->send-back idempotence."""
+    torch = torch_cuda()
+
+    async def go():
+        async with cb.gen_server_client(cuda_api, port) as (server, client):
+            ep = next(iter(server.list_clients()))
+            n = 1 << 30
+            src = torch.empty(n, dtype=torch.uint8, device="cuda")
+            src.view(torch.int64).copy_(torch.arange(n // 8, device="cuda", dtype=torch.int64) * 2654435761)
+            mid = torch.zeros(n, dtype=torch.uint8, device="cuda")
+            back = torch.zeros(n, dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            f = server.arecv(mid, 1, 0xFFFF)
+            await client.asend(src, 1)
+            assert await f == (1, n)
+            f = client.arecv(back, 2, 0xFFFF)
+            await server.asend(ep, mid, 2)
+            assert await f == (2, n)
+            torch.cuda.synchronize()
+            s0 = int(src.view(torch.int64).sum())
+            assert int(mid.view(torch.int64).sum()) == s0 and int(back.view(torch.int64).sum()) == s0
+            assert torch.equal(back, src)
+
+    run(go(), timeout=300)
+
+
+def test_many_endpoints_wildcard_fanin(cuda_api, port):
+    """BASELINE config 4 shape on one GPU: 7 peers each send 4 MiB tagged with their rank;
+    wildcard receives identify the source from sender_tag."""
+    torch = torch_cuda()
+
+    async def go():
+        server = cuda_api.Server()
+        server.listen("127.0.0.1", port)
+        clients = [cuda_api.Client() for _ in range(7)]
+        await asyncio.gather(*[c.aconnect("127.0.0.1", port) for c in clients])
+        n = 4 << 20
+        srcs = [torch.full((n,), r + 1, dtype=torch.uint8, device="cuda") for r in range(7)]
+        dsts = [torch.zeros(n, dtype=torch.uint8, device="cuda") for _ in range(7)]
+        torch.cuda.synchronize()
+        recvs = [server.arecv(d, 0, 0) for d in dsts]
+        await asyncio.gather(*[c.asend(srcs[r], r) for r, c in enumerate(clients)])
+        res = await asyncio.gather(*recvs)
+        torch.cuda.synchronize()
+        assert sorted(t for t, _ in res) == list(range(7))
+        for (tag, length), d in zip(res, dsts):
+            assert length == n and bool((d == tag + 1).all())
+        await asyncio.gather(*[c.aclose() for c in clients])
+        await server.aclose()
+
+    run(go())
+
+
+def test_c_abi_direct_device_pointers(cuda_api, port):
+    """Drive the C ABI by hand (no Python API classes): post/poll with raw device pointers."""
+    torch = torch_cuda()
+    import starway_b200 as sw
+    from starway_b200._core import SwCompletion
+
+    lib = sw._api.lib
+    ctx = cuda_api.get_context()
+    h = ctx._h
+    srv = lib.sw_worker_create(h, 1)
+    cli = lib.sw_worker_create(h, 2)
+    assert lib.sw_listen(h, srv, b"127.0.0.1", port) == 0
+    n = 1 << 20
+    src = torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda")
+    dst = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+
+    # the poller thread of the Python context would steal completions: use the ops table hook
+    got = {}
+
+    def waiter(kind):
+        ev = asyncio.Event()
+        return ev
+
+    async def go():
+        loop = asyncio.get_running_loop()
+
+        def submit(fn):
+            fut = loop.create_future()
+            ctx.submit(fn, ("fut", loop, fut, None, None))
+            return fut
+
+        await submit(lambda: lib.sw_connect(h, cli, b"127.0.0.1", port))
+        r = submit(lambda: lib.sw_post_recv(h, srv, dst.data_ptr(), n, 1, 0xFFFF, 2))
+        await submit(lambda: lib.sw_post_send(h, cli, 0, src.data_ptr(), n, 1, 2))
+        assert await r == (1, n)
+        await submit(lambda: lib.sw_post_flush(h, cli))
+        await submit(lambda: lib.sw_close(h, cli))
+        await submit(lambda: lib.sw_close(h, srv))
+
+    run(go())
+    torch.cuda.synchronize()
+    assert torch.equal(dst, src)
+    st = ctx.stats()
+    assert st["bulk_tma_launches"] > 0 and st["put_launches"] > 0 and st["match_launches"] > 0
