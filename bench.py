@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py — tagged send/recv throughput of starway_b200 (driver contract: see the task brief).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA, sm_100a)
+  python bench.py --impl reference --gpus N ...            reference arm: the reference's CPU path
+                                                           (restated, oracle/cpu_engine.cpp) on host cores
+  python bench.py --sweep                                  size sweep 64 B - 1 GiB (BASELINE config 3) -> JSON lines
+
+Workload (BASELINE.json configs[1]): point-to-point asend/arecv of 1 MiB buffers, tag=1,
+tag_mask=0xFFFF.  One step = a window of WINDOW messages: the receiver posts WINDOW receives,
+the sender issues WINDOW sends then aflush(); the step ends when every receive has completed.
+  N == 1: Server and Client on the same GPU (loopback; HBM-bound: 2 x payload bytes of traffic)
+  N  > 1: rank r sends to rank (r+1) % N over NVLink and receives from (r-1) % N; per-GPU work is
+          fixed (weak scaling); no collective on the data path (torch.distributed/gloo is used only
+          to exchange address blobs and to take the max time over ranks).
+`value` uses device-resident buffers; `e2e` runs the same steps with (pinned) HOST buffers through the
+public API, so host->device and device->host copies are inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import asyncio
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+MSG_BYTES = 1 << 20
+WINDOW = 64
+POOL_SETS = 4  # 4 x 64 MiB sources + 4 x 64 MiB destinations = 512 MiB > 126 MB L2
+TAG, MASK = 1, 0xFFFF
+METRIC = "tagged send/recv GB/s & Mmsg/s vs size, 1/2/4/8 B200; NVLink roofline %"
+NVLINK_MEASURED_GBS = 770.0  # /opt/skills/guides/B200_PROFILING.md: measured peer copy per direction (900 nominal)
+
+
+def new_loop_runner():
+    try:
+        import uvloop
+
+        return uvloop.run
+    except Exception:
+        return asyncio.run
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+
+    def _loop(self):
+        nv = self._nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        if self._nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=1)
+        return {
+            "sm_mhz": statistics.median(self.samples) if self.samples else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+        }
+
+
+# ----------------------------------------------------------------------------------------- our arm
+async def window_step(server, client, eps, srcs, dsts):
+    recvs = [server.arecv(d, TAG, MASK) for d in dsts]
+    sends = [client.asend(s, TAG) for s in srcs]
+    await asyncio.gather(*sends)
+    await client.aflush()
+    res = await asyncio.gather(*recvs)
+    return res
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch N>1 with torch.distributed.run)"
+    torch.cuda.set_device(local_rank)
+    os.environ["STARWAY_DEVICE"] = str(local_rank)
+    import starway_b200 as sw
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    ctx = sw.get_context()
+    ctx.set_option("profile", 1)
+    peaks, peaks_src = measured_peaks()
+    msg, window = args.msg_bytes, args.window
+    dev = torch.device("cuda", local_rank)
+
+    async def main():
+        server = sw.Server()
+        addr = server.listen_address()
+        addrs = [addr]
+        if dist is not None:
+            addrs = [None] * world
+            dist.all_gather_object(addrs, addr)
+        client = sw.Client()
+        await client.aconnect_address(addrs[(rank + 1) % world])
+        for _ in range(2000):
+            if server.list_clients():
+                break
+            await asyncio.sleep(0.005)
+        eps = list(server.list_clients())
+        assert eps, "no inbound endpoint"
+        barrier()
+
+        # ---- device-resident buffers (inputs larger than L2: POOL_SETS rotating sets)
+        g = torch.Generator(device=dev).manual_seed(0xB200 + rank)
+        src = [[torch.randint(0, 256, (msg,), dtype=torch.uint8, device=dev, generator=g) for _ in range(window)]
+               for _ in range(POOL_SETS)]
+        dst = [[torch.full((msg,), 0xEE, dtype=torch.uint8, device=dev) for _ in range(window)]
+               for _ in range(POOL_SETS)]
+        torch.cuda.synchronize()
+
+        async def timed(nsteps, srcs, dsts, sync):
+            for i in range(nsteps):
+                k = i % POOL_SETS
+                res = await window_step(server, client, eps, srcs[k], dsts[k])
+                assert all(r == (TAG, msg) for r in res)
+            sync()
+
+        # warm-up, then bit-exactness of one full window against the sources of the sending rank
+        await timed(max(args.warmup, 3), src, dst, torch.cuda.synchronize)
+        if world == 1:
+            for s, d in zip(src[0], dst[0]):
+                assert torch.equal(s, d), "payload mismatch"
+        barrier()
+        torch.cuda.synchronize()
+        ctx.reset_stats()
+        clocks = ClockSampler(local_rank)
+        clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        t0 = time.perf_counter()
+        await timed(args.steps, src, dst, torch.cuda.synchronize)
+        t1 = time.perf_counter()
+        e1.record()
+        e1.synchronize()
+        barrier()
+        clk = clocks.stop()
+        st = ctx.stats()
+        dev_ms = e0.elapsed_time(e1)
+        wall_ms = (t1 - t0) * 1e3
+        ms = max(dev_ms, wall_ms)
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        step_bytes = window * msg
+        value = world * step_bytes * args.steps / (ms * 1e-3) / 1e9
+
+        # ---- e2e: same steps, pinned HOST buffers through the public API (H2D + D2H inside)
+        hsrc = [[torch.from_numpy(np.random.default_rng(rank * 1000 + k * 100 + j).integers(0, 256, msg, dtype=np.uint8)).pin_memory().numpy()
+                 for j in range(window)] for k in range(2)]
+        hdst = [[torch.empty(msg, dtype=torch.uint8).pin_memory().numpy() for _ in range(window)] for k in range(2)]
+
+        async def timed_host(nsteps):
+            for i in range(nsteps):
+                k = i % 2
+                res = await window_step(server, client, eps, hsrc[k], hdst[k])
+                assert all(r == (TAG, msg) for r in res)
+
+        await timed_host(3)
+        if world == 1:
+            for s, d in zip(hsrc[0], hdst[0]):
+                assert np.array_equal(s, d), "host payload mismatch"
+        barrier()
+        torch.cuda.synchronize()
+        e2e_steps = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        await timed_host(e2e_steps)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        barrier()
+        e2e_ms = (t1 - t0) * 1e3
+        if dist is not None:
+            t = torch.tensor([e2e_ms], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t[0])
+        e2e_value = world * step_bytes * e2e_steps / (e2e_ms * 1e-3) / 1e9
+
+        await client.aclose()
+        barrier()
+        await server.aclose()
+        return value, ms, st, clk, e2e_value, step_bytes
+
+    value, ms, st, clk, e2e_value, step_bytes = new_loop_runner()(main())
+
+    # ---- roofline of the dominant kernel (sw_bulk_tma_kernel), from CUDA events recorded on the
+    #      stream the kernel is launched on (engine profiling hooks), averaged over the timed region
+    launches = max(1, st["bulk_event_launches"])
+    avg_ms = st["bulk_event_ms"] / launches
+    payload_per_launch = st["bulk_event_bytes"] / launches
+    if world == 1:
+        algo_bytes = 2 * payload_per_launch  # loopback: read N + write N bytes of HBM
+        peak, bound, peak_note = float(peaks["hbm_gbs"]), "hbm", f"HBM copy, {peaks_src}"
+    else:
+        algo_bytes = payload_per_launch  # N payload bytes cross NVLink in one direction
+        peak, bound, peak_note = NVLINK_MEASURED_GBS, "nvlink", "NVLink per direction: measured peer copy 770 GB/s (B200_PROFILING.md; 900 nominal)"
+    achieved = algo_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("world") == world:
+            traffic = tj["dram_bytes_per_payload_byte"] * payload_per_launch
+    except Exception:
+        pass
+    roofline = {
+        "bound": bound, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+        "frac": round(achieved / peak, 4), "traffic": traffic, "kernel": "sw_bulk_tma_kernel",
+        "launches": st["bulk_event_launches"], "avg_launch_us": round(avg_ms * 1e3, 2),
+        "payload_bytes_per_launch": int(payload_per_launch), "peak_source": peak_note,
+    }
+    gpu_launches = int(st["put_launches"] + st["match_launches"] + st["deliver_launches"]
+                       + st["bulk_tma_launches"] + st["bulk_simt_launches"])
+    if rank != 0:
+        sw.shutdown()
+        return
+    cpu = cpu_baseline_run(args.msg_bytes, args.window, budget_s=12.0) if (world == 1 and not args.no_cpu_baseline) else None
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {
+            "workload": f"configs[1]: point-to-point asend/arecv, {msg} B device buffers, tag=1 tag_mask=0xFFFF, "
+                        f"window {window} msgs/step + aflush; "
+                        + ("1 GPU loopback (Server+Client on cuda:0)" if world == 1 else f"ring over {world} GPUs, rank r -> r+1 over NVLink"),
+            "msg_bytes": msg, "window": window,
+            "l2": f"inputs larger than L2: {POOL_SETS} rotating buffer sets, {2 * POOL_SETS * window * msg >> 20} MiB footprint",
+            "timing": "wall clock + CUDA events between device-wide synchronisations, max over ranks",
+            "api": "public asyncio API (one Future per message, as the reference)",
+        },
+        "mmsg_per_s": round(world * window * args.steps / (ms * 1e-3) / 1e6, 4),
+        "nvlink_roofline_frac": None if world == 1 else round(value / world / 900.0, 4),
+        "clocks": clk,
+        "e2e": {"value": round(e2e_value, 2), "unit": "GB/s", "h2d_bytes_per_step": step_bytes, "d2h_bytes_per_step": step_bytes,
+                "buffers": "pinned host NumPy arrays through Client.asend/Server.arecv"},
+        "gpu_launches": gpu_launches,
+        "roofline": roofline,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    sw.shutdown()
+
+
+# ----------------------------------------------------------------------------------------- CPU baseline / reference arm
+def cpu_baseline_run(msg, window, budget_s=12.0, steps=None, warmup=2):
+    """Times the restated reference (oracle/cpu_engine.cpp: spinning worker thread per object,
+    1-slot mailboxes, per-completion GIL + call_soon_threadsafe, single-threaded memcpy) on the
+    same workload shape with host NumPy buffers."""
+    import numpy as np
+
+    from oracle import starway_cpu as cpu
+
+    async def main():
+        port = 40000 + (os.getpid() % 20000)
+        s, c = cpu.make_pair(port)
+        await c.aconnect("127.0.0.1", port)
+        srcs = [np.random.default_rng(j).integers(0, 256, msg, dtype=np.uint8) for j in range(window)]
+        dsts = [np.zeros(msg, dtype=np.uint8) for _ in range(window)]
+
+        async def step():
+            recvs = [s.arecv(d, TAG, MASK) for d in dsts]
+            sends = [c.asend(x, TAG) for x in srcs]
+            await asyncio.gather(*sends)
+            await c.aflush()
+            res = await asyncio.gather(*recvs)
+            assert all(r == (TAG, msg) for r in res)
+
+        for _ in range(warmup):
+            await step()
+        assert all(np.array_equal(a, b) for a, b in zip(srcs, dsts))
+        n, t0 = 0, time.perf_counter()
+        while True:
+            await step()
+            n += 1
+            el = time.perf_counter() - t0
+            if (steps is not None and n >= steps) or (steps is None and el > budget_s) or el > 150:
+                break
+        await c.aclose()
+        await s.aclose()
+        return n, el
+
+    n, el = new_loop_runner()(main())
+    return {
+        "value": round(n * window * msg / el / 1e9, 3), "unit": "GB/s", "cores": 3, "kind": "port",
+        "threads": "2 spinning native worker threads (1 per Server/Client object) + 1 Python thread",
+        "host_cpus_available": len(os.sched_getaffinity(0)),
+        "sample": f"{n} steps of {window} x {msg} B host NumPy messages, tag=1 mask=0xFFFF, Server+Client in one process "
+                  f"({el:.1f} s); restated reference (libucp absent: oracle/cpu_engine.cpp + oracle/tagmatch.c)",
+        "mmsg_per_s": round(n * window / el / 1e6, 4), "ms_per_step": round(el / n * 1e3, 3),
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # the reference arm is a host-CPU measurement: rank 0 alone runs it
+    cpu = cpu_baseline_run(args.msg_bytes, args.window, steps=args.steps, warmup=max(1, min(args.warmup, 3)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"configs[1] shape on host cores: {args.msg_bytes} B host NumPy buffers, tag=1 tag_mask=0xFFFF, "
+                               f"window {args.window} msgs/step + aflush, Server+Client in one process",
+                   "msg_bytes": args.msg_bytes, "window": args.window},
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--msg-bytes", type=int, default=MSG_BYTES)
+    ap.add_argument("--window", type=int, default=WINDOW)
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -151,23 +151,47 @@ def _is_torch_tensor(obj: Any) -> bool:
     return mod == "torch" or mod.startswith("torch.")
 
 
+_U8 = np.dtype(np.uint8)
+_np_cache: dict[int, tuple] = {}  # id(array) -> (weakref, ptr, nbytes, writeable): preallocated buffers are reused
+
+
+def _np_fast(arr: np.ndarray):
+    import weakref
+
+    key = id(arr)
+    hit = _np_cache.get(key)
+    if hit is not None and hit[0]() is arr:
+        return hit
+    if len(_np_cache) > 8192:
+        _np_cache.clear()
+    hit = (weakref.ref(arr), arr.__array_interface__["data"][0], arr.nbytes, arr.flags.writeable)
+    _np_cache[key] = hit
+    return hit
+
+
 def as_buffer(obj: Any, writable: bool):
     """-> (ptr, nbytes, mem_kind, keepalive).  1-D contiguous uint8, host or device."""
-    if isinstance(obj, np.ndarray):
+    tp = type(obj)
+    if tp is np.ndarray:
         arr = obj
-        if writable:
-            if arr.dtype != np.uint8 or arr.ndim != 1 or not arr.flags.c_contiguous or not arr.flags.writeable:
+        if arr.dtype is _U8 and arr.strides == (1,):
+            _, ptr, nbytes, wr = _np_fast(arr)
+            if writable and not wr:
                 raise TypeError("recv buffer must be a writable, contiguous 1-D uint8 array")
-        else:
+            return ptr, nbytes, SW_MEM_HOST, arr
+        if arr.dtype != np.uint8 or arr.ndim != 1 or not arr.flags.c_contiguous:
+            if writable:
+                raise TypeError("recv buffer must be a writable, contiguous 1-D uint8 array")
             if arr.ndim != 1:
                 raise TypeError("send buffer must be 1-D")
             if arr.dtype != np.uint8:
                 # nanobind's ndarray caster converts implicitly (reference tests pass int64 arrays,
                 # tests/test_basic.py:562); the temporary is kept alive until completion
                 arr = arr.astype(np.uint8)
-            if not arr.flags.c_contiguous:
-                arr = np.ascontiguousarray(arr)
-        return arr.ctypes.data, arr.nbytes, SW_MEM_HOST, arr
+            arr = np.ascontiguousarray(arr)
+        elif writable and not arr.flags.writeable:
+            raise TypeError("recv buffer must be a writable, contiguous 1-D uint8 array")
+        return arr.__array_interface__["data"][0], arr.nbytes, SW_MEM_HOST, arr
     if _is_torch_tensor(obj):
         t = obj
         if t.dim() != 1 or not t.is_contiguous():
@@ -176,8 +200,9 @@ def as_buffer(obj: Any, writable: bool):
             if writable:
                 raise TypeError("recv buffer must be a uint8 tensor")
             t = t.view(-1).contiguous().view(dtype=__import__("torch").uint8)
-        nbytes = t.numel() * t.element_size()
-        return t.data_ptr(), nbytes, (SW_MEM_DEVICE if t.is_cuda else SW_MEM_HOST), t
+        return t.data_ptr(), t.numel(), (SW_MEM_DEVICE if t.is_cuda else SW_MEM_HOST), t
+    if isinstance(obj, np.ndarray):
+        return as_buffer(np.asarray(obj), writable)
     cai = getattr(obj, "__cuda_array_interface__", None)
     if cai is not None:
         shape = cai["shape"]
@@ -194,6 +219,9 @@ def as_buffer(obj: Any, writable: bool):
 def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None) -> SimpleNamespace:
     """Build Context/Server/Client/ServerEndpoint classes on top of a loaded C-ABI library."""
     declare(lib)
+    _post_send, _post_recv = lib.sw_post_send, lib.sw_post_recv
+    _get_running_loop = asyncio.get_running_loop
+    _U64MASK = 0xFFFFFFFFFFFFFFFF
 
     def _err() -> str:
         s = lib.sw_last_error()
@@ -203,10 +231,14 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None) -> S
         return lib.sw_status_string(code).decode()
 
     class Context:
-        """One per (process, device): owns the native context and the completion poller.
+        """One per (process, device): owns the native context and completion delivery.
 
-        Replaces the reference's global ``Context()`` (``__init__.py:68``) plus the
-        per-object UCX progress threads."""
+        Replaces the reference's global ``Context()`` (``__init__.py:68``) plus the per-object UCX
+        progress threads.  Completions are drained by the asyncio loop itself: the native
+        completion queue signals an eventfd that is registered with ``loop.add_reader``, so futures
+        are resolved on the loop thread in batches with no thread hand-off ("asyncio futures resolve
+        from CUDA-event polling").  A fallback poller thread serves raw-callback users and loops the
+        context was not registered with."""
 
         def __init__(self, device: int | None = None):
             if device is None:
@@ -218,7 +250,11 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None) -> S
             self._lock = threading.Lock()
             self._ops: dict[int, tuple] = {}
             self._servers: dict[int, Any] = {}
+            self._efd = lib.sw_event_fd(self._h)
+            self._readers: dict[Any, bool] = {}
+            self._buf = (SwCompletion * 512)()
             self._stop = False
+            self._wake = threading.Event()
             self._thread = threading.Thread(target=self._poll_loop, name="starway-b200-poller", daemon=True)
             self._thread.start()
 
@@ -231,61 +267,107 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None) -> S
                 self._ops[op] = entry
             return op
 
+        def ensure_reader(self, loop) -> None:
+            """Register the completion eventfd with `loop` (must be called on the loop's thread)."""
+            if loop in self._readers or self._efd < 0:
+                return
+            try:
+                if asyncio.get_running_loop() is not loop:
+                    return
+                loop.add_reader(self._efd, self._drain, loop)
+                self._readers[loop] = True
+            except (RuntimeError, NotImplementedError, OSError):
+                pass
+
         # -- completion side ---------------------------------------------------
+        def _dispatch(self, n: int, buf, here) -> None:
+            """Deliver n polled completions.  `here` is the loop whose thread we are on (or None)."""
+            with self._lock:
+                pop = self._ops.pop
+                items = []
+                for i in range(n):
+                    c = buf[i]
+                    k = c.kind
+                    if k == SW_OP_ACCEPT:
+                        items.append((None, k, c.status, c.worker, c.ep))
+                    else:
+                        items.append((pop(c.op_id, None), k, c.status, c.sender_tag, c.length))
+            batches: dict[Any, list] = {}
+            for entry, kind, status, a, b in items:
+                if kind == SW_OP_ACCEPT:
+                    srv = self._servers.get(a)
+                    if srv is not None:
+                        srv._on_accept(b)
+                    continue
+                if entry is None:
+                    continue
+                if entry[0] == "fut":
+                    _, loop, fut, _keep, post_ok = entry
+                    if status == 0:
+                        if post_ok is not None:
+                            post_ok()
+                        val = (a, b) if kind == SW_OP_RECV else None
+                        if loop is here:
+                            if not fut.done():
+                                fut.set_result(val)
+                        else:
+                            batches.setdefault(loop, []).append((fut, True, val))
+                    else:
+                        if loop is here:
+                            if not fut.done():
+                                fut.set_exception(Exception(status_string(status)))
+                        else:
+                            batches.setdefault(loop, []).append((fut, False, status_string(status)))
+                else:  # raw callbacks (reference: invoked on the native worker thread)
+                    _, done, fail, _keep = entry
+                    try:
+                        if status == 0:
+                            if kind == SW_OP_RECV:
+                                done(a, b)
+                            elif kind == SW_OP_CONNECT:
+                                done("")
+                            else:
+                                done()
+                        else:
+                            if kind == SW_OP_CONNECT:
+                                done(status_string(status))
+                            elif fail is not None:
+                                fail(status_string(status))
+                    except Exception as exc:  # never kill the dispatcher
+                        print(f"starway_b200: exception in user callback: {exc!r}")
+            for loop, lst in batches.items():
+                try:
+                    loop.call_soon_threadsafe(_resolve_batch, lst)
+                except RuntimeError:
+                    pass  # loop already closed
+
+        def _drain(self, loop) -> None:
+            """eventfd reader callback: runs on `loop`'s thread."""
+            h, buf = self._h, self._buf
+            if not h:
+                return
+            while True:
+                n = lib.sw_poll(h, buf, 512)
+                if n <= 0:
+                    return
+                self._dispatch(n, buf, loop)
+                if n < 512:
+                    return
+
         def _poll_loop(self):
             buf = (SwCompletion * 512)()
             while not self._stop:
+                if self._readers:
+                    # an asyncio loop drains the queue itself; only watch for loops that went away
+                    for lp in list(self._readers):
+                        if lp.is_closed():
+                            self._readers.pop(lp, None)
+                    if self._readers:
+                        self._wake.wait(0.05)
+                        continue
                 n = lib.sw_wait(self._h, buf, 512, 50)
-                if n <= 0:
-                    continue
-                batches: dict[Any, list] = {}
-                with self._lock:
-                    items = []
-                    for i in range(n):
-                        c = buf[i]
-                        if c.kind == SW_OP_ACCEPT:
-                            items.append((None, c.kind, c.status, c.worker, c.ep))
-                        else:
-                            items.append((self._ops.pop(c.op_id, None), c.kind, c.status, c.sender_tag, c.length))
-                for entry, kind, status, a, b in items:
-                    if kind == SW_OP_ACCEPT:
-                        srv = self._servers.get(a)
-                        if srv is not None:
-                            srv._on_accept(b)
-                        continue
-                    if entry is None:
-                        continue
-                    if entry[0] == "fut":
-                        _, loop, fut, _keep, post_ok = entry
-                        if status == 0:
-                            if post_ok is not None:
-                                post_ok()
-                            val = (a, b) if kind == SW_OP_RECV else None
-                            batches.setdefault(loop, []).append((fut, True, val))
-                        else:
-                            batches.setdefault(loop, []).append((fut, False, status_string(status)))
-                    else:  # raw callbacks, invoked on the poller thread (reference: on the worker thread)
-                        _, done, fail, _keep = entry
-                        try:
-                            if status == 0:
-                                if kind == SW_OP_RECV:
-                                    done(a, b)
-                                elif kind == SW_OP_CONNECT:
-                                    done("")
-                                else:
-                                    done()
-                            else:
-                                if kind == SW_OP_CONNECT:
-                                    done(status_string(status))
-                                elif fail is not None:
-                                    fail(status_string(status))
-                        except Exception as exc:  # never kill the poller
-                            print(f"starway_b200: exception in user callback: {exc!r}")
-                for loop, lst in batches.items():
-                    try:
-                        loop.call_soon_threadsafe(_resolve_batch, lst)
-                    except RuntimeError:
-                        pass  # loop already closed
+                if n > 0:
+                    self._dispatch(n, buf, None)
 
         def stats(self) -> dict:
             s = SwStats()
@@ -305,7 +387,15 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None) -> S
         def close(self):
             if self._h:
                 self._stop = True
+                self._wake.set()
                 self._thread.join(timeout=2.0)
+                for lp in list(self._readers):
+                    try:
+                        if not lp.is_closed():
+                            lp.remove_reader(self._efd)
+                    except Exception:
+                        pass
+                self._readers.clear()
                 h, self._h = self._h, None
                 lib.sw_ctx_destroy(h)
 
@@ -392,7 +482,10 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None) -> S
         def _future(self, loop):
             if loop is None:
                 loop = asyncio.get_running_loop()
-            return loop, asyncio.Future(loop=loop)
+            ctx = self._ctx
+            if loop not in ctx._readers:
+                ctx.ensure_reader(loop)
+            return loop, loop.create_future()
 
         def _post_recv(self, buffer, tag, tag_mask, entry_of):
             ptr, n, mem, keep = as_buffer(buffer, writable=True)
@@ -406,8 +499,19 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None) -> S
             self._post_recv(buffer, tag, tag_mask, lambda keep: ("cb", done_callback, fail_callback, keep))
 
         def arecv(self, buffer, tag: int, tag_mask: int, loop: asyncio.AbstractEventLoop | None = None):
-            loop, fut = self._future(loop)
-            self._post_recv(buffer, tag, tag_mask, lambda keep: ("fut", loop, fut, keep, None))
+            # hot path: no helper calls / closures
+            ctx = self._ctx
+            if loop is None:
+                loop = _get_running_loop()
+            if loop not in ctx._readers:
+                ctx.ensure_reader(loop)
+            fut = loop.create_future()
+            ptr, n, mem, keep = as_buffer(buffer, True)
+            with ctx._lock:
+                op = _post_recv(ctx._h, self._w, ptr, n, tag & _U64MASK, tag_mask & _U64MASK, mem)
+                if not op:
+                    raise RuntimeError(_err())
+                ctx._ops[op] = ("fut", loop, fut, keep, None)
             return fut
 
         def flush(self, done_callback, fail_callback):
@@ -494,8 +598,18 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None) -> S
             self._post_send(client_ep, buffer, tag, lambda keep: ("cb", done_callback, fail_callback, keep))
 
         def asend(self, client_ep, buffer, tag: int, loop: asyncio.AbstractEventLoop | None = None):
-            loop, fut = self._future(loop)
-            self._post_send(client_ep, buffer, tag, lambda keep: ("fut", loop, fut, keep, None))
+            ctx = self._ctx
+            if loop is None:
+                loop = _get_running_loop()
+            if loop not in ctx._readers:
+                ctx.ensure_reader(loop)
+            fut = loop.create_future()
+            ptr, n, mem, keep = as_buffer(buffer, False)
+            with ctx._lock:
+                op = _post_send(ctx._h, self._w, client_ep._id, ptr, n, tag & _U64MASK, mem)
+                if not op:
+                    raise RuntimeError(_err())
+                ctx._ops[op] = ("fut", loop, fut, keep, None)
             return fut
 
         def flush_ep(self, client_ep, done_callback, fail_callback):
@@ -560,8 +674,18 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None) -> S
             self._post_send(buffer, tag, lambda keep: ("cb", done_callback, fail_callback, keep))
 
         def asend(self, buffer, tag: int, loop: asyncio.AbstractEventLoop | None = None):
-            loop, fut = self._future(loop)
-            self._post_send(buffer, tag, lambda keep: ("fut", loop, fut, keep, None))
+            ctx = self._ctx
+            if loop is None:
+                loop = _get_running_loop()
+            if loop not in ctx._readers:
+                ctx.ensure_reader(loop)
+            fut = loop.create_future()
+            ptr, n, mem, keep = as_buffer(buffer, False)
+            with ctx._lock:
+                op = _post_send(ctx._h, self._w, 0, ptr, n, tag & _U64MASK, mem)
+                if not op:
+                    raise RuntimeError(_err())
+                ctx._ops[op] = ("fut", loop, fut, keep, None)
             return fut
 
         def evaluate_perf(self, msg_size: int) -> float:

@@ -253,7 +253,18 @@ struct StagingPool {
 struct Worker;
 struct Ctx;
 
+// Intrusive node of the lock-free multi-producer submission queue (replaces the reference's
+// 1-slot Channel<T> mailboxes, chan.hpp:84-120: any number of ops can be in flight).
+struct SqNode {
+  SqNode* next = nullptr;
+  int kind = 0;
+  Worker* w = nullptr;
+  void* p = nullptr;
+  bool heap = false;
+};
+
 struct SendOp {
+  SqNode sqn;
   uint64_t op_id = 0;
   Worker* w = nullptr;
   struct Ep* ep = nullptr;
@@ -268,7 +279,10 @@ struct SendOp {
   uint64_t rndv_seq = 0;
 };
 
+constexpr int MEM_PINNED = 3;  // internal: host memory the device can address directly (cudaHostAlloc)
+
 struct RecvOp {
+  SqNode sqn;
   uint64_t op_id = 0;
   Worker* w = nullptr;
   uint8_t* ptr = nullptr;
@@ -281,12 +295,15 @@ struct RecvOp {
 };
 
 struct FlushOp {
+  SqNode sqn;
   uint64_t op_id = 0;
   struct Ep* ep = nullptr;               // nullptr: every endpoint of the worker
   std::map<struct Ep*, uint64_t> marks;  // per-endpoint: sends with sseq < mark must be complete
 };
 
 struct BulkJob {
+  double t_enq = 0;
+  bool host_side = false;  // source or destination is pinned host memory: use the SIMT copy
   Worker* w = nullptr;
   struct Ep* ep = nullptr;
   uint64_t recv_op = 0;
@@ -298,7 +315,10 @@ struct BulkJob {
   int32_t fail_status = 0;
 };
 
+constexpr uint32_t EP_MAGIC = 0x53574550u, WORKER_MAGIC = 0x5357574Bu;
+
 struct Ep {
+  uint32_t magic = EP_MAGIC;
   uint64_t id = 0;
   Worker* owner = nullptr;
   uint32_t index = 0;  // index of the inbound ring in the owner's match state
@@ -343,6 +363,7 @@ struct Ep {
 };
 
 struct Worker {
+  uint32_t magic = WORKER_MAGIC;
   uint64_t id = 0;
   int kind = 0;
   Ctx* ctx = nullptr;
@@ -376,11 +397,6 @@ struct Worker {
 };
 
 enum : int { SQ_SEND = 1, SQ_RECV = 2, SQ_FLUSH = 3, SQ_CLOSE = 4, SQ_NEW_EP = 5, SQ_REGISTER = 6 };
-struct SqItem {
-  int kind;
-  Worker* w;
-  void* p;
-};
 
 struct PutItem {
   Ep* ep;
@@ -429,9 +445,7 @@ struct Ctx {
   std::unordered_map<uint64_t, Worker*> workers;
   std::unordered_map<uint64_t, Ep*> eps;
   // submission queue
-  std::mutex sq_mu;
-  std::vector<SqItem> sq;
-  std::atomic<uint32_t> sq_count{0};
+  std::atomic<SqNode*> sq_head{nullptr};
   // completion queue
   std::mutex cq_mu;
   std::condition_variable cq_cv;
@@ -455,7 +469,8 @@ struct Ctx {
   // options
   std::atomic<int64_t> opt_eager_max{SW_EAGER_MAX};
   std::atomic<int64_t> opt_ring_slots{SW_RING_SLOTS_DEFAULT};
-  std::atomic<int64_t> opt_bulk_mode{0}, opt_bulk_stages{4}, opt_bulk_stage_bytes{32768}, opt_bulk_ctas{2};
+  std::atomic<int64_t> opt_bulk_mode{0}, opt_bulk_stages{8}, opt_bulk_stage_bytes{24576}, opt_bulk_ctas{1};
+  std::atomic<int64_t> opt_coalesce_us{40}, opt_coalesce_bytes{32 << 20};
   std::atomic<int64_t> opt_heap_small{4096}, opt_heap_big{512};
   std::atomic<int64_t> opt_profile{0};
   // stats
@@ -470,14 +485,15 @@ std::vector<Ctx*> g_ctxs;
 void push_completion(Ctx* c, const sw_completion& comp) {
   {
     std::lock_guard<std::mutex> lk(c->cq_mu);
+    const bool was_empty = c->cq.empty();
     c->cq.push_back(comp);
+    if (was_empty && c->efd >= 0) {
+      uint64_t one = 1;
+      ssize_t r = write(c->efd, &one, sizeof(one));
+      (void)r;
+    }
   }
   c->cq_cv.notify_one();
-  if (c->efd >= 0) {
-    uint64_t one = 1;
-    ssize_t r = write(c->efd, &one, sizeof(one));
-    (void)r;
-  }
   std::lock_guard<std::mutex> lk(c->st_mu);
   c->stats.completions++;
 }
@@ -595,7 +611,7 @@ void fill_blob(Ctx* c, Worker* w) {
 
 Ep* ep_new(Ctx* c, Worker* w) {
   Ep* ep = new Ep();
-  ep->id = c->next_id.fetch_add(1);
+  ep->id = (uint64_t)(uintptr_t)ep;
   ep->owner = w;
   memset(&ep->info, 0, sizeof(ep->info));
   return ep;
@@ -655,10 +671,18 @@ ShmCtl* shm_attach(const char* name, size_t& size_out) {
   return s;
 }
 
-void sq_push(Ctx* c, int kind, Worker* w, void* p) {
-  std::lock_guard<std::mutex> lk(c->sq_mu);
-  c->sq.push_back(SqItem{kind, w, p});
-  c->sq_count.fetch_add(1, std::memory_order_release);
+void sq_push(Ctx* c, int kind, Worker* w, void* p, SqNode* n = nullptr) {
+  if (!n) {
+    n = new SqNode();
+    n->heap = true;
+  }
+  n->kind = kind;
+  n->w = w;
+  n->p = p;
+  SqNode* head = c->sq_head.load(std::memory_order_relaxed);
+  do {
+    n->next = head;
+  } while (!c->sq_head.compare_exchange_weak(head, n, std::memory_order_release, std::memory_order_relaxed));
 }
 
 // ============================================================================ connection: server side
@@ -1014,7 +1038,17 @@ bool pump_sends(Ctx* c) {
           memset(&r, 0, sizeof(r));
           uint64_t base = 0, size = 0;
           int srcdev = c->device;
-          if (op->mem == SW_MEM_HOST) {
+          if (op->mem == SW_MEM_HOST && ep->in_process) {
+            swgpu::PtrInfo pi;
+            swgpu::ptr_info(op->ptr, &pi);
+            if (pi.is_pinned) op->mem = MEM_PINNED;  // same process: the receiver's kernel reads it in place
+          }
+          if (op->mem == MEM_PINNED) {
+            base = (uint64_t)(uintptr_t)op->ptr;
+            size = op->len;
+            r.src_ptr = base;
+            r.pad[0] = 1;  // source is pinned host memory
+          } else if (op->mem == SW_MEM_HOST) {
             if (!op->dev_staging) {
               op->dev_staging = c->staging.get(op->len, &op->staging_size);
               if (!op->dev_staging) {
@@ -1150,6 +1184,11 @@ bool pump_match(Ctx* c, Worker* w) {
     while (!w->new_posts.empty() && np < SW_MAX_POSTS && w->posted_est + np < SW_PQ_CAP / 2) {
       RecvOp* r = w->new_posts.front();
       uint64_t buf = (uint64_t)(uintptr_t)r->ptr;
+      if (r->mem == SW_MEM_HOST && r->cap > HOST_BOUNCE_MAX) {
+        swgpu::PtrInfo pi;
+        swgpu::ptr_info(r->ptr, &pi);
+        if (pi.is_pinned) r->mem = MEM_PINNED;  // the pull kernel writes the caller's pinned buffer directly
+      }
       if (r->mem == SW_MEM_HOST) {
         if (r->cap <= HOST_BOUNCE_MAX) {
           r->pinned_bounce = c->host_pool.get(r->cap);
@@ -1256,6 +1295,11 @@ bool poll_match(Ctx* c, Worker* w) {
     j.tag = r.tag;
     j.len = r.len;
     j.rts = r.rts;
+    j.t_enq = now_s();
+    {
+      auto rit = w->recvs.find(r.op_id);
+      j.host_side = (r.rts.pad[0] & 1) != 0 || (rit != w->recvs.end() && rit->second->mem == MEM_PINNED);
+    }
     if (r.status != SW_OK) {
       j.failed = true;
       j.fail_status = r.status;
@@ -1319,6 +1363,18 @@ void bulk_job_done(Ctx* c, BulkJob& j, int32_t status) {
 bool pump_bulk(Ctx* c) {
   if (c->pending_bulk.empty()) return false;
   if ((c->bulk_tail - c->bulk_head) >= (uint32_t)N_BULK_BLOCKS) return false;
+  {
+    // Coalesce: while more matches are on their way (ops queued, puts or matches in flight), hold the
+    // launch until enough bytes are pending or the oldest job has waited opt_coalesce_us.
+    bool upstream = c->sq_head.load(std::memory_order_acquire) != nullptr || c->put_head != c->put_tail;
+    for (Worker* w : c->active) upstream |= w->match_inflight || !w->new_posts.empty();
+    if (upstream) {
+      uint64_t bytes = 0;
+      for (auto& j : c->pending_bulk) bytes += j.len;
+      double age_us = (now_s() - c->pending_bulk.front().t_enq) * 1e6;
+      if (bytes < (uint64_t)c->opt_coalesce_bytes.load() && age_us < (double)c->opt_coalesce_us.load()) return false;
+    }
+  }
   BulkBlock& b = c->bulk_blocks[c->bulk_tail % N_BULK_BLOCKS];
   b.jobs.clear();
   b.bytes = 0;
@@ -1378,7 +1434,7 @@ bool pump_bulk(Ctx* c) {
   for (BulkJob& j : b.jobs) {
     uint64_t src = j.src, dst = j.dst, len = j.len;
     // receives into host memory were redirected to device staging at post time
-    if (tune.mode == 0 && ((src | dst) & 15) == 0 && len >= 16) {
+    if (tune.mode == 0 && !j.host_side && ((src | dst) & 15) == 0 && len >= 16) {
       uint64_t body = len & ~15ull;
       for (uint64_t off = 0; off < body; off += seg) tma.push_back(SwSeg{src + off, dst + off, std::min(seg, body - off), 0});
       if (len > body) simt.push_back(SwSeg{src + body, dst + body, len - body, 0});
@@ -1657,14 +1713,26 @@ bool progress_close(Ctx* c, Worker* w) {
 
 // ============================================================================ progress thread
 void drain_sq(Ctx* c) {
-  if (c->sq_count.load(std::memory_order_acquire) == 0) return;
-  std::vector<SqItem> items;
-  {
-    std::lock_guard<std::mutex> lk(c->sq_mu);
-    items.swap(c->sq);
-    c->sq_count.store(0, std::memory_order_release);
+  if (c->sq_head.load(std::memory_order_acquire) == nullptr) return;
+  SqNode* list = c->sq_head.exchange(nullptr, std::memory_order_acquire);
+  // the stack is LIFO: reverse it to recover submission order
+  SqNode* rev = nullptr;
+  while (list) {
+    SqNode* nx = list->next;
+    list->next = rev;
+    rev = list;
+    list = nx;
   }
-  for (SqItem& it : items) {
+  struct Item {
+    int kind;
+    Worker* w;
+    void* p;
+  };
+  while (rev) {
+    SqNode* node = rev;
+    rev = rev->next;
+    Item it{node->kind, node->w, node->p};  // the op that embeds `node` may be freed below
+    if (node->heap) delete node;
     Worker* w = it.w;
     switch (it.kind) {
       case SQ_REGISTER: {
@@ -1779,15 +1847,15 @@ void progress_main(Ctx* c) {
   }
 }
 
+// Handles are the object addresses (objects live until sw_ctx_destroy); a magic word and the
+// owning context guard against stale or foreign values.
 Worker* find_worker(Ctx* c, sw_worker_t id) {
-  std::lock_guard<std::mutex> lk(c->mu);
-  auto it = c->workers.find(id);
-  return it == c->workers.end() ? nullptr : it->second;
+  Worker* w = (Worker*)(uintptr_t)id;
+  return (w && w->magic == WORKER_MAGIC && w->ctx == c) ? w : nullptr;
 }
 Ep* find_ep(Ctx* c, sw_ep_t id) {
-  std::lock_guard<std::mutex> lk(c->mu);
-  auto it = c->eps.find(id);
-  return it == c->eps.end() ? nullptr : it->second;
+  Ep* ep = (Ep*)(uintptr_t)id;
+  return (ep && ep->magic == EP_MAGIC && ep->owner && ep->owner->ctx == c) ? ep : nullptr;
 }
 
 int classify_mem(const void* ptr, int mem_kind) {
@@ -1932,6 +2000,8 @@ int sw_set_option(sw_ctx* ctx, const char* key, int64_t value) {
   else if (k == "heap_small_blocks") c->opt_heap_small = std::max<int64_t>(1, value);
   else if (k == "heap_big_blocks") c->opt_heap_big = std::max<int64_t>(1, value);
   else if (k == "profile") c->opt_profile = value;
+  else if (k == "coalesce_us") c->opt_coalesce_us = value;
+  else if (k == "coalesce_bytes") c->opt_coalesce_bytes = value;
   else {
     set_error("unknown option " + k);
     return -1;
@@ -1961,7 +2031,7 @@ sw_worker_t sw_worker_create(sw_ctx* ctx, int kind) {
     return 0;
   }
   Worker* w = new Worker();
-  w->id = c->next_id.fetch_add(1);
+  w->id = (uint64_t)(uintptr_t)w;
   w->kind = kind;
   w->ctx = c;
   std::lock_guard<std::mutex> lk(c->mu);
@@ -2148,7 +2218,7 @@ uint64_t sw_post_send(sw_ctx* ctx, sw_worker_t wid, sw_ep_t epid, const void* pt
   op->tag = tag;
   op->mem = len ? classify_mem(ptr, mem_kind) : SW_MEM_DEVICE;
   uint64_t id = op->op_id;
-  sq_push(c, SQ_SEND, w, op);
+  sq_push(c, SQ_SEND, w, op, &op->sqn);
   return id;
 }
 
@@ -2166,7 +2236,7 @@ uint64_t sw_post_recv(sw_ctx* ctx, sw_worker_t wid, void* ptr, size_t cap, uint6
   r->mask = tag_mask;
   r->mem = cap ? classify_mem(ptr, mem_kind) : SW_MEM_DEVICE;
   uint64_t id = r->op_id;
-  sq_push(c, SQ_RECV, w, r);
+  sq_push(c, SQ_RECV, w, r, &r->sqn);
   return id;
 }
 
@@ -2177,7 +2247,7 @@ uint64_t sw_post_flush(sw_ctx* ctx, sw_worker_t wid) {
   FlushOp* f = new FlushOp();
   f->op_id = c->next_id.fetch_add(1);
   uint64_t id = f->op_id;
-  sq_push(c, SQ_FLUSH, w, f);
+  sq_push(c, SQ_FLUSH, w, f, &f->sqn);
   return id;
 }
 uint64_t sw_post_flush_ep(sw_ctx* ctx, sw_worker_t wid, sw_ep_t epid) {
@@ -2193,7 +2263,7 @@ uint64_t sw_post_flush_ep(sw_ctx* ctx, sw_worker_t wid, sw_ep_t epid) {
   f->op_id = c->next_id.fetch_add(1);
   f->ep = ep;
   uint64_t id = f->op_id;
-  sq_push(c, SQ_FLUSH, w, f);
+  sq_push(c, SQ_FLUSH, w, f, &f->sqn);
   return id;
 }
 

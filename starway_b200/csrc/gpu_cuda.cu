@@ -366,7 +366,10 @@ int launch_bulk(stream_t s, const SwSeg* segs, uint32_t nseg, const BulkTuning* 
       g_err = "bulk tuning exceeds shared memory";
       return -1;
     }
-    uint32_t grid = (uint32_t)(g_sms * (t->ctas_per_sm > 0 ? t->ctas_per_sm : 1));
+    int ctas = t->ctas_per_sm > 0 ? t->ctas_per_sm : 1;
+    const int fit = (int)((size_t)(228 * 1024) / (smem + 1024 + 128));   // CTAs of this size resident per SM
+    if (ctas > fit) ctas = fit < 1 ? 1 : fit;
+    uint32_t grid = (uint32_t)(g_sms * ctas);
     if (grid > nseg) grid = nseg;
     sw_bulk_tma_kernel<<<grid, 32, smem, (cudaStream_t)s>>>(segs, nseg, (uint32_t)sb, (uint32_t)stages);
   } else {
