@@ -30,6 +30,7 @@
 #include <string.h>
 #include <sys/eventfd.h>
 #include <sys/mman.h>
+#include <sys/prctl.h>
 #include <sys/socket.h>
 #include <sys/stat.h>
 #include <sys/un.h>
@@ -1804,6 +1805,7 @@ void drain_sq(Ctx* c) {
 
 void progress_main(Ctx* c) {
   swgpu::bind_thread(c->device);
+  prctl(PR_SET_TIMERSLACK, 1000UL, 0, 0, 0);  // 1 us timer slack: short sleeps stay short
   uint64_t iter = 0;
   double last_active = now_s();
   while (!c->stop.load(std::memory_order_acquire)) {
@@ -1829,26 +1831,34 @@ void progress_main(Ctx* c) {
     }
     iter++;
     bool inflight = (c->put_head != c->put_tail) || (c->bulk_head != c->bulk_tail) || !c->post_copies.empty();
-    for (Worker* w : c->active) inflight |= w->match_inflight;
+    bool expecting = false;  // operations whose completion depends on a peer's doorbell / FIN
+    for (Worker* w : c->active) {
+      inflight |= w->match_inflight;
+      if (w->close_phase >= 4) continue;
+      expecting |= !w->recvs.empty() || !w->flushes.empty() || w->close_phase != 0;
+      for (Ep* ep : w->eps) expecting |= !ep->rndv_wait.empty() || !ep->sendq.empty();
+    }
     if (active || inflight) {
       last_active = now_s();
     } else {
+      // The reference's worker threads spin at 100 % (main.cpp:361, 1126).  Here: spin while work is
+      // outstanding or was seen recently, then back off progressively.
       double idle = now_s() - last_active;
-      if (idle > 0.02) {
-        struct timespec ts = {0, 200000};
+      if (expecting && idle < 0.25) {
+        if (idle > 0.002) sched_yield();
+      } else if (idle > 1.0) {
+        struct timespec ts = {0, 300000};
         nanosleep(&ts, nullptr);
-      } else if (idle > 0.001) {
-        struct timespec ts = {0, 20000};
+      } else if (idle > 0.02) {
+        struct timespec ts = {0, 30000};
         nanosleep(&ts, nullptr);
-      } else if (idle > 0.0001) {
+      } else if (idle > 0.002) {
         sched_yield();
       }
     }
   }
 }
 
-// Handles are the object addresses (objects live until sw_ctx_destroy); a magic word and the
-// owning context guard against stale or foreign values.
 Worker* find_worker(Ctx* c, sw_worker_t id) {
   Worker* w = (Worker*)(uintptr_t)id;
   return (w && w->magic == WORKER_MAGIC && w->ctx == c) ? w : nullptr;

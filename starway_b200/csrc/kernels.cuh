@@ -351,6 +351,22 @@ __global__ void __launch_bounds__(32) sw_match_kernel(SwMatchState* __restrict__
       mine.tag = mine.mask = mine.buf = mine.cap = mine.op_id = 0;
       if (base + lane < n_posts) mine = in->posts[base + lane];
       const uint32_t cnt = min(32u, n_posts - base);
+      if (r.u_count == 0 && SW_PQ_CAP - (r.p_tail - r.p_head) >= cnt) {
+        // fast path: nothing is waiting in the unexpected queue, so every receive of this chunk
+        // is simply appended -- 32 receives per step, one lane each
+        if (lane < cnt) {
+          const uint64_t s = (r.p_tail + lane) & PQM;
+          st->p_tag[s] = mine.tag;
+          st->p_mask[s] = mine.mask;
+          st->p_buf[s] = mine.buf;
+          st->p_cap[s] = mine.cap;
+          st->p_op[s] = mine.op_id;
+          st->p_valid[s] = 1;
+        }
+        r.p_tail += cnt;
+        r.p_count += cnt;
+        continue;
+      }
       for (uint32_t j = 0; j < cnt; j++) {
         const uint64_t tag = sw_shfl64(mine.tag, j), mask = sw_shfl64(mine.mask, j);
         const uint64_t buf = sw_shfl64(mine.buf, j), cap = sw_shfl64(mine.cap, j);
@@ -498,7 +514,77 @@ __global__ void __launch_bounds__(32) sw_match_kernel(SwMatchState* __restrict__
           h_kind = static_cast<uint32_t>(b.z);
           h_magic = static_cast<uint32_t>(b.w);
         }
-        for (uint32_t j = 0; j < chunk && !blocked; j++) {
+        // ---- fast path: pair up to 32 arrivals with the first posted receives in ONE step when every
+        // one of those receives accepts every one of those arrivals (all wildcard masks, or all
+        // arrivals carry the same tag): arrival j then goes to the j-th valid posted entry, exactly
+        // what the sequential rule (earliest-posted matching receive) produces.
+        uint32_t j0 = 0;
+        while (j0 < chunk && r.p_count) {
+          while (__ballot_sync(0xffffffffu, w_valid != 0) == 0 && wb + 32 <= r.p_tail) {
+            wb += 32;
+            load_pwin();
+          }
+          const uint32_t V = __ballot_sync(0xffffffffu, w_valid != 0);
+          if (!V) break;
+          const uint32_t lt = (1u << lane) - 1;
+          const uint32_t k = min(chunk - j0, static_cast<uint32_t>(__popc(V)));
+          const uint32_t rnk = __popc(V & lt);
+          const bool in_k = w_valid && rnk < k;
+          bool compat = __ballot_sync(0xffffffffu, in_k && w_mask != 0) == 0;
+          if (!compat) {
+            const uint64_t T = sw_shfl64(h_tag, j0);
+            const bool same = __ballot_sync(0xffffffffu, lane >= j0 && lane < j0 + k && h_tag != T) == 0;
+            if (same) compat = __ballot_sync(0xffffffffu, in_k && !sw_tag_match(T, w_tag, w_mask)) == 0;
+          }
+          if (!compat) break;
+          if (__ballot_sync(0xffffffffu, lane >= j0 && lane < j0 + k &&
+                                             (h_magic != SW_SLOT_MAGIC || h_seq != cons + (lane - j0) + 1)))
+            r.err |= 1;
+          const int srcl = static_cast<int>(min(j0 + rnk, 31u));
+          const uint64_t a_tag = sw_shfl64(h_tag, srcl), a_len = sw_shfl64(h_len, srcl);
+          const uint64_t a_slot = sw_shfl64(my_slot, srcl);
+          const uint32_t a_kind = __shfl_sync(0xffffffffu, h_kind, srcl);
+          const bool a_rts = a_kind == SW_KIND_RTS;
+          const uint32_t eager_m = __ballot_sync(0xffffffffu, in_k && !a_rts);
+          const uint32_t rts_m = __ballot_sync(0xffffffffu, in_k && a_rts);
+          if (in_k) {
+            const bool trunc = a_len > w_cap;
+            if (!a_rts) {
+              SwJob* jb = &st->jobs[r.n_jobs + __popc(eager_m & lt)];
+              jb->src = a_slot + SW_SLOT_HDR;
+              jb->dst = w_buf;
+              jb->len = trunc ? 0 : a_len;
+              jb->op_id = w_op;
+              jb->tag = a_tag;
+              jb->msg_len = a_len;
+              jb->status = trunc ? SW_ERR_MESSAGE_TRUNCATED : SW_OK;
+              jb->kind = SW_JOB_DELIVER;
+            } else {
+              SwRndvRec* rec = &out->rndv[r.n_rndv + __popc(rts_m & lt)];
+              const int4* sp = reinterpret_cast<const int4*>(a_slot + SW_SLOT_HDR);
+              int4* dp = reinterpret_cast<int4*>(&rec->rts);
+#pragma unroll
+              for (int q = 0; q < 8; q++) dp[q] = sw_ld16(sp + q);
+              rec->op_id = w_op;
+              rec->dst = w_buf;
+              rec->cap = w_cap;
+              rec->tag = a_tag;
+              rec->len = a_len;
+              rec->ep = ep;
+              rec->status = trunc ? SW_ERR_MESSAGE_TRUNCATED : SW_OK;
+            }
+            w_valid = 0;
+            st->p_valid[(wb + lane) & PQM] = 0;
+          }
+          r.n_jobs += __popc(eager_m);
+          r.n_rndv += __popc(rts_m);
+          r.p_count -= k;
+          j0 += k;
+          cons += k;
+          budget -= k;
+          consumed_total += k;
+        }
+        for (uint32_t j = j0; j < chunk && !blocked; j++) {
           const uint64_t stag = sw_shfl64(h_tag, j), mlen = sw_shfl64(h_len, j), seq = sw_shfl64(h_seq, j);
           const uint32_t kind = __shfl_sync(0xffffffffu, h_kind, j);
           const uint32_t magic = __shfl_sync(0xffffffffu, h_magic, j);

@@ -373,3 +373,60 @@ def test_c_abi_direct_device_pointers(cuda_api, port):
     assert torch.equal(dst, src)
     st = ctx.stats()
     assert st["bulk_tma_launches"] > 0 and st["put_launches"] > 0 and st["match_launches"] > 0
+
+
+@pytest.mark.parametrize("size", [70000, (1 << 20) + 3, 32 << 20])
+def test_pinned_host_buffers_direct_path(cuda_api, port, size):
+    """Pinned (cudaHostAlloc) NumPy buffers: the pull kernel reads/writes them in place (no staging)."""
+    torch = torch_cuda()
+
+    async def go():
+        async with cb.gen_server_client(cuda_api, port) as (server, client):
+            ep = next(iter(server.list_clients()))
+            src_t = torch.empty(size, dtype=torch.uint8).pin_memory()
+            src_t.copy_(torch.from_numpy(np.random.default_rng(size).integers(0, 256, size, dtype=np.uint8)))
+            dst_t = torch.zeros(size + 32, dtype=torch.uint8).pin_memory()
+            src, dst = src_t.numpy(), dst_t.numpy()
+            fut = server.arecv(dst[:size], 3, U64)
+            await client.asend(src, 3)
+            assert await fut == (3, size)
+            np.testing.assert_array_equal(dst[:size], src)
+            assert (dst[size:] == 0).all()
+            # device -> pinned host and pinned host -> device
+            dev = torch.from_numpy(src).cuda()
+            dst[:] = 0
+            fut = client.arecv(dst[5 : 5 + size], 4, U64)
+            await server.asend(ep, dev, 4)
+            assert await fut == (4, size)
+            np.testing.assert_array_equal(dst[5 : 5 + size], src)
+            back = torch.zeros(size, dtype=torch.uint8, device="cuda")
+            fut = server.arecv(back, 5, U64)
+            await client.asend(src, 5)
+            assert await fut == (5, size)
+            torch.cuda.synchronize()
+            assert torch.equal(back.cpu(), src_t)
+
+    run(go())
+
+
+def test_storm_small_messages_fast_path(cuda_api, port):
+    """20k x 64 B with pre-posted full-mask receives on one tag (vectorised matcher path) and
+    wildcard receives; every message delivered exactly once, FIFO per sender, bytes exact."""
+    torch = torch_cuda()
+
+    async def go():
+        async with cb.gen_server_client(cuda_api, port) as (server, client):
+            n = 20000
+            src = torch.randint(0, 256, (n, 64), dtype=torch.uint8, device="cuda")
+            dst = torch.zeros((n, 64), dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            recvs = [server.arecv(dst[i], 7 if i % 2 == 0 else 0, U64 if i % 2 == 0 else 0) for i in range(n)]
+            sends = [client.asend(src[i], 7) for i in range(n)]
+            await asyncio.gather(*sends)
+            await client.aflush()
+            res = await asyncio.gather(*recvs)
+            torch.cuda.synchronize()
+            assert all(r == (7, 64) for r in res)
+            assert torch.equal(dst, src)  # FIFO: i-th posted receive got the i-th message
+
+    run(go())
