@@ -436,6 +436,7 @@ constexpr int N_PUT_BLOCKS = 4;
 constexpr int N_BULK_BLOCKS = 3;
 constexpr uint32_t MAX_SEGS = 8192;
 constexpr size_t HOST_BOUNCE_MAX = 65536;
+constexpr size_t MAX_MAPPINGS = 4096;
 
 struct Ctx {
   int device = 0;
@@ -1232,11 +1233,9 @@ bool pump_match(Ctx* c, Worker* w) {
   in->max_arrivals = SW_MAX_ARRIVALS;
   const bool prof = c->opt_profile.load() != 0;
   if (prof) swgpu::event_record(w->mev_start, c->s_match);
-  if (swgpu::launch_match(c->s_match, w->mstate, in, w->mout) != 0)
-    fprintf(stderr, "starway_b200: match launch failed: %s\n", swgpu::last_error());
   uint32_t max_jobs = np + (uint32_t)std::min<uint64_t>(unseen, SW_MAX_ARRIVALS);
-  if (swgpu::launch_deliver(c->s_match, w->mstate, w->mout, max_jobs) != 0)
-    fprintf(stderr, "starway_b200: deliver launch failed: %s\n", swgpu::last_error());
+  if (swgpu::launch_match_deliver(c->s_match, w->mstate, in, w->mout, max_jobs) != 0)
+    fprintf(stderr, "starway_b200: match/deliver launch failed: %s\n", swgpu::last_error());
   swgpu::event_record(w->mev, c->s_match);
   w->match_inflight = true;
   w->match_posts_inflight = np;
@@ -1316,15 +1315,19 @@ void* resolve_mapping(Ctx* c, BulkJob& j) {
   key.append((const char*)&j.rts.src_pid, sizeof(j.rts.src_pid));
   auto it = c->mappings.find(key);
   if (it == c->mappings.end()) {
-    // bound the cache: drop idle mappings
-    if (c->mappings.size() >= 64) {
-      for (auto m = c->mappings.begin(); m != c->mappings.end();) {
-        if (m->second.refs == 0) {
-          swgpu::ipc_close(m->second.base);
-          m = c->mappings.erase(m);
-        } else {
-          ++m;
-        }
+    // Bound the cache (PyTorch's caching allocator hands out many small segments: a few hundred
+    // distinct IPC handles are normal).  Opening/closing a mapping costs ~100s of us, so only
+    // the least recently used idle quarter is dropped when the bound is hit.
+    if (c->mappings.size() >= MAX_MAPPINGS) {
+      std::vector<std::pair<double, std::string>> idle;
+      for (auto& kv : c->mappings)
+        if (kv.second.refs == 0) idle.emplace_back(kv.second.last_use, kv.first);
+      std::sort(idle.begin(), idle.end());
+      size_t drop = std::max<size_t>(1, idle.size() / 4);
+      for (size_t i = 0; i < drop && i < idle.size(); i++) {
+        auto m = c->mappings.find(idle[i].second);
+        swgpu::ipc_close(m->second.base);
+        c->mappings.erase(m);
       }
     }
     void* base = nullptr;

@@ -72,6 +72,8 @@ int match_state_set_ring(SwMatchState* st, uint32_t ep, void* ring_base, uint32_
 int launch_put(stream_t s, const SwPutDesc* descs, uint32_t n);
 int launch_match(stream_t s, SwMatchState* st, const SwMatchIn* in, SwMatchOut* out);
 int launch_deliver(stream_t s, SwMatchState* st, SwMatchOut* out, uint32_t max_jobs);
+// match + deliver for one batch: a single fused launch when the batch is small
+int launch_match_deliver(stream_t s, SwMatchState* st, const SwMatchIn* in, SwMatchOut* out, uint32_t max_jobs);
 int launch_bulk(stream_t s, const SwSeg* segs, uint32_t nseg, const BulkTuning* tune);
 
 }  // namespace swgpu

@@ -330,6 +330,20 @@ int match_state_set_ring(SwMatchState* st, uint32_t ep, void* ring_base, uint32_
 int launch_put(stream_t s, const SwPutDesc* descs, uint32_t n) {
   if (!n) return 0;
   const uint32_t warps_per_cta = 8;
+  if (n <= SW_PUT_INLINE) {
+    // descriptors (and RTS payloads, which live in host memory next to them) by value
+    SwPutArgs a;
+    a.n = n;
+    a.pad = 0;
+    for (uint32_t i = 0; i < n; i++) {
+      a.d[i] = descs[i];
+      if (descs[i].kind == SW_KIND_RTS) memcpy(&a.r[i], (const void*)(uintptr_t)descs[i].src, sizeof(SwRts));
+    }
+    uint32_t grid = (n + warps_per_cta - 1) / warps_per_cta;
+    sw_put_inline_kernel<<<grid, warps_per_cta * 32, 0, (cudaStream_t)s>>>(a);
+    SW_CUDA(cudaGetLastError());
+    return 0;
+  }
   uint32_t grid = (n + warps_per_cta - 1) / warps_per_cta;
   const uint32_t cap = (uint32_t)g_sms * 8;
   if (grid > cap) grid = cap;
@@ -338,10 +352,34 @@ int launch_put(stream_t s, const SwPutDesc* descs, uint32_t n) {
   return 0;
 }
 
+static void fill_match_args(SwMatchArgs& a, const SwMatchIn* in) {
+  a.n_posts = in->n_posts;
+  a.n_eps = in->n_eps;
+  a.max_arrivals = in->max_arrivals;
+  a.pad = 0;
+  for (uint32_t e = 0; e < SW_INLINE_EPS; e++) a.produced[e] = e < in->n_eps ? in->produced[e] : 0;
+  const uint32_t np = in->n_posts <= SW_INLINE_POSTS ? in->n_posts : 0;
+  for (uint32_t i = 0; i < np; i++) a.posts[i] = in->posts[i];
+}
+
 int launch_match(stream_t s, SwMatchState* st, const SwMatchIn* in, SwMatchOut* out) {
-  sw_match_kernel<<<1, 32, 0, (cudaStream_t)s>>>(st, in, out);
+  SwMatchArgs a;
+  fill_match_args(a, in);
+  sw_match_kernel<<<1, 32, 0, (cudaStream_t)s>>>(st, in, out, a);
   SW_CUDA(cudaGetLastError());
   return 0;
+}
+
+int launch_match_deliver(stream_t s, SwMatchState* st, const SwMatchIn* in, SwMatchOut* out, uint32_t max_jobs) {
+  if (max_jobs <= 192) {
+    SwMatchArgs a;
+    fill_match_args(a, in);
+    sw_match_deliver_kernel<<<1, SW_FUSED_THREADS, 0, (cudaStream_t)s>>>(st, in, out, a);
+    SW_CUDA(cudaGetLastError());
+    return 0;
+  }
+  if (launch_match(s, st, in, out) != 0) return -1;
+  return launch_deliver(s, st, out, max_jobs);
 }
 
 int launch_deliver(stream_t s, SwMatchState* st, SwMatchOut* out, uint32_t max_jobs) {

@@ -154,6 +154,47 @@ __global__ void __launch_bounds__(256) sw_put_kernel(const SwPutDesc* __restrict
   }
 }
 
+// Small batches: descriptors and RTS payloads travel as kernel parameters (no PCIe read on the
+// latency-critical path).
+constexpr uint32_t SW_PUT_INLINE = 32;
+struct SwPutArgs {
+  uint32_t n, pad;
+  SwPutDesc d[SW_PUT_INLINE];
+  SwRts r[SW_PUT_INLINE];   // used when d[i].kind == SW_KIND_RTS
+};
+__global__ void __launch_bounds__(256) sw_put_inline_kernel(const __grid_constant__ SwPutArgs a) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t i = warp; i < a.n; i += nwarps) {
+    const SwPutDesc d = a.d[i];
+    uint8_t* slot = reinterpret_cast<uint8_t*>(d.dst);
+    if (d.kind == SW_KIND_RTS) {
+      if (lane < 8) {
+        const int4 v = reinterpret_cast<const int4*>(&a.r[i])[lane];
+        sw_st16(slot + SW_SLOT_HDR + 16 * lane, v);
+      }
+    } else {
+      sw_copy(slot + SW_SLOT_HDR, reinterpret_cast<const uint8_t*>(d.src), d.len, lane, 32);
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) {
+      int4 h0, h1;
+      h0.x = static_cast<int>(d.tag & 0xffffffffu);
+      h0.y = static_cast<int>(d.tag >> 32);
+      h0.z = static_cast<int>(d.msg_len & 0xffffffffu);
+      h0.w = static_cast<int>(d.msg_len >> 32);
+      h1.x = static_cast<int>(d.seq & 0xffffffffu);
+      h1.y = static_cast<int>(d.seq >> 32);
+      h1.z = static_cast<int>(d.kind);
+      h1.w = static_cast<int>(SW_SLOT_MAGIC);
+      sw_st16(slot, h0);
+      sw_st16(slot + 16, h1);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ K2: tag match
 // One warp per worker.  The queues live in device memory; the warp keeps a 32-entry
 // register window over the head of the queue it is searching so that FIFO traffic
@@ -222,9 +263,20 @@ __device__ __forceinline__ void sw_emit_match(SwMatchState* st, SwMatchOut* out,
   }
 }
 
-__global__ void __launch_bounds__(32) sw_match_kernel(SwMatchState* __restrict__ st, const SwMatchIn* __restrict__ in,
-                                                      SwMatchOut* __restrict__ out) {
-  const uint32_t lane = threadIdx.x;
+// Launch scalars travel as kernel parameters (constant bank) instead of being read from pinned host
+// memory over PCIe: with <= SW_INLINE_EPS rings and <= SW_INLINE_POSTS new receives a match launch
+// performs no host-memory read at all.
+constexpr uint32_t SW_INLINE_EPS = 8;
+constexpr uint32_t SW_INLINE_POSTS = 32;
+struct SwMatchArgs {
+  uint32_t n_posts, n_eps, max_arrivals, pad;
+  uint64_t produced[SW_INLINE_EPS];
+  SwPost posts[SW_INLINE_POSTS];
+};
+
+__device__ __forceinline__ void sw_match_body(SwMatchState* __restrict__ st, const SwMatchIn* __restrict__ in,
+                                              SwMatchOut* __restrict__ out, const SwMatchArgs& a,
+                                              const uint32_t lane) {
   SwMatchRegs r;
   r.p_head = st->p_head;
   r.p_tail = st->p_tail;
@@ -327,7 +379,7 @@ __global__ void __launch_bounds__(32) sw_match_kernel(SwMatchState* __restrict__
   }
 
   // ================================================================ phase 1: new receives
-  const uint32_t n_posts = in->n_posts;
+  const uint32_t n_posts = a.n_posts;
   if (n_posts) {
     // register window over the unexpected queue: lane L caches entry (wb + L)
     uint64_t wb = r.u_head;
@@ -349,7 +401,7 @@ __global__ void __launch_bounds__(32) sw_match_kernel(SwMatchState* __restrict__
     for (uint32_t base = 0; base < n_posts; base += 32) {
       SwPost mine;
       mine.tag = mine.mask = mine.buf = mine.cap = mine.op_id = 0;
-      if (base + lane < n_posts) mine = in->posts[base + lane];
+      if (base + lane < n_posts) mine = (n_posts <= SW_INLINE_POSTS) ? a.posts[base + lane] : in->posts[base + lane];
       const uint32_t cnt = min(32u, n_posts - base);
       if (r.u_count == 0 && SW_PQ_CAP - (r.p_tail - r.p_head) >= cnt) {
         // fast path: nothing is waiting in the unexpected queue, so every receive of this chunk
@@ -488,14 +540,14 @@ __global__ void __launch_bounds__(32) sw_match_kernel(SwMatchState* __restrict__
       }
     };
     load_pwin();
-    const uint32_t n_eps = in->n_eps;
-    uint32_t budget = min(in->max_arrivals, SW_MAX_ARRIVALS);
+    const uint32_t n_eps = a.n_eps;
+    uint32_t budget = min(a.max_arrivals, SW_MAX_ARRIVALS);
     uint32_t consumed_total = 0;
     const uint32_t rr = n_eps ? (st->rr_ep % n_eps) : 0;
     for (uint32_t e = 0; e < n_eps; e++) {
       const uint32_t ep = (rr + e) % n_eps;
       uint64_t cons = st->ring_cons[ep];
-      const uint64_t prod = in->produced[ep];
+      const uint64_t prod = (n_eps <= SW_INLINE_EPS) ? a.produced[ep] : in->produced[ep];
       const uint64_t ring = st->ring_base[ep];
       const uint64_t smask = st->ring_slots[ep] - 1;
       bool blocked = false;
@@ -717,6 +769,42 @@ __global__ void __launch_bounds__(32) sw_match_kernel(SwMatchState* __restrict__
   }
 }
 
+__global__ void __launch_bounds__(32) sw_match_kernel(SwMatchState* __restrict__ st, const SwMatchIn* __restrict__ in,
+                                                      SwMatchOut* __restrict__ out,
+                                                      const __grid_constant__ SwMatchArgs a) {
+  sw_match_body(st, in, out, a, threadIdx.x);
+}
+
+__device__ __forceinline__ void sw_deliver_one(const SwJob& j, SwMatchOut* __restrict__ out, uint32_t i,
+                                               uint32_t lane) {
+  sw_copy(reinterpret_cast<uint8_t*>(j.dst), reinterpret_cast<const uint8_t*>(j.src), j.len, lane, 32);
+  if (lane == 0) {
+    // the host reads the record only after the launch's CUDA event has completed
+    SwCqe c;
+    c.op_id = j.op_id;
+    c.tag = j.tag;
+    c.len = j.msg_len;
+    c.status = j.status;
+    c.kind = j.kind;
+    out->cq[i] = c;
+  }
+}
+
+// Fused variant for small batches: warp 0 matches, then the whole CTA delivers -- one launch
+// instead of two on the latency-critical path.
+constexpr uint32_t SW_FUSED_THREADS = 512;
+__global__ void __launch_bounds__(SW_FUSED_THREADS) sw_match_deliver_kernel(SwMatchState* __restrict__ st,
+                                                                            const SwMatchIn* __restrict__ in,
+                                                                            SwMatchOut* __restrict__ out,
+                                                                            const __grid_constant__ SwMatchArgs a) {
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) sw_match_body(st, in, out, a, lane);
+  __threadfence_block();
+  __syncthreads();
+  const uint32_t n = st->n_jobs;
+  for (uint32_t i = warp; i < n; i += SW_FUSED_THREADS / 32) sw_deliver_one(st->jobs[i], out, i, lane);
+}
+
 // ------------------------------------------------------------------ deliver
 // One warp per job: copy the eager payload (ring slot or heap block) into the posted
 // receive buffer, then publish the completion record into pinned host memory.
@@ -725,21 +813,7 @@ __global__ void __launch_bounds__(256) sw_deliver_kernel(SwMatchState* __restric
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t n = st->n_jobs;
-  for (uint32_t i = warp; i < n; i += nwarps) {
-    const SwJob j = st->jobs[i];
-    sw_copy(reinterpret_cast<uint8_t*>(j.dst), reinterpret_cast<const uint8_t*>(j.src), j.len, lane, 32);
-    __threadfence_system();
-    __syncwarp();
-    if (lane == 0) {
-      SwCqe c;
-      c.op_id = j.op_id;
-      c.tag = j.tag;
-      c.len = j.msg_len;
-      c.status = j.status;
-      c.kind = j.kind;
-      out->cq[i] = c;
-    }
-  }
+  for (uint32_t i = warp; i < n; i += nwarps) sw_deliver_one(st->jobs[i], out, i, lane);
 }
 
 // ------------------------------------------------------------------ K3/K5: bulk copy, TMA staged

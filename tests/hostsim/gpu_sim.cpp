@@ -409,6 +409,11 @@ int launch_deliver(stream_t, SwMatchState* st, SwMatchOut* out, uint32_t) {
   return 0;
 }
 
+int launch_match_deliver(stream_t s, SwMatchState* st, const SwMatchIn* in, SwMatchOut* out, uint32_t max_jobs) {
+  launch_match(s, st, in, out);
+  return launch_deliver(s, st, out, max_jobs);
+}
+
 int launch_bulk(stream_t, const SwSeg* segs, uint32_t nseg, const BulkTuning*) {
   for (uint32_t i = 0; i < nseg; i++)
     memcpy((void*)(uintptr_t)segs[i].dst, (const void*)(uintptr_t)segs[i].src, segs[i].len);
