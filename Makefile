@@ -13,6 +13,7 @@ ORACLE    := oracle/liboracle_tagmatch.so
 CPUENG    := oracle/libstarway_cpu.so
 HOSTSIM   := tests/hostsim/libstarway_hostsim.so
 PROBE     := tests/gpu_probe/sw_probe
+ABIBENCH  := tests/gpu_probe/abi_bench
 
 ENGINE_SRCS := $(CSRC)/engine.cpp
 ENGINE_HDRS := $(CSRC)/gpu.h $(CSRC)/sw_device.h include/starway_b200.h
@@ -23,7 +24,7 @@ lib: $(LIB)
 oracle: $(ORACLE) $(CPUENG)
 oracle-core: $(ORACLE)
 hostsim: $(HOSTSIM)
-probe: $(PROBE)
+probe: $(PROBE) $(ABIBENCH)
 
 build/gpu_cuda.o: $(CSRC)/gpu_cuda.cu $(CSRC)/kernels.cuh $(CSRC)/gpu.h $(CSRC)/sw_device.h
 	@mkdir -p build
@@ -65,7 +66,10 @@ $(HOSTSIM): build/engine_sim.o build/gpu_sim.o build/tagmatch.o
 $(PROBE): tests/gpu_probe/probe.cu build/gpu_cuda.o build/tagmatch.o
 	$(NVCC) $(NVFLAGS) -o $@ tests/gpu_probe/probe.cu build/gpu_cuda.o build/tagmatch.o
 
+$(ABIBENCH): tests/gpu_probe/abi_bench.cpp $(LIB) include/starway_b200.h
+	$(CXX) -O2 -std=c++17 -I/usr/local/cuda/include -o $@ tests/gpu_probe/abi_bench.cpp -Lstarway_b200 -lstarway_b200 -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,'$$ORIGIN/../../starway_b200' -Wl,-rpath,/usr/local/cuda/lib64
+
 clean:
-	rm -rf build $(LIB) $(ORACLE) $(CPUENG) $(HOSTSIM) $(PROBE)
+	rm -rf build $(LIB) $(ORACLE) $(CPUENG) $(HOSTSIM) $(PROBE) $(ABIBENCH)
 
 .PHONY: all lib oracle oracle-core hostsim probe clean

@@ -136,7 +136,8 @@ __global__ void __launch_bounds__(256) sw_put_kernel(const SwPutDesc* __restrict
     const SwPutDesc d = descs[i];
     uint8_t* slot = reinterpret_cast<uint8_t*>(d.dst);
     sw_copy(slot + SW_SLOT_HDR, reinterpret_cast<const uint8_t*>(d.src), d.len, lane, 32);
-    __threadfence_system();
+    // The slot is consumed only by a kernel launched after the host has seen this launch's CUDA
+    // event and rung the doorbell: the kernel boundary orders payload and header for the consumer.
     __syncwarp();
     if (lane == 0) {
       int4 h0, h1;
@@ -177,7 +178,6 @@ __global__ void __launch_bounds__(256) sw_put_inline_kernel(const __grid_constan
     } else {
       sw_copy(slot + SW_SLOT_HDR, reinterpret_cast<const uint8_t*>(d.src), d.len, lane, 32);
     }
-    __threadfence_system();
     __syncwarp();
     if (lane == 0) {
       int4 h0, h1;
