@@ -320,9 +320,114 @@ def mode_storm(args):
     sw.shutdown()
 
 
+# ----------------------------------------------------------------------------------------- configs 1 + 2 (latency)
+def mode_pingpong(args):
+    """Round-trip latency: config 1 (4 B host NumPy buffers, tag=1 tag_mask=0xFFFF) and config 2
+    (one 1 MiB device buffer), reference scenario shape `pingpong-flag` (scenarios.py:238-266).
+    world 1: Server+Client in one process on one GPU; world 2: rank 0 client <-> rank 1 server."""
+    import numpy as np
+
+    torch, sw, dist, rank, world, local = setup()
+    assert world in (1, 2)
+    dev = torch.device("cuda", local)
+
+    async def main():
+        server = sw.Server()
+        addr = server.listen_address()
+        addrs = [addr]
+        if dist:
+            addrs = [None] * world
+            dist.all_gather_object(addrs, addr)
+        client = sw.Client()
+        await client.aconnect_address(addrs[(rank + 1) % world])
+        for _ in range(2000):
+            if server.list_clients():
+                break
+            await asyncio.sleep(0.005)
+        ep = next(iter(server.list_clients()))
+        cases = [("config1: 4 B host NumPy", 4, "host", 100, 1000), ("64 B device", 64, "dev", 100, 1000),
+                 ("8 KiB device (eager max)", 8128, "dev", 50, 500), ("config2: 1 MiB device", 1 << 20, "dev", 20, 200),
+                 ("64 MiB device", 64 << 20, "dev", 5, 30)]
+        for name, n, where, warm, iters in cases:
+            if where == "host":
+                mk = lambda: np.arange(n, dtype=np.uint8)  # noqa: E731
+            else:
+                mk = lambda: torch.arange(n, dtype=torch.uint8, device=dev) if n <= 256 else torch.ones(n, dtype=torch.uint8, device=dev)  # noqa: E731
+            ping, pong, rping, rpong = mk(), mk(), mk(), mk()
+            if where == "dev":
+                torch.cuda.synchronize()
+            if dist:
+                await asyncio.get_running_loop().run_in_executor(None, dist.barrier)
+            samples = []
+            for i in range(warm + iters):
+                t0 = time.perf_counter()
+                if world == 1:
+                    f = server.arecv(rping, 1, 0xFFFF)
+                    await client.asend(ping, 1)
+                    await f
+                    f = client.arecv(rpong, 2, 0xFFFF)
+                    await server.asend(ep, pong, 2)
+                    await f
+                elif rank == 0:
+                    f = client.arecv(rpong, 2, 0xFFFF)
+                    await client.asend(ping, 1)
+                    await f
+                else:
+                    await server.arecv(rping, 1, 0xFFFF)
+                    await server.asend(ep, pong, 2)
+                if i >= warm:
+                    samples.append(time.perf_counter() - t0)
+            if rank == 0:
+                samples.sort()
+                med = samples[len(samples) // 2]
+                emit(args, {"scenario": "pingpong", "case": name, "n_gpus": world, "msg_bytes": n, "buffers": where,
+                            "rtt_us_median": round(med * 1e6, 2), "rtt_us_p10": round(samples[len(samples) // 10] * 1e6, 2),
+                            "one_way_us": round(med * 5e5, 2), "iters": iters,
+                            "gbs_one_way": round(n / (med / 2) / 1e9, 3)})
+        if dist:
+            await asyncio.get_running_loop().run_in_executor(None, dist.barrier)
+        await client.aclose()
+        if dist:
+            await asyncio.get_running_loop().run_in_executor(None, dist.barrier)
+        await server.aclose()
+
+    runner()(main())
+    sw.shutdown()
+    if rank == 0:
+        # the restated reference on host cores, same shape (config 1 is the reference's own CPU-runnable case)
+        from oracle import starway_cpu as cpu
+
+        async def cpu_main():
+            port = 45000 + os.getpid() % 10000
+            s, c = cpu.make_pair(port)
+            await c.aconnect("127.0.0.1", port)
+            for n, warm, iters in ((4, 100, 1000), (1 << 20, 20, 200)):
+                a, b, ra, rb = (np.arange(n, dtype=np.uint8) for _ in range(4))
+                samples = []
+                for i in range(warm + iters):
+                    t0 = time.perf_counter()
+                    f = s.arecv(ra, 1, 0xFFFF)
+                    await c.asend(a, 1)
+                    await f
+                    f = c.arecv(rb, 2, 0xFFFF)
+                    await s.asend(0, b, 2)
+                    await f
+                    if i >= warm:
+                        samples.append(time.perf_counter() - t0)
+                samples.sort()
+                med = samples[len(samples) // 2]
+                emit(args, {"scenario": "pingpong", "impl": "cpu_baseline (restated reference, oracle/cpu_engine.cpp)",
+                            "msg_bytes": n, "buffers": "host", "rtt_us_median": round(med * 1e6, 2),
+                            "one_way_us": round(med * 5e5, 2), "cores": 3, "host_cpus": len(os.sched_getaffinity(0))})
+            await c.aclose()
+            await s.aclose()
+
+        runner()(cpu_main())
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("mode", choices=["sweep", "allpairs", "storm"])
+    ap.add_argument("mode", choices=["sweep", "allpairs", "storm", "pingpong"])
     ap.add_argument("--out", default=None)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--max-bytes", type=int, default=0)
@@ -330,7 +435,7 @@ def main():
     ap.add_argument("--rounds", type=int, default=50)
     ap.add_argument("--total-msgs", type=int, default=1_000_000)
     args = ap.parse_args()
-    {"sweep": mode_sweep, "allpairs": mode_allpairs, "storm": mode_storm}[args.mode](args)
+    {"sweep": mode_sweep, "allpairs": mode_allpairs, "storm": mode_storm, "pingpong": mode_pingpong}[args.mode](args)
 
 
 if __name__ == "__main__":

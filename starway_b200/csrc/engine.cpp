@@ -452,6 +452,7 @@ struct Ctx {
   std::mutex cq_mu;
   std::condition_variable cq_cv;
   std::deque<sw_completion> cq;
+  std::vector<sw_completion> cq_local;  // progress-thread staging
   int efd = -1;
   // progress thread
   std::thread thr;
@@ -484,11 +485,16 @@ std::mutex g_ctx_mu;
 std::vector<Ctx*> g_ctxs;
 
 // ============================================================================ completions
-void push_completion(Ctx* c, const sw_completion& comp) {
+// Completions produced by the progress thread are staged locally and published once per loop
+// iteration: one lock, one condvar signal, one eventfd write per batch.
+thread_local bool tls_is_progress = false;
+
+void publish_completions(Ctx* c, const sw_completion* comps, size_t n) {
+  if (!n) return;
   {
     std::lock_guard<std::mutex> lk(c->cq_mu);
     const bool was_empty = c->cq.empty();
-    c->cq.push_back(comp);
+    for (size_t i = 0; i < n; i++) c->cq.push_back(comps[i]);
     if (was_empty && c->efd >= 0) {
       uint64_t one = 1;
       ssize_t r = write(c->efd, &one, sizeof(one));
@@ -497,7 +503,21 @@ void push_completion(Ctx* c, const sw_completion& comp) {
   }
   c->cq_cv.notify_one();
   std::lock_guard<std::mutex> lk(c->st_mu);
-  c->stats.completions++;
+  c->stats.completions += n;
+}
+
+void push_completion(Ctx* c, const sw_completion& comp) {
+  if (tls_is_progress) {
+    c->cq_local.push_back(comp);
+    return;
+  }
+  publish_completions(c, &comp, 1);
+}
+
+void flush_completions(Ctx* c) {
+  if (c->cq_local.empty()) return;
+  publish_completions(c, c->cq_local.data(), c->cq_local.size());
+  c->cq_local.clear();
 }
 void complete(Ctx* c, Worker* w, uint64_t op_id, uint32_t kind, int32_t status, uint64_t tag = 0, uint64_t len = 0,
               uint64_t ep = 0) {
@@ -1809,6 +1829,7 @@ void drain_sq(Ctx* c) {
 void progress_main(Ctx* c) {
   swgpu::bind_thread(c->device);
   prctl(PR_SET_TIMERSLACK, 1000UL, 0, 0, 0);  // 1 us timer slack: short sleeps stay short
+  tls_is_progress = true;
   uint64_t iter = 0;
   double last_active = now_s();
   while (!c->stop.load(std::memory_order_acquire)) {
@@ -1827,6 +1848,7 @@ void progress_main(Ctx* c) {
     }
     active |= poll_bulk(c);
     active |= pump_bulk(c);
+    flush_completions(c);
     // forget fully closed workers
     if ((iter & 1023) == 0) {
       c->active.erase(std::remove_if(c->active.begin(), c->active.end(), [](Worker* w) { return w->close_phase >= 4; }),
@@ -1860,6 +1882,7 @@ void progress_main(Ctx* c) {
       }
     }
   }
+  flush_completions(c);
 }
 
 Worker* find_worker(Ctx* c, sw_worker_t id) {
