@@ -112,10 +112,10 @@ class ClockSampler:
 async def window_step(server, client, eps, srcs, dsts):
     recvs = [server.arecv(d, TAG, MASK) for d in dsts]
     sends = [client.asend(s, TAG) for s in srcs]
-    await asyncio.gather(*sends)
+    for f in sends:  # awaiting in order is cheaper than asyncio.gather (no per-future callbacks)
+        await f
     await client.aflush()
-    res = await asyncio.gather(*recvs)
-    return res
+    return [await f for f in recvs]
 
 
 def run_ours(args):

@@ -284,46 +284,45 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None) -> S
             """Deliver n polled completions.  `here` is the loop whose thread we are on (or None)."""
             with self._lock:
                 pop = self._ops.pop
-                items = []
-                for i in range(n):
-                    c = buf[i]
-                    k = c.kind
-                    if k == SW_OP_ACCEPT:
-                        items.append((None, k, c.status, c.worker, c.ep))
-                    else:
-                        items.append((pop(c.op_id, None), k, c.status, c.sender_tag, c.length))
-            batches: dict[Any, list] = {}
-            for entry, kind, status, a, b in items:
-                if kind == SW_OP_ACCEPT:
-                    srv = self._servers.get(a)
-                    if srv is not None:
-                        srv._on_accept(b)
-                    continue
+                entries = [pop(buf[i].op_id, None) for i in range(n)]
+            batches: dict[Any, list] | None = None
+            for i in range(n):
+                entry = entries[i]
+                c = buf[i]
+                kind = c.kind
                 if entry is None:
+                    if kind == SW_OP_ACCEPT:
+                        srv = self._servers.get(c.worker)
+                        if srv is not None:
+                            srv._on_accept(c.ep)
                     continue
+                status = c.status
                 if entry[0] == "fut":
                     _, loop, fut, _keep, post_ok = entry
                     if status == 0:
                         if post_ok is not None:
                             post_ok()
-                        val = (a, b) if kind == SW_OP_RECV else None
+                        val = (c.sender_tag, c.length) if kind == SW_OP_RECV else None
                         if loop is here:
                             if not fut.done():
                                 fut.set_result(val)
-                        else:
-                            batches.setdefault(loop, []).append((fut, True, val))
+                            continue
+                        item = (fut, True, val)
                     else:
                         if loop is here:
                             if not fut.done():
                                 fut.set_exception(Exception(status_string(status)))
-                        else:
-                            batches.setdefault(loop, []).append((fut, False, status_string(status)))
+                            continue
+                        item = (fut, False, status_string(status))
+                    if batches is None:
+                        batches = {}
+                    batches.setdefault(loop, []).append(item)
                 else:  # raw callbacks (reference: invoked on the native worker thread)
                     _, done, fail, _keep = entry
                     try:
                         if status == 0:
                             if kind == SW_OP_RECV:
-                                done(a, b)
+                                done(c.sender_tag, c.length)
                             elif kind == SW_OP_CONNECT:
                                 done("")
                             else:
@@ -335,11 +334,12 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None) -> S
                                 fail(status_string(status))
                     except Exception as exc:  # never kill the dispatcher
                         print(f"starway_b200: exception in user callback: {exc!r}")
-            for loop, lst in batches.items():
-                try:
-                    loop.call_soon_threadsafe(_resolve_batch, lst)
-                except RuntimeError:
-                    pass  # loop already closed
+            if batches:
+                for loop, lst in batches.items():
+                    try:
+                        loop.call_soon_threadsafe(_resolve_batch, lst)
+                    except RuntimeError:
+                        pass  # loop already closed
 
         def _drain(self, loop) -> None:
             """eventfd reader callback: runs on `loop`'s thread."""

@@ -609,7 +609,7 @@ bool worker_alloc_device(Ctx* c, Worker* w) {
   }
   w->min = (SwMatchIn*)swgpu::host_alloc(sizeof(SwMatchIn));
   w->mout = (SwMatchOut*)swgpu::host_alloc(sizeof(SwMatchOut));
-  w->mev = swgpu::event_create(0);
+  w->mev = swgpu::event_create(1);
   w->mev_start = swgpu::event_create(1);
   if (!w->min || !w->mout || !w->mev) {
     set_error(std::string("worker pinned alloc: ") + swgpu::last_error());
