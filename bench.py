@@ -227,6 +227,7 @@ def run_ours(args):
         barrier()
         torch.cuda.synchronize()
         e2e_steps = max(3, min(args.steps, 10))
+        ctx.reset_stats()
         t0 = time.perf_counter()
         await timed_host(e2e_steps)
         torch.cuda.synchronize()
@@ -238,13 +239,20 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_ms = float(t[0])
         e2e_value = world * step_bytes * e2e_steps / (e2e_ms * 1e-3) / 1e9
+        st2 = ctx.stats()
+        e2e_diag = {"ms_per_step": round(e2e_ms / e2e_steps, 3),
+                    "bulk_kernel_ms_per_step": round(st2["bulk_event_ms"] / e2e_steps, 3),
+                    "bulk_launches_per_step": round((st2["bulk_tma_launches"] + st2["bulk_simt_launches"]) / e2e_steps, 1),
+                    "put_kernel_ms_per_step": round(st2["put_event_ms"] / e2e_steps, 3),
+                    "staged_h2d_bytes_per_step": int(st2["h2d_bytes"] / e2e_steps),
+                    "staged_d2h_bytes_per_step": int(st2["d2h_bytes"] / e2e_steps)}
 
         await client.aclose()
         barrier()
         await server.aclose()
-        return value, ms, st, clk, e2e_value, step_bytes
+        return value, ms, st, clk, e2e_value, step_bytes, e2e_diag
 
-    value, ms, st, clk, e2e_value, step_bytes = new_loop_runner()(main())
+    value, ms, st, clk, e2e_value, step_bytes, e2e_diag = new_loop_runner()(main())
 
     # ---- roofline of the dominant kernel (sw_bulk_tma_kernel), from CUDA events recorded on the
     #      stream the kernel is launched on (engine profiling hooks), averaged over the timed region
@@ -295,7 +303,7 @@ def run_ours(args):
         "nvlink_roofline_frac": None if world == 1 else round(value / world / 900.0, 4),
         "clocks": clk,
         "e2e": {"value": round(e2e_value, 2), "unit": "GB/s", "h2d_bytes_per_step": step_bytes, "d2h_bytes_per_step": step_bytes,
-                "buffers": "pinned host NumPy arrays through Client.asend/Server.arecv"},
+                "buffers": "pinned host NumPy arrays through Client.asend/Server.arecv", "rank0_breakdown": e2e_diag},
         "gpu_launches": gpu_launches,
         "roofline": roofline,
     }

@@ -103,7 +103,8 @@ def mode_sweep(args):
             t0 = time.perf_counter()
             for _ in range(iters):
                 sends = [client.asend(b, DATA_TAG) for b in bufs]
-                await asyncio.gather(*sends)
+                for f in sends:
+                    await f
                 await client.aflush()
             await a
             return time.perf_counter() - t0
@@ -112,8 +113,8 @@ def mode_sweep(args):
             """server side: pre-post every receive, ack when the last one completed."""
             bufs = [dst_pool[(j * n) % (pool_bytes - n + 1):][:n] for j in range(window)] if n * window <= pool_bytes else [dst_pool[:n]] * window
             recvs = [server.arecv(bufs[j % window], DATA_TAG, U64) for j in range(window * iters)]
-            res = await asyncio.gather(*recvs)
-            assert all(r == (DATA_TAG, n) for r in res)
+            for f in recvs:
+                assert await f == (DATA_TAG, n)
             await server.asend(ep, ack, ACK_TAG)
 
         async def sync():

@@ -437,6 +437,7 @@ constexpr int N_BULK_BLOCKS = 3;
 constexpr uint32_t MAX_SEGS = 8192;
 constexpr size_t HOST_BOUNCE_MAX = 65536;
 constexpr size_t MAX_MAPPINGS = 4096;
+constexpr uint64_t STAGE_BATCH_BYTES = 4ull << 20;
 
 struct Ctx {
   int device = 0;
@@ -1025,7 +1026,8 @@ bool pump_sends(Ctx* c) {
   if ((c->put_tail - c->put_head) >= (uint32_t)N_PUT_BLOCKS) return false;
   PutBlock& b = c->put_blocks[c->put_tail % N_PUT_BLOCKS];
   uint32_t n = 0;
-  uint64_t bytes = 0, h2d = 0;
+  uint64_t bytes = 0, h2d = 0, staged_bytes = 0;
+  bool batch_full = false;
   const uint64_t eager_max = (uint64_t)std::min<int64_t>(c->opt_eager_max.load(), SW_EAGER_MAX);
   b.items.clear();
   for (Worker* w : c->active) {
@@ -1071,6 +1073,13 @@ bool pump_sends(Ctx* c) {
             r.src_ptr = base;
             r.pad[0] = 1;  // source is pinned host memory
           } else if (op->mem == SW_MEM_HOST) {
+            // Staged sends are published batch by batch: keep batches small so that the receiver can
+            // start pulling the first payloads while later ones are still being uploaded.
+            if (!op->dev_staging && n > 0 && staged_bytes + op->len > STAGE_BATCH_BYTES) {
+              batch_full = true;
+              break;
+            }
+            if (!op->dev_staging) staged_bytes += op->len;
             if (!op->dev_staging) {
               op->dev_staging = c->staging.get(op->len, &op->staging_size);
               if (!op->dev_staging) {
@@ -1125,9 +1134,9 @@ bool pump_sends(Ctx* c) {
         bytes += d.len;
         n++;
       }
-      if (n >= PUT_BATCH) break;
+      if (n >= PUT_BATCH || batch_full) break;
     }
-    if (n >= PUT_BATCH) break;
+    if (n >= PUT_BATCH || batch_full) break;
   }
   if (!n) return false;
   const bool prof = c->opt_profile.load() != 0;

@@ -564,6 +564,61 @@ static void bench_latency(FILE* json) {
   }
 }
 
+// ------------------------------------------------------------------ pinned host memory paths
+static void bench_hostmem(FILE* json) {
+  stream_t st = stream_create();
+  const size_t N = 64u << 20;
+  uint8_t *hs = (uint8_t*)host_alloc(N), *hd = (uint8_t*)host_alloc(N);
+  uint8_t *ds = (uint8_t*)dev_alloc(N), *dd = (uint8_t*)dev_alloc(N);
+  REQ(hs && hd && ds && dd);
+  for (size_t i = 0; i < N; i++) hs[i] = (uint8_t)(i * 7 + (i >> 11));
+  CK(cudaMemcpy(ds, hs, N, cudaMemcpyHostToDevice));
+  SwSeg* segs = (SwSeg*)host_alloc(sizeof(SwSeg) * 65536);
+  struct Case {
+    const char* name;
+    uint8_t *src, *dst;
+  } cases[] = {{"host->host", hs, hd}, {"host->dev", hs, dd}, {"dev->host", ds, hd}};
+  for (auto& c : cases) {
+    for (int mode = 0; mode < 3; mode++) {
+      float best = 1e30f;
+      const char* mname = mode == 0 ? "tma" : (mode == 1 ? "simt" : "cudaMemcpyAsync");
+      for (uint64_t seg : {uint64_t(1) << 16, uint64_t(1) << 18, uint64_t(1) << 20}) {
+        if (mode == 2 && seg != (1u << 16)) continue;
+        memset(hd, 0, N);
+        CK(cudaMemset(dd, 0, N));
+        auto v = make_segs((uint64_t)c.src, (uint64_t)c.dst, N, seg);
+        memcpy(segs, v.data(), v.size() * sizeof(SwSeg));
+        event_t a = event_create(1), b = event_create(1);
+        float bb = 1e30f;
+        for (int it = 0; it < 5; it++) {
+          event_record(a, st);
+          if (mode == 2) {
+            CK(cudaMemcpyAsync(c.dst, c.src, N, cudaMemcpyDefault, (cudaStream_t)st));
+          } else {
+            BulkTuning t{mode, 8, 24576, mode ? 8 : 1};
+            REQ(launch_bulk(st, segs, (uint32_t)v.size(), &t) == 0);
+          }
+          event_record(b, st);
+          REQ(event_sync(b) == 0);
+          float ms = event_elapsed_ms(a, b);
+          if (it > 0 && ms < bb) bb = ms;
+        }
+        // verify
+        std::vector<uint8_t> chk(N);
+        if (c.dst == hd) memcpy(chk.data(), hd, N); else CK(cudaMemcpy(chk.data(), dd, N, cudaMemcpyDeviceToHost));
+        REQ(memcmp(chk.data(), hs, N) == 0);
+        printf("[hostmem] %-10s %-16s seg=%7llu: %8.3f ms %7.1f GB/s\n", c.name, mname, (unsigned long long)seg, bb, N / (bb * 1e-3) / 1e9);
+        if (json)
+          fprintf(json, "{\"bench\":\"hostmem\",\"path\":\"%s\",\"mode\":\"%s\",\"seg\":%llu,\"ms\":%.4f,\"gbs\":%.1f}\n", c.name, mname,
+                  (unsigned long long)seg, bb, N / (bb * 1e-3) / 1e9);
+        if (bb < best) best = bb;
+        event_destroy(a);
+        event_destroy(b);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ 2-process CUDA IPC
 static int ipc_child(const char* path) {
   int n = device_count();
@@ -659,6 +714,7 @@ int main(int argc, char** argv) {
   }
   if (cmd == "latency" || cmd == "all") bench_latency(json);
   if (cmd == "bench" || cmd == "all") bench_single(json);
+  if (cmd == "hostmem") bench_hostmem(json);
   if (cmd == "ipc" || cmd == "all") test_ipc(argv[0]);
   if (cmd == "peer" || cmd == "all") bench_peer(json);
   if (json) fclose(json);
