@@ -214,10 +214,14 @@ def run_ours(args):
                  for j in range(window)] for k in range(2)]
         hdst = [[torch.empty(msg, dtype=torch.uint8).pin_memory().numpy() for _ in range(window)] for k in range(2)]
 
+        marks = []
+
         async def timed_host(nsteps):
             for i in range(nsteps):
                 k = i % 2
+                marks.append(("e2e_step_begin", time.monotonic()))
                 res = await window_step(server, client, eps, hsrc[k], hdst[k])
+                marks.append(("e2e_step_end", time.monotonic()))
                 assert all(r == (TAG, msg) for r in res)
 
         await timed_host(3)
@@ -239,6 +243,10 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_ms = float(t[0])
         e2e_value = world * step_bytes * e2e_steps / (e2e_ms * 1e-3) / 1e9
+        if os.environ.get("STARWAY_TRACE"):
+            with open(os.environ["STARWAY_TRACE"] + f".py.{os.getpid()}", "w") as f:
+                for name, t in marks:
+                    f.write(f"{t:.7f} {name} 0 0\n")
         st2 = ctx.stats()
         e2e_diag = {"ms_per_step": round(e2e_ms / e2e_steps, 3),
                     "bulk_kernel_ms_per_step": round(st2["bulk_event_ms"] / e2e_steps, 3),

@@ -477,10 +477,26 @@ struct Ctx {
   std::atomic<int64_t> opt_coalesce_us{40}, opt_coalesce_bytes{32 << 20};
   std::atomic<int64_t> opt_heap_small{4096}, opt_heap_big{512};
   std::atomic<int64_t> opt_profile{0};
+  // 1: same-process pinned host sources are read in place by the receiver's kernel (one host->host
+  // kernel, ~37 GB/s); 0: stage them through device memory so upload and download overlap (PCIe duplex)
+  std::atomic<int64_t> opt_pinned_send_direct{0};
   // stats
   std::mutex st_mu;
   sw_stats stats;
+  // optional event trace of the progress thread (STARWAY_TRACE=<file>): time-stamped pipeline events
+  struct TraceRec {
+    double t;
+    const char* what;
+    uint64_t a, b;
+  };
+  std::vector<TraceRec> trace;
+  std::string trace_path;
+  bool tracing = false;
 };
+
+inline void trace(Ctx* c, const char* what, uint64_t a = 0, uint64_t b = 0) {
+  if (c->tracing && c->trace.size() < (1u << 22)) c->trace.push_back(Ctx::TraceRec{now_s(), what, a, b});
+}
 
 std::mutex g_ctx_mu;
 std::vector<Ctx*> g_ctxs;
@@ -1062,7 +1078,7 @@ bool pump_sends(Ctx* c) {
           memset(&r, 0, sizeof(r));
           uint64_t base = 0, size = 0;
           int srcdev = c->device;
-          if (op->mem == SW_MEM_HOST && ep->in_process) {
+          if (op->mem == SW_MEM_HOST && ep->in_process && c->opt_pinned_send_direct.load()) {
             swgpu::PtrInfo pi;
             swgpu::ptr_info(op->ptr, &pi);
             if (pi.is_pinned) op->mem = MEM_PINNED;  // same process: the receiver's kernel reads it in place
@@ -1087,7 +1103,9 @@ bool pump_sends(Ctx* c) {
                 send_finished(c, op, SW_ERR_NO_MEMORY);
                 continue;
               }
+              trace(c, "h2d_enqueue", op->len);
               swgpu::memcpy_h2d(op->dev_staging, op->ptr, op->len, c->s_put);
+              trace(c, "h2d_enqueued", op->len);
               h2d += op->len;
             }
             base = (uint64_t)(uintptr_t)op->dev_staging;
@@ -1141,6 +1159,7 @@ bool pump_sends(Ctx* c) {
   if (!n) return false;
   const bool prof = c->opt_profile.load() != 0;
   if (prof) swgpu::event_record(b.ev_start, c->s_put);
+  trace(c, "put_launch", n, bytes + h2d);
   if (swgpu::launch_put(c->s_put, b.descs, n) != 0)
     fprintf(stderr, "starway_b200: put launch failed: %s\n", swgpu::last_error());
   swgpu::event_record(b.ev, c->s_put);
@@ -1169,6 +1188,7 @@ bool poll_puts(Ctx* c) {
         c->stats.put_event_launches++;
       }
     }
+    trace(c, "put_done", b.items.size());
     // publish the slots (doorbell), then complete the eager sends
     for (PutItem& it : b.items) {
       it.ep->out_published++;
@@ -1263,6 +1283,7 @@ bool pump_match(Ctx* c, Worker* w) {
   const bool prof = c->opt_profile.load() != 0;
   if (prof) swgpu::event_record(w->mev_start, c->s_match);
   uint32_t max_jobs = np + (uint32_t)std::min<uint64_t>(unseen, SW_MAX_ARRIVALS);
+  trace(c, "match_launch", np, unseen);
   if (swgpu::launch_match_deliver(c->s_match, w->mstate, in, w->mout, max_jobs) != 0)
     fprintf(stderr, "starway_b200: match/deliver launch failed: %s\n", swgpu::last_error());
   swgpu::event_record(w->mev, c->s_match);
@@ -1283,6 +1304,7 @@ bool poll_match(Ctx* c, Worker* w) {
   if (q < 0) fprintf(stderr, "starway_b200: match/deliver kernel failed: %s\n", swgpu::last_error());
   w->match_inflight = false;
   SwMatchOut* out = w->mout;
+  trace(c, "match_done", out->n_jobs, out->n_rndv);
   if (c->opt_profile.load()) {
     float ms = swgpu::event_elapsed_ms(w->mev_start, w->mev);
     if (ms >= 0) {
@@ -1480,6 +1502,7 @@ bool pump_bulk(Ctx* c) {
   if (nsimt) memcpy(b.segs + ntma, simt.data(), sizeof(SwSeg) * nsimt);
   const bool prof = c->opt_profile.load() != 0;
   if (prof) swgpu::event_record(b.ev_start, c->s_bulk);
+  trace(c, "bulk_launch", b.jobs.size(), b.bytes);
   int rc = 0;
   if (ntma) rc |= swgpu::launch_bulk(c->s_bulk, b.segs, ntma, &tune);
   if (nsimt) {
@@ -1516,6 +1539,7 @@ bool poll_bulk(Ctx* c) {
         c->stats.bulk_event_bytes += b.bytes;
       }
     }
+    trace(c, "bulk_done", b.jobs.size(), b.bytes);
     for (BulkJob& j : b.jobs) bulk_job_done(c, j, q < 0 ? SW_ERR_IO_ERROR : SW_OK);
     b.jobs.clear();
     b.busy = false;
@@ -1561,6 +1585,7 @@ bool poll_ctl(Ctx* c, Ep* ep) {
     any = true;
     switch (m.type) {
       case CTL_FIN: {
+        trace(c, "fin_recv", m.a);
         ep->cancel_wait.erase(m.a);
         auto it = ep->rndv_wait.find(m.a);
         if (it != ep->rndv_wait.end()) {
@@ -1979,6 +2004,12 @@ sw_ctx* sw_ctx_create(int device) {
   if (const char* e = getenv("STARWAY_BULK_STAGES")) c->opt_bulk_stages = atoll(e);
   if (const char* e = getenv("STARWAY_BULK_STAGE_BYTES")) c->opt_bulk_stage_bytes = atoll(e);
   if (const char* e = getenv("STARWAY_BULK_CTAS")) c->opt_bulk_ctas = atoll(e);
+  if (const char* e = getenv("STARWAY_PINNED_SEND_DIRECT")) c->opt_pinned_send_direct = atoll(e);
+  if (const char* e = getenv("STARWAY_TRACE")) {
+    c->trace_path = std::string(e) + "." + std::to_string((int)getpid());
+    c->tracing = true;
+    c->trace.reserve(1u << 20);
+  }
   c->thr = std::thread(progress_main, c);
   std::lock_guard<std::mutex> lk(g_ctx_mu);
   g_ctxs.push_back(c);
@@ -1999,6 +2030,12 @@ void sw_ctx_destroy(sw_ctx* ctx) {
   for (Worker* w : ws) sw_worker_destroy(ctx, w->id);
   c->stop.store(true, std::memory_order_release);
   if (c->thr.joinable()) c->thr.join();
+  if (c->tracing) {
+    if (FILE* f = fopen(c->trace_path.c_str(), "w")) {
+      for (auto& r : c->trace) fprintf(f, "%.7f %s %llu %llu\n", r.t, r.what, (unsigned long long)r.a, (unsigned long long)r.b);
+      fclose(f);
+    }
+  }
   swgpu::bind_thread(c->device);
   for (int i = 0; i < N_PUT_BLOCKS; i++) {
     PutBlock& b = c->put_blocks[i];
@@ -2045,6 +2082,7 @@ int sw_set_option(sw_ctx* ctx, const char* key, int64_t value) {
   else if (k == "heap_small_blocks") c->opt_heap_small = std::max<int64_t>(1, value);
   else if (k == "heap_big_blocks") c->opt_heap_big = std::max<int64_t>(1, value);
   else if (k == "profile") c->opt_profile = value;
+  else if (k == "pinned_send_direct") c->opt_pinned_send_direct = value;
   else if (k == "coalesce_us") c->opt_coalesce_us = value;
   else if (k == "coalesce_bytes") c->opt_coalesce_bytes = value;
   else {
