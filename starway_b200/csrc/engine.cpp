@@ -404,7 +404,10 @@ struct PutItem {
   SendOp* op;
   bool rndv;
 };
+constexpr uint32_t STAGE_SEGS = 1024;
 struct PutBlock {
+  SwSeg* segs = nullptr;   // pinned-host -> device staging uploads of this batch (TMA kernel)
+  uint32_t nsegs = 0;
   SwPutDesc* descs = nullptr;
   SwRts* rts = nullptr;
   uint8_t* stage = nullptr;
@@ -438,6 +441,7 @@ constexpr uint32_t MAX_SEGS = 8192;
 constexpr size_t HOST_BOUNCE_MAX = 65536;
 constexpr size_t MAX_MAPPINGS = 4096;
 constexpr uint64_t STAGE_BATCH_BYTES = 4ull << 20;
+constexpr uint64_t STAGE_SEG_BYTES = 32768;
 
 struct Ctx {
   int device = 0;
@@ -479,7 +483,7 @@ struct Ctx {
   std::atomic<int64_t> opt_profile{0};
   // 1: same-process pinned host sources are read in place by the receiver's kernel (one host->host
   // kernel, ~37 GB/s); 0: stage them through device memory so upload and download overlap (PCIe duplex)
-  std::atomic<int64_t> opt_pinned_send_direct{0};
+  std::atomic<int64_t> opt_pinned_send_direct{1};
   // stats
   std::mutex st_mu;
   sw_stats stats;
@@ -1046,6 +1050,7 @@ bool pump_sends(Ctx* c) {
   bool batch_full = false;
   const uint64_t eager_max = (uint64_t)std::min<int64_t>(c->opt_eager_max.load(), SW_EAGER_MAX);
   b.items.clear();
+  b.nsegs = 0;
   for (Worker* w : c->active) {
     for (Ep* ep : w->eps) {
       while (!ep->sendq.empty() && n < PUT_BATCH) {
@@ -1103,9 +1108,22 @@ bool pump_sends(Ctx* c) {
                 send_finished(c, op, SW_ERR_NO_MEMORY);
                 continue;
               }
-              trace(c, "h2d_enqueue", op->len);
-              swgpu::memcpy_h2d(op->dev_staging, op->ptr, op->len, c->s_put);
-              trace(c, "h2d_enqueued", op->len);
+              swgpu::PtrInfo hpi;
+              swgpu::ptr_info(op->ptr, &hpi);
+              const uint64_t pieces = (op->len + STAGE_SEG_BYTES - 1) / STAGE_SEG_BYTES;
+              if (hpi.is_pinned && ((uintptr_t)op->ptr & 15) == 0 && b.nsegs + pieces + 1 <= STAGE_SEGS) {
+                // pinned source: the upload is part of this batch's device work (TMA bulk kernel
+                // reading host memory), no per-message copy-engine operation
+                const uint64_t body = op->len & ~15ull;
+                for (uint64_t off = 0; off < body; off += STAGE_SEG_BYTES)
+                  b.segs[b.nsegs++] = SwSeg{(uint64_t)(uintptr_t)op->ptr + off, (uint64_t)(uintptr_t)op->dev_staging + off,
+                                            std::min<uint64_t>(STAGE_SEG_BYTES, body - off), 0};
+                if (op->len > body)
+                  swgpu::memcpy_h2d((uint8_t*)op->dev_staging + body, op->ptr + body, op->len - body, c->s_put);
+              } else {
+                trace(c, "h2d_enqueue", op->len);
+                swgpu::memcpy_h2d(op->dev_staging, op->ptr, op->len, c->s_put);
+              }
               h2d += op->len;
             }
             base = (uint64_t)(uintptr_t)op->dev_staging;
@@ -1159,6 +1177,12 @@ bool pump_sends(Ctx* c) {
   if (!n) return false;
   const bool prof = c->opt_profile.load() != 0;
   if (prof) swgpu::event_record(b.ev_start, c->s_put);
+  if (b.nsegs) {
+    swgpu::BulkTuning up{0, 8, 24576, 1};
+    trace(c, "stage_upload_launch", b.nsegs, staged_bytes);
+    if (swgpu::launch_bulk(c->s_put, b.segs, b.nsegs, &up) != 0)
+      fprintf(stderr, "starway_b200: staging upload launch failed: %s\n", swgpu::last_error());
+  }
   trace(c, "put_launch", n, bytes + h2d);
   if (swgpu::launch_put(c->s_put, b.descs, n) != 0)
     fprintf(stderr, "starway_b200: put launch failed: %s\n", swgpu::last_error());
@@ -1981,9 +2005,10 @@ sw_ctx* sw_ctx_create(int device) {
     b.descs = (SwPutDesc*)swgpu::host_alloc(sizeof(SwPutDesc) * PUT_BATCH);
     b.rts = (SwRts*)swgpu::host_alloc(sizeof(SwRts) * PUT_BATCH);
     b.stage = (uint8_t*)swgpu::host_alloc((size_t)PUT_BATCH * SW_SLOT_BYTES);
+    b.segs = (SwSeg*)swgpu::host_alloc(sizeof(SwSeg) * STAGE_SEGS);
     b.ev = swgpu::event_create(1);
     b.ev_start = swgpu::event_create(1);
-    ok = b.descs && b.rts && b.stage && b.ev && b.ev_start;
+    ok = b.descs && b.rts && b.stage && b.segs && b.ev && b.ev_start;
   }
   for (int i = 0; ok && i < N_BULK_BLOCKS; i++) {
     BulkBlock& b = c->bulk_blocks[i];
@@ -2042,6 +2067,7 @@ void sw_ctx_destroy(sw_ctx* ctx) {
     swgpu::host_free(b.descs);
     swgpu::host_free(b.rts);
     swgpu::host_free(b.stage);
+    swgpu::host_free(b.segs);
     if (b.ev) swgpu::event_destroy(b.ev);
     if (b.ev_start) swgpu::event_destroy(b.ev_start);
   }
