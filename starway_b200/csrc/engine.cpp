@@ -484,6 +484,10 @@ struct Ctx {
   // 1: same-process pinned host sources are read in place by the receiver's kernel (one host->host
   // kernel, ~37 GB/s); 0: stage them through device memory so upload and download overlap (PCIe duplex)
   std::atomic<int64_t> opt_pinned_send_direct{1};
+  // 1: upload pinned host sources with the TMA bulk kernel; 0 (default): copy engine (cudaMemcpyAsync).
+  // Measured on B200 (profiles/r01_e2e_staging_variants.md): the copy engine leaves the SMs and more of
+  // the PCIe duplex budget to the concurrent download kernel (43.8 vs 37.9 GB/s at N=2).
+  std::atomic<int64_t> opt_stage_upload_kernel{0};
   // stats
   std::mutex st_mu;
   sw_stats stats;
@@ -1111,7 +1115,8 @@ bool pump_sends(Ctx* c) {
               swgpu::PtrInfo hpi;
               swgpu::ptr_info(op->ptr, &hpi);
               const uint64_t pieces = (op->len + STAGE_SEG_BYTES - 1) / STAGE_SEG_BYTES;
-              if (hpi.is_pinned && ((uintptr_t)op->ptr & 15) == 0 && b.nsegs + pieces + 1 <= STAGE_SEGS) {
+              if (c->opt_stage_upload_kernel.load() && hpi.is_pinned && ((uintptr_t)op->ptr & 15) == 0 &&
+                  b.nsegs + pieces + 1 <= STAGE_SEGS) {
                 // pinned source: the upload is part of this batch's device work (TMA bulk kernel
                 // reading host memory), no per-message copy-engine operation
                 const uint64_t body = op->len & ~15ull;
@@ -2109,6 +2114,7 @@ int sw_set_option(sw_ctx* ctx, const char* key, int64_t value) {
   else if (k == "heap_big_blocks") c->opt_heap_big = std::max<int64_t>(1, value);
   else if (k == "profile") c->opt_profile = value;
   else if (k == "pinned_send_direct") c->opt_pinned_send_direct = value;
+  else if (k == "stage_upload_kernel") c->opt_stage_upload_kernel = value;
   else if (k == "coalesce_us") c->opt_coalesce_us = value;
   else if (k == "coalesce_bytes") c->opt_coalesce_bytes = value;
   else {
