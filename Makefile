@@ -12,6 +12,8 @@ LIB       := starway_b200/libstarway_b200.so
 ORACLE    := oracle/liboracle_tagmatch.so
 CPUENG    := oracle/libstarway_cpu.so
 HOSTSIM   := tests/hostsim/libstarway_hostsim.so
+FASTPATH  := starway_b200/_fastpath.so
+PYINC     := $(shell python -c "import sysconfig; print(sysconfig.get_paths()['include'])")
 PROBE     := tests/gpu_probe/sw_probe
 ABIBENCH  := tests/gpu_probe/abi_bench
 
@@ -20,7 +22,7 @@ ENGINE_HDRS := $(CSRC)/gpu.h $(CSRC)/sw_device.h include/starway_b200.h
 
 all: lib oracle hostsim probe
 
-lib: $(LIB)
+lib: $(LIB) $(FASTPATH)
 oracle: $(ORACLE) $(CPUENG)
 oracle-core: $(ORACLE)
 hostsim: $(HOSTSIM)
@@ -37,6 +39,10 @@ build/engine.o: $(ENGINE_SRCS) $(ENGINE_HDRS)
 # The product library: host progress engine + CUDA kernels.  No CPU fallback is linked in.
 $(LIB): build/engine.o build/gpu_cuda.o
 	$(NVCC) $(ARCH) -shared -cudart static -Xlinker -Bsymbolic -Xlinker --version-script=$(CSRC)/exports.map -o $@ $^ -lpthread -lrt -ldl
+
+# CPython fast path of the binding layer (post / poll / future resolution); optional at run time
+$(FASTPATH): $(CSRC)/fastpath.c
+	$(CC) -O2 -g -fPIC -shared -Wall -I$(PYINC) -o $@ $<
 
 # Test infrastructure -------------------------------------------------------------
 build/tagmatch.o: oracle/tagmatch.c oracle/tagmatch.h
@@ -70,6 +76,6 @@ $(ABIBENCH): tests/gpu_probe/abi_bench.cpp $(LIB) include/starway_b200.h
 	$(CXX) -O2 -std=c++17 -I/usr/local/cuda/include -o $@ tests/gpu_probe/abi_bench.cpp -Lstarway_b200 -lstarway_b200 -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,'$$ORIGIN/../../starway_b200' -Wl,-rpath,/usr/local/cuda/lib64
 
 clean:
-	rm -rf build $(LIB) $(ORACLE) $(CPUENG) $(HOSTSIM) $(PROBE) $(ABIBENCH)
+	rm -rf build $(LIB) $(FASTPATH) $(ORACLE) $(CPUENG) $(HOSTSIM) $(PROBE) $(ABIBENCH)
 
 .PHONY: all lib oracle oracle-core hostsim probe clean

@@ -32,6 +32,11 @@ from typing import Any
 
 import numpy as np
 
+try:  # C fast path of the binding layer (starway_b200/csrc/fastpath.c); the ctypes code below is the fallback
+    from . import _fastpath
+except ImportError:  # pragma: no cover
+    _fastpath = None
+
 # ----------------------------------------------------------------------------- C structs
 SW_WORKER_SERVER = 1
 SW_WORKER_CLIENT = 2
@@ -216,7 +221,7 @@ def as_buffer(obj: Any, writable: bool):
 
 
 # ----------------------------------------------------------------------------- API factory
-def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None) -> SimpleNamespace:
+def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_fastpath: bool = True) -> SimpleNamespace:
     """Build Context/Server/Client/ServerEndpoint classes on top of a loaded C-ABI library."""
     declare(lib)
     _post_send, _post_recv = lib.sw_post_send, lib.sw_post_recv
@@ -255,6 +260,11 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None) -> S
             self._buf = (SwCompletion * 512)()
             self._stop = False
             self._wake = threading.Event()
+            self._fp = None
+            if _fastpath is not None and use_fastpath:
+                addr = lambda f: ctypes.cast(f, ctypes.c_void_p).value  # noqa: E731
+                self._fp = _fastpath.Binding(addr(lib.sw_post_send), addr(lib.sw_post_recv), addr(lib.sw_poll), self._h,
+                                             self._ops, as_buffer, self.ensure_reader, self._slow, _err, status_string)
             self._thread = threading.Thread(target=self._poll_loop, name="starway-b200-poller", daemon=True)
             self._thread.start()
 
@@ -341,10 +351,29 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None) -> S
                     except RuntimeError:
                         pass  # loop already closed
 
+        def _slow(self, entry, kind, status, sender_tag, length, worker, ep, here) -> None:
+            """One completion the C fast path does not handle itself (accept, raw callbacks, other loops)."""
+            if entry is None:
+                if kind == SW_OP_ACCEPT:
+                    srv = self._servers.get(worker)
+                    if srv is not None:
+                        srv._on_accept(ep)
+                return
+            c = SwCompletion(0, status, kind, sender_tag, length, worker, ep)
+            buf = (SwCompletion * 1)(c)
+            op = -1 - id(entry)  # re-insert under a private key so that _dispatch finds it
+            with self._lock:
+                self._ops[op & 0xFFFFFFFFFFFFFFFF] = entry
+            buf[0].op_id = op & 0xFFFFFFFFFFFFFFFF
+            self._dispatch(1, buf, here)
+
         def _drain(self, loop) -> None:
             """eventfd reader callback: runs on `loop`'s thread."""
             h, buf = self._h, self._buf
             if not h:
+                return
+            if self._fp is not None:
+                self._fp.drain(loop)
                 return
             while True:
                 n = lib.sw_poll(h, buf, 512)
@@ -501,6 +530,8 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None) -> S
         def arecv(self, buffer, tag: int, tag_mask: int, loop: asyncio.AbstractEventLoop | None = None):
             # hot path: no helper calls / closures
             ctx = self._ctx
+            if loop is None and ctx._fp is not None:
+                return ctx._fp.arecv(self._w, buffer, tag, tag_mask)
             if loop is None:
                 loop = _get_running_loop()
             if loop not in ctx._readers:
@@ -599,6 +630,8 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None) -> S
 
         def asend(self, client_ep, buffer, tag: int, loop: asyncio.AbstractEventLoop | None = None):
             ctx = self._ctx
+            if loop is None and ctx._fp is not None:
+                return ctx._fp.asend(self._w, client_ep._id, buffer, tag)
             if loop is None:
                 loop = _get_running_loop()
             if loop not in ctx._readers:
@@ -675,6 +708,8 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None) -> S
 
         def asend(self, buffer, tag: int, loop: asyncio.AbstractEventLoop | None = None):
             ctx = self._ctx
+            if loop is None and ctx._fp is not None:
+                return ctx._fp.asend(self._w, 0, buffer, tag)
             if loop is None:
                 loop = _get_running_loop()
             if loop not in ctx._readers:

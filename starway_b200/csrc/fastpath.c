@@ -1,0 +1,377 @@
+/* starway_b200 — CPython fast path for the binding layer (NOT part of the compute path).
+ *
+ * The reference reaches its engine through nanobind (C++), so its per-operation cost in the
+ * binding is ~1 us.  A pure-ctypes shim costs ~3.5 us per asend/arecv and ~1.5 us per completion,
+ * which caps the API-level message rate.  This module does the same three things the Python shim
+ * does — resolve the buffer, call sw_post_send / sw_post_recv, resolve asyncio futures from
+ * sw_poll — in C under the GIL.  It holds no engine logic: the function pointers it calls are the
+ * C-ABI entry points of whichever library `_core.bind()` was given.  Without it `_core.py` falls
+ * back to its ctypes implementation of the same steps.
+ */
+#define PY_SSIZE_T_CLEAN
+#include <Python.h>
+#include <stdint.h>
+#include <string.h>
+
+typedef struct {
+  uint64_t op_id;
+  int32_t status;
+  uint32_t kind;
+  uint64_t sender_tag;
+  uint64_t length;
+  uint64_t worker;
+  uint64_t ep;
+} sw_completion;
+
+typedef uint64_t (*post_send_fn)(void*, uint64_t, uint64_t, const void*, size_t, uint64_t, int);
+typedef uint64_t (*post_recv_fn)(void*, uint64_t, void*, size_t, uint64_t, uint64_t, int);
+typedef int (*poll_fn)(void*, sw_completion*, int);
+
+enum { SW_OP_RECV = 2 };
+
+typedef struct {
+  PyObject_HEAD
+  post_send_fn post_send;
+  post_recv_fn post_recv;
+  poll_fn poll;
+  void* ctx;
+  PyObject* ops;            /* dict shared with the Python shim: op id -> ("fut", loop, fut, keep, post_ok) */
+  PyObject* resolve;        /* resolve(obj, writable) -> (ptr, nbytes, mem, keep)    [slow path: as_buffer] */
+  PyObject* ensure_reader;  /* ensure_reader(loop) */
+  PyObject* slow;           /* slow(entry, kind, status, sender_tag, length, worker, ep, here_loop) */
+  PyObject* last_error;     /* last_error() -> str */
+  PyObject* status_string;  /* status_string(code) -> str */
+  PyObject* get_running_loop;
+  PyObject* cache;          /* id(obj) -> (weakref, ptr, nbytes, mem, writable) */
+  PyObject* last_loop;      /* loop whose reader registration was already ensured (borrowed identity) */
+  PyObject* str_fut;        /* interned "fut" */
+  PyObject* str_create_future;
+  PyObject* str_set_result;
+  PyObject* str_set_exception;
+  sw_completion buf[512];
+} Binding;
+
+static void Binding_dealloc(Binding* self) {
+  Py_XDECREF(self->ops);
+  Py_XDECREF(self->resolve);
+  Py_XDECREF(self->ensure_reader);
+  Py_XDECREF(self->slow);
+  Py_XDECREF(self->last_error);
+  Py_XDECREF(self->status_string);
+  Py_XDECREF(self->get_running_loop);
+  Py_XDECREF(self->cache);
+  Py_XDECREF(self->last_loop);
+  Py_XDECREF(self->str_fut);
+  Py_XDECREF(self->str_create_future);
+  Py_XDECREF(self->str_set_result);
+  Py_XDECREF(self->str_set_exception);
+  Py_TYPE(self)->tp_free((PyObject*)self);
+}
+
+static int Binding_init(Binding* self, PyObject* args, PyObject* kw) {
+  unsigned long long ps, pr, pl, ctx;
+  PyObject *ops, *resolve, *ensure_reader, *slow, *last_error, *status_string;
+  if (!PyArg_ParseTuple(args, "KKKKO!OOOOO", &ps, &pr, &pl, &ctx, &PyDict_Type, &ops, &resolve, &ensure_reader, &slow,
+                        &last_error, &status_string))
+    return -1;
+  self->post_send = (post_send_fn)(uintptr_t)ps;
+  self->post_recv = (post_recv_fn)(uintptr_t)pr;
+  self->poll = (poll_fn)(uintptr_t)pl;
+  self->ctx = (void*)(uintptr_t)ctx;
+  Py_INCREF(ops);
+  self->ops = ops;
+  Py_INCREF(resolve);
+  self->resolve = resolve;
+  Py_INCREF(ensure_reader);
+  self->ensure_reader = ensure_reader;
+  Py_INCREF(slow);
+  self->slow = slow;
+  Py_INCREF(last_error);
+  self->last_error = last_error;
+  Py_INCREF(status_string);
+  self->status_string = status_string;
+  PyObject* asyncio = PyImport_ImportModule("asyncio");
+  if (!asyncio) return -1;
+  self->get_running_loop = PyObject_GetAttrString(asyncio, "get_running_loop");
+  Py_DECREF(asyncio);
+  if (!self->get_running_loop) return -1;
+  self->cache = PyDict_New();
+  self->last_loop = NULL;
+  self->str_fut = PyUnicode_InternFromString("fut");
+  self->str_create_future = PyUnicode_InternFromString("create_future");
+  self->str_set_result = PyUnicode_InternFromString("set_result");
+  self->str_set_exception = PyUnicode_InternFromString("set_exception");
+  if (!self->cache || !self->str_fut || !self->str_create_future || !self->str_set_result || !self->str_set_exception)
+    return -1;
+  return 0;
+}
+
+/* -> 0 ok, -1 error.  keep is a NEW reference. */
+static int resolve_buffer(Binding* self, PyObject* obj, int writable, void** ptr, size_t* nbytes, int* mem,
+                          PyObject** keep) {
+  PyObject* key = PyLong_FromVoidPtr(obj);
+  if (!key) return -1;
+  PyObject* hit = PyDict_GetItemWithError(self->cache, key); /* borrowed */
+  if (hit) {
+    PyObject* ref = PyTuple_GET_ITEM(hit, 0);
+    PyObject* target = NULL;
+#if PY_VERSION_HEX >= 0x030D0000
+    if (PyWeakref_GetRef(ref, &target) < 0) target = NULL;
+#else
+    target = PyWeakref_GetObject(ref);
+    Py_XINCREF(target);
+#endif
+    if (target == obj && (!writable || PyTuple_GET_ITEM(hit, 4) == Py_True)) {
+      Py_DECREF(target);
+      *ptr = PyLong_AsVoidPtr(PyTuple_GET_ITEM(hit, 1));
+      *nbytes = PyLong_AsSize_t(PyTuple_GET_ITEM(hit, 2));
+      *mem = (int)PyLong_AsLong(PyTuple_GET_ITEM(hit, 3));
+      Py_DECREF(key);
+      Py_INCREF(obj);
+      *keep = obj;
+      return 0;
+    }
+    Py_XDECREF(target);
+  } else if (PyErr_Occurred()) {
+    Py_DECREF(key);
+    return -1;
+  }
+  /* slow path: the Python shim validates / converts (dtype, contiguity, device) */
+  PyObject* res = PyObject_CallFunctionObjArgs(self->resolve, obj, writable ? Py_True : Py_False, NULL);
+  if (!res) {
+    Py_DECREF(key);
+    return -1;
+  }
+  if (!PyTuple_Check(res) || PyTuple_GET_SIZE(res) != 4) {
+    Py_DECREF(res);
+    Py_DECREF(key);
+    PyErr_SetString(PyExc_TypeError, "resolve() must return (ptr, nbytes, mem, keep)");
+    return -1;
+  }
+  *ptr = PyLong_AsVoidPtr(PyTuple_GET_ITEM(res, 0));
+  *nbytes = PyLong_AsSize_t(PyTuple_GET_ITEM(res, 1));
+  *mem = (int)PyLong_AsLong(PyTuple_GET_ITEM(res, 2));
+  *keep = PyTuple_GET_ITEM(res, 3);
+  Py_INCREF(*keep);
+  if (PyErr_Occurred()) {
+    Py_DECREF(*keep);
+    Py_DECREF(res);
+    Py_DECREF(key);
+    return -1;
+  }
+  /* cache only when the buffer object itself is what stays alive (no conversion happened) */
+  if (*keep == obj) {
+    PyObject* ref = PyWeakref_NewRef(obj, NULL);
+    if (ref) {
+      if (PyDict_GET_SIZE(self->cache) > 16384) PyDict_Clear(self->cache);
+      PyObject* ent = PyTuple_Pack(5, ref, PyTuple_GET_ITEM(res, 0), PyTuple_GET_ITEM(res, 1), PyTuple_GET_ITEM(res, 2),
+                                   writable ? Py_True : Py_False);
+      if (ent) {
+        PyDict_SetItem(self->cache, key, ent);
+        Py_DECREF(ent);
+      }
+      Py_DECREF(ref);
+    }
+    PyErr_Clear(); /* objects that do not support weak references are simply not cached */
+  }
+  Py_DECREF(res);
+  Py_DECREF(key);
+  return 0;
+}
+
+static PyObject* running_loop(Binding* self) {
+  PyObject* loop = PyObject_CallNoArgs(self->get_running_loop);
+  if (!loop) return NULL;
+  if (loop != self->last_loop) {
+    PyObject* r = PyObject_CallOneArg(self->ensure_reader, loop);
+    if (!r) {
+      Py_DECREF(loop);
+      return NULL;
+    }
+    Py_DECREF(r);
+    Py_XDECREF(self->last_loop);
+    Py_INCREF(loop);
+    self->last_loop = loop;
+  }
+  return loop;
+}
+
+static PyObject* raise_last_error(Binding* self) {
+  PyObject* msg = PyObject_CallNoArgs(self->last_error);
+  if (msg) {
+    PyErr_SetObject(PyExc_RuntimeError, msg);
+    Py_DECREF(msg);
+  }
+  return NULL;
+}
+
+static PyObject* register_op(Binding* self, uint64_t op, PyObject* loop, PyObject* fut, PyObject* keep) {
+  PyObject* key = PyLong_FromUnsignedLongLong(op);
+  PyObject* entry = key ? PyTuple_Pack(5, self->str_fut, loop, fut, keep, Py_None) : NULL;
+  int rc = entry ? PyDict_SetItem(self->ops, key, entry) : -1;
+  Py_XDECREF(key);
+  Py_XDECREF(entry);
+  if (rc < 0) {
+    Py_DECREF(fut);
+    return NULL;
+  }
+  return fut;
+}
+
+/* asend(worker, ep, buffer, tag) -> Future */
+static PyObject* Binding_asend(Binding* self, PyObject* const* args, Py_ssize_t nargs) {
+  if (nargs != 4) {
+    PyErr_SetString(PyExc_TypeError, "asend(worker, ep, buffer, tag)");
+    return NULL;
+  }
+  uint64_t worker = PyLong_AsUnsignedLongLong(args[0]);
+  uint64_t ep = PyLong_AsUnsignedLongLong(args[1]);
+  uint64_t tag = PyLong_AsUnsignedLongLongMask(args[3]);
+  if (PyErr_Occurred()) return NULL;
+  void* ptr;
+  size_t n;
+  int mem;
+  PyObject* keep;
+  if (resolve_buffer(self, args[2], 0, &ptr, &n, &mem, &keep) < 0) return NULL;
+  PyObject* loop = running_loop(self);
+  PyObject* fut = loop ? PyObject_CallMethodNoArgs(loop, self->str_create_future) : NULL;
+  if (!fut) {
+    Py_XDECREF(loop);
+    Py_DECREF(keep);
+    return NULL;
+  }
+  /* the GIL is held from the post to the table insert: no other Python thread can observe the gap */
+  uint64_t op = self->post_send(self->ctx, worker, ep, ptr, n, tag, mem);
+  PyObject* ret = op ? register_op(self, op, loop, fut, keep) : (Py_DECREF(fut), raise_last_error(self));
+  Py_DECREF(loop);
+  Py_DECREF(keep);
+  return ret;
+}
+
+/* arecv(worker, buffer, tag, mask) -> Future */
+static PyObject* Binding_arecv(Binding* self, PyObject* const* args, Py_ssize_t nargs) {
+  if (nargs != 4) {
+    PyErr_SetString(PyExc_TypeError, "arecv(worker, buffer, tag, tag_mask)");
+    return NULL;
+  }
+  uint64_t worker = PyLong_AsUnsignedLongLong(args[0]);
+  uint64_t tag = PyLong_AsUnsignedLongLongMask(args[2]);
+  uint64_t mask = PyLong_AsUnsignedLongLongMask(args[3]);
+  if (PyErr_Occurred()) return NULL;
+  void* ptr;
+  size_t n;
+  int mem;
+  PyObject* keep;
+  if (resolve_buffer(self, args[1], 1, &ptr, &n, &mem, &keep) < 0) return NULL;
+  PyObject* loop = running_loop(self);
+  PyObject* fut = loop ? PyObject_CallMethodNoArgs(loop, self->str_create_future) : NULL;
+  if (!fut) {
+    Py_XDECREF(loop);
+    Py_DECREF(keep);
+    return NULL;
+  }
+  uint64_t op = self->post_recv(self->ctx, worker, ptr, n, tag, mask, mem);
+  PyObject* ret = op ? register_op(self, op, loop, fut, keep) : (Py_DECREF(fut), raise_last_error(self));
+  Py_DECREF(loop);
+  Py_DECREF(keep);
+  return ret;
+}
+
+static void swallow_invalid_state(void) {
+  /* a future cancelled by the caller (asyncio.wait_for timeout ...) refuses the result: ignore */
+  if (PyErr_Occurred()) PyErr_Clear();
+}
+
+/* drain(loop): resolve every pending completion; runs on `loop`'s thread (eventfd reader) */
+static PyObject* Binding_drain(Binding* self, PyObject* here) {
+  for (;;) {
+    int n = self->poll(self->ctx, self->buf, 512);
+    if (n <= 0) break;
+    for (int i = 0; i < n; i++) {
+      const sw_completion c = self->buf[i];
+      PyObject* key = PyLong_FromUnsignedLongLong(c.op_id);
+      if (!key) return NULL;
+      PyObject* entry = PyDict_GetItemWithError(self->ops, key); /* borrowed */
+      if (entry) {
+        Py_INCREF(entry);
+        PyDict_DelItem(self->ops, key);
+      } else if (PyErr_Occurred()) {
+        Py_DECREF(key);
+        return NULL;
+      }
+      Py_DECREF(key);
+      int fast = entry && PyTuple_Check(entry) && PyTuple_GET_SIZE(entry) == 5 &&
+                 PyTuple_GET_ITEM(entry, 0) == self->str_fut && PyTuple_GET_ITEM(entry, 1) == here &&
+                 PyTuple_GET_ITEM(entry, 4) == Py_None;
+      if (fast) {
+        PyObject* fut = PyTuple_GET_ITEM(entry, 2);
+        PyObject* r = NULL;
+        if (c.status == 0) {
+          if (c.kind == SW_OP_RECV) {
+            PyObject* val = Py_BuildValue("(KK)", (unsigned long long)c.sender_tag, (unsigned long long)c.length);
+            if (val) {
+              r = PyObject_CallMethodOneArg(fut, self->str_set_result, val);
+              Py_DECREF(val);
+            }
+          } else {
+            r = PyObject_CallMethodOneArg(fut, self->str_set_result, Py_None);
+          }
+        } else {
+          PyObject* msg = PyObject_CallFunction(self->status_string, "i", (int)c.status);
+          PyObject* exc = msg ? PyObject_CallOneArg(PyExc_Exception, msg) : NULL;
+          if (exc) r = PyObject_CallMethodOneArg(fut, self->str_set_exception, exc);
+          Py_XDECREF(msg);
+          Py_XDECREF(exc);
+        }
+        if (!r) swallow_invalid_state();
+        Py_XDECREF(r);
+      } else {
+        /* accept notifications, raw callbacks, other loops, banner callbacks: the Python shim */
+        PyObject* r = PyObject_CallFunction(self->slow, "OIiKKKKO", entry ? entry : Py_None, (unsigned)c.kind, (int)c.status,
+                                            (unsigned long long)c.sender_tag, (unsigned long long)c.length,
+                                            (unsigned long long)c.worker, (unsigned long long)c.ep, here);
+        if (!r) {
+          Py_XDECREF(entry);
+          return NULL;
+        }
+        Py_DECREF(r);
+      }
+      Py_XDECREF(entry);
+    }
+    if (n < 512) break;
+  }
+  Py_RETURN_NONE;
+}
+
+static PyMethodDef Binding_methods[] = {
+    {"asend", (PyCFunction)(void (*)(void))Binding_asend, METH_FASTCALL, "asend(worker, ep, buffer, tag) -> Future"},
+    {"arecv", (PyCFunction)(void (*)(void))Binding_arecv, METH_FASTCALL, "arecv(worker, buffer, tag, mask) -> Future"},
+    {"drain", (PyCFunction)Binding_drain, METH_O, "drain(loop): resolve pending completions on the loop thread"},
+    {NULL, NULL, 0, NULL}};
+
+static PyTypeObject BindingType = {
+    PyVarObject_HEAD_INIT(NULL, 0).tp_name = "starway_b200._fastpath.Binding",
+    .tp_basicsize = sizeof(Binding),
+    .tp_flags = Py_TPFLAGS_DEFAULT,
+    .tp_new = PyType_GenericNew,
+    .tp_init = (initproc)Binding_init,
+    .tp_dealloc = (destructor)Binding_dealloc,
+    .tp_methods = Binding_methods,
+};
+
+static struct PyModuleDef moddef = {PyModuleDef_HEAD_INIT, "_fastpath",
+                                    "C fast path of the starway_b200 binding layer (post / poll / future resolution)", -1,
+                                    NULL};
+
+PyMODINIT_FUNC PyInit__fastpath(void) {
+  if (PyType_Ready(&BindingType) < 0) return NULL;
+  PyObject* m = PyModule_Create(&moddef);
+  if (!m) return NULL;
+  Py_INCREF(&BindingType);
+  if (PyModule_AddObject(m, "Binding", (PyObject*)&BindingType) < 0) {
+    Py_DECREF(&BindingType);
+    Py_DECREF(m);
+    return NULL;
+  }
+  return m;
+}
