@@ -474,6 +474,11 @@ struct Ctx {
   HostPool host_pool;
   StagingPool staging;
   std::map<std::string, Mapping> mappings;  // key: pid + ipc handle bytes
+  struct HandleEnt {
+    uint64_t base;
+    uint8_t handle[64];
+  };
+  std::unordered_map<uint64_t, HandleEnt> handle_cache;  // CUDA buffer id -> exported IPC handle
   // options
   std::atomic<int64_t> opt_eager_max{SW_EAGER_MAX};
   std::atomic<int64_t> opt_ring_slots{SW_RING_SLOTS_DEFAULT};
@@ -1085,7 +1090,7 @@ bool pump_sends(Ctx* c) {
           rndv = true;
           SwRts& r = b.rts[n];
           memset(&r, 0, sizeof(r));
-          uint64_t base = 0, size = 0;
+          uint64_t base = 0, size = 0, buffer_id = 0;
           int srcdev = c->device;
           if (op->mem == SW_MEM_HOST && ep->in_process && c->opt_pinned_send_direct.load()) {
             swgpu::PtrInfo pi;
@@ -1135,24 +1140,40 @@ bool pump_sends(Ctx* c) {
             size = op->staging_size;
             r.src_ptr = base;
           } else {
-            swgpu::PtrInfo pi;
-            swgpu::ptr_info(op->ptr, &pi);
-            base = pi.base;
-            size = pi.size;
-            srcdev = pi.device;
             r.src_ptr = (uint64_t)(uintptr_t)op->ptr;
-            if (!ep->in_process && (!pi.is_device || base == 0)) {
-              ep->sendq.pop_front();
-              set_error("rendezvous source is not a CUDA device allocation");
-              send_finished(c, op, SW_ERR_INVALID_PARAM);
-              continue;
+            if (!ep->in_process) {
+              // a peer in another process maps the allocation: it needs base, size and an IPC handle
+              swgpu::PtrInfo pi;
+              swgpu::ptr_info(op->ptr, &pi);
+              base = pi.base;
+              size = pi.size;
+              srcdev = pi.device;
+              buffer_id = pi.buffer_id;
+              if (!pi.is_device || base == 0) {
+                ep->sendq.pop_front();
+                set_error("rendezvous source is not a CUDA device allocation");
+                send_finished(c, op, SW_ERR_INVALID_PARAM);
+                continue;
+              }
             }
           }
-          if (!ep->in_process && swgpu::ipc_get((void*)(uintptr_t)base, r.ipc_handle) != 0) {
-            fprintf(stderr, "starway_b200: cudaIpcGetMemHandle failed: %s\n", swgpu::last_error());
-            ep->sendq.pop_front();
-            send_finished(c, op, SW_ERR_INVALID_PARAM);
-            continue;
+          if (!ep->in_process) {
+            // IPC handles are cached per allocation (CUDA buffer id: changes if the address is re-allocated)
+            auto hit = buffer_id ? c->handle_cache.find(buffer_id) : c->handle_cache.end();
+            if (hit != c->handle_cache.end() && hit->second.base == base) {
+              memcpy(r.ipc_handle, hit->second.handle, 64);
+            } else if (swgpu::ipc_get((void*)(uintptr_t)base, r.ipc_handle) != 0) {
+              fprintf(stderr, "starway_b200: cudaIpcGetMemHandle failed: %s\n", swgpu::last_error());
+              ep->sendq.pop_front();
+              send_finished(c, op, SW_ERR_INVALID_PARAM);
+              continue;
+            } else if (buffer_id) {
+              if (c->handle_cache.size() > 8192) c->handle_cache.clear();
+              Ctx::HandleEnt he;
+              he.base = base;
+              memcpy(he.handle, r.ipc_handle, 64);
+              c->handle_cache[buffer_id] = he;
+            }
           }
           r.alloc_base = base;
           r.alloc_size = size;

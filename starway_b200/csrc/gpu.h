@@ -19,6 +19,7 @@ struct PtrInfo {
   int device;         // ordinal for device memory
   uint64_t base;      // allocation base (device memory)
   uint64_t size;      // allocation size (device memory)
+  uint64_t buffer_id; // unique id of the allocation (changes when the address is re-allocated); 0: unknown
 };
 
 struct BulkTuning {

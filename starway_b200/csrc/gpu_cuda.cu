@@ -130,41 +130,57 @@ int ipc_close(void* p) {
   return 0;
 }
 
+// One driver call (cuPointerGetAttributes, resolved through cudaGetDriverEntryPoint so that the
+// library has no link-time libcuda dependency) answers everything the engine needs about a pointer.
 int ptr_info(const void* p, PtrInfo* out) {
   memset(out, 0, sizeof(*out));
+  typedef int (*attrs_fn)(unsigned int, int*, void**, unsigned long long);
+  static attrs_fn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuPointerGetAttributes", &f, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<attrs_fn>(f);
+    else
+      cudaGetLastError();
+  });
+  if (fn) {
+    // CU_POINTER_ATTRIBUTE_MEMORY_TYPE=2, DEVICE_ORDINAL=9, RANGE_START_ADDR=11, RANGE_SIZE=12, BUFFER_ID=7
+    int attrs[5] = {2, 9, 11, 12, 7};
+    unsigned int mem_type = 0;
+    int ordinal = -1;
+    unsigned long long start = 0, buffer_id = 0;
+    size_t range = 0;
+    void* data[5] = {&mem_type, &ordinal, &start, &range, &buffer_id};
+    if (fn(5, attrs, data, (unsigned long long)(uintptr_t)p) == 0) {
+      if (mem_type == 2 /* CU_MEMORYTYPE_DEVICE */) {
+        out->is_device = 1;
+        out->device = ordinal;
+        out->base = start;
+        out->size = range;
+        out->buffer_id = buffer_id;
+      } else if (mem_type == 1 /* CU_MEMORYTYPE_HOST: pinned / registered */) {
+        out->is_pinned = 1;
+      } else if (mem_type == 3 /* unified */) {
+        out->is_device = 1;
+        out->device = ordinal;
+      }
+      return 0;
+    }
+  }
   cudaPointerAttributes a;
   cudaError_t e = cudaPointerGetAttributes(&a, p);
   if (e != cudaSuccess) {
     cudaGetLastError();
     return 0;  // plain host memory unknown to CUDA
   }
-  if (a.type == cudaMemoryTypeDevice) {
+  if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) {
     out->is_device = 1;
     out->device = a.device;
-    // allocation range through the driver entry point (no link-time libcuda dependency)
-    typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
-    static range_fn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-      void* f = nullptr;
-      cudaDriverEntryPointQueryResult qr;
-      if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &qr) == cudaSuccess &&
-          qr == cudaDriverEntryPointSuccess)
-        fn = reinterpret_cast<range_fn>(f);
-      else
-        cudaGetLastError();
-    });
-    unsigned long long base = 0;
-    size_t size = 0;
-    if (fn && fn(&base, &size, (unsigned long long)(uintptr_t)p) == 0) {
-      out->base = base;
-      out->size = size;
-    }
   } else if (a.type == cudaMemoryTypeHost) {
     out->is_pinned = 1;
-  } else if (a.type == cudaMemoryTypeManaged) {
-    out->is_device = 1;
-    out->device = a.device;
   }
   return 0;
 }

@@ -15,8 +15,19 @@ def pytest_configure(config):
 
 @pytest.fixture
 def port():
-    # reference tests/test_basic.py:18-20
-    return random.randint(10000, 50000)
+    # reference tests/test_basic.py:18-20 draws random.randint(10000, 50000); that collides now and then
+    # with a live socket ("Address already in use"), so ask the kernel for a port that is free right now
+    import socket
+
+    for _ in range(20):
+        cand = random.randint(10000, 30000)  # below the ephemeral range (32768+): no outgoing socket lands here
+        with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
+            try:
+                s.bind(("127.0.0.1", cand))
+                return cand
+            except OSError:
+                continue
+    return random.randint(10000, 30000)
 
 
 @pytest.fixture(scope="session")

@@ -11,7 +11,7 @@ from starway_b200 import _core
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libstarway_hostsim.so")
 
 
-def load():
+def load(use_fastpath: bool = True):
     if not os.path.exists(LIB_PATH):
         raise ImportError(f"{LIB_PATH} missing: run `make hostsim`")
-    return _core.bind(ctypes.CDLL(LIB_PATH), lambda: int(os.environ.get("SW_SIM_DEVICE", "0")))
+    return _core.bind(ctypes.CDLL(LIB_PATH), lambda: int(os.environ.get("SW_SIM_DEVICE", "0")), use_fastpath=use_fastpath)

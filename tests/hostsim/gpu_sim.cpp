@@ -30,6 +30,7 @@ static std::mutex g_mu;
 struct DevAlloc {
   size_t size;
   std::string name;
+  uint64_t id;
 };
 static std::map<uintptr_t, DevAlloc> g_allocs;       // our "device" allocations (shm backed)
 static std::map<uintptr_t, size_t> g_opened;         // mappings opened through ipc_open
@@ -86,7 +87,7 @@ void* dev_alloc_raw(size_t bytes) {
     g_err = "mmap failed";
     return nullptr;
   }
-  g_allocs[(uintptr_t)p] = DevAlloc{sz, name};
+  g_allocs[(uintptr_t)p] = DevAlloc{sz, name, ((uint64_t)getpid() << 32) | (uint64_t)g_counter};
   return p;
 }
 void* dev_alloc(size_t bytes) { return dev_alloc_raw(bytes); }  // fresh shm is zero-filled
@@ -177,6 +178,7 @@ int ptr_info(const void* p, PtrInfo* out) {
       out->device = g_device;
       out->base = it->first;
       out->size = it->second.size;
+      out->buffer_id = it->second.id;
     }
   }
   return 0;
