@@ -163,7 +163,7 @@ int ptr_info(const void* p, PtrInfo* out) {
         out->buffer_id = buffer_id;
       } else if (mem_type == 1 /* CU_MEMORYTYPE_HOST: pinned / registered */) {
         out->is_pinned = 1;
-      } else if (mem_type == 3 /* unified */) {
+      } else if (mem_type == 4 /* CU_MEMORYTYPE_UNIFIED */) {
         out->is_device = 1;
         out->device = ordinal;
       }
