@@ -302,6 +302,8 @@ struct FlushOp {
   std::map<struct Ep*, uint64_t> marks;  // per-endpoint: sends with sseq < mark must be complete
 };
 
+struct Mapping;
+
 struct BulkJob {
   double t_enq = 0;
   bool host_side = false;  // source or destination is pinned host memory: use the SIMT copy
@@ -311,7 +313,7 @@ struct BulkJob {
   uint64_t dst = 0, cap = 0, tag = 0, len = 0;
   SwRts rts;
   uint64_t src = 0;
-  void* mapping = nullptr;
+  Mapping* mapping = nullptr;
   bool failed = false;
   int32_t fail_status = 0;
 };
@@ -420,6 +422,7 @@ struct BulkBlock {
   swgpu::event_t ev = nullptr, ev_start = nullptr;
   bool busy = false;
   std::vector<BulkJob> jobs;
+  std::vector<SwSeg> tma, simt;  // scratch, capacity retained across launches
   uint64_t bytes = 0;
 };
 struct PostCopy {  // device staging -> host user buffer after delivery
@@ -432,6 +435,19 @@ struct Mapping {
   void* base;
   uint32_t refs;
   double last_use;
+};
+struct MapKey {   // (exporting pid, cudaIpcMemHandle_t bytes)
+  uint32_t pid;
+  uint8_t handle[64];
+  bool operator==(const MapKey& o) const { return pid == o.pid && memcmp(handle, o.handle, 64) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = 0xcbf29ce484222325ull ^ k.pid;
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(k.handle);
+    for (int i = 0; i < 8; i++) h = (h ^ w[i]) * 0x100000001b3ull;
+    return (size_t)h;
+  }
 };
 
 constexpr uint32_t PUT_BATCH = 512;
@@ -473,7 +489,7 @@ struct Ctx {
   std::deque<PostCopy> post_copies;
   HostPool host_pool;
   StagingPool staging;
-  std::map<std::string, Mapping> mappings;  // key: pid + ipc handle bytes
+  std::unordered_map<MapKey, Mapping, MapKeyHash> mappings;  // node addresses are stable
   struct HandleEnt {
     uint64_t base;
     uint8_t handle[64];
@@ -1412,18 +1428,19 @@ bool poll_match(Ctx* c, Worker* w) {
 
 // ============================================================================ progress: rendezvous pulls
 void* resolve_mapping(Ctx* c, BulkJob& j) {
-  std::string key((const char*)j.rts.ipc_handle, 64);
-  key.append((const char*)&j.rts.src_pid, sizeof(j.rts.src_pid));
+  MapKey key;
+  key.pid = j.rts.src_pid;
+  memcpy(key.handle, j.rts.ipc_handle, 64);
   auto it = c->mappings.find(key);
   if (it == c->mappings.end()) {
     // Bound the cache (PyTorch's caching allocator hands out many small segments: a few hundred
     // distinct IPC handles are normal).  Opening/closing a mapping costs ~100s of us, so only
     // the least recently used idle quarter is dropped when the bound is hit.
     if (c->mappings.size() >= MAX_MAPPINGS) {
-      std::vector<std::pair<double, std::string>> idle;
+      std::vector<std::pair<double, MapKey>> idle;
       for (auto& kv : c->mappings)
         if (kv.second.refs == 0) idle.emplace_back(kv.second.last_use, kv.first);
-      std::sort(idle.begin(), idle.end());
+      std::sort(idle.begin(), idle.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
       size_t drop = std::max<size_t>(1, idle.size() / 4);
       for (size_t i = 0; i < drop && i < idle.size(); i++) {
         auto m = c->mappings.find(idle[i].second);
@@ -1440,16 +1457,12 @@ void* resolve_mapping(Ctx* c, BulkJob& j) {
   }
   it->second.refs++;
   it->second.last_use = now_s();
-  j.mapping = it->second.base;
+  j.mapping = &it->second;
   return it->second.base;
 }
 void release_mapping(Ctx* c, BulkJob& j) {
-  if (!j.mapping) return;
-  for (auto& kv : c->mappings)
-    if (kv.second.base == j.mapping) {
-      if (kv.second.refs) kv.second.refs--;
-      break;
-    }
+  (void)c;
+  if (j.mapping && j.mapping->refs) j.mapping->refs--;
   j.mapping = nullptr;
 }
 
@@ -1535,7 +1548,10 @@ bool pump_bulk(Ctx* c) {
   seg = std::max<uint64_t>(seg, std::max<uint64_t>(unit, 65536 / unit * unit));
   seg = std::min<uint64_t>(seg, 4u << 20);
   while ((b.bytes / seg) + 2 * b.jobs.size() + 2 > MAX_SEGS) seg *= 2;
-  std::vector<SwSeg> tma, simt;
+  std::vector<SwSeg>& tma = b.tma;
+  std::vector<SwSeg>& simt = b.simt;
+  tma.clear();
+  simt.clear();
   for (BulkJob& j : b.jobs) {
     uint64_t src = j.src, dst = j.dst, len = j.len;
     // receives into host memory were redirected to device staging at post time
