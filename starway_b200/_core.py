@@ -270,6 +270,8 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
 
         # -- submission helpers ------------------------------------------------
         def submit(self, post: Callable[[], int], entry: tuple) -> int:
+            if not self._h:
+                raise RuntimeError("starway_b200 context is closed")
             with self._lock:
                 op = post()
                 if not op:
@@ -415,6 +417,7 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
 
         def close(self):
             if self._h:
+                self._fp = None  # the C fast path holds the raw context pointer
                 self._stop = True
                 self._wake.set()
                 self._thread.join(timeout=2.0)
@@ -538,6 +541,8 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
                 ctx.ensure_reader(loop)
             fut = loop.create_future()
             ptr, n, mem, keep = as_buffer(buffer, True)
+            if not ctx._h:
+                raise RuntimeError("starway_b200 context is closed")
             with ctx._lock:
                 op = _post_recv(ctx._h, self._w, ptr, n, tag & _U64MASK, tag_mask & _U64MASK, mem)
                 if not op:
@@ -638,6 +643,8 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
                 ctx.ensure_reader(loop)
             fut = loop.create_future()
             ptr, n, mem, keep = as_buffer(buffer, False)
+            if not ctx._h:
+                raise RuntimeError("starway_b200 context is closed")
             with ctx._lock:
                 op = _post_send(ctx._h, self._w, client_ep._id, ptr, n, tag & _U64MASK, mem)
                 if not op:
@@ -716,6 +723,8 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
                 ctx.ensure_reader(loop)
             fut = loop.create_future()
             ptr, n, mem, keep = as_buffer(buffer, False)
+            if not ctx._h:
+                raise RuntimeError("starway_b200 context is closed")
             with ctx._lock:
                 op = _post_send(ctx._h, self._w, 0, ptr, n, tag & _U64MASK, mem)
                 if not op:

@@ -1874,8 +1874,10 @@ void drain_sq(Ctx* c) {
         SendOp* op = (SendOp*)it.p;
         int st = w->status.load(std::memory_order_acquire);
         if (st != SW_ST_RUNNING || w->close_phase != 0) {
-          // reference: submitted after close began -> UCS_ERR_NOT_CONNECTED (main.cpp:619-622)
-          complete(c, w, op->op_id, SW_OP_SEND, st == SW_ST_RUNNING ? SW_ERR_CANCELED : SW_ERR_NOT_CONNECTED);
+          // The op was accepted while the worker was running and close overtook it in the queue:
+          // like a mailbox-resident op in the reference it is cancelled (main.cpp:680-701).  Ops
+          // posted after close began are refused synchronously by sw_post_* (reference: RuntimeError).
+          complete(c, w, op->op_id, SW_OP_SEND, SW_ERR_CANCELED);
           delete op;
           break;
         }
@@ -1888,7 +1890,7 @@ void drain_sq(Ctx* c) {
         RecvOp* r = (RecvOp*)it.p;
         int st = w->status.load(std::memory_order_acquire);
         if (st != SW_ST_RUNNING || w->close_phase != 0) {
-          complete(c, w, r->op_id, SW_OP_RECV, st == SW_ST_RUNNING ? SW_ERR_CANCELED : SW_ERR_NOT_CONNECTED);
+          complete(c, w, r->op_id, SW_OP_RECV, SW_ERR_CANCELED);
           delete r;
           break;
         }
@@ -1899,8 +1901,7 @@ void drain_sq(Ctx* c) {
         FlushOp* f = (FlushOp*)it.p;
         int st = w->status.load(std::memory_order_acquire);
         if (st != SW_ST_RUNNING || w->close_phase != 0) {
-          complete(c, w, f->op_id, f->ep ? SW_OP_FLUSH_EP : SW_OP_FLUSH,
-                   st == SW_ST_RUNNING ? SW_ERR_CANCELED : SW_ERR_NOT_CONNECTED);
+          complete(c, w, f->op_id, f->ep ? SW_OP_FLUSH_EP : SW_OP_FLUSH, SW_ERR_CANCELED);
           delete f;
           break;
         }

@@ -35,3 +35,54 @@ def test_two_process_client_send_with_flush_good(sim_api, port):
 @pytest.mark.parametrize("seed", range(12))
 def test_random_schedule_vs_oracle(sim_api, port, seed):
     run(cb.case_random_schedule_vs_oracle(sim_api, port, seed, quiesce=0.002))
+
+
+def _proc_connect_and_die(port, q):
+    import os
+    import signal
+
+    api = cb.load_api("sim")
+
+    async def inner():
+        client = api.Client()
+        await client.aconnect(cb.SERVER_ADDR, port)
+        await client.asend(__import__("numpy").arange(100, dtype="uint8"), 5)  # eager: delivered
+        big = __import__("numpy").ones(1 << 20, dtype="uint8")
+        client.asend(big, 6)  # rendezvous: never matched before we die
+        await asyncio.sleep(0.2)
+        q.put("ready")
+        await asyncio.sleep(30)
+
+    try:
+        asyncio.run(inner())
+    finally:
+        os.kill(os.getpid(), signal.SIGKILL)
+
+
+def test_peer_killed_does_not_hang_close(sim_api, port):
+    """Failure handling the reference leaves to UCX: a peer that dies without closing must
+    not wedge the survivor — delivered eager data stays readable and aclose() returns."""
+    import multiprocessing as mp
+
+    import numpy as np
+
+    async def go():
+        server = sim_api.Server()
+        server.listen(cb.SERVER_ADDR, port)
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        p = ctx.Process(target=_proc_connect_and_die, args=(port, q))
+        p.start()
+        loop = asyncio.get_running_loop()
+        assert await loop.run_in_executor(None, q.get, True, 60) == "ready"
+        p.kill()
+        p.join()
+        buf = np.zeros(100, dtype=np.uint8)
+        assert await asyncio.wait_for(server.arecv(buf, 5, (1 << 64) - 1), 10) == (5, 100)
+        np.testing.assert_array_equal(buf, np.arange(100, dtype=np.uint8))
+        pending = server.arecv(np.zeros(8, dtype=np.uint8), 77, (1 << 64) - 1)
+        await asyncio.wait_for(server.aclose(), 15)
+        with pytest.raises(Exception, match="cancel"):
+            await pending
+
+    run(go())
