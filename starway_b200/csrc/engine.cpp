@@ -1966,10 +1966,14 @@ void progress_main(Ctx* c) {
     }
     if (active || inflight) {
       last_active = now_s();
+      if (!active)
+        for (int k = 0; k < 8; k++) __builtin_ia32_pause();  // polling device events: yield the core's pipeline
     } else {
       // The reference's worker threads spin at 100 % (main.cpp:361, 1126).  Here: spin while work is
       // outstanding or was seen recently, then back off progressively.
       double idle = now_s() - last_active;
+      // be a polite hyper-thread sibling: the Python thread of this rank may share the core
+      for (int k = 0; k < 32; k++) __builtin_ia32_pause();
       if (expecting && idle < 0.25) {
         if (idle > 0.002) sched_yield();
       } else if (idle > 1.0) {
