@@ -592,6 +592,58 @@ async def case_random_schedule_vs_oracle(api, port, seed, bufs=HostBufs, n_event
     return n_posted, n_unexp
 
 
+# ------------------------------------------------------------------ error paths beyond the reference's tests
+async def case_send_to_closed_peer_fails_cleanly(api, port):
+    """After the client closed, the server's endpoint stays listed (reference :53-56) but sends to it
+    fail (UCX: connection reset) instead of hanging; the server keeps working for other clients."""
+    server = api.Server()
+    server.listen(SERVER_ADDR, port)
+    c1, c2 = api.Client(), api.Client()
+    await c1.aconnect(SERVER_ADDR, port)
+    ep1 = next(iter(server.list_clients()))
+    await c2.aconnect(SERVER_ADDR, port)
+    ep2 = next(iter(server.list_clients() - {ep1}))
+    await c1.aclose()
+    await asyncio.sleep(0.05)
+    for n in (16, 100000):
+        try:
+            await asyncio.wait_for(server.asend(ep1, np.zeros(n, dtype=np.uint8), 1), 10)
+            raise AssertionError("send to a closed peer must fail")
+        except AssertionError:
+            raise
+        except Exception as e:
+            assert "reset" in str(e) or "not connected" in str(e), e
+    await asyncio.wait_for(server.aflush(), 10)  # nothing outstanding: flush still completes
+    buf = np.zeros(32, dtype=np.uint8)
+    f = c2.arecv(buf, 9, 0xFFFF)
+    await server.asend(ep2, np.arange(32, dtype=np.uint8), 9)
+    assert await f == (9, 32)
+    await c2.aclose()
+    await server.aclose()
+
+
+async def case_bad_address_blob(api, port):
+    client = api.Client()
+    try:
+        await asyncio.wait_for(client.aconnect_address(b"\x00" * 16), 5)
+        raise AssertionError("garbage address must not connect")
+    except AssertionError:
+        raise
+    except Exception:
+        pass
+    client2 = api.Client()
+    server = api.Server()
+    blob = bytearray(server.listen_address())
+    await server.aclose()           # the bootstrap socket is gone
+    try:
+        await asyncio.wait_for(client2.aconnect_address(bytes(blob)), 5)
+        raise AssertionError("stale address must not connect")
+    except AssertionError:
+        raise
+    except Exception as e:
+        assert "not connected" in str(e), e
+
+
 SINGLE_PROCESS_CASES = [
     case_server_listen_client_connect_close,
     case_worker_address_connection_roundtrip,
@@ -612,4 +664,6 @@ SINGLE_PROCESS_CASES = [
     case_shutdown_with_in_flight_ops,
     case_implicit_destruction_without_close,
     case_readme_quickstart,
+    case_send_to_closed_peer_fails_cleanly,
+    case_bad_address_blob,
 ]
