@@ -224,6 +224,11 @@ def run_ours(args):
                 marks.append(("e2e_step_end", time.monotonic()))
                 assert all(r == (TAG, msg) for r in res)
 
+        if args.no_e2e:
+            await client.aclose()
+            barrier()
+            await server.aclose()
+            return value, ms, st, clk, float("nan"), step_bytes, {}
         await timed_host(3)
         if world == 1:
             for s, d in zip(hsrc[0], hdst[0]):
@@ -398,6 +403,7 @@ def main():
     ap.add_argument("--msg-bytes", type=int, default=MSG_BYTES)
     ap.add_argument("--window", type=int, default=WINDOW)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (ncu launch lists of the device-resident steps)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -11,6 +11,13 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+    # the native pieces are built in-tree by `make` (== __graft_entry__.build()); build them on demand
+    needed = ["starway_b200/libstarway_b200.so", "starway_b200/_fastpath.so", "oracle/liboracle_tagmatch.so",
+              "oracle/libstarway_cpu.so", "tests/hostsim/libstarway_hostsim.so"]
+    if any(not os.path.exists(os.path.join(ROOT, p)) for p in needed):
+        import subprocess
+
+        subprocess.check_call(["make", "-C", ROOT, "-j", "8", "lib", "oracle", "hostsim"])
 
 
 @pytest.fixture
