@@ -315,7 +315,7 @@ def run_ours(args):
         "mmsg_per_s": round(world * window * args.steps / (ms * 1e-3) / 1e6, 4),
         "nvlink_roofline_frac": None if world == 1 else round(value / world / 900.0, 4),
         "clocks": clk,
-        "e2e": {"value": round(e2e_value, 2), "unit": "GB/s", "h2d_bytes_per_step": step_bytes, "d2h_bytes_per_step": step_bytes,
+        "e2e": {"value": None if args.no_e2e else round(e2e_value, 2), "unit": "GB/s", "h2d_bytes_per_step": step_bytes, "d2h_bytes_per_step": step_bytes,
                 "buffers": "pinned host NumPy arrays through Client.asend/Server.arecv", "rank0_breakdown": e2e_diag},
         "gpu_launches": gpu_launches,
         "roofline": roofline,

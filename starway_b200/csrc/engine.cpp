@@ -2484,8 +2484,9 @@ int sw_ep_info_get(sw_ctx* ctx, sw_worker_t wid, sw_ep_t epid, sw_ep_info* out) 
   return 0;
 }
 
-// reference evaluate_perf (main.cpp:452-467, 666-678): UCX's analytic estimate; here a
-// latency + size/bandwidth model from the measured curves (seconds)
+// reference evaluate_perf (main.cpp:452-467, 666-678) returns UCX's analytic time estimate for a
+// message size.  Here: latency + size / bandwidth with constants fitted to the measured curves
+// (profiles/r01_pingpong_*.jsonl one-way latencies, r01_sweep_*.jsonl asymptotic bandwidths), seconds.
 double sw_evaluate_perf(sw_ctx* ctx, sw_worker_t wid, sw_ep_t epid, size_t msg_size) {
   Ctx* c = (Ctx*)ctx;
   Worker* w = find_worker(c, wid);
@@ -2494,9 +2495,12 @@ double sw_evaluate_perf(sw_ctx* ctx, sw_worker_t wid, sw_ep_t epid, size_t msg_s
     return -1.0;
   }
   Ep* ep = epid ? find_ep(c, epid) : (w->eps.empty() ? nullptr : w->eps[0]);
-  bool local = !ep || ep->in_process || ep->peer_device == c->device;
-  double lat = msg_size <= SW_EAGER_MAX ? 12e-6 : 30e-6;
-  double bw = local ? 2.8e12 : 7.0e11;
+  const bool same_gpu = !ep || ep->in_process || ep->peer_device == c->device;
+  const bool eager = msg_size <= (size_t)c->opt_eager_max.load();
+  // one-way: put launch + match launch (+ bulk launch and FIN for rendezvous) + asyncio wake-up
+  const double lat = same_gpu ? (eager ? 47e-6 : 62e-6) : (eager ? 49e-6 : 68e-6);
+  // HBM copy (3.1 TB/s payload) on one GPU, NVLink pull (0.74 TB/s) between GPUs
+  const double bw = same_gpu ? 3.1e12 : 7.4e11;
   return lat + (double)msg_size / bw;
 }
 
