@@ -378,6 +378,7 @@ struct Worker {
   swgpu::event_t mev = nullptr, mev_start = nullptr;
   bool match_inflight = false;
   uint32_t match_posts_inflight = 0;
+  SwMatchScalars msc;       // queue cursors reported by the last match launch (handed back by value)
   std::vector<Ep*> eps;  // index == Ep::index
   // receives
   std::deque<RecvOp*> new_posts;
@@ -657,6 +658,10 @@ bool worker_alloc_device(Ctx* c, Worker* w) {
   w->mout = (SwMatchOut*)swgpu::host_alloc(sizeof(SwMatchOut));
   w->mev = swgpu::event_create(1);
   w->mev_start = swgpu::event_create(1);
+  memset(&w->msc, 0, sizeof(w->msc));
+  w->msc.n_free_small = (uint32_t)c->opt_heap_small.load();
+  w->msc.n_free_big = (uint32_t)c->opt_heap_big.load();
+  w->msc.valid = 1;
   if (!w->min || !w->mout || !w->mev) {
     set_error(std::string("worker pinned alloc: ") + swgpu::last_error());
     return false;
@@ -1350,7 +1355,16 @@ bool pump_match(Ctx* c, Worker* w) {
   if (prof) swgpu::event_record(w->mev_start, c->s_match);
   uint32_t max_jobs = np + (uint32_t)std::min<uint64_t>(unseen, SW_MAX_ARRIVALS);
   trace(c, "match_launch", np, unseen);
-  if (swgpu::launch_match_deliver(c->s_match, w->mstate, in, w->mout, max_jobs) != 0)
+  const SwMatchScalars* sc = nullptr;
+  if (w->eps.size() <= SW_SC_EPS) {
+    for (Ep* ep : w->eps) {
+      w->msc.ring_cons[ep->index] = ep->in->consumed.load(std::memory_order_relaxed);  // == device ring cursor
+      w->msc.ring_base[ep->index] = (uint64_t)(uintptr_t)ep->ring;
+      w->msc.ring_slots[ep->index] = ep->ring_slots;
+    }
+    sc = &w->msc;
+  }
+  if (swgpu::launch_match_deliver(c->s_match, w->mstate, in, w->mout, max_jobs, sc) != 0)
     fprintf(stderr, "starway_b200: match/deliver launch failed: %s\n", swgpu::last_error());
   swgpu::event_record(w->mev, c->s_match);
   w->match_inflight = true;
@@ -1380,6 +1394,15 @@ bool poll_match(Ctx* c, Worker* w) {
     }
   }
   if (out->err) fprintf(stderr, "starway_b200: device matcher reported inconsistency 0x%x\n", out->err);
+  {
+    // keep the ring entries (filled per launch), take the queue cursors the kernel reported
+    SwMatchScalars next = out->sc;
+    memcpy(next.ring_cons, w->msc.ring_cons, sizeof(next.ring_cons));
+    memcpy(next.ring_base, w->msc.ring_base, sizeof(next.ring_base));
+    memcpy(next.ring_slots, w->msc.ring_slots, sizeof(next.ring_slots));
+    next.valid = out->sc.valid;
+    w->msc = next;
+  }
   // credits first: the slots are free again
   bool stalled = false;
   for (Ep* ep : w->eps) {

@@ -74,7 +74,9 @@ int launch_put(stream_t s, const SwPutDesc* descs, uint32_t n);
 int launch_match(stream_t s, SwMatchState* st, const SwMatchIn* in, SwMatchOut* out);
 int launch_deliver(stream_t s, SwMatchState* st, SwMatchOut* out, uint32_t max_jobs);
 // match + deliver for one batch: a single fused launch when the batch is small
-int launch_match_deliver(stream_t s, SwMatchState* st, const SwMatchIn* in, SwMatchOut* out, uint32_t max_jobs);
+// `sc`: the queue cursors reported by the previous launch of this worker (nullptr: read them on the device)
+int launch_match_deliver(stream_t s, SwMatchState* st, const SwMatchIn* in, SwMatchOut* out, uint32_t max_jobs,
+                         const SwMatchScalars* sc);
 int launch_bulk(stream_t s, const SwSeg* segs, uint32_t nseg, const BulkTuning* tune);
 
 }  // namespace swgpu

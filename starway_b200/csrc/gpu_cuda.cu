@@ -368,7 +368,11 @@ int launch_put(stream_t s, const SwPutDesc* descs, uint32_t n) {
   return 0;
 }
 
-static void fill_match_args(SwMatchArgs& a, const SwMatchIn* in) {
+static void fill_match_args(SwMatchArgs& a, const SwMatchIn* in, const SwMatchScalars* sc = nullptr) {
+  if (sc)
+    a.sc = *sc;
+  else
+    memset(&a.sc, 0, sizeof(a.sc));
   a.n_posts = in->n_posts;
   a.n_eps = in->n_eps;
   a.max_arrivals = in->max_arrivals;
@@ -386,10 +390,11 @@ int launch_match(stream_t s, SwMatchState* st, const SwMatchIn* in, SwMatchOut* 
   return 0;
 }
 
-int launch_match_deliver(stream_t s, SwMatchState* st, const SwMatchIn* in, SwMatchOut* out, uint32_t max_jobs) {
-  if (max_jobs <= 192) {
+int launch_match_deliver(stream_t s, SwMatchState* st, const SwMatchIn* in, SwMatchOut* out, uint32_t max_jobs,
+                         const SwMatchScalars* sc) {
+  if (max_jobs <= SW_FUSED_MAX_JOBS) {
     SwMatchArgs a;
-    fill_match_args(a, in);
+    fill_match_args(a, in, sc);
     sw_match_deliver_kernel<<<1, SW_FUSED_THREADS, 0, (cudaStream_t)s>>>(st, in, out, a);
     SW_CUDA(cudaGetLastError());
     return 0;

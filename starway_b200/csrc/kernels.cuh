@@ -220,11 +220,11 @@ __device__ __forceinline__ uint64_t sw_shfl64(uint64_t v, int src) {
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 
-__device__ __forceinline__ void sw_emit_job(SwMatchState* st, SwMatchRegs& r, uint32_t lane, uint64_t src,
+__device__ __forceinline__ void sw_emit_job(SwJob* jobs, SwMatchRegs& r, uint32_t lane, uint64_t src,
                                             uint64_t dst, uint64_t len, uint64_t op, uint64_t tag, uint64_t msg_len,
                                             int32_t status, uint32_t kind) {
   if (lane == 0) {
-    SwJob* j = &st->jobs[r.n_jobs];
+    SwJob* j = &jobs[r.n_jobs];
     j->src = src;
     j->dst = dst;
     j->len = len;
@@ -239,12 +239,12 @@ __device__ __forceinline__ void sw_emit_job(SwMatchState* st, SwMatchRegs& r, ui
 
 // Hand a matched message to the receive (buf, cap, op).  `payload` points at the eager
 // bytes or at the SwRts (slot payload or heap block).
-__device__ __forceinline__ void sw_emit_match(SwMatchState* st, SwMatchOut* out, SwMatchRegs& r, uint32_t lane,
+__device__ __forceinline__ void sw_emit_match(SwJob* jobs, SwMatchOut* out, SwMatchRegs& r, uint32_t lane,
                                               bool is_rts, uint64_t payload, uint64_t stag, uint64_t msg_len,
                                               uint32_t ep, uint64_t buf, uint64_t cap, uint64_t op) {
   const bool trunc = msg_len > cap;
   if (!is_rts) {
-    sw_emit_job(st, r, lane, payload, buf, trunc ? 0 : msg_len, op, stag, msg_len,
+    sw_emit_job(jobs, r, lane, payload, buf, trunc ? 0 : msg_len, op, stag, msg_len,
                 trunc ? SW_ERR_MESSAGE_TRUNCATED : SW_OK, SW_JOB_DELIVER);
   } else {
     SwRndvRec* rec = &out->rndv[r.n_rndv];
@@ -271,26 +271,43 @@ constexpr uint32_t SW_INLINE_POSTS = 32;
 struct SwMatchArgs {
   uint32_t n_posts, n_eps, max_arrivals, pad;
   uint64_t produced[SW_INLINE_EPS];
+  SwMatchScalars sc;   // sc.valid: queue cursors + ring cursors by value (host mirror of the last launch)
   SwPost posts[SW_INLINE_POSTS];
 };
+static_assert(SW_SC_EPS == SW_INLINE_EPS, "cursor mirror covers the inline endpoints");
 
-__device__ __forceinline__ void sw_match_body(SwMatchState* __restrict__ st, const SwMatchIn* __restrict__ in,
+// returns the number of jobs emitted into `jobs`
+__device__ __forceinline__ uint32_t sw_match_body(SwMatchState* __restrict__ st, const SwMatchIn* __restrict__ in,
                                               SwMatchOut* __restrict__ out, const SwMatchArgs& a,
-                                              const uint32_t lane) {
+                                              SwJob* __restrict__ jobs, const uint32_t lane) {
   SwMatchRegs r;
-  r.p_head = st->p_head;
-  r.p_tail = st->p_tail;
-  r.u_head = st->u_head;
-  r.u_tail = st->u_tail;
-  r.p_count = st->p_count;
-  r.u_count = st->u_count;
+  const bool by_value = a.sc.valid != 0 && a.n_eps <= SW_SC_EPS;
+  if (by_value) {
+    r.p_head = a.sc.p_head;
+    r.p_tail = a.sc.p_tail;
+    r.u_head = a.sc.u_head;
+    r.u_tail = a.sc.u_tail;
+    r.p_count = a.sc.p_count;
+    r.u_count = a.sc.u_count;
+    r.n_free_small = a.sc.n_free_small;
+    r.n_free_big = a.sc.n_free_big;
+    r.n_pend_small = a.sc.n_pend_small;
+    r.n_pend_big = a.sc.n_pend_big;
+  } else {
+    r.p_head = st->p_head;
+    r.p_tail = st->p_tail;
+    r.u_head = st->u_head;
+    r.u_tail = st->u_tail;
+    r.p_count = st->p_count;
+    r.u_count = st->u_count;
+    r.n_free_small = st->n_free_small;
+    r.n_free_big = st->n_free_big;
+    r.n_pend_small = st->n_pend_small;
+    r.n_pend_big = st->n_pend_big;
+  }
   r.n_jobs = 0;
   r.n_rndv = 0;
   r.err = 0;
-  r.n_free_small = st->n_free_small;
-  r.n_free_big = st->n_free_big;
-  r.n_pend_small = st->n_pend_small;
-  r.n_pend_big = st->n_pend_big;
 
   // deferred heap frees of the previous launch become allocatable now (its deliver
   // kernel has finished: same stream)
@@ -479,7 +496,7 @@ __device__ __forceinline__ void sw_match_body(SwMatchState* __restrict__ st, con
         }
         if (found) {
           r.u_count--;
-          sw_emit_match(st, out, r, lane, (f_meta & SW_UMETA_RTS) != 0, f_data, f_tag, f_len,
+          sw_emit_match(jobs, out, r, lane, (f_meta & SW_UMETA_RTS) != 0, f_data, f_tag, f_len,
                         f_meta & SW_UMETA_EPMASK, buf, cap, op);
           // the heap block is released one launch later (after this launch's deliver kernel)
           if (lane == 0) {
@@ -495,7 +512,7 @@ __device__ __forceinline__ void sw_match_body(SwMatchState* __restrict__ st, con
         } else {
           if (r.p_tail - r.p_head >= SW_PQ_CAP) {
             r.err |= 2;   // posted queue overflow (the host throttles before this can happen)
-            sw_emit_job(st, r, lane, 0, 0, 0, op, 0, 0, SW_ERR_NO_MEMORY, SW_JOB_DELIVER);
+            sw_emit_job(jobs, r, lane, 0, 0, 0, op, 0, 0, SW_ERR_NO_MEMORY, SW_JOB_DELIVER);
           } else {
             if (lane == 0) {
               const uint64_t s = r.p_tail & PQM;
@@ -543,13 +560,13 @@ __device__ __forceinline__ void sw_match_body(SwMatchState* __restrict__ st, con
     const uint32_t n_eps = a.n_eps;
     uint32_t budget = min(a.max_arrivals, SW_MAX_ARRIVALS);
     uint32_t consumed_total = 0;
-    const uint32_t rr = n_eps ? (st->rr_ep % n_eps) : 0;
+    const uint32_t rr = n_eps ? ((by_value ? a.sc.rr_ep : st->rr_ep) % n_eps) : 0;
     for (uint32_t e = 0; e < n_eps; e++) {
       const uint32_t ep = (rr + e) % n_eps;
-      uint64_t cons = st->ring_cons[ep];
+      uint64_t cons = by_value ? a.sc.ring_cons[ep] : st->ring_cons[ep];
       const uint64_t prod = (n_eps <= SW_INLINE_EPS) ? a.produced[ep] : in->produced[ep];
-      const uint64_t ring = st->ring_base[ep];
-      const uint64_t smask = st->ring_slots[ep] - 1;
+      const uint64_t ring = by_value ? a.sc.ring_base[ep] : st->ring_base[ep];
+      const uint64_t smask = (by_value ? a.sc.ring_slots[ep] : st->ring_slots[ep]) - 1;
       bool blocked = false;
       while (cons < prod && budget > 0 && !blocked) {
         const uint32_t chunk = static_cast<uint32_t>(min(static_cast<uint64_t>(min(32u, budget)), prod - cons));
@@ -602,7 +619,7 @@ __device__ __forceinline__ void sw_match_body(SwMatchState* __restrict__ st, con
           if (in_k) {
             const bool trunc = a_len > w_cap;
             if (!a_rts) {
-              SwJob* jb = &st->jobs[r.n_jobs + __popc(eager_m & lt)];
+              SwJob* jb = &jobs[r.n_jobs + __popc(eager_m & lt)];
               jb->src = a_slot + SW_SLOT_HDR;
               jb->dst = w_buf;
               jb->len = trunc ? 0 : a_len;
@@ -694,7 +711,7 @@ __device__ __forceinline__ void sw_match_body(SwMatchState* __restrict__ st, con
           }
           if (found) {
             r.p_count--;
-            sw_emit_match(st, out, r, lane, is_rts, payload, stag, mlen, ep, f_buf, f_cap, f_op);
+            sw_emit_match(jobs, out, r, lane, is_rts, payload, stag, mlen, ep, f_buf, f_cap, f_op);
           } else {
             // unexpected: park the payload (or the RTS descriptor) on the heap, free the slot
             const uint64_t need = is_rts ? sizeof(SwRts) : mlen;
@@ -713,7 +730,7 @@ __device__ __forceinline__ void sw_match_body(SwMatchState* __restrict__ st, con
               r.n_free_small--;
             const uint64_t haddr = big ? reinterpret_cast<uint64_t>(st->heap_big) + uint64_t(blk) * SW_HEAP_BIG_BYTES
                                        : reinterpret_cast<uint64_t>(st->heap_small) + uint64_t(blk) * SW_HEAP_SMALL_BYTES;
-            sw_emit_job(st, r, lane, payload, haddr, need, 0, stag, mlen, SW_OK, SW_JOB_STASH);
+            sw_emit_job(jobs, r, lane, payload, haddr, need, 0, stag, mlen, SW_OK, SW_JOB_STASH);
             if (lane == 0) {
               const uint64_t s = r.u_tail & UQM;
               st->u_tag[s] = stag;
@@ -743,6 +760,7 @@ __device__ __forceinline__ void sw_match_body(SwMatchState* __restrict__ st, con
     r.p_head = wb;
     if (lane == 0) {
       st->rr_ep = rr + 1;
+      out->sc.rr_ep = rr + 1;
       out->n_arrivals = consumed_total;
     }
   }
@@ -766,13 +784,25 @@ __device__ __forceinline__ void sw_match_body(SwMatchState* __restrict__ st, con
     out->err = r.err;
     out->heap_small_free = r.n_free_small;
     out->heap_big_free = r.n_free_big;
+    out->sc.p_head = r.p_head;
+    out->sc.p_tail = r.p_tail;
+    out->sc.u_head = r.u_head;
+    out->sc.u_tail = r.u_tail;
+    out->sc.p_count = r.p_count;
+    out->sc.u_count = r.u_count;
+    out->sc.n_free_small = r.n_free_small;
+    out->sc.n_free_big = r.n_free_big;
+    out->sc.n_pend_small = r.n_pend_small;
+    out->sc.n_pend_big = r.n_pend_big;
+    out->sc.valid = 1;
   }
+  return r.n_jobs;
 }
 
 __global__ void __launch_bounds__(32) sw_match_kernel(SwMatchState* __restrict__ st, const SwMatchIn* __restrict__ in,
                                                       SwMatchOut* __restrict__ out,
                                                       const __grid_constant__ SwMatchArgs a) {
-  sw_match_body(st, in, out, a, threadIdx.x);
+  (void)sw_match_body(st, in, out, a, st->jobs, threadIdx.x);
 }
 
 __device__ __forceinline__ void sw_deliver_one(const SwJob& j, SwMatchOut* __restrict__ out, uint32_t i,
@@ -793,16 +823,22 @@ __device__ __forceinline__ void sw_deliver_one(const SwJob& j, SwMatchOut* __res
 // Fused variant for small batches: warp 0 matches, then the whole CTA delivers -- one launch
 // instead of two on the latency-critical path.
 constexpr uint32_t SW_FUSED_THREADS = 512;
+constexpr uint32_t SW_FUSED_MAX_JOBS = 192;   // the host uses the fused launch only for batches this small
 __global__ void __launch_bounds__(SW_FUSED_THREADS) sw_match_deliver_kernel(SwMatchState* __restrict__ st,
                                                                             const SwMatchIn* __restrict__ in,
                                                                             SwMatchOut* __restrict__ out,
                                                                             const __grid_constant__ SwMatchArgs a) {
+  // the job list of a fused launch lives in shared memory: no global round trip between the phases
+  __shared__ SwJob s_jobs[SW_FUSED_MAX_JOBS];
+  __shared__ uint32_t s_njobs;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0) sw_match_body(st, in, out, a, lane);
-  __threadfence_block();
+  if (warp == 0) {
+    const uint32_t nj = sw_match_body(st, in, out, a, s_jobs, lane);
+    if (lane == 0) s_njobs = nj;
+  }
   __syncthreads();
-  const uint32_t n = st->n_jobs;
-  for (uint32_t i = warp; i < n; i += SW_FUSED_THREADS / 32) sw_deliver_one(st->jobs[i], out, i, lane);
+  const uint32_t n = s_njobs;
+  for (uint32_t i = warp; i < n; i += SW_FUSED_THREADS / 32) sw_deliver_one(s_jobs[i], out, i, lane);
 }
 
 // ------------------------------------------------------------------ deliver

@@ -139,6 +139,21 @@ struct SwRndvRec {  // pinned host: match kernel -> host (receiver pulls the pay
   SwRts rts;
 };
 
+// Queue cursors of one worker.  The match kernel is the only writer; it reports them after every
+// launch (SwMatchOut::sc) and the host hands them back as kernel parameters for the next launch, so a
+// launch does not start with a chain of dependent global loads.
+constexpr uint32_t SW_SC_EPS = 8;
+struct SwMatchScalars {
+  uint64_t p_head, p_tail, u_head, u_tail;
+  uint32_t p_count, u_count;
+  uint32_t n_free_small, n_free_big, n_pend_small, n_pend_big;
+  uint32_t rr_ep;
+  uint32_t valid;                     // 0: the kernel reads the cursors from SwMatchState
+  uint64_t ring_cons[SW_SC_EPS];
+  uint64_t ring_base[SW_SC_EPS];
+  uint32_t ring_slots[SW_SC_EPS];
+};
+
 struct SwMatchOut {  // pinned host
   uint32_t n_jobs;
   uint32_t n_rndv;
@@ -149,6 +164,7 @@ struct SwMatchOut {  // pinned host
   uint32_t heap_small_free;
   uint32_t heap_big_free;
   uint64_t consumed[SW_MAX_EPS];  // slots consumed so far on each inbound ring
+  SwMatchScalars sc;              // queue cursors after this launch
   SwCqe cq[SW_MAX_JOBS];
   SwRndvRec rndv[SW_MAX_JOBS];
 };

@@ -394,6 +394,18 @@ int launch_match(stream_t, SwMatchState* st, const SwMatchIn* in, SwMatchOut* ou
   out->n_unexp = st->u_count;
   out->heap_small_free = st->n_free_small;
   out->heap_big_free = st->n_free_big;
+  out->sc.p_head = st->p_head;
+  out->sc.p_tail = st->p_tail;
+  out->sc.u_head = st->u_head;
+  out->sc.u_tail = st->u_tail;
+  out->sc.p_count = st->p_count;
+  out->sc.u_count = st->u_count;
+  out->sc.n_free_small = st->n_free_small;
+  out->sc.n_free_big = st->n_free_big;
+  out->sc.n_pend_small = st->n_pend_small;
+  out->sc.n_pend_big = st->n_pend_big;
+  out->sc.rr_ep = st->rr_ep;
+  out->sc.valid = 1;
   return 0;
 }
 
@@ -411,7 +423,8 @@ int launch_deliver(stream_t, SwMatchState* st, SwMatchOut* out, uint32_t) {
   return 0;
 }
 
-int launch_match_deliver(stream_t s, SwMatchState* st, const SwMatchIn* in, SwMatchOut* out, uint32_t max_jobs) {
+int launch_match_deliver(stream_t s, SwMatchState* st, const SwMatchIn* in, SwMatchOut* out, uint32_t max_jobs,
+                         const SwMatchScalars*) {
   launch_match(s, st, in, out);
   return launch_deliver(s, st, out, max_jobs);
 }
