@@ -217,15 +217,16 @@ struct StagingPool {
   size_t cached = 0;
   static constexpr size_t MAX_CACHED = 6ull << 30;
   void* get(size_t n, size_t* got) {
-    auto it = free_blocks.lower_bound(n);
-    if (it != free_blocks.end() && it->first <= 2 * n + 4096) {
+    const size_t need = (n + 0xFFFFF) & ~(size_t)0xFFFFF;  // blocks come in 1 MiB granules
+    auto it = free_blocks.lower_bound(need);
+    if (it != free_blocks.end() && it->first <= 2 * need) {
       void* p = it->second;
       *got = it->first;
       cached -= it->first;
       free_blocks.erase(it);
       return p;
     }
-    size_t sz = (n + 0xFFFFF) & ~(size_t)0xFFFFF;  // 1 MiB granules
+    size_t sz = need;
     void* p = swgpu::dev_alloc_raw(sz);
     if (!p && !free_blocks.empty()) {
       destroy();

@@ -644,6 +644,74 @@ async def case_bad_address_blob(api, port):
         assert "not connected" in str(e), e
 
 
+async def case_multi_sender_invariants(api, port, seed=0, bufs=HostBufs, n_clients=3, per_client=150):
+    """Several senders, mixed eager / rendezvous sizes, wildcard and per-sender masked receives posted
+    concurrently.  Cross-sender order is unspecified (Appendix A.3d), so this checks invariants:
+    every message is delivered exactly once with the right bytes, every receive got a tag its mask
+    accepts, and per sender the messages land on receives in posting order (non-overtaking)."""
+    rng = np.random.default_rng(seed)
+    server = api.Server()
+    server.listen(SERVER_ADDR, port)
+    clients = [api.Client() for _ in range(n_clients)]
+    for c in clients:
+        await c.aconnect(SERVER_ADDR, port)
+    sizes = [1, 64, 700, 8128, 8129, 40000, 300000]
+
+    def content(c, i, n):
+        return ((np.arange(n, dtype=np.uint32) * 2654435761 + c * 977 + i * 131) >> 13).astype(np.uint8)
+
+    msgs = {c: [int(rng.choice(sizes)) for _ in range(per_client)] for c in range(n_clients)}
+    total = n_clients * per_client
+    # receives: some masked to one sender (tag high half = sender id), the rest wildcard.  Masked
+    # receives are posted first: an earlier-posted receive wins, so a wildcard can never take a message
+    # a masked receive still needs (which would leave that receive without a sender).
+    n_masked = {c: int(rng.integers(per_client // 4, per_client // 2)) for c in range(n_clients)}
+    masked = [("masked", c) for c in range(n_clients) for _ in range(n_masked[c])]
+    rng.shuffle(masked)
+    plan = [tuple(m) for m in masked] + [("wild", None)] * (total - len(masked))
+    plan = [(k, None if c is None else int(c)) for k, c in plan]
+    cap = max(sizes)
+    rbufs, futs = [], []
+    for kind, c in plan:
+        b = bufs.alloc(cap)
+        rbufs.append(b)
+        bufs.sync()
+        if kind == "masked":
+            futs.append(server.arecv(b, c << 32, 0xFFFFFFFF00000000))
+        else:
+            futs.append(server.arecv(b, 0, 0))
+
+    keep = []
+
+    async def sender(c):
+        for i, n in enumerate(msgs[c]):
+            t = bufs.from_np(content(c, i, n))
+            keep.append(t)
+            bufs.sync()
+            await clients[c].asend(t, (c << 32) | i)
+        await clients[c].aflush()
+
+    await asyncio.gather(*[sender(c) for c in range(n_clients)])
+    res = [await asyncio.wait_for(f, 60) for f in futs]
+    bufs.sync()
+    seen = set()
+    last = {c: -1 for c in range(n_clients)}
+    for (kind, want_c), (tag, length), b in zip(plan, res, rbufs):
+        c, i = tag >> 32, tag & 0xFFFFFFFF
+        assert (c, i) not in seen
+        seen.add((c, i))
+        if kind == "masked":
+            assert c == want_c
+        assert length == msgs[c][i]
+        assert i > last[c], f"sender {c}: message {i} overtook {last[c]}"
+        last[c] = i
+        np.testing.assert_array_equal(bufs.to_np(b)[:length], content(c, i, length))
+    assert len(seen) == total
+    for c in clients:
+        await c.aclose()
+    await server.aclose()
+
+
 SINGLE_PROCESS_CASES = [
     case_server_listen_client_connect_close,
     case_worker_address_connection_roundtrip,

@@ -208,6 +208,37 @@ def test_random_schedules_vs_oracle(cuda_api, port, seed):
     run(cb.case_random_schedule_vs_oracle(cuda_api, port, seed, Dev))
 
 
+def _dev_bufs():
+    torch = torch_cuda()
+
+    class Dev:
+        @staticmethod
+        def alloc(cap):
+            return torch.full((cap,), 0xEE, dtype=torch.uint8, device="cuda")
+
+        @staticmethod
+        def from_np(a):
+            return torch.from_numpy(a).cuda()
+
+        @staticmethod
+        def to_np(b):
+            return b.cpu().numpy()
+
+        sync = staticmethod(torch.cuda.synchronize)
+
+    return Dev
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_multi_sender_invariants_device(cuda_api, port, seed):
+    run(cb.case_multi_sender_invariants(cuda_api, port, seed, _dev_bufs()))
+
+
+@pytest.mark.parametrize("seed", [3])
+def test_multi_sender_invariants_host(cuda_api, port, seed):
+    run(cb.case_multi_sender_invariants(cuda_api, port, seed))
+
+
 def test_unexpected_flood_out_of_order(cuda_api, port):
     """More unexpected eager messages than ring slots (1024): the matcher parks them on the
     device heap, credits flow back, and receives posted in REVERSE tag order still pair up."""

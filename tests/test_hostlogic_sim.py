@@ -86,3 +86,8 @@ def test_peer_killed_does_not_hang_close(sim_api, port):
             await pending
 
     run(go())
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_multi_sender_invariants(sim_api, port, seed):
+    run(cb.case_multi_sender_invariants(sim_api, port, seed))
