@@ -379,6 +379,7 @@ struct Worker {
   swgpu::event_t mev = nullptr, mev_start = nullptr;
   bool match_inflight = false;
   uint32_t match_posts_inflight = 0;
+  uint64_t stall_unseen = 0;
   SwMatchScalars msc;       // queue cursors reported by the last match launch (handed back by value)
   std::vector<Ep*> eps;  // index == Ep::index
   // receives
@@ -1348,7 +1349,11 @@ bool pump_match(Ctx* c, Worker* w) {
     uint64_t seen = ep->in->consumed.load(std::memory_order_relaxed);
     if (p > seen) unseen += p - seen;
   }
-  if (np == 0 && (unseen == 0 || (w->match_posts_inflight == 0xFFFFFFFFu && !stalled_retry))) return false;
+  // a launch that consumed nothing (rings stalled on the unexpected heap) is repeated only when
+  // something changed: new receives, or new slots on any ring
+  if (np == 0 && (unseen == 0 || (w->match_posts_inflight == 0xFFFFFFFFu && !stalled_retry && unseen == w->stall_unseen)))
+    return false;
+  w->stall_unseen = unseen;
   in->n_posts = np;
   in->n_eps = (uint32_t)w->eps.size();
   in->max_arrivals = SW_MAX_ARRIVALS;

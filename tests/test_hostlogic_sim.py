@@ -91,3 +91,40 @@ def test_peer_killed_does_not_hang_close(sim_api, port):
 @pytest.mark.parametrize("seed", range(4))
 def test_multi_sender_invariants(sim_api, port, seed):
     run(cb.case_multi_sender_invariants(sim_api, port, seed))
+
+
+def test_stalled_ring_does_not_block_other_senders(sim_api, port):
+    """Unexpected-heap exhaustion back-pressures ONE ring; traffic of other endpoints that matches
+    posted receives must still flow (no head-of-line blocking across senders)."""
+    import numpy as np
+
+    async def go():
+        ctx = sim_api.get_context()
+        old = ctx.get_option("heap_big_blocks")
+        ctx.set_option("heap_big_blocks", 2)
+        try:
+            server = sim_api.Server()
+            server.listen(cb.SERVER_ADDR, port)
+        finally:
+            ctx.set_option("heap_big_blocks", old)
+        a, b = sim_api.Client(), sim_api.Client()
+        await a.aconnect(cb.SERVER_ADDR, port)
+        await b.aconnect(cb.SERVER_ADDR, port)
+        want = np.zeros(4096, dtype=np.uint8)
+        fut = server.arecv(want, 0x77, (1 << 64) - 1)
+        floods = [asyncio.ensure_future(a.asend(np.full(4096, i, dtype=np.uint8), 0x10 + i)) for i in range(10)]
+        await asyncio.sleep(0.2)  # ring A is now stalled behind a full heap
+        await b.asend(np.full(4096, 0xAB, dtype=np.uint8), 0x77)
+        assert await asyncio.wait_for(fut, 10) == (0x77, 4096)
+        assert (want == 0xAB).all()
+        # draining the flood releases the stall, in order
+        for i in range(10):
+            buf = np.zeros(4096, dtype=np.uint8)
+            assert await asyncio.wait_for(server.arecv(buf, 0, 0), 10) == (0x10 + i, 4096)
+            assert (buf == i).all()
+        await asyncio.gather(*floods)
+        await a.aclose()
+        await b.aclose()
+        await server.aclose()
+
+    run(go())
