@@ -1340,8 +1340,6 @@ bool pump_match(Ctx* c, Worker* w) {
   }
   // arrivals can only make progress when something new happened: new slots, or new
   // receives that may unblock a ring stalled on the unexpected heap
-  static thread_local std::unordered_map<Worker*, uint64_t> dummy;
-  (void)dummy;
   bool stalled_retry = np > 0;
   uint64_t unseen = 0;
   for (Ep* ep : w->eps) {

@@ -1,11 +1,13 @@
 // starway_b200 — hand-written sm_100a kernels for the tagged-messaging hot path.
 //
 //   sw_put_kernel       eager / RTS put: vectorised stores into the peer's inbound ring
+//   sw_put_inline_kernel  same, descriptors + RTS payloads as kernel parameters (batches <= 32)
 //                       (replaces the eager leg of ucp_tag_send_nbx, reference main.cpp:370,1136)
 //   sw_match_kernel     device-resident posted / unexpected queues + tag matching
 //                       (replaces ucp_tag_recv_nbx + the matching inside ucp_worker_progress,
 //                        reference main.cpp:404,1172,362,1127)
 //   sw_deliver_kernel   slot/heap -> user buffer copies + completion records
+//   sw_match_deliver_kernel  both in one launch for small batches (job list in shared memory)
 //   sw_bulk_tma_kernel  rendezvous / loopback bulk copy, cp.async.bulk global->smem->global
 //                       with an mbarrier pipeline (replaces the rendezvous leg of ucp_tag_send_nbx)
 //   sw_bulk_simt_kernel generic-alignment bulk copy (fallback + comparison)

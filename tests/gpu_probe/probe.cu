@@ -564,6 +564,58 @@ static void bench_latency(FILE* json) {
   }
 }
 
+// ------------------------------------------------------------------ tuning sweep of the TMA bulk kernel
+static void bench_tune(FILE* json) {
+  const size_t N = 64u << 20;
+  uint8_t* a = (uint8_t*)dev_alloc(N);
+  uint8_t* b = (uint8_t*)dev_alloc(N);
+  uint8_t* remote = nullptr;
+  if (device_count() > 1) {
+    CK(cudaSetDevice(1));
+    CK(cudaMalloc(&remote, N));
+    CK(cudaMemset(remote, 1, N));
+    CK(cudaDeviceEnablePeerAccess(0, 0));
+    CK(cudaSetDevice(0));
+    CK(cudaDeviceEnablePeerAccess(1, 0));
+  }
+  stream_t st = stream_create();
+  SwSeg* segs = (SwSeg*)host_alloc(sizeof(SwSeg) * 65536);
+  const size_t FLUSH = 256u << 20;
+  void* flush = dev_alloc(FLUSH);
+  for (int where = 0; where < (remote ? 2 : 1); where++) {
+    for (size_t bytes : {size_t(16) << 20, size_t(32) << 20, size_t(64) << 20}) {
+      struct R { float ms; int st, sb, ct; uint64_t seg; };
+      std::vector<R> res;
+      for (int stages : {3, 4, 6, 8})
+        for (int sb : {8192, 16384, 24576, 32768, 49152})
+          for (int ctas : {1, 2, 3, 4})
+            for (uint64_t seg : {uint64_t(32) << 10, uint64_t(64) << 10, uint64_t(128) << 10, uint64_t(256) << 10}) {
+              if ((size_t)stages * sb * ctas > 220 * 1024) continue;
+              if (seg % sb != 0 && seg > (uint64_t)sb) continue;
+              auto v = make_segs((uint64_t)(where ? remote : a), (uint64_t)b, bytes, seg);
+              memcpy(segs, v.data(), v.size() * sizeof(SwSeg));
+              BulkTuning t{0, stages, sb, ctas};
+              float ms = time_bulk(st, segs, (uint32_t)v.size(), t, 4, where ? nullptr : flush, FLUSH);
+              res.push_back(R{ms, stages, sb, ctas, seg});
+            }
+      std::sort(res.begin(), res.end(), [](const R& x, const R& y) { return x.ms < y.ms; });
+      for (size_t i = 0; i < res.size() && i < 6; i++) {
+        printf("[tune %s %3zu MiB] #%zu stages=%d stage=%5d ctas=%d seg=%6llu: %.3f ms %.1f GB/s\n", where ? "pull" : "loop",
+               bytes >> 20, i, res[i].st, res[i].sb, res[i].ct, (unsigned long long)res[i].seg, res[i].ms,
+               bytes / (res[i].ms * 1e-3) / 1e9);
+        if (json)
+          fprintf(json, "{\"bench\":\"tune\",\"where\":\"%s\",\"bytes\":%zu,\"rank\":%zu,\"stages\":%d,\"stage_bytes\":%d,\"ctas\":%d,\"seg\":%llu,\"ms\":%.4f}\n",
+                  where ? "pull" : "loop", bytes, i, res[i].st, res[i].sb, res[i].ct, (unsigned long long)res[i].seg, res[i].ms);
+      }
+      // the engine's default
+      for (auto& r : res)
+        if (r.st == 8 && r.sb == 24576 && r.ct == 1 && r.seg == (128u << 10))
+          printf("[tune %s %3zu MiB] default(8x24K,1cta,seg128K): %.3f ms %.1f GB/s\n", where ? "pull" : "loop", bytes >> 20,
+                 r.ms, bytes / (r.ms * 1e-3) / 1e9);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ pinned host memory paths
 static void bench_hostmem(FILE* json) {
   stream_t st = stream_create();
@@ -715,6 +767,7 @@ int main(int argc, char** argv) {
   if (cmd == "latency" || cmd == "all") bench_latency(json);
   if (cmd == "bench" || cmd == "all") bench_single(json);
   if (cmd == "hostmem") bench_hostmem(json);
+  if (cmd == "tune") bench_tune(json);
   if (cmd == "ipc" || cmd == "all") test_ipc(argv[0]);
   if (cmd == "peer" || cmd == "all") bench_peer(json);
   if (json) fclose(json);
