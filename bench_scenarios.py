@@ -21,6 +21,7 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+os.environ.setdefault("STARWAY_QUIET", "1")  # no "Connected!" banners: stdout carries JSON lines only
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 

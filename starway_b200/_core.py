@@ -221,6 +221,15 @@ def as_buffer(obj: Any, writable: bool):
 
 
 # ----------------------------------------------------------------------------- API factory
+def _banner(msg: str) -> None:
+    """The reference prints "Connected!" / "Client closed!" / "Server closed!" (__init__.py:91,224,256).
+    Kept for drop-in behaviour; STARWAY_QUIET=1 silences them (benchmarks print one JSON line)."""
+    import os
+
+    if os.environ.get("STARWAY_QUIET") != "1":
+        print(msg)
+
+
 def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_fastpath: bool = True) -> SimpleNamespace:
     """Build Context/Server/Client/ServerEndpoint classes on top of a loaded C-ABI library."""
     declare(lib)
@@ -570,7 +579,7 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
         def _aclose(self, loop, banner):
             loop, fut = self._future(loop)
             h, w = self._ctx._h, self._w
-            self._ctx.submit(lambda: lib.sw_close(h, w), ("fut", loop, fut, None, lambda: print(banner)))
+            self._ctx.submit(lambda: lib.sw_close(h, w), ("fut", loop, fut, None, lambda: _banner(banner)))
             return fut
 
     class Server(_Base):
@@ -686,7 +695,7 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
             loop, fut = self._future(loop)
             h, w = self._ctx._h, self._w
             self._ctx.submit(
-                lambda: lib.sw_connect(h, w, addr.encode(), port), ("fut", loop, fut, None, lambda: print("Connected!"))
+                lambda: lib.sw_connect(h, w, addr.encode(), port), ("fut", loop, fut, None, lambda: _banner("Connected!"))
             )
             return fut
 
@@ -696,7 +705,7 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
             blob = bytes(remote_address)
             self._ctx.submit(
                 lambda: lib.sw_connect_address(h, w, blob, len(blob)),
-                ("fut", loop, fut, blob, lambda: print("Connected!")),
+                ("fut", loop, fut, blob, lambda: _banner("Connected!")),
             )
             return fut
 
