@@ -712,6 +712,90 @@ async def case_multi_sender_invariants(api, port, seed=0, bufs=HostBufs, n_clien
     await server.aclose()
 
 
+# ------------------------------------------------------------------ chaos
+OK_ERRORS = ("cancel", "reset", "not connected", "truncated")
+
+
+async def case_chaos(api, port, seed, n_ops=120, bufs=None):
+    bufs = bufs or HostBufs
+    rng = np.random.default_rng(seed)
+    server = api.Server()
+    server.listen(SERVER_ADDR, port)
+    clients = [api.Client() for _ in range(3)]
+    for c in clients:
+        await c.aconnect(SERVER_ADDR, port)
+    eps = list(server.list_clients())
+    alive = [True] * len(clients)
+    futs, checks, keep = [], [], []
+    sizes = [0, 1, 100, 8128, 8129, 50000, 400000]
+
+    def payload(tag, n):
+        return ((np.arange(n, dtype=np.uint32) * 31 + tag * 7) & 0xFF).astype(np.uint8)
+
+    for step in range(n_ops):
+        r = rng.random()
+        try:
+            if r < 0.35:  # client -> server send
+                i = int(rng.integers(0, len(clients)))
+                if alive[i]:
+                    n, tag = int(rng.choice(sizes)), int(rng.integers(1, 6))
+                    t = bufs.from_np(payload(tag, n))
+                    keep.append(t)
+                    bufs.sync()
+                    futs.append(clients[i].asend(t, tag))
+            elif r < 0.5:  # server -> client send
+                i = int(rng.integers(0, len(eps)))
+                n, tag = int(rng.choice(sizes)), int(rng.integers(1, 6))
+                t = bufs.from_np(payload(tag, n))
+                keep.append(t)
+                bufs.sync()
+                futs.append(server.asend(eps[i], t, tag))
+            elif r < 0.8:  # server receive
+                tag = int(rng.integers(1, 7))
+                mask = int(rng.choice([0, 0xFFFF, (1 << 64) - 1]))
+                buf = bufs.alloc(int(rng.choice([16, 9000, 500000])))
+                bufs.sync()
+                f = server.arecv(buf, tag, mask)
+                futs.append(f)
+                checks.append((f, buf))
+            elif r < 0.9:  # client receive
+                i = int(rng.integers(0, len(clients)))
+                if alive[i]:
+                    buf = bufs.alloc(500000)
+                    bufs.sync()
+                    f = clients[i].arecv(buf, 0, 0)
+                    futs.append(f)
+                    checks.append((f, buf))
+            elif r < 0.95:
+                futs.append(server.aflush() if rng.random() < 0.5 else clients[0].aflush() if alive[0] else server.aflush())
+            else:  # close a client in the middle of everything
+                i = int(rng.integers(0, len(clients)))
+                if alive[i] and sum(alive) > 1:
+                    alive[i] = False
+                    await asyncio.wait_for(clients[i].aclose(), 20)
+        except RuntimeError:
+            pass  # posting on a closed worker raises synchronously (reference behaviour)
+        if rng.random() < 0.3:
+            await asyncio.sleep(0.001)
+    await asyncio.sleep(0.05)
+    for i, c in enumerate(clients):
+        if alive[i]:
+            await asyncio.wait_for(c.aclose(), 20)
+    await asyncio.wait_for(server.aclose(), 20)
+    res = await asyncio.wait_for(asyncio.gather(*futs, return_exceptions=True), 30)
+    for x in res:
+        if isinstance(x, Exception):
+            assert any(k in str(x) for k in OK_ERRORS), repr(x)
+    bufs.sync()
+    for f, buf in checks:
+        if f.exception() is None:
+            tag, length = f.result()
+            got = bufs.to_np(buf)
+            np.testing.assert_array_equal(got[:length], payload(tag & 0xFFFF, length))
+            assert (got[length:] == 0xEE).all()
+
+
+
 SINGLE_PROCESS_CASES = [
     case_server_listen_client_connect_close,
     case_worker_address_connection_roundtrip,

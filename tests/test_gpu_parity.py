@@ -239,6 +239,18 @@ def test_multi_sender_invariants_host(cuda_api, port, seed):
     run(cb.case_multi_sender_invariants(cuda_api, port, seed))
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_chaos_host_buffers(cuda_api, port, seed):
+    """Random sends / receives / flushes / mid-stream closes (tests/cases_basic.py::case_chaos) on the
+    real asynchronous device path."""
+    run(cb.case_chaos(cuda_api, port, seed))
+
+
+@pytest.mark.parametrize("seed", [4, 5, 6, 7])
+def test_chaos_device_buffers(cuda_api, port, seed):
+    run(cb.case_chaos(cuda_api, port, seed, bufs=_dev_bufs()))
+
+
 def test_unexpected_flood_out_of_order(cuda_api, port):
     """More unexpected eager messages than ring slots (1024): the matcher parks them on the
     device heap, credits flow back, and receives posted in REVERSE tag order still pair up."""
