@@ -61,6 +61,10 @@ int init(int device) {
   SW_CUDA(cudaFuncGetAttributes(&fa, sw_bulk_tma_kernel));
   g_max_smem_optin -= (int)fa.sharedSizeBytes;   // static mbarrier storage counts against the opt-in limit
   SW_CUDA(cudaFuncSetAttribute(sw_bulk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem_optin));
+  SW_CUDA(cudaFuncSetAttribute(sw_bulk_tma_inline_kernel<SW_BULK_INLINE_SEGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               g_max_smem_optin));
+  SW_CUDA(cudaFuncSetAttribute(sw_bulk_tma_inline_kernel<SW_BULK_INLINE_SEGS_SMALL>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem_optin));
   return 0;
 }
 int bind_thread(int device) {
@@ -430,7 +434,25 @@ int launch_bulk(stream_t s, const SwSeg* segs, uint32_t nseg, const BulkTuning* 
     if (ctas > fit) ctas = fit < 1 ? 1 : fit;
     uint32_t grid = (uint32_t)(g_sms * ctas);
     if (grid > nseg) grid = nseg;
-    sw_bulk_tma_kernel<<<grid, 32, smem, (cudaStream_t)s>>>(segs, nseg, (uint32_t)sb, (uint32_t)stages);
+    if (nseg <= SW_BULK_INLINE_SEGS_SMALL) {
+      SwSegArgs<SW_BULK_INLINE_SEGS_SMALL> a;
+      a.nseg = nseg;
+      a.stage_bytes = (uint32_t)sb;
+      a.nstages = (uint32_t)stages;
+      a.pad = 0;
+      memcpy(a.seg, segs, sizeof(SwSeg) * nseg);
+      sw_bulk_tma_inline_kernel<SW_BULK_INLINE_SEGS_SMALL><<<grid, 32, smem, (cudaStream_t)s>>>(a);
+    } else if (nseg <= SW_BULK_INLINE_SEGS) {
+      static thread_local SwSegArgs<SW_BULK_INLINE_SEGS> a;   // 24 KiB: keep it off the stack
+      a.nseg = nseg;
+      a.stage_bytes = (uint32_t)sb;
+      a.nstages = (uint32_t)stages;
+      a.pad = 0;
+      memcpy(a.seg, segs, sizeof(SwSeg) * nseg);
+      sw_bulk_tma_inline_kernel<SW_BULK_INLINE_SEGS><<<grid, 32, smem, (cudaStream_t)s>>>(a);
+    } else {
+      sw_bulk_tma_kernel<<<grid, 32, smem, (cudaStream_t)s>>>(segs, nseg, (uint32_t)sb, (uint32_t)stages);
+    }
   } else {
     uint32_t grid = (uint32_t)(g_sms * (t->ctas_per_sm > 0 ? t->ctas_per_sm : 4));
     if (grid > nseg) grid = nseg;

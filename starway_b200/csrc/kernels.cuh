@@ -862,8 +862,9 @@ __global__ void __launch_bounds__(256) sw_deliver_kernel(SwMatchState* __restric
 // multiples of 16 B (the host routes anything else to sw_bulk_simt_kernel).
 constexpr int SW_BULK_MAX_STAGES = 8;
 
-__global__ void __launch_bounds__(32) sw_bulk_tma_kernel(const SwSeg* __restrict__ segs, uint32_t nseg,
-                                                         uint32_t stage_bytes, uint32_t nstages) {
+// The copy loop, shared by the two entry points below (segment list in memory / in the parameter bank).
+template <class SegAt>
+__device__ __forceinline__ void sw_bulk_tma_body(SegAt seg_at, uint32_t nseg, uint32_t stage_bytes, uint32_t nstages) {
   extern __shared__ __align__(128) uint8_t sw_smem[];
   __shared__ __align__(8) uint64_t full[SW_BULK_MAX_STAGES];
   if (threadIdx.x != 0) return;
@@ -876,7 +877,7 @@ __global__ void __launch_bounds__(32) sw_bulk_tma_kernel(const SwSeg* __restrict
   uint64_t off = 0;
   SwSeg cur;
   cur.src = cur.dst = cur.len = 0;
-  if (s < nseg) cur = segs[s];
+  if (s < nseg) cur = seg_at(s);
   uint64_t st_dst[SW_BULK_MAX_STAGES];
   uint32_t st_bytes[SW_BULK_MAX_STAGES];
 
@@ -888,7 +889,7 @@ __global__ void __launch_bounds__(32) sw_bulk_tma_kernel(const SwSeg* __restrict
     while (s < nseg && off >= cur.len) {
       s += gridDim.x;
       off = 0;
-      if (s < nseg) cur = segs[s];
+      if (s < nseg) cur = seg_at(s);
     }
     if (s >= nseg) return false;
     const uint64_t left = cur.len - off;
@@ -919,6 +920,25 @@ __global__ void __launch_bounds__(32) sw_bulk_tma_kernel(const SwSeg* __restrict
     done++;
   }
   sw_bulk_wait_all();
+}
+
+__global__ void __launch_bounds__(32) sw_bulk_tma_kernel(const SwSeg* __restrict__ segs, uint32_t nseg,
+                                                         uint32_t stage_bytes, uint32_t nstages) {
+  sw_bulk_tma_body([segs](uint32_t i) { return segs[i]; }, nseg, stage_bytes, nstages);
+}
+
+// Launches with few segments carry the list in the kernel parameter bank: the first bulk load of
+// every CTA is not preceded by a read of pinned host memory over PCIe.
+constexpr uint32_t SW_BULK_INLINE_SEGS = 768;        // 24 KiB of the 32 KiB parameter space
+constexpr uint32_t SW_BULK_INLINE_SEGS_SMALL = 96;   // 3 KiB: the latency-critical small launches
+template <uint32_t N>
+struct SwSegArgs {
+  uint32_t nseg, stage_bytes, nstages, pad;
+  SwSeg seg[N];
+};
+template <uint32_t N>
+__global__ void __launch_bounds__(32) sw_bulk_tma_inline_kernel(const __grid_constant__ SwSegArgs<N> a) {
+  sw_bulk_tma_body([&a](uint32_t i) { return a.seg[i]; }, a.nseg, a.stage_bytes, a.nstages);
 }
 
 // ------------------------------------------------------------------ bulk copy, SIMT vectorised
