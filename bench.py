@@ -236,7 +236,7 @@ def run_ours(args):
                 assert np.array_equal(s, d), "host payload mismatch"
         barrier()
         torch.cuda.synchronize()
-        e2e_steps = max(3, min(args.steps, 10))
+        e2e_steps = max(3, min(args.steps, 40))
         ctx.reset_stats()
         t0 = time.perf_counter()
         await timed_host(e2e_steps)
@@ -398,8 +398,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--msg-bytes", type=int, default=MSG_BYTES)
     ap.add_argument("--window", type=int, default=WINDOW)

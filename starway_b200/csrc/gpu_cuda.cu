@@ -61,8 +61,6 @@ int init(int device) {
   SW_CUDA(cudaFuncGetAttributes(&fa, sw_bulk_tma_kernel));
   g_max_smem_optin -= (int)fa.sharedSizeBytes;   // static mbarrier storage counts against the opt-in limit
   SW_CUDA(cudaFuncSetAttribute(sw_bulk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem_optin));
-  SW_CUDA(cudaFuncSetAttribute(sw_bulk_tma_inline_kernel<SW_BULK_INLINE_SEGS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               g_max_smem_optin));
   SW_CUDA(cudaFuncSetAttribute(sw_bulk_tma_inline_kernel<SW_BULK_INLINE_SEGS_SMALL>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem_optin));
   return 0;
@@ -442,14 +440,6 @@ int launch_bulk(stream_t s, const SwSeg* segs, uint32_t nseg, const BulkTuning* 
       a.pad = 0;
       memcpy(a.seg, segs, sizeof(SwSeg) * nseg);
       sw_bulk_tma_inline_kernel<SW_BULK_INLINE_SEGS_SMALL><<<grid, 32, smem, (cudaStream_t)s>>>(a);
-    } else if (nseg <= SW_BULK_INLINE_SEGS) {
-      static thread_local SwSegArgs<SW_BULK_INLINE_SEGS> a;   // 24 KiB: keep it off the stack
-      a.nseg = nseg;
-      a.stage_bytes = (uint32_t)sb;
-      a.nstages = (uint32_t)stages;
-      a.pad = 0;
-      memcpy(a.seg, segs, sizeof(SwSeg) * nseg);
-      sw_bulk_tma_inline_kernel<SW_BULK_INLINE_SEGS><<<grid, 32, smem, (cudaStream_t)s>>>(a);
     } else {
       sw_bulk_tma_kernel<<<grid, 32, smem, (cudaStream_t)s>>>(segs, nseg, (uint32_t)sb, (uint32_t)stages);
     }

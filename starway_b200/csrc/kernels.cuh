@@ -929,8 +929,10 @@ __global__ void __launch_bounds__(32) sw_bulk_tma_kernel(const SwSeg* __restrict
 
 // Launches with few segments carry the list in the kernel parameter bank: the first bulk load of
 // every CTA is not preceded by a read of pinned host memory over PCIe.
-constexpr uint32_t SW_BULK_INLINE_SEGS = 768;        // 24 KiB of the 32 KiB parameter space
-constexpr uint32_t SW_BULK_INLINE_SEGS_SMALL = 96;   // 3 KiB: the latency-critical small launches
+// Only the latency-critical small launches take this route: the parameter block stays under the
+// classic 4 KiB limit.  Measured on B200: a 24 KiB parameter block (768 segments) made every
+// launch cost more on the host than the first-segment PCIe read it saved (bench N=2 360 -> 227 GB/s).
+constexpr uint32_t SW_BULK_INLINE_SEGS_SMALL = 96;   // 3 KiB
 template <uint32_t N>
 struct SwSegArgs {
   uint32_t nseg, stage_bytes, nstages, pad;
