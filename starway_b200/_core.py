@@ -25,7 +25,9 @@ from __future__ import annotations
 import asyncio
 import atexit
 import ctypes
+import os
 import threading
+import time
 from collections.abc import Callable
 from types import SimpleNamespace
 from typing import Any
@@ -235,6 +237,7 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
     declare(lib)
     _post_send, _post_recv = lib.sw_post_send, lib.sw_post_recv
     _get_running_loop = asyncio.get_running_loop
+    _monotonic_ns = time.monotonic_ns
     _U64MASK = 0xFFFFFFFFFFFFFFFF
 
     def _err() -> str:
@@ -270,6 +273,10 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
             self._stop = False
             self._wake = threading.Event()
             self._fp = None
+            self._spin_ns = int(float(os.environ.get("STARWAY_SPIN_US", "200")) * 1000)
+            self._spin_loop = None
+            self._spin_seen = -1
+            self._spin_deadline = 0
             if _fastpath is not None and use_fastpath:
                 addr = lambda f: ctypes.cast(f, ctypes.c_void_p).value  # noqa: E731
                 self._fp = _fastpath.Binding(addr(lib.sw_post_send), addr(lib.sw_post_recv), addr(lib.sw_poll), self._h,
@@ -286,6 +293,8 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
                 if not op:
                     raise RuntimeError(_err())
                 self._ops[op] = entry
+            if self._spin_loop is None:
+                self._kick()
             return op
 
         def ensure_reader(self, loop) -> None:
@@ -297,6 +306,10 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
                     return
                 loop.add_reader(self._efd, self._drain, loop)
                 self._readers[loop] = True
+                sl = self._spin_loop
+                if sl is not None and sl is not loop and not sl.is_running():
+                    self._stop_spin(None)
+                loop.call_soon(self._drain, loop)  # anything published before the reader existed
             except (RuntimeError, NotImplementedError, OSError):
                 pass
 
@@ -378,25 +391,86 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
             buf[0].op_id = op & 0xFFFFFFFFFFFFFFFF
             self._dispatch(1, buf, here)
 
-        def _drain(self, loop) -> None:
-            """eventfd reader callback: runs on `loop`'s thread."""
+        def _drain(self, loop) -> int:
+            """eventfd reader callback: runs on `loop`'s thread.  Returns the number of completions."""
             h, buf = self._h, self._buf
             if not h:
-                return
+                return 0
             if self._fp is not None:
-                self._fp.drain(loop)
-                return
+                return self._fp.drain(loop)
+            total = 0
             while True:
                 n = lib.sw_poll(h, buf, 512)
                 if n <= 0:
-                    return
+                    return total
+                total += n
                 self._dispatch(n, buf, loop)
                 if n < 512:
-                    return
+                    return total
+
+        # -- adaptive busy-polling of the completion queue ---------------------------------------
+        # Waking a thread that sleeps in epoll on the eventfd costs 10-40 us, several times the device
+        # pipeline of a small message.  After a submission the loop therefore polls the completion
+        # queue from a self-re-arming call_soon callback (other callbacks and I/O keep running between
+        # polls) until nothing has happened for `spin_us`; then it returns to the eventfd.  While it
+        # polls, the engine skips the eventfd write (option "consumer_polling").
+        def _kick(self) -> None:
+            if self._spin_loop is not None or self._spin_ns <= 0:
+                return
+            try:
+                loop = _get_running_loop()
+            except RuntimeError:
+                return
+            if loop not in self._readers or not self._h:
+                return
+            self._spin_loop = loop
+            self._spin_seen = -1
+            self._spin_deadline = _monotonic_ns() + self._spin_ns
+            lib.sw_set_option(self._h, b"consumer_polling", 1)
+            try:
+                loop.call_soon(self._spin, loop)
+            except RuntimeError:
+                self._stop_spin(None)
+
+        def _spin(self, loop) -> None:
+            if self._spin_loop is not loop:
+                return
+            again = False
+            try:
+                n = self._drain(loop)
+                pending = len(self._ops)
+                if pending and self._h:
+                    now = _monotonic_ns()
+                    if n or pending != self._spin_seen:
+                        self._spin_seen = pending
+                        self._spin_deadline = now + self._spin_ns
+                    if now < self._spin_deadline:
+                        loop.call_soon(self._spin, loop)
+                        again = True
+            finally:
+                if not again:
+                    self._stop_spin(loop)
+
+        def _stop_spin(self, loop) -> None:
+            self._spin_loop = None
+            if self._h:
+                lib.sw_set_option(self._h, b"consumer_polling", 0)
+                if loop is not None:
+                    self._drain(loop)  # completions published while the wake-up was suppressed
 
         def _poll_loop(self):
             buf = (SwCompletion * 512)()
             while not self._stop:
+                sl = self._spin_loop
+                if sl is not None and not sl.is_running():
+                    # the polling loop stopped with its callback still queued: hand delivery back
+                    self._stop_spin(None)
+                    for lp in list(self._readers):
+                        if not lp.is_closed():
+                            try:
+                                lp.call_soon_threadsafe(self._drain, lp)
+                            except RuntimeError:
+                                pass
                 if self._readers:
                     # an asyncio loop drains the queue itself; only watch for loops that went away
                     for lp in list(self._readers):
@@ -543,7 +617,10 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
             # hot path: no helper calls / closures
             ctx = self._ctx
             if loop is None and ctx._fp is not None:
-                return ctx._fp.arecv(self._w, buffer, tag, tag_mask)
+                fut = ctx._fp.arecv(self._w, buffer, tag, tag_mask)
+                if ctx._spin_loop is None:
+                    ctx._kick()
+                return fut
             if loop is None:
                 loop = _get_running_loop()
             if loop not in ctx._readers:
@@ -557,6 +634,8 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
                 if not op:
                     raise RuntimeError(_err())
                 ctx._ops[op] = ("fut", loop, fut, keep, None)
+            if ctx._spin_loop is None:
+                ctx._kick()
             return fut
 
         def flush(self, done_callback, fail_callback):
@@ -645,7 +724,10 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
         def asend(self, client_ep, buffer, tag: int, loop: asyncio.AbstractEventLoop | None = None):
             ctx = self._ctx
             if loop is None and ctx._fp is not None:
-                return ctx._fp.asend(self._w, client_ep._id, buffer, tag)
+                fut = ctx._fp.asend(self._w, client_ep._id, buffer, tag)
+                if ctx._spin_loop is None:
+                    ctx._kick()
+                return fut
             if loop is None:
                 loop = _get_running_loop()
             if loop not in ctx._readers:
@@ -659,6 +741,8 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
                 if not op:
                     raise RuntimeError(_err())
                 ctx._ops[op] = ("fut", loop, fut, keep, None)
+            if ctx._spin_loop is None:
+                ctx._kick()
             return fut
 
         def flush_ep(self, client_ep, done_callback, fail_callback):
@@ -725,7 +809,10 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
         def asend(self, buffer, tag: int, loop: asyncio.AbstractEventLoop | None = None):
             ctx = self._ctx
             if loop is None and ctx._fp is not None:
-                return ctx._fp.asend(self._w, 0, buffer, tag)
+                fut = ctx._fp.asend(self._w, 0, buffer, tag)
+                if ctx._spin_loop is None:
+                    ctx._kick()
+                return fut
             if loop is None:
                 loop = _get_running_loop()
             if loop not in ctx._readers:
@@ -739,6 +826,8 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
                 if not op:
                     raise RuntimeError(_err())
                 ctx._ops[op] = ("fut", loop, fut, keep, None)
+            if ctx._spin_loop is None:
+                ctx._kick()
             return fut
 
         def evaluate_perf(self, msg_size: int) -> float:

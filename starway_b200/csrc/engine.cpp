@@ -475,6 +475,10 @@ struct Ctx {
   // completion queue
   std::mutex cq_mu;
   std::condition_variable cq_cv;
+  std::atomic<uint32_t> cq_count{0};        // == cq.size(), readable without the lock
+  std::atomic<int> cq_waiters{0};           // threads blocked in sw_wait
+  std::atomic<int> consumer_polling{0};     // option "consumer_polling": skip the eventfd wake-up
+  std::atomic<int> efd_signaled{0};         // the eventfd counter is non-zero
   std::deque<sw_completion> cq;
   std::vector<sw_completion> cq_local;  // progress-thread staging
   int efd = -1;
@@ -540,17 +544,22 @@ thread_local bool tls_is_progress = false;
 
 void publish_completions(Ctx* c, const sw_completion* comps, size_t n) {
   if (!n) return;
+  bool was_empty;
   {
     std::lock_guard<std::mutex> lk(c->cq_mu);
-    const bool was_empty = c->cq.empty();
+    was_empty = c->cq.empty();
     for (size_t i = 0; i < n; i++) c->cq.push_back(comps[i]);
-    if (was_empty && c->efd >= 0) {
-      uint64_t one = 1;
-      ssize_t r = write(c->efd, &one, sizeof(one));
-      (void)r;
-    }
+    c->cq_count.store((uint32_t)c->cq.size(), std::memory_order_seq_cst);
   }
-  c->cq_cv.notify_one();
+  // A consumer that announced it is busy-polling (option "consumer_polling") needs no wake-up: it
+  // clears the flag and polls once more before it goes back to sleeping on the eventfd.
+  if (was_empty && c->efd >= 0 && !c->consumer_polling.load(std::memory_order_seq_cst)) {
+    c->efd_signaled.store(1, std::memory_order_release);
+    uint64_t one = 1;
+    ssize_t r = write(c->efd, &one, sizeof(one));
+    (void)r;
+  }
+  if (c->cq_waiters.load(std::memory_order_seq_cst)) c->cq_cv.notify_one();
   std::lock_guard<std::mutex> lk(c->st_mu);
   c->stats.completions += n;
 }
@@ -565,6 +574,7 @@ void push_completion(Ctx* c, const sw_completion& comp) {
 
 void flush_completions(Ctx* c) {
   if (c->cq_local.empty()) return;
+  trace(c, "publish", c->cq_local.size());
   publish_completions(c, c->cq_local.data(), c->cq_local.size());
   c->cq_local.clear();
 }
@@ -1875,6 +1885,7 @@ bool progress_close(Ctx* c, Worker* w) {
 void drain_sq(Ctx* c) {
   if (c->sq_head.load(std::memory_order_acquire) == nullptr) return;
   SqNode* list = c->sq_head.exchange(nullptr, std::memory_order_acquire);
+  trace(c, "sq_drain");
   // the stack is LIFO: reverse it to recover submission order
   SqNode* rev = nullptr;
   while (list) {
@@ -2195,6 +2206,7 @@ int sw_set_option(sw_ctx* ctx, const char* key, int64_t value) {
   else if (k == "stage_upload_kernel") c->opt_stage_upload_kernel = value;
   else if (k == "coalesce_us") c->opt_coalesce_us = value;
   else if (k == "coalesce_bytes") c->opt_coalesce_bytes = value;
+  else if (k == "consumer_polling") c->consumer_polling.store(value != 0, std::memory_order_seq_cst);
   else {
     set_error("unknown option " + k);
     return -1;
@@ -2460,36 +2472,44 @@ uint64_t sw_post_flush_ep(sw_ctx* ctx, sw_worker_t wid, sw_ep_t epid) {
   return id;
 }
 
+static void clear_efd_if_empty(Ctx* c) {  // cq_mu held
+  if (c->cq.empty() && c->efd >= 0 && c->efd_signaled.exchange(0, std::memory_order_acq_rel)) {
+    uint64_t v;
+    ssize_t r = read(c->efd, &v, sizeof(v));
+    (void)r;
+  }
+}
+
 int sw_poll(sw_ctx* ctx, sw_completion* out, int max) {
   Ctx* c = (Ctx*)ctx;
+  // nothing queued and no stale eventfd signal: no lock, no system call (busy-polling consumers)
+  if (c->cq_count.load(std::memory_order_seq_cst) == 0 && !c->efd_signaled.load(std::memory_order_acquire)) return 0;
   std::lock_guard<std::mutex> lk(c->cq_mu);
   int n = 0;
   while (n < max && !c->cq.empty()) {
     out[n++] = c->cq.front();
     c->cq.pop_front();
   }
-  if (c->cq.empty() && c->efd >= 0) {
-    uint64_t v;
-    ssize_t r = read(c->efd, &v, sizeof(v));
-    (void)r;
-  }
+  c->cq_count.store((uint32_t)c->cq.size(), std::memory_order_seq_cst);
+  clear_efd_if_empty(c);
   return n;
 }
 
 int sw_wait(sw_ctx* ctx, sw_completion* out, int max, int timeout_ms) {
   Ctx* c = (Ctx*)ctx;
   std::unique_lock<std::mutex> lk(c->cq_mu);
-  if (c->cq.empty()) c->cq_cv.wait_for(lk, std::chrono::milliseconds(timeout_ms), [&] { return !c->cq.empty(); });
+  if (c->cq.empty()) {
+    c->cq_waiters.fetch_add(1, std::memory_order_seq_cst);
+    c->cq_cv.wait_for(lk, std::chrono::milliseconds(timeout_ms), [&] { return !c->cq.empty(); });
+    c->cq_waiters.fetch_sub(1, std::memory_order_seq_cst);
+  }
   int n = 0;
   while (n < max && !c->cq.empty()) {
     out[n++] = c->cq.front();
     c->cq.pop_front();
   }
-  if (c->cq.empty() && c->efd >= 0) {
-    uint64_t v;
-    ssize_t r = read(c->efd, &v, sizeof(v));
-    (void)r;
-  }
+  c->cq_count.store((uint32_t)c->cq.size(), std::memory_order_seq_cst);
+  clear_efd_if_empty(c);
   return n;
 }
 

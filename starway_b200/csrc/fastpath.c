@@ -284,9 +284,11 @@ static void swallow_invalid_state(void) {
 
 /* drain(loop): resolve every pending completion; runs on `loop`'s thread (eventfd reader) */
 static PyObject* Binding_drain(Binding* self, PyObject* here) {
+  long total = 0;
   for (;;) {
     int n = self->poll(self->ctx, self->buf, 512);
     if (n <= 0) break;
+    total += n;
     for (int i = 0; i < n; i++) {
       const sw_completion c = self->buf[i];
       PyObject* key = PyLong_FromUnsignedLongLong(c.op_id);
@@ -340,13 +342,13 @@ static PyObject* Binding_drain(Binding* self, PyObject* here) {
     }
     if (n < 512) break;
   }
-  Py_RETURN_NONE;
+  return PyLong_FromLong(total);
 }
 
 static PyMethodDef Binding_methods[] = {
     {"asend", (PyCFunction)(void (*)(void))Binding_asend, METH_FASTCALL, "asend(worker, ep, buffer, tag) -> Future"},
     {"arecv", (PyCFunction)(void (*)(void))Binding_arecv, METH_FASTCALL, "arecv(worker, buffer, tag, mask) -> Future"},
-    {"drain", (PyCFunction)Binding_drain, METH_O, "drain(loop): resolve pending completions on the loop thread"},
+    {"drain", (PyCFunction)Binding_drain, METH_O, "drain(loop) -> int: resolve pending completions on the loop thread"},
     {NULL, NULL, 0, NULL}};
 
 static PyTypeObject BindingType = {

@@ -94,3 +94,67 @@ def test_cancelled_future_and_explicit_loop(sim_api, port):
             assert await f2 == (6, 4)
 
     run(go())
+
+
+# ---------------------------------------------------------------- adaptive completion polling
+def test_spin_disabled_uses_eventfd_only(sim_api, port):
+    ctx = sim_api.get_context()
+    saved, ctx._spin_ns = ctx._spin_ns, 0
+    try:
+        run(cb.case_concurrent_send_recv(sim_api, port))
+        assert ctx._spin_loop is None
+    finally:
+        ctx._spin_ns = saved
+
+
+def test_spin_times_out_and_eventfd_takes_over(sim_api, port):
+    """A receive that stays pending longer than the polling budget must still complete (the loop has
+    gone back to sleeping on the eventfd by then)."""
+    async def go():
+        ctx = sim_api.get_context()
+        async with cb.gen_server_client(sim_api, port) as (server, client):
+            buf = np.zeros(16, dtype=np.uint8)
+            f = server.arecv(buf, 7, 0xFF)
+            await asyncio.sleep(0.05)           # >> STARWAY_SPIN_US
+            assert ctx._spin_loop is None       # polling has stopped, the op is still pending
+            assert not f.done()
+            await client.asend(np.full(16, 9, dtype=np.uint8), 7)
+            assert await f == (7, 16) and (buf == 9).all()
+
+    run(go())
+
+
+def test_loop_stopped_while_polling(sim_api, port):
+    """The loop returns while its polling callback is still queued; the next loop on the same context
+    must receive its completions (suppressed wake-ups are re-enabled by the watchdog / new reader)."""
+    ctx = sim_api.get_context()
+    state = {}
+
+    async def first():
+        server = sim_api.Server()
+        server.listen("127.0.0.1", port)
+        client = sim_api.Client()
+        await client.aconnect("127.0.0.1", port)
+        buf = np.zeros(4, dtype=np.uint8)
+        state.update(server=server, client=client, buf=buf, fut_loop=asyncio.get_running_loop())
+        server.arecv(buf, 1, 0xFF)              # leaves an op pending -> the loop is polling when it returns
+        assert ctx._spin_loop is not None or ctx._spin_ns <= 0
+
+    async def second():
+        server, client = state["server"], state["client"]
+        buf2 = np.zeros(4, dtype=np.uint8)
+        await client.asend(np.arange(4, dtype=np.uint8), 1)     # matches the receive posted by the first loop
+        f = server.arecv(buf2, 2, 0xFF)
+        await client.asend(np.arange(4, dtype=np.uint8) + 1, 2)
+        assert await f == (2, 4)
+        await client.aclose()
+        await server.aclose()
+
+    loop1 = asyncio.new_event_loop()
+    try:
+        loop1.run_until_complete(asyncio.wait_for(first(), 30))
+    finally:
+        pass  # loop1 is left un-closed on purpose (stopped, polling callback still queued)
+    run(second())
+    assert (state["buf"] == np.arange(4)).all()
+    loop1.close()
