@@ -376,7 +376,10 @@ struct Worker {
   SwMatchState* mstate = nullptr;
   SwMatchIn* min = nullptr;
   SwMatchOut* mout = nullptr;
-  swgpu::event_t mev = nullptr, mev_start = nullptr;
+  swgpu::event_t mev = nullptr, mev_start = nullptr, mev_fast = nullptr;
+  uint64_t mdone_seq = 0;
+  uint32_t mspins = 0;
+  bool mflag_mode = false, mtimed = false;
   bool match_inflight = false;
   uint32_t match_posts_inflight = 0;
   uint64_t stall_unseen = 0;
@@ -416,13 +419,20 @@ struct PutBlock {
   SwPutDesc* descs = nullptr;
   SwRts* rts = nullptr;
   uint8_t* stage = nullptr;
-  swgpu::event_t ev = nullptr, ev_start = nullptr;
+  swgpu::event_t ev = nullptr, ev_start = nullptr;   // timing pair (option profile >= 2)
+  swgpu::event_t ev_fast = nullptr;                  // completion only (timing disabled)
+  uint64_t* done = nullptr;                          // pinned host: completion flag of small launches
+  uint64_t done_seq = 0;
+  uint32_t spins = 0;
+  bool flag_mode = false, timed = false;
   bool busy = false;
   std::vector<PutItem> items;
 };
 struct BulkBlock {
   SwSeg* segs = nullptr;
-  swgpu::event_t ev = nullptr, ev_start = nullptr;
+  swgpu::event_t ev = nullptr, ev_start = nullptr;   // timing pair (option profile >= 1)
+  swgpu::event_t ev_fast = nullptr;                  // completion only (timing disabled)
+  bool timed = false;
   bool busy = false;
   std::vector<BulkJob> jobs;
   std::vector<SwSeg> tma, simt;  // scratch, capacity retained across launches
@@ -507,6 +517,10 @@ struct Ctx {
   std::atomic<int64_t> opt_ring_slots{SW_RING_SLOTS_DEFAULT};
   std::atomic<int64_t> opt_bulk_mode{0}, opt_bulk_stages{8}, opt_bulk_stage_bytes{24576}, opt_bulk_ctas{1};
   std::atomic<int64_t> opt_coalesce_us{40}, opt_coalesce_bytes{32 << 20};
+  // small put / match launches announce completion through a flag in pinned host memory
+  // (launch -> seen 7.4 us vs 15.2 us through a timing event on B200, profiles/r01_probe_floor.log)
+  std::atomic<int64_t> opt_done_flags{1};
+  uint64_t flag_seq = 0;
   std::atomic<int64_t> opt_heap_small{4096}, opt_heap_big{512};
   std::atomic<int64_t> opt_profile{0};
   // 1: same-process pinned host sources are read in place by the receiver's kernel (one host->host
@@ -670,6 +684,7 @@ bool worker_alloc_device(Ctx* c, Worker* w) {
   w->mout = (SwMatchOut*)swgpu::host_alloc(sizeof(SwMatchOut));
   w->mev = swgpu::event_create(1);
   w->mev_start = swgpu::event_create(1);
+  w->mev_fast = swgpu::event_create(0);
   memset(&w->msc, 0, sizeof(w->msc));
   w->msc.n_free_small = (uint32_t)c->opt_heap_small.load();
   w->msc.n_free_big = (uint32_t)c->opt_heap_big.load();
@@ -1243,8 +1258,8 @@ bool pump_sends(Ctx* c) {
     if (n >= PUT_BATCH || batch_full) break;
   }
   if (!n) return false;
-  const bool prof = c->opt_profile.load() != 0;
-  if (prof) swgpu::event_record(b.ev_start, c->s_put);
+  b.timed = c->opt_profile.load() >= 2;
+  if (b.timed) swgpu::event_record(b.ev_start, c->s_put);
   if (b.nsegs) {
     swgpu::BulkTuning up{0, 8, 24576, 1};
     trace(c, "stage_upload_launch", b.nsegs, staged_bytes);
@@ -1252,9 +1267,13 @@ bool pump_sends(Ctx* c) {
       fprintf(stderr, "starway_b200: staging upload launch failed: %s\n", swgpu::last_error());
   }
   trace(c, "put_launch", n, bytes + h2d);
-  if (swgpu::launch_put(c->s_put, b.descs, n) != 0)
-    fprintf(stderr, "starway_b200: put launch failed: %s\n", swgpu::last_error());
-  swgpu::event_record(b.ev, c->s_put);
+  swgpu::DoneFlag df{b.done, ++c->flag_seq};
+  const int lr = swgpu::launch_put(c->s_put, b.descs, n, (b.timed || !c->opt_done_flags.load()) ? nullptr : &df);
+  if (lr < 0) fprintf(stderr, "starway_b200: put launch failed: %s\n", swgpu::last_error());
+  b.flag_mode = lr == 1;
+  b.done_seq = df.value;
+  b.spins = 0;
+  if (!b.flag_mode) swgpu::event_record(b.timed ? b.ev : b.ev_fast, c->s_put);
   b.busy = true;
   c->put_tail++;
   std::lock_guard<std::mutex> lk(c->st_mu);
@@ -1269,10 +1288,17 @@ bool poll_puts(Ctx* c) {
   bool any = false;
   while (c->put_head != c->put_tail) {
     PutBlock& b = c->put_blocks[c->put_head % N_PUT_BLOCKS];
-    int q = swgpu::event_query(b.ev);
+    int q;
+    if (b.flag_mode) {
+      q = __atomic_load_n(b.done, __ATOMIC_ACQUIRE) == b.done_seq ? 0 : 1;
+      // a faulted launch never writes its flag: look at the stream now and then
+      if (q == 1 && (++b.spins & 0x3FF) == 0 && swgpu::stream_query(c->s_put) < 0) q = -1;
+    } else {
+      q = swgpu::event_query(b.timed ? b.ev : b.ev_fast);
+    }
     if (q == 1) break;
     if (q < 0) fprintf(stderr, "starway_b200: put kernel failed: %s\n", swgpu::last_error());
-    if (c->opt_profile.load()) {
+    if (b.timed) {
       float ms = swgpu::event_elapsed_ms(b.ev_start, b.ev);
       if (ms >= 0) {
         std::lock_guard<std::mutex> lk(c->st_mu);
@@ -1374,8 +1400,8 @@ bool pump_match(Ctx* c, Worker* w) {
   in->n_posts = np;
   in->n_eps = (uint32_t)w->eps.size();
   in->max_arrivals = SW_MAX_ARRIVALS;
-  const bool prof = c->opt_profile.load() != 0;
-  if (prof) swgpu::event_record(w->mev_start, c->s_match);
+  w->mtimed = c->opt_profile.load() >= 2;
+  if (w->mtimed) swgpu::event_record(w->mev_start, c->s_match);
   uint32_t max_jobs = np + (uint32_t)std::min<uint64_t>(unseen, SW_MAX_ARRIVALS);
   trace(c, "match_launch", np, unseen);
   const SwMatchScalars* sc = nullptr;
@@ -1387,9 +1413,14 @@ bool pump_match(Ctx* c, Worker* w) {
     }
     sc = &w->msc;
   }
-  if (swgpu::launch_match_deliver(c->s_match, w->mstate, in, w->mout, max_jobs, sc) != 0)
-    fprintf(stderr, "starway_b200: match/deliver launch failed: %s\n", swgpu::last_error());
-  swgpu::event_record(w->mev, c->s_match);
+  swgpu::DoneFlag df{nullptr, ++c->flag_seq};
+  const int lr = swgpu::launch_match_deliver(c->s_match, w->mstate, in, w->mout, max_jobs, sc,
+                                             (w->mtimed || !c->opt_done_flags.load()) ? nullptr : &df);
+  if (lr < 0) fprintf(stderr, "starway_b200: match/deliver launch failed: %s\n", swgpu::last_error());
+  w->mflag_mode = lr == 1;
+  w->mdone_seq = df.value;
+  w->mspins = 0;
+  if (!w->mflag_mode) swgpu::event_record(w->mtimed ? w->mev : w->mev_fast, c->s_match);
   w->match_inflight = true;
   w->match_posts_inflight = np;
   w->posted_est += np;
@@ -1402,13 +1433,19 @@ bool pump_match(Ctx* c, Worker* w) {
 
 bool poll_match(Ctx* c, Worker* w) {
   if (!w->match_inflight) return false;
-  int q = swgpu::event_query(w->mev);
+  int q;
+  if (w->mflag_mode) {
+    q = __atomic_load_n(&w->mout->done_seq, __ATOMIC_ACQUIRE) == w->mdone_seq ? 0 : 1;
+    if (q == 1 && (++w->mspins & 0x3FF) == 0 && swgpu::stream_query(c->s_match) < 0) q = -1;
+  } else {
+    q = swgpu::event_query(w->mtimed ? w->mev : w->mev_fast);
+  }
   if (q == 1) return false;
   if (q < 0) fprintf(stderr, "starway_b200: match/deliver kernel failed: %s\n", swgpu::last_error());
   w->match_inflight = false;
   SwMatchOut* out = w->mout;
   trace(c, "match_done", out->n_jobs, out->n_rndv);
-  if (c->opt_profile.load()) {
+  if (w->mtimed) {
     float ms = swgpu::event_elapsed_ms(w->mev_start, w->mev);
     if (ms >= 0) {
       std::lock_guard<std::mutex> lk(c->st_mu);
@@ -1612,8 +1649,8 @@ bool pump_bulk(Ctx* c) {
   uint32_t ntma = (uint32_t)tma.size(), nsimt = (uint32_t)simt.size();
   if (ntma) memcpy(b.segs, tma.data(), sizeof(SwSeg) * ntma);
   if (nsimt) memcpy(b.segs + ntma, simt.data(), sizeof(SwSeg) * nsimt);
-  const bool prof = c->opt_profile.load() != 0;
-  if (prof) swgpu::event_record(b.ev_start, c->s_bulk);
+  b.timed = c->opt_profile.load() != 0;
+  if (b.timed) swgpu::event_record(b.ev_start, c->s_bulk);
   trace(c, "bulk_launch", b.jobs.size(), b.bytes);
   int rc = 0;
   if (ntma) rc |= swgpu::launch_bulk(c->s_bulk, b.segs, ntma, &tune);
@@ -1624,7 +1661,7 @@ bool pump_bulk(Ctx* c) {
     rc |= swgpu::launch_bulk(c->s_bulk, b.segs + ntma, nsimt, &t2);
   }
   if (rc) fprintf(stderr, "starway_b200: bulk launch failed: %s\n", swgpu::last_error());
-  swgpu::event_record(b.ev, c->s_bulk);
+  swgpu::event_record(b.timed ? b.ev : b.ev_fast, c->s_bulk);
   b.busy = true;
   c->bulk_tail++;
   std::lock_guard<std::mutex> lk(c->st_mu);
@@ -1639,10 +1676,10 @@ bool poll_bulk(Ctx* c) {
   bool any = false;
   while (c->bulk_head != c->bulk_tail) {
     BulkBlock& b = c->bulk_blocks[c->bulk_head % N_BULK_BLOCKS];
-    int q = swgpu::event_query(b.ev);
+    int q = swgpu::event_query(b.timed ? b.ev : b.ev_fast);
     if (q == 1) break;
     if (q < 0) fprintf(stderr, "starway_b200: bulk kernel failed: %s\n", swgpu::last_error());
-    if (c->opt_profile.load()) {
+    if (b.timed) {
       float ms = swgpu::event_elapsed_ms(b.ev_start, b.ev);
       if (ms >= 0) {
         std::lock_guard<std::mutex> lk(c->st_mu);
@@ -1789,7 +1826,8 @@ void worker_release(Ctx* c, Worker* w, bool leak_rings) {
   w->mout = nullptr;
   if (w->mev) swgpu::event_destroy(w->mev);
   if (w->mev_start) swgpu::event_destroy(w->mev_start);
-  w->mev = w->mev_start = nullptr;
+  if (w->mev_fast) swgpu::event_destroy(w->mev_fast);
+  w->mev = w->mev_start = w->mev_fast = nullptr;
   if (w->tcp_fd >= 0) close(w->tcp_fd);
   if (w->unix_fd >= 0) close(w->unix_fd);
   w->tcp_fd = w->unix_fd = -1;
@@ -2102,14 +2140,18 @@ sw_ctx* sw_ctx_create(int device) {
     b.segs = (SwSeg*)swgpu::host_alloc(sizeof(SwSeg) * STAGE_SEGS);
     b.ev = swgpu::event_create(1);
     b.ev_start = swgpu::event_create(1);
-    ok = b.descs && b.rts && b.stage && b.segs && b.ev && b.ev_start;
+    b.ev_fast = swgpu::event_create(0);
+    b.done = (uint64_t*)swgpu::host_alloc(64);
+    if (b.done) *b.done = 0;
+    ok = b.descs && b.rts && b.stage && b.segs && b.ev && b.ev_start && b.ev_fast && b.done;
   }
   for (int i = 0; ok && i < N_BULK_BLOCKS; i++) {
     BulkBlock& b = c->bulk_blocks[i];
     b.segs = (SwSeg*)swgpu::host_alloc(sizeof(SwSeg) * MAX_SEGS);
     b.ev = swgpu::event_create(1);
     b.ev_start = swgpu::event_create(1);
-    ok = b.segs && b.ev && b.ev_start;
+    b.ev_fast = swgpu::event_create(0);
+    ok = b.segs && b.ev && b.ev_start && b.ev_fast;
   }
   if (!ok) {
     set_error(std::string("sw_ctx_create: ") + swgpu::last_error());
@@ -2162,12 +2204,15 @@ void sw_ctx_destroy(sw_ctx* ctx) {
     swgpu::host_free(b.rts);
     swgpu::host_free(b.stage);
     swgpu::host_free(b.segs);
+    swgpu::host_free(b.done);
     if (b.ev) swgpu::event_destroy(b.ev);
     if (b.ev_start) swgpu::event_destroy(b.ev_start);
+    if (b.ev_fast) swgpu::event_destroy(b.ev_fast);
   }
   for (int i = 0; i < N_BULK_BLOCKS; i++) {
     BulkBlock& b = c->bulk_blocks[i];
     swgpu::host_free(b.segs);
+    if (b.ev_fast) swgpu::event_destroy(b.ev_fast);
     if (b.ev) swgpu::event_destroy(b.ev);
     if (b.ev_start) swgpu::event_destroy(b.ev_start);
   }
@@ -2206,6 +2251,7 @@ int sw_set_option(sw_ctx* ctx, const char* key, int64_t value) {
   else if (k == "stage_upload_kernel") c->opt_stage_upload_kernel = value;
   else if (k == "coalesce_us") c->opt_coalesce_us = value;
   else if (k == "coalesce_bytes") c->opt_coalesce_bytes = value;
+  else if (k == "done_flags") c->opt_done_flags = value;
   else if (k == "consumer_polling") c->consumer_polling.store(value != 0, std::memory_order_seq_cst);
   else {
     set_error("unknown option " + k);

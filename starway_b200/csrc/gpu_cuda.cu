@@ -200,6 +200,12 @@ int stream_destroy(stream_t s) {
   SW_CUDA(cudaStreamDestroy((cudaStream_t)s));
   return 0;
 }
+int stream_query(stream_t s) {
+  cudaError_t r = cudaStreamQuery((cudaStream_t)s);
+  if (r == cudaSuccess) return 0;
+  if (r == cudaErrorNotReady) return 1;
+  return fail(r, "cudaStreamQuery");
+}
 int stream_sync(stream_t s) {
   SW_CUDA(cudaStreamSynchronize((cudaStream_t)s));
   return 0;
@@ -345,22 +351,30 @@ int match_state_set_ring(SwMatchState* st, uint32_t ep, void* ring_base, uint32_
 }
 
 // ---------------------------------------------------------------- launches
-int launch_put(stream_t s, const SwPutDesc* descs, uint32_t n) {
+int launch_put(stream_t s, const SwPutDesc* descs, uint32_t n, const DoneFlag* done) {
   if (!n) return 0;
   const uint32_t warps_per_cta = 8;
-  if (n <= SW_PUT_INLINE) {
+  uint32_t n_rts = 0;
+  if (n <= SW_PUT_INLINE)
+    for (uint32_t i = 0; i < n; i++) n_rts += descs[i].kind == SW_KIND_RTS;
+  if (n <= SW_PUT_INLINE && n_rts <= SW_PUT_INLINE_RTS) {
     // descriptors (and RTS payloads, which live in host memory next to them) by value
     SwPutArgs a;
     a.n = n;
     a.pad = 0;
+    a.done_flag = done ? (uint64_t)(uintptr_t)done->flag : 0;
+    a.done_value = done ? done->value : 0;
+    uint32_t r = 0;
     for (uint32_t i = 0; i < n; i++) {
       a.d[i] = descs[i];
-      if (descs[i].kind == SW_KIND_RTS) memcpy(&a.r[i], (const void*)(uintptr_t)descs[i].src, sizeof(SwRts));
+      if (descs[i].kind == SW_KIND_RTS) {
+        memcpy(&a.r[r], (const void*)(uintptr_t)descs[i].src, sizeof(SwRts));
+        a.d[i].src = r++;
+      }
     }
-    uint32_t grid = (n + warps_per_cta - 1) / warps_per_cta;
-    sw_put_inline_kernel<<<grid, warps_per_cta * 32, 0, (cudaStream_t)s>>>(a);
+    sw_put_inline_kernel<<<1, n * 32, 0, (cudaStream_t)s>>>(a);   // one CTA, one warp per message
     SW_CUDA(cudaGetLastError());
-    return 0;
+    return done ? 1 : 0;
   }
   uint32_t grid = (n + warps_per_cta - 1) / warps_per_cta;
   const uint32_t cap = (uint32_t)g_sms * 8;
@@ -379,6 +393,7 @@ static void fill_match_args(SwMatchArgs& a, const SwMatchIn* in, const SwMatchSc
   a.n_eps = in->n_eps;
   a.max_arrivals = in->max_arrivals;
   a.pad = 0;
+  a.done_value = 0;
   for (uint32_t e = 0; e < SW_INLINE_EPS; e++) a.produced[e] = e < in->n_eps ? in->produced[e] : 0;
   const uint32_t np = in->n_posts <= SW_INLINE_POSTS ? in->n_posts : 0;
   for (uint32_t i = 0; i < np; i++) a.posts[i] = in->posts[i];
@@ -393,13 +408,14 @@ int launch_match(stream_t s, SwMatchState* st, const SwMatchIn* in, SwMatchOut* 
 }
 
 int launch_match_deliver(stream_t s, SwMatchState* st, const SwMatchIn* in, SwMatchOut* out, uint32_t max_jobs,
-                         const SwMatchScalars* sc) {
+                         const SwMatchScalars* sc, const DoneFlag* done) {
   if (max_jobs <= SW_FUSED_MAX_JOBS) {
     SwMatchArgs a;
     fill_match_args(a, in, sc);
+    a.done_value = done ? done->value : 0;
     sw_match_deliver_kernel<<<1, SW_FUSED_THREADS, 0, (cudaStream_t)s>>>(st, in, out, a);
     SW_CUDA(cudaGetLastError());
-    return 0;
+    return done ? 1 : 0;
   }
   if (launch_match(s, st, in, out) != 0) return -1;
   return launch_deliver(s, st, out, max_jobs);

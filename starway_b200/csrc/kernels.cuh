@@ -160,21 +160,29 @@ __global__ void __launch_bounds__(256) sw_put_kernel(const SwPutDesc* __restrict
 // Small batches: descriptors and RTS payloads travel as kernel parameters (no PCIe read on the
 // latency-critical path).
 constexpr uint32_t SW_PUT_INLINE = 32;
+constexpr uint32_t SW_PUT_INLINE_RTS = 16;   // keeps the parameter block under the classic 4 KiB
 struct SwPutArgs {
   uint32_t n, pad;
-  SwPutDesc d[SW_PUT_INLINE];
-  SwRts r[SW_PUT_INLINE];   // used when d[i].kind == SW_KIND_RTS
+  uint64_t done_flag;           // pinned-host word (0: none) that receives done_value when every slot is written
+  uint64_t done_value;
+  SwPutDesc d[SW_PUT_INLINE];   // for kind == SW_KIND_RTS, d[i].src is an index into r[]
+  SwRts r[SW_PUT_INLINE_RTS];
 };
-__global__ void __launch_bounds__(256) sw_put_inline_kernel(const __grid_constant__ SwPutArgs a) {
+static_assert(sizeof(SwPutArgs) <= 4096, "inline put parameters");
+// ONE CTA, one warp per message.  Completion is announced by a flag in pinned host memory: the
+// barrier collects every warp's stores, thread 0's system-scope fence orders them (cumulatively)
+// before the flag.  Measured on B200 (`sw_probe floor`): launch -> flag seen 7.4 us, launch -> timing
+// event seen 15.2 us.
+__global__ void __launch_bounds__(SW_PUT_INLINE * 32) sw_put_inline_kernel(const __grid_constant__ SwPutArgs a) {
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t nwarps = blockDim.x >> 5;
   for (uint32_t i = warp; i < a.n; i += nwarps) {
     const SwPutDesc d = a.d[i];
     uint8_t* slot = reinterpret_cast<uint8_t*>(d.dst);
     if (d.kind == SW_KIND_RTS) {
       if (lane < 8) {
-        const int4 v = reinterpret_cast<const int4*>(&a.r[i])[lane];
+        const int4 v = reinterpret_cast<const int4*>(&a.r[d.src & (SW_PUT_INLINE_RTS - 1)])[lane];
         sw_st16(slot + SW_SLOT_HDR + 16 * lane, v);
       }
     } else {
@@ -193,6 +201,13 @@ __global__ void __launch_bounds__(256) sw_put_inline_kernel(const __grid_constan
       h1.w = static_cast<int>(SW_SLOT_MAGIC);
       sw_st16(slot, h0);
       sw_st16(slot + 16, h1);
+    }
+  }
+  if (a.done_flag) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      *reinterpret_cast<volatile uint64_t*>(a.done_flag) = a.done_value;
     }
   }
 }
@@ -272,6 +287,7 @@ constexpr uint32_t SW_INLINE_EPS = 8;
 constexpr uint32_t SW_INLINE_POSTS = 32;
 struct SwMatchArgs {
   uint32_t n_posts, n_eps, max_arrivals, pad;
+  uint64_t done_value;   // fused launch: value stored to SwMatchOut::done_seq at the very end (0: none)
   uint64_t produced[SW_INLINE_EPS];
   SwMatchScalars sc;   // sc.valid: queue cursors + ring cursors by value (host mirror of the last launch)
   SwPost posts[SW_INLINE_POSTS];
@@ -811,7 +827,7 @@ __device__ __forceinline__ void sw_deliver_one(const SwJob& j, SwMatchOut* __res
                                                uint32_t lane) {
   sw_copy(reinterpret_cast<uint8_t*>(j.dst), reinterpret_cast<const uint8_t*>(j.src), j.len, lane, 32);
   if (lane == 0) {
-    // the host reads the record only after the launch's CUDA event has completed
+    // the host reads the record only after the launch has completed (CUDA event, or the done flag)
     SwCqe c;
     c.op_id = j.op_id;
     c.tag = j.tag;
@@ -841,6 +857,15 @@ __global__ void __launch_bounds__(SW_FUSED_THREADS) sw_match_deliver_kernel(SwMa
   __syncthreads();
   const uint32_t n = s_njobs;
   for (uint32_t i = warp; i < n; i += SW_FUSED_THREADS / 32) sw_deliver_one(s_jobs[i], out, i, lane);
+  if (a.done_value) {
+    // completion flag in pinned host memory (see sw_put_inline_kernel): queue state, delivered
+    // payloads and completion records of every warp are ordered before it
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      *reinterpret_cast<volatile uint64_t*>(&out->done_seq) = a.done_value;
+    }
+  }
 }
 
 // ------------------------------------------------------------------ deliver

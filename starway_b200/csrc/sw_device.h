@@ -165,6 +165,9 @@ struct SwMatchOut {  // pinned host
   uint32_t heap_big_free;
   uint64_t consumed[SW_MAX_EPS];  // slots consumed so far on each inbound ring
   SwMatchScalars sc;              // queue cursors after this launch
+  uint64_t done_seq;              // written last by a fused match+deliver launch (system-scope release):
+                                  // the host spins on it instead of on a CUDA event
+  uint64_t pad_done[7];
   SwCqe cq[SW_MAX_JOBS];
   SwRndvRec rndv[SW_MAX_JOBS];
 };

@@ -20,8 +20,7 @@ def pytest_configure(config):
         subprocess.check_call(["make", "-C", ROOT, "-j", "8", "lib", "oracle", "hostsim"])
 
 
-@pytest.fixture
-def port():
+def free_port():
     # reference tests/test_basic.py:18-20 draws random.randint(10000, 50000); that collides now and then
     # with a live socket ("Address already in use"), so ask the kernel for a port that is free right now
     import socket
@@ -35,6 +34,11 @@ def port():
             except OSError:
                 continue
     return random.randint(10000, 30000)
+
+
+@pytest.fixture
+def port():
+    return free_port()
 
 
 @pytest.fixture(scope="session")

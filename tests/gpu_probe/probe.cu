@@ -5,6 +5,7 @@
 //   sw_probe peer                  2-GPU in-process peer pull/push bandwidth, cudaMemcpyPeer ceiling
 //   sw_probe ipc                   2-process CUDA-IPC mapping check + pull bandwidth
 //   sw_probe latency               launch + event-poll latency of the small kernels
+//   sw_probe floor                 launch -> completion-seen floor: event vs flag in pinned memory, per-hop cost
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -518,6 +519,23 @@ static void bench_latency(FILE* json) {
       if (json)
         fprintf(json, "{\"bench\":\"put_latency\",\"n\":%d,\"len\":%d,\"us\":%.2f}\n", n, len, best * 1e6);
       event_destroy(ev);
+      if (n <= 32) {   // the single-CTA variant announces completion through a flag in pinned memory
+        static uint64_t* flag = (uint64_t*)host_alloc(64);
+        static uint64_t seq = 0;
+        double bestf = 1e9;
+        for (int it = 0; it < 50; it++) {
+          DoneFlag df{flag, ++seq};
+          double t0 = now_s();
+          REQ(launch_put(st, descs, n, &df) == 1);
+          while (*(volatile uint64_t*)flag != seq) {
+          }
+          double t1 = now_s();
+          if (it > 5) bestf = std::min(bestf, t1 - t0);
+        }
+        printf("[latency] put n=%4d len=%5d: launch+flag %.2f us\n", n, len, bestf * 1e6);
+        if (json)
+          fprintf(json, "{\"bench\":\"put_latency_flag\",\"n\":%d,\"len\":%d,\"us\":%.2f}\n", n, len, bestf * 1e6);
+      }
     }
   }
   // match+deliver on a FIFO workload
@@ -561,6 +579,32 @@ static void bench_latency(FILE* json) {
     printf("[latency] match+deliver n=%4d x 64B: %.2f us (%.2f Mmsg/s)\n", n, best * 1e6, n / best / 1e6);
     if (json) fprintf(json, "{\"bench\":\"match_deliver_latency\",\"n\":%d,\"us\":%.2f}\n", n, best * 1e6);
     event_destroy(ev);
+    if (2 * n <= 192) {   // fused single-CTA launch, completion flag in SwMatchOut::done_seq
+      static uint64_t seq = 0;
+      double bestf = 1e9;
+      for (int it = 0; it < 30; it++) {
+        for (int i = 0; i < n; i++) {
+          descs[i].dst = (uint64_t)(ring + (size_t)((prod + i) % 1024) * SW_SLOT_BYTES);
+          descs[i].seq = prod + i + 1;
+        }
+        launch_put(st, descs, n);
+        stream_sync(st);
+        prod += n;
+        in->n_posts = n;
+        in->produced[0] = prod;
+        for (int i = 0; i < n; i++) in->posts[i] = SwPost{1, 0xFFFF, (uint64_t)(dst + (size_t)i * 8192), 8192, op++};
+        DoneFlag df{nullptr, ++seq};
+        double t0 = now_s();
+        REQ(launch_match_deliver(st, ms, in, out, 2 * n, nullptr, &df) == 1);
+        while (*(volatile uint64_t*)&out->done_seq != seq) {
+        }
+        double t1 = now_s();
+        REQ(out->err == 0 && out->n_jobs == (uint32_t)n);
+        if (it > 3) bestf = std::min(bestf, t1 - t0);
+      }
+      printf("[latency] fused match+deliver n=%4d x 64B: launch+flag %.2f us\n", n, bestf * 1e6);
+      if (json) fprintf(json, "{\"bench\":\"match_deliver_latency_flag\",\"n\":%d,\"us\":%.2f}\n", n, bestf * 1e6);
+    }
   }
 }
 
@@ -749,6 +793,160 @@ static void test_ipc(const char* self) {
   dev_free(buf);
 }
 
+
+// ------------------------------------------------------------------ launch/completion floor
+// What one launch -> "host knows it finished" costs on this box, by completion mechanism.
+struct FloorArgs {
+  volatile uint64_t* flag;
+  uint64_t value;
+  const uint64_t* chain;   // pointer-chasing array in device memory
+  uint32_t hops;
+  uint32_t pad;
+  uint8_t ballast[1536];   // the match launch carries ~1.5 KiB of parameters
+};
+__global__ void floor_empty_kernel() {}
+__global__ void floor_flag_kernel(volatile uint64_t* flag, uint64_t value) {
+  __threadfence_system();
+  *flag = value;
+}
+__global__ void __launch_bounds__(512) floor_cta_flag_kernel(const __grid_constant__ FloorArgs a) {
+  uint64_t idx = threadIdx.x & 7;
+  if (threadIdx.x < 32)
+    for (uint32_t h = 0; h < a.hops; h++) idx = a.chain[idx];   // dependent global loads
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    *a.flag = a.value + (idx & 0);
+  }
+}
+
+static double median(std::vector<double>& v) {
+  std::sort(v.begin(), v.end());
+  return v[v.size() / 2];
+}
+
+static void bench_floor(FILE* json) {
+  cudaStream_t st;
+  CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  uint64_t* flag;
+  CK(cudaHostAlloc((void**)&flag, 64, cudaHostAllocPortable | cudaHostAllocMapped));
+  *flag = 0;
+  uint64_t* chain;
+  {
+    // scattered chain over 64 MiB so that hops miss L2 lines of each other (but may hit L2 when re-run)
+    const size_t n = (64u << 20) / 8;
+    std::vector<uint64_t> h(n);
+    std::mt19937_64 rng(1);
+    for (size_t i = 0; i < n; i++) h[i] = rng() % n;
+    CK(cudaMalloc((void**)&chain, n * 8));
+    CK(cudaMemcpy(chain, h.data(), n * 8, cudaMemcpyHostToDevice));
+  }
+  const int iters = 400;
+  auto report = [&](const char* name, std::vector<double>& total, std::vector<double>* api = nullptr) {
+    const double m = median(total) * 1e6;
+    std::vector<double> s = total;
+    const double p10 = s[s.size() / 10] * 1e6;
+    if (api) {
+      printf("[floor] %-58s median %6.2f us  p10 %6.2f us  (API calls %5.2f us)\n", name, m, p10, median(*api) * 1e6);
+    } else {
+      printf("[floor] %-58s median %6.2f us  p10 %6.2f us\n", name, m, p10);
+    }
+    if (json) fprintf(json, "{\"bench\":\"floor\",\"case\":\"%s\",\"us\":%.2f,\"p10_us\":%.2f}\n", name, m, p10);
+  };
+  for (int timing = 0; timing < 2; timing++) {
+    cudaEvent_t ev;
+    CK(cudaEventCreateWithFlags(&ev, timing ? cudaEventDefault : cudaEventDisableTiming));
+    std::vector<double> tot, api;
+    for (int i = 0; i < iters; i++) {
+      const double t0 = now_s();
+      floor_empty_kernel<<<1, 32, 0, st>>>();
+      CK(cudaEventRecord(ev, st));
+      const double t1 = now_s();
+      while (cudaEventQuery(ev) == cudaErrorNotReady) {
+      }
+      const double t2 = now_s();
+      if (i >= 20) {
+        tot.push_back(t2 - t0);
+        api.push_back(t1 - t0);
+      }
+    }
+    report(timing ? "empty kernel + event (timing enabled), cudaEventQuery spin" : "empty kernel + event (timing disabled), cudaEventQuery spin",
+           tot, &api);
+    CK(cudaEventDestroy(ev));
+  }
+  uint64_t seq = 0;
+  {
+    std::vector<double> tot, api;
+    for (int i = 0; i < iters; i++) {
+      const double t0 = now_s();
+      floor_flag_kernel<<<1, 32, 0, st>>>(flag, ++seq);
+      const double t1 = now_s();
+      while (*(volatile uint64_t*)flag != seq) {
+      }
+      const double t2 = now_s();
+      if (i >= 20) {
+        tot.push_back(t2 - t0);
+        api.push_back(t1 - t0);
+      }
+    }
+    report("flag kernel (fence.sys + store to pinned host), host spins on the flag", tot, &api);
+  }
+  for (uint32_t hops : {0u, 1u, 3u, 6u, 12u}) {
+    static FloorArgs a;
+    a.flag = flag;
+    a.chain = chain;
+    a.hops = hops;
+    std::vector<double> tot, api;
+    for (int i = 0; i < iters; i++) {
+      a.value = ++seq;
+      const double t0 = now_s();
+      floor_cta_flag_kernel<<<1, 512, 0, st>>>(a);
+      const double t1 = now_s();
+      while (*(volatile uint64_t*)flag != seq) {
+      }
+      const double t2 = now_s();
+      if (i >= 20) {
+        tot.push_back(t2 - t0);
+        api.push_back(t1 - t0);
+      }
+    }
+    char name[96];
+    snprintf(name, sizeof name, "512-thread CTA, 1.5 KiB params, %2u dependent loads, flag", hops);
+    report(name, tot, &api);
+  }
+  {
+    // same with an event recorded behind it (what the engine did before flags)
+    static FloorArgs a;
+    a.flag = flag;
+    a.chain = chain;
+    a.hops = 3;
+    cudaEvent_t ev;
+    CK(cudaEventCreateWithFlags(&ev, cudaEventDefault));
+    std::vector<double> tot, api;
+    for (int i = 0; i < iters; i++) {
+      a.value = ++seq;
+      const double t0 = now_s();
+      floor_cta_flag_kernel<<<1, 512, 0, st>>>(a);
+      CK(cudaEventRecord(ev, st));
+      const double t1 = now_s();
+      while (cudaEventQuery(ev) == cudaErrorNotReady) {
+      }
+      const double t2 = now_s();
+      if (i >= 20) {
+        tot.push_back(t2 - t0);
+        api.push_back(t1 - t0);
+      }
+    }
+    report("512-thread CTA, 1.5 KiB params,  3 dependent loads, timing event", tot, &api);
+    CK(cudaEventDestroy(ev));
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  CK(cudaFree(chain));
+  CK(cudaFreeHost(flag));
+  CK(cudaStreamDestroy(st));
+}
+
 int main(int argc, char** argv) {
   std::string cmd = argc > 1 ? argv[1] : "correctness";
   if (cmd == "ipc-child") return ipc_child(argv[2]);
@@ -766,6 +964,7 @@ int main(int argc, char** argv) {
   }
   if (cmd == "latency" || cmd == "all") bench_latency(json);
   if (cmd == "bench" || cmd == "all") bench_single(json);
+  if (cmd == "floor") bench_floor(json);
   if (cmd == "hostmem") bench_hostmem(json);
   if (cmd == "tune") bench_tune(json);
   if (cmd == "ipc" || cmd == "all") test_ipc(argv[0]);

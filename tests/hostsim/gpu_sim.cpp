@@ -187,6 +187,7 @@ int ptr_info(const void* p, PtrInfo* out) {
 stream_t stream_create() { return (stream_t)(uintptr_t)1; }
 int stream_destroy(stream_t) { return 0; }
 int stream_sync(stream_t) { return 0; }
+int stream_query(stream_t) { return 0; }
 event_t event_create(int) { return (event_t)(uintptr_t)1; }
 int event_destroy(event_t) { return 0; }
 int event_record(event_t, stream_t) { return 0; }
@@ -246,7 +247,7 @@ int match_state_set_ring(SwMatchState* st, uint32_t ep, void* ring_base, uint32_
 }
 
 // ---------------------------------------------------------------- "kernels"
-int launch_put(stream_t, const SwPutDesc* descs, uint32_t n) {
+int launch_put(stream_t, const SwPutDesc* descs, uint32_t n, const DoneFlag* done) {
   for (uint32_t i = 0; i < n; i++) {
     const SwPutDesc& d = descs[i];
     uint8_t* slot = (uint8_t*)(uintptr_t)d.dst;
@@ -260,6 +261,13 @@ int launch_put(stream_t, const SwPutDesc* descs, uint32_t n) {
     h.magic = SW_SLOT_MAGIC;
     __atomic_thread_fence(__ATOMIC_RELEASE);
     memcpy(slot, &h, 32);
+  }
+  // same split as the CUDA backend: only the small (single-CTA) variant announces itself by flag
+  uint32_t n_rts = 0;
+  for (uint32_t i = 0; i < n; i++) n_rts += descs[i].kind == SW_KIND_RTS;
+  if (done && n <= 32 && n_rts <= 16) {
+    __atomic_store_n((uint64_t*)done->flag, done->value, __ATOMIC_RELEASE);
+    return 1;
   }
   return 0;
 }
@@ -424,9 +432,14 @@ int launch_deliver(stream_t, SwMatchState* st, SwMatchOut* out, uint32_t) {
 }
 
 int launch_match_deliver(stream_t s, SwMatchState* st, const SwMatchIn* in, SwMatchOut* out, uint32_t max_jobs,
-                         const SwMatchScalars*) {
+                         const SwMatchScalars*, const DoneFlag* done) {
   launch_match(s, st, in, out);
-  return launch_deliver(s, st, out, max_jobs);
+  if (launch_deliver(s, st, out, max_jobs) != 0) return -1;
+  if (done && max_jobs <= 192) {   // the fused single-CTA launch of the CUDA backend
+    __atomic_store_n(&out->done_seq, done->value, __ATOMIC_RELEASE);
+    return 1;
+  }
+  return 0;
 }
 
 int launch_bulk(stream_t, const SwSeg* segs, uint32_t nseg, const BulkTuning*) {

@@ -128,3 +128,20 @@ def test_stalled_ring_does_not_block_other_senders(sim_api, port):
         await server.aclose()
 
     run(go())
+
+
+@pytest.mark.parametrize("opts", [{"done_flags": 0}, {"profile": 2}, {"profile": 1}],
+                         ids=["events_only", "timed_events", "bulk_timing"])
+def test_completion_detection_modes(sim_api, port, opts):
+    """Engine side of the completion-flag / event split (the GPU suite runs the same on hardware)."""
+    from tests.conftest import free_port
+
+    ctx = sim_api.get_context()
+    try:
+        for k, v in opts.items():
+            ctx.set_option(k, v)
+        run(cb.case_random_schedule_vs_oracle(sim_api, port, 11))
+        run(cb.case_chaos(sim_api, free_port(), 21))
+    finally:
+        ctx.set_option("done_flags", 1)
+        ctx.set_option("profile", 0)
