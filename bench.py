@@ -257,7 +257,6 @@ def run_ours(args):
         e2e_diag = {"ms_per_step": round(e2e_ms / e2e_steps, 3),
                     "bulk_kernel_ms_per_step": round(st2["bulk_event_ms"] / e2e_steps, 3),
                     "bulk_launches_per_step": round((st2["bulk_tma_launches"] + st2["bulk_simt_launches"]) / e2e_steps, 1),
-                    "put_kernel_ms_per_step": round(st2["put_event_ms"] / e2e_steps, 3),
                     "staged_h2d_bytes_per_step": int(st2["h2d_bytes"] / e2e_steps),
                     "staged_d2h_bytes_per_step": int(st2["d2h_bytes"] / e2e_steps)}
 
