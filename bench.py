@@ -131,6 +131,10 @@ def run_ours(args):
     os.environ["STARWAY_DEVICE"] = str(local_rank)
     import starway_b200 as sw
 
+    # one process per GPU, bound to the GPU's NUMA node before any host buffer is allocated (the
+    # launcher's job -- `numactl --cpunodebind` -- done here because the driver launches us bare)
+    numa_bound = sw.bind_to_device_numa(local_rank)
+
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -311,6 +315,7 @@ def run_ours(args):
             "l2": f"inputs larger than L2: {POOL_SETS} rotating buffer sets, {2 * POOL_SETS * window * msg >> 20} MiB footprint",
             "timing": "wall clock + CUDA events between device-wide synchronisations, max over ranks",
             "api": "public asyncio API (one Future per message, as the reference)",
+            "numa": "rank bound to the GPU-local CPUs" if numa_bound else "no CPU binding applied",
         },
         "mmsg_per_s": round(world * window * args.steps / (ms * 1e-3) / 1e6, 4),
         "nvlink_roofline_frac": None if world == 1 else round(value / world / 900.0, 4),

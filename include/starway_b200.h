@@ -106,6 +106,10 @@ const char* sw_backend_name(void);
 const char* sw_last_error(void);              /* thread-local message of the last failed call */
 const char* sw_status_string(int32_t status); /* ucs_status_string() equivalents */
 int sw_device_count(void);
+/* CPUs on the NUMA node the GPU hangs off, as a Linux cpulist ("0-31,64-95"); returns its length, or
+ * -1 when unknown.  The progress thread of a context binds itself to these CPUs (as UCX/NCCL helper
+ * threads do); a launcher that wants host buffers NUMA-local binds the rank's process the same way. */
+int sw_device_local_cpus(int device, char* out, size_t cap);
 sw_ctx* sw_ctx_create(int device);            /* NULL on failure (no GPU => failure, no fallback) */
 void sw_ctx_destroy(sw_ctx* ctx);
 int sw_ctx_device(sw_ctx* ctx);

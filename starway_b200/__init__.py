@@ -55,6 +55,8 @@ shutdown = _api.shutdown
 status_string = _api.status_string
 backend_name = _api.backend_name
 device_count = _api.device_count
+local_cpus = _api.local_cpus
+bind_to_device_numa = _api.bind_to_device_numa
 
 
 def check_sys_libs() -> str:
@@ -70,6 +72,8 @@ __all__ = [
     "check_sys_libs",
     "get_context",
     "shutdown",
+    "local_cpus",
+    "bind_to_device_numa",
     "status_string",
     "backend_name",
     "device_count",

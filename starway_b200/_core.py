@@ -117,6 +117,7 @@ C_ABI = {
     "sw_ctx_create": (_vp, [_int]),
     "sw_ctx_destroy": (None, [_vp]),
     "sw_ctx_device": (_int, [_vp]),
+    "sw_device_local_cpus": (_int, [_int, ctypes.c_char_p, _sz]),
     "sw_set_option": (_int, [_vp, _cp, _i64]),
     "sw_get_option": (_i64, [_vp, _cp]),
     "sw_worker_create": (_u64, [_vp, _int]),
@@ -523,6 +524,32 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
             else:
                 fut.set_exception(Exception(val))
 
+    def local_cpus(device: int | None = None) -> set[int]:
+        """CPUs on the NUMA node of `device` (empty when unknown)."""
+        if device is None:
+            device = default_device() if default_device else 0
+        buf = ctypes.create_string_buffer(1024)
+        if lib.sw_device_local_cpus(int(device), buf, 1024) <= 0:
+            return set()
+        cpus: set[int] = set()
+        for part in buf.value.decode().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        return cpus
+
+    def bind_to_device_numa(device: int | None = None) -> bool:
+        """Restrict the calling thread (and the threads it starts later) to the CPUs next to `device`,
+        so that host buffers it allocates are NUMA-local to the GPU's PCIe root — what a launcher
+        does with `numactl --cpunodebind`.  Returns False when nothing was changed."""
+        try:
+            want = local_cpus(device) & os.sched_getaffinity(0)
+            if not want or want == os.sched_getaffinity(0):
+                return False
+            os.sched_setaffinity(0, want)
+            return True
+        except (OSError, AttributeError, ValueError):
+            return False
+
     _state = SimpleNamespace(ctx=None)
     _state_lock = threading.Lock()
 
@@ -847,4 +874,6 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
         status_string=status_string,
         backend_name=lambda: lib.sw_backend_name().decode(),
         device_count=lambda: lib.sw_device_count(),
+        local_cpus=local_cpus,
+        bind_to_device_numa=bind_to_device_numa,
     )

@@ -16,6 +16,8 @@
 // becomes an exchange of CUDA IPC handles over a TCP / abstract-unix bootstrap socket.
 //
 // This file contains no CUDA: the device is reached through gpu.h only.
+#include <pthread.h>
+#include <sched.h>
 #include "starway_b200.h"
 
 #include <arpa/inet.h>
@@ -2012,8 +2014,81 @@ void drain_sq(Ctx* c) {
   }
 }
 
+// ============================================================================ NUMA placement
+// GPU-local CPUs from sysfs (what `nvidia-smi topo -m` prints as CPU affinity).  Pinned control
+// blocks and staging buffers are allocated, and the progress thread runs, next to the GPU's PCIe
+// root: on the 2-socket B200 boxes a rank whose host memory sits on the other socket moves its
+// host<->device traffic over UPI (measured: per-GPU e2e rate halves from N=2 to N=4).
+std::string device_cpulist(int device) {
+  char bus[64];
+  if (swgpu::device_pci_bus_id(device, bus, sizeof bus) != 0) return "";
+  std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+  FILE* f = fopen(path.c_str(), "r");
+  if (!f) return "";
+  char line[1024];
+  std::string out;
+  if (fgets(line, sizeof line, f)) out = line;
+  fclose(f);
+  while (!out.empty() && (out.back() == '\n' || out.back() == ' ')) out.pop_back();
+  return out;
+}
+
+bool parse_cpulist(const std::string& s, cpu_set_t* set) {
+  CPU_ZERO(set);
+  int n = 0;
+  size_t i = 0;
+  while (i < s.size()) {
+    char* end = nullptr;
+    long a = strtol(s.c_str() + i, &end, 10);
+    if (end == s.c_str() + i) return false;
+    long b = a;
+    i = (size_t)(end - s.c_str());
+    if (i < s.size() && s[i] == '-') {
+      b = strtol(s.c_str() + i + 1, &end, 10);
+      i = (size_t)(end - s.c_str());
+    }
+    for (long k = a; k <= b && k < CPU_SETSIZE; k++) {
+      CPU_SET((int)k, set);
+      n++;
+    }
+    if (i < s.size() && s[i] == ',') i++;
+  }
+  return n > 0;
+}
+
+// GPU-local CPUs that this process is allowed to run on; false when there is nothing to do
+bool device_cpuset(int device, cpu_set_t* out) {
+  if (const char* e = getenv("STARWAY_AFFINITY"))
+    if (atoi(e) == 0) return false;
+  cpu_set_t local, allowed;
+  if (!parse_cpulist(device_cpulist(device), &local)) return false;
+  if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return false;
+  CPU_AND(out, &local, &allowed);
+  return CPU_COUNT(out) > 0 && !CPU_EQUAL(out, &allowed);
+}
+
+// binds the calling thread to the GPU-local CPUs for the lifetime of the object (allocations made
+// meanwhile are first-touched on that node)
+struct ScopedAffinity {
+  cpu_set_t saved;
+  bool active = false;
+  explicit ScopedAffinity(int device) {
+    cpu_set_t want;
+    if (!device_cpuset(device, &want)) return;
+    if (pthread_getaffinity_np(pthread_self(), sizeof saved, &saved) != 0) return;
+    active = pthread_setaffinity_np(pthread_self(), sizeof want, &want) == 0;
+  }
+  ~ScopedAffinity() {
+    if (active) pthread_setaffinity_np(pthread_self(), sizeof saved, &saved);
+  }
+};
+
 void progress_main(Ctx* c) {
   swgpu::bind_thread(c->device);
+  {
+    cpu_set_t want;
+    if (device_cpuset(c->device, &want)) pthread_setaffinity_np(pthread_self(), sizeof want, &want);
+  }
   prctl(PR_SET_TIMERSLACK, 1000UL, 0, 0, 0);  // 1 us timer slack: short sleeps stay short
   tls_is_progress = true;
   uint64_t iter = 0;
@@ -2123,6 +2198,7 @@ sw_ctx* sw_ctx_create(int device) {
     set_error(std::string("sw_ctx_create: ") + swgpu::last_error());
     return nullptr;
   }
+  ScopedAffinity numa(device);
   Ctx* c = new Ctx();
   c->device = device;
   c->uuid = rand64() | 1;
@@ -2178,6 +2254,17 @@ sw_ctx* sw_ctx_create(int device) {
 }
 
 int sw_ctx_device(sw_ctx* ctx) { return ((Ctx*)ctx)->device; }
+
+int sw_device_local_cpus(int device, char* out, size_t cap) {
+  if (swgpu::init(device) != 0) {
+    set_error(std::string("sw_device_local_cpus: ") + swgpu::last_error());
+    return -1;
+  }
+  std::string s = device_cpulist(device);
+  if (s.empty() || s.size() + 1 > cap) return -1;
+  memcpy(out, s.c_str(), s.size() + 1);
+  return (int)s.size();
+}
 
 void sw_ctx_destroy(sw_ctx* ctx) {
   Ctx* c = (Ctx*)ctx;
@@ -2281,6 +2368,7 @@ sw_worker_t sw_worker_create(sw_ctx* ctx, int kind) {
     set_error("bad worker kind");
     return 0;
   }
+  ScopedAffinity numa(c->device);
   Worker* w = new Worker();
   w->id = (uint64_t)(uintptr_t)w;
   w->kind = kind;

@@ -36,6 +36,7 @@ int device_count();
 int init(int device);                 // binds the calling thread to `device`
 int bind_thread(int device);          // cudaSetDevice for helper threads
 int sm_count();
+int device_pci_bus_id(int device, char* out, int cap);   // "0000:1b:00.0"; < 0 when unknown
 
 void* dev_alloc(size_t bytes);        // IPC-shareable device allocation, zeroed
 void* dev_alloc_raw(size_t bytes);    // same, contents undefined (large staging buffers)

@@ -70,6 +70,14 @@ int bind_thread(int device) {
   return 0;
 }
 int sm_count() { return g_sms; }
+int device_pci_bus_id(int device, char* out, int cap) {
+  if (cap < 16) return -1;
+  cudaError_t r = cudaDeviceGetPCIBusId(out, cap, device);
+  if (r != cudaSuccess) return fail(r, "cudaDeviceGetPCIBusId");
+  for (char* p = out; *p; p++)
+    if (*p >= 'A' && *p <= 'Z') *p = (char)(*p - 'A' + 'a');   // sysfs spells it in lower case
+  return 0;
+}
 
 void* dev_alloc(size_t bytes) {
   void* p = nullptr;

@@ -53,6 +53,7 @@ int init(int device) {
 }
 int bind_thread(int) { return 0; }
 int sm_count() { return 8; }
+int device_pci_bus_id(int, char*, int) { return -1; }
 
 static void cleanup_all() {
   std::lock_guard<std::mutex> lk(g_mu);

@@ -158,3 +158,13 @@ def test_loop_stopped_while_polling(sim_api, port):
     run(second())
     assert (state["buf"] == np.arange(4)).all()
     loop1.close()
+
+
+def test_numa_helpers_are_noops_without_topology(sim_api):
+    # the CPU stand-in backend has no PCI topology: nothing is known, nothing is changed
+    import os
+
+    before = os.sched_getaffinity(0)
+    assert sim_api.local_cpus(0) == set()
+    assert sim_api.bind_to_device_numa(0) is False
+    assert os.sched_getaffinity(0) == before

@@ -521,3 +521,21 @@ def test_pingpong_latency_small_messages(cuda_api, port):
             assert med < 200e-6
 
     run(go())
+
+
+def test_numa_local_cpus(cuda_api):
+    """sw_device_local_cpus parses the GPU's sysfs cpulist; binding keeps the process runnable."""
+    import os
+
+    cpus = cuda_api.local_cpus(0)
+    allowed = os.sched_getaffinity(0)
+    if not cpus:
+        pytest.skip("no PCI topology visible in sysfs")
+    assert cpus <= set(range(os.cpu_count() or 4096))
+    changed = cuda_api.bind_to_device_numa(0)
+    try:
+        now = os.sched_getaffinity(0)
+        assert now and now <= allowed
+        assert (now == (cpus & allowed)) if changed else True
+    finally:
+        os.sched_setaffinity(0, allowed)
