@@ -320,6 +320,10 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
             with self._lock:
                 pop = self._ops.pop
                 entries = [pop(buf[i].op_id, None) for i in range(n)]
+            fp = self._fp
+            if fp is not None and None in entries:
+                # operations posted through the C fast path live in its own table
+                entries = [e if e is not None else fp.take(buf[i].op_id) for i, e in enumerate(entries)]
             batches: dict[Any, list] | None = None
             for i in range(n):
                 entry = entries[i]
@@ -439,7 +443,7 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
             again = False
             try:
                 n = self._drain(loop)
-                pending = len(self._ops)
+                pending = len(self._ops) + (self._fp.pending() if self._fp is not None else 0)
                 if pending and self._h:
                     now = _monotonic_ns()
                     if n or pending != self._spin_seen:

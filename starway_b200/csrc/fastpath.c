@@ -29,8 +29,21 @@ typedef int (*poll_fn)(void*, sw_completion*, int);
 
 enum { SW_OP_RECV = 2 };
 
+/* Pending fast-path operations: op id -> (loop, future, keep-alive), open addressing with linear
+ * probing.  The engine hands out sequential op ids, so `op & mask` spreads them perfectly; keeping
+ * the entries in C saves a PyLong key, a 5-tuple and a dict insert + delete per operation. */
+typedef struct {
+  uint64_t op; /* 0: empty */
+  PyObject* loop;
+  PyObject* fut;
+  PyObject* keep;
+} OpSlot;
+
 typedef struct {
   PyObject_HEAD
+  OpSlot* tab;
+  size_t tab_cap; /* power of two */
+  size_t tab_count;
   post_send_fn post_send;
   post_recv_fn post_recv;
   poll_fn poll;
@@ -51,7 +64,77 @@ typedef struct {
   sw_completion buf[512];
 } Binding;
 
+static void tab_clear(Binding* self) {
+  for (size_t i = 0; i < self->tab_cap; i++) {
+    if (self->tab[i].op) {
+      Py_XDECREF(self->tab[i].loop);
+      Py_XDECREF(self->tab[i].fut);
+      Py_XDECREF(self->tab[i].keep);
+    }
+  }
+  PyMem_Free(self->tab);
+  self->tab = NULL;
+  self->tab_cap = self->tab_count = 0;
+}
+
+static OpSlot* tab_find(Binding* self, uint64_t op) {
+  if (!self->tab_count || !op) return NULL; /* op 0: accept notifications carry no operation */
+  const size_t mask = self->tab_cap - 1;
+  for (size_t i = (size_t)op & mask;; i = (i + 1) & mask) {
+    if (self->tab[i].op == op) return &self->tab[i];
+    if (self->tab[i].op == 0) return NULL;
+  }
+}
+
+static void tab_place(OpSlot* tab, size_t mask, OpSlot v) {
+  size_t i = (size_t)v.op & mask;
+  while (tab[i].op) i = (i + 1) & mask;
+  tab[i] = v;
+}
+
+/* takes new references to loop / fut / keep */
+static int tab_insert(Binding* self, uint64_t op, PyObject* loop, PyObject* fut, PyObject* keep) {
+  if ((self->tab_count + 1) * 2 > self->tab_cap) {
+    const size_t ncap = self->tab_cap ? self->tab_cap * 2 : 1024;
+    OpSlot* nt = (OpSlot*)PyMem_Calloc(ncap, sizeof(OpSlot));
+    if (!nt) {
+      PyErr_NoMemory();
+      return -1;
+    }
+    for (size_t i = 0; i < self->tab_cap; i++)
+      if (self->tab[i].op) tab_place(nt, ncap - 1, self->tab[i]);
+    PyMem_Free(self->tab);
+    self->tab = nt;
+    self->tab_cap = ncap;
+  }
+  OpSlot v = {op, loop, fut, keep};
+  Py_INCREF(loop);
+  Py_INCREF(fut);
+  Py_INCREF(keep);
+  tab_place(self->tab, self->tab_cap - 1, v);
+  self->tab_count++;
+  return 0;
+}
+
+/* removes *s (its references now belong to the caller): backward-shift deletion */
+static void tab_remove(Binding* self, OpSlot* s) {
+  const size_t mask = self->tab_cap - 1;
+  size_t i = (size_t)(s - self->tab), j = i;
+  for (;;) {
+    j = (j + 1) & mask;
+    if (self->tab[j].op == 0) break;
+    const size_t k = (size_t)self->tab[j].op & mask; /* home position of the entry at j */
+    const int stays = (i <= j) ? (i < k && k <= j) : (i < k || k <= j);
+    if (stays) continue;
+    self->tab[i] = self->tab[j];
+    i = j;
+  }
+  self->tab[i].op = 0;
+  self->tab_count--;
+}
+
 static void Binding_dealloc(Binding* self) {
+  tab_clear(self);
   Py_XDECREF(self->ops);
   Py_XDECREF(self->resolve);
   Py_XDECREF(self->ensure_reader);
@@ -74,6 +157,8 @@ static int Binding_init(Binding* self, PyObject* args, PyObject* kw) {
   if (!PyArg_ParseTuple(args, "KKKKO!OOOOO", &ps, &pr, &pl, &ctx, &PyDict_Type, &ops, &resolve, &ensure_reader, &slow,
                         &last_error, &status_string))
     return -1;
+  self->tab = NULL;
+  self->tab_cap = self->tab_count = 0;
   self->post_send = (post_send_fn)(uintptr_t)ps;
   self->post_recv = (post_recv_fn)(uintptr_t)pr;
   self->poll = (poll_fn)(uintptr_t)pl;
@@ -206,12 +291,7 @@ static PyObject* raise_last_error(Binding* self) {
 }
 
 static PyObject* register_op(Binding* self, uint64_t op, PyObject* loop, PyObject* fut, PyObject* keep) {
-  PyObject* key = PyLong_FromUnsignedLongLong(op);
-  PyObject* entry = key ? PyTuple_Pack(5, self->str_fut, loop, fut, keep, Py_None) : NULL;
-  int rc = entry ? PyDict_SetItem(self->ops, key, entry) : -1;
-  Py_XDECREF(key);
-  Py_XDECREF(entry);
-  if (rc < 0) {
+  if (tab_insert(self, op, loop, fut, keep) < 0) {
     Py_DECREF(fut);
     return NULL;
   }
@@ -282,6 +362,31 @@ static void swallow_invalid_state(void) {
   if (PyErr_Occurred()) PyErr_Clear();
 }
 
+/* set the result / exception of a future that belongs to the loop we are running on */
+static int resolve_future(Binding* self, PyObject* fut, const sw_completion* c) {
+  PyObject* r = NULL;
+  if (c->status == 0) {
+    if (c->kind == SW_OP_RECV) {
+      PyObject* val = Py_BuildValue("(KK)", (unsigned long long)c->sender_tag, (unsigned long long)c->length);
+      if (val) {
+        r = PyObject_CallMethodOneArg(fut, self->str_set_result, val);
+        Py_DECREF(val);
+      }
+    } else {
+      r = PyObject_CallMethodOneArg(fut, self->str_set_result, Py_None);
+    }
+  } else {
+    PyObject* msg = PyObject_CallFunction(self->status_string, "i", (int)c->status);
+    PyObject* exc = msg ? PyObject_CallOneArg(PyExc_Exception, msg) : NULL;
+    if (exc) r = PyObject_CallMethodOneArg(fut, self->str_set_exception, exc);
+    Py_XDECREF(msg);
+    Py_XDECREF(exc);
+  }
+  if (!r) swallow_invalid_state();
+  Py_XDECREF(r);
+  return 0;
+}
+
 /* drain(loop): resolve every pending completion; runs on `loop`'s thread (eventfd reader) */
 static PyObject* Binding_drain(Binding* self, PyObject* here) {
   long total = 0;
@@ -291,6 +396,31 @@ static PyObject* Binding_drain(Binding* self, PyObject* here) {
     total += n;
     for (int i = 0; i < n; i++) {
       const sw_completion c = self->buf[i];
+      OpSlot* slot = tab_find(self, c.op_id);
+      if (slot) {
+        PyObject *loop = slot->loop, *fut = slot->fut, *keep = slot->keep; /* references move to us */
+        tab_remove(self, slot);
+        int rc = 0;
+        if (loop == here) {
+          rc = resolve_future(self, fut, &c);
+        } else {
+          /* a future of another loop: the Python shim hands it over with call_soon_threadsafe */
+          PyObject* entry = PyTuple_Pack(5, self->str_fut, loop, fut, keep, Py_None);
+          PyObject* r = entry ? PyObject_CallFunction(self->slow, "OIiKKKKO", entry, (unsigned)c.kind, (int)c.status,
+                                                      (unsigned long long)c.sender_tag, (unsigned long long)c.length,
+                                                      (unsigned long long)c.worker, (unsigned long long)c.ep, here)
+                              : NULL;
+          if (!r) rc = -1;
+          Py_XDECREF(r);
+          Py_XDECREF(entry);
+        }
+        Py_DECREF(loop);
+        Py_DECREF(fut);
+        Py_DECREF(keep);
+        if (rc < 0) return NULL;
+        continue;
+      }
+      /* not a fast-path operation: the table shared with the Python shim */
       PyObject* key = PyLong_FromUnsignedLongLong(c.op_id);
       if (!key) return NULL;
       PyObject* entry = PyDict_GetItemWithError(self->ops, key); /* borrowed */
@@ -306,27 +436,10 @@ static PyObject* Binding_drain(Binding* self, PyObject* here) {
                  PyTuple_GET_ITEM(entry, 0) == self->str_fut && PyTuple_GET_ITEM(entry, 1) == here &&
                  PyTuple_GET_ITEM(entry, 4) == Py_None;
       if (fast) {
-        PyObject* fut = PyTuple_GET_ITEM(entry, 2);
-        PyObject* r = NULL;
-        if (c.status == 0) {
-          if (c.kind == SW_OP_RECV) {
-            PyObject* val = Py_BuildValue("(KK)", (unsigned long long)c.sender_tag, (unsigned long long)c.length);
-            if (val) {
-              r = PyObject_CallMethodOneArg(fut, self->str_set_result, val);
-              Py_DECREF(val);
-            }
-          } else {
-            r = PyObject_CallMethodOneArg(fut, self->str_set_result, Py_None);
-          }
-        } else {
-          PyObject* msg = PyObject_CallFunction(self->status_string, "i", (int)c.status);
-          PyObject* exc = msg ? PyObject_CallOneArg(PyExc_Exception, msg) : NULL;
-          if (exc) r = PyObject_CallMethodOneArg(fut, self->str_set_exception, exc);
-          Py_XDECREF(msg);
-          Py_XDECREF(exc);
+        if (resolve_future(self, PyTuple_GET_ITEM(entry, 2), &c) < 0) {
+          Py_XDECREF(entry);
+          return NULL;
         }
-        if (!r) swallow_invalid_state();
-        Py_XDECREF(r);
       } else {
         /* accept notifications, raw callbacks, other loops, banner callbacks: the Python shim */
         PyObject* r = PyObject_CallFunction(self->slow, "OIiKKKKO", entry ? entry : Py_None, (unsigned)c.kind, (int)c.status,
@@ -345,7 +458,29 @@ static PyObject* Binding_drain(Binding* self, PyObject* here) {
   return PyLong_FromLong(total);
 }
 
+/* take(op_id) -> ("fut", loop, fut, keep, None) | None: hands a fast-path entry to the Python shim
+ * (completions polled by the fallback poller thread instead of a loop's reader) */
+static PyObject* Binding_take(Binding* self, PyObject* arg) {
+  uint64_t op = PyLong_AsUnsignedLongLong(arg);
+  if (PyErr_Occurred()) return NULL;
+  OpSlot* slot = tab_find(self, op);
+  if (!slot) Py_RETURN_NONE;
+  PyObject *loop = slot->loop, *fut = slot->fut, *keep = slot->keep;
+  tab_remove(self, slot);
+  PyObject* entry = PyTuple_Pack(5, self->str_fut, loop, fut, keep, Py_None);
+  Py_DECREF(loop);
+  Py_DECREF(fut);
+  Py_DECREF(keep);
+  return entry;
+}
+
+static PyObject* Binding_pending(Binding* self, PyObject* Py_UNUSED(ignored)) {
+  return PyLong_FromSize_t(self->tab_count);
+}
+
 static PyMethodDef Binding_methods[] = {
+    {"take", (PyCFunction)Binding_take, METH_O, "take(op_id) -> entry tuple or None"},
+    {"pending", (PyCFunction)Binding_pending, METH_NOARGS, "pending() -> int: fast-path operations awaiting completion"},
     {"asend", (PyCFunction)(void (*)(void))Binding_asend, METH_FASTCALL, "asend(worker, ep, buffer, tag) -> Future"},
     {"arecv", (PyCFunction)(void (*)(void))Binding_arecv, METH_FASTCALL, "arecv(worker, buffer, tag, mask) -> Future"},
     {"drain", (PyCFunction)Binding_drain, METH_O, "drain(loop) -> int: resolve pending completions on the loop thread"},

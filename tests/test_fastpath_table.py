@@ -1,0 +1,138 @@
+"""The C fast path keeps its pending operations in an open-addressing table (fastpath.c: OpSlot).
+Drive it against a stub engine (post = next id, poll = whatever the test queued) so that
+out-of-order completion, growth, backward-shift deletion and the hand-over to the Python shim
+(`take`) are checked in isolation from the real engine."""
+import asyncio
+import ctypes
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+STUB = r"""
+#include <stdint.h>
+#include <stddef.h>
+#include <string.h>
+typedef struct { uint64_t op_id; int32_t status; uint32_t kind; uint64_t sender_tag, length, worker, ep; } comp;
+static uint64_t next_id = 0;
+static comp q[1 << 16];
+static int qh = 0, qt = 0;
+uint64_t st_post_send(void* c, uint64_t w, uint64_t ep, const void* p, size_t n, uint64_t tag, int mem) { return ++next_id; }
+uint64_t st_post_recv(void* c, uint64_t w, void* p, size_t n, uint64_t tag, uint64_t mask, int mem) { return ++next_id; }
+void st_complete(uint64_t op, int32_t status, uint32_t kind, uint64_t tag, uint64_t len) {
+  comp x; memset(&x, 0, sizeof x); x.op_id = op; x.status = status; x.kind = kind; x.sender_tag = tag; x.length = len;
+  q[qt++ & 0xFFFF] = x;
+}
+uint64_t st_last_id(void) { return next_id; }
+int st_poll(void* c, comp* out, int max) { int n = 0; while (n < max && qh != qt) out[n++] = q[qh++ & 0xFFFF]; return n; }
+"""
+
+
+@pytest.fixture(scope="module")
+def stub(tmp_path_factory):
+    from starway_b200 import _core
+
+    if _core._fastpath is None:
+        pytest.skip("_fastpath.so not built")
+    d = tmp_path_factory.mktemp("stub")
+    (d / "stub.c").write_text(STUB)
+    subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", str(d / "libstub.so"), str(d / "stub.c")])
+    lib = ctypes.CDLL(str(d / "libstub.so"))
+    lib.st_complete.argtypes = [ctypes.c_uint64, ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint64]
+    lib.st_last_id.restype = ctypes.c_uint64
+    return lib, _core
+
+
+def make_binding(lib, _core, ops, slow_calls):
+    addr = lambda f: ctypes.cast(f, ctypes.c_void_p).value  # noqa: E731
+
+    def slow(entry, kind, status, tag, length, worker, ep, here):
+        slow_calls.append((entry, kind, status, tag, length))
+
+    return _core._fastpath.Binding(addr(lib.st_post_send), addr(lib.st_post_recv), addr(lib.st_poll), 0, ops,
+                                   _core.as_buffer, lambda loop: None, slow, lambda: "stub error",
+                                   lambda s: f"status {s}")
+
+
+def test_out_of_order_completion_growth_and_deletion(stub):
+    lib, _core = stub
+    rng = random.Random(7)
+
+    async def go():
+        loop = asyncio.get_running_loop()
+        ops, slow_calls = {}, []
+        fp = make_binding(lib, _core, ops, slow_calls)
+        buf = np.zeros(8, dtype=np.uint8)
+        live = {}  # future -> expected result
+        posted = 0
+        for rnd in range(60):
+            for _ in range(rng.randrange(1, 400)):  # grows the table past its initial capacity, repeatedly
+                if rng.random() < 0.5:
+                    f = fp.arecv(1, buf, 1, 0xFFFF)
+                    kind = 2
+                else:
+                    f = fp.asend(1, 0, buf, 1)
+                    kind = 1
+                posted += 1
+                live[posted] = (f, kind)
+            assert fp.pending() == len(live)
+            ids = list(live)
+            rng.shuffle(ids)
+            done = ids[: rng.randrange(0, len(ids) + 1)]
+            for op in done:
+                status = -16 if op % 17 == 0 else 0
+                lib.st_complete(op, status, live[op][1], op * 3, op * 5)
+            assert fp.drain(loop) == len(done)
+            for op in done:
+                f, kind = live.pop(op)
+                assert f.done()
+                if op % 17 == 0:
+                    assert str(f.exception()) == "status -16"
+                elif kind == 2:
+                    assert f.result() == (op * 3, op * 5)
+                else:
+                    assert f.result() is None
+            assert fp.pending() == len(live)
+            assert all(not f.done() for f, _ in live.values())
+        # leftovers: handed to the Python shim one by one
+        for op, (f, kind) in list(live.items()):
+            entry = fp.take(op)
+            assert entry[0] == "fut" and entry[1] is loop and entry[2] is f
+            assert fp.take(op) is None
+        assert fp.pending() == 0 and not slow_calls and not ops
+        # unknown ids and op 0 (accept notifications) go to the slow path untouched
+        lib.st_complete(0, 0, 5, 0, 0)
+        lib.st_complete(10**12, 0, 1, 0, 0)
+        assert fp.drain(loop) == 2
+        assert [c[0] for c in slow_calls] == [None, None]
+
+    asyncio.run(go())
+
+
+def test_future_of_another_loop_goes_through_the_shim(stub):
+    lib, _core = stub
+    ops, slow_calls = {}, []
+    fp = make_binding(lib, _core, ops, slow_calls)
+    buf = np.zeros(8, dtype=np.uint8)
+    state = {}
+
+    async def first():
+        state["fut"] = fp.asend(1, 0, buf, 9)
+        state["loop"] = asyncio.get_running_loop()
+
+    loop1 = asyncio.new_event_loop()
+    loop1.run_until_complete(first())
+
+    async def second():
+        here = asyncio.get_running_loop()
+        op = lib.st_last_id()
+        lib.st_complete(op, 0, 1, 0, 0)
+        assert fp.drain(here) == 1
+        # not resolved here: handed to the shim, which would call_soon_threadsafe on the owning loop
+        assert not state["fut"].done() and fp.pending() == 0
+        (entry, kind, status, _tag, _len), = slow_calls
+        assert entry[0] == "fut" and entry[1] is state["loop"] and entry[2] is state["fut"] and (kind, status) == (1, 0)
+
+    asyncio.run(second())
+    loop1.close()
