@@ -267,7 +267,38 @@ struct SqNode {
   bool heap = false;
 };
 
+// Operation records are allocated on the posting thread and freed on the progress thread; going
+// through malloc that is a cross-thread free per operation.  Freed blocks go onto a lock-free
+// return stack instead (push only: no ABA), and an allocating thread takes the WHOLE stack into a
+// thread-local cache when its cache runs dry.
+template <class T>
+struct OpPool {
+  struct Node {
+    Node* next;
+  };
+  static inline std::atomic<Node*> returned{nullptr};
+  static inline thread_local Node* cache = nullptr;
+  static void* get() {
+    Node* n = cache;
+    if (!n) n = returned.exchange(nullptr, std::memory_order_acquire);
+    if (n) {
+      cache = n->next;
+      return n;
+    }
+    return ::operator new(sizeof(T) < sizeof(Node) ? sizeof(Node) : sizeof(T));
+  }
+  static void put(void* p) {
+    Node* n = static_cast<Node*>(p);
+    Node* h = returned.load(std::memory_order_relaxed);
+    do {
+      n->next = h;
+    } while (!returned.compare_exchange_weak(h, n, std::memory_order_release, std::memory_order_relaxed));
+  }
+};
+
 struct SendOp {
+  static void* operator new(size_t) { return OpPool<SendOp>::get(); }
+  static void operator delete(void* p) { OpPool<SendOp>::put(p); }
   SqNode sqn;
   uint64_t op_id = 0;
   Worker* w = nullptr;
@@ -286,6 +317,8 @@ struct SendOp {
 constexpr int MEM_PINNED = 3;  // internal: host memory the device can address directly (cudaHostAlloc)
 
 struct RecvOp {
+  static void* operator new(size_t) { return OpPool<RecvOp>::get(); }
+  static void operator delete(void* p) { OpPool<RecvOp>::put(p); }
   SqNode sqn;
   uint64_t op_id = 0;
   Worker* w = nullptr;
@@ -477,20 +510,22 @@ constexpr uint64_t STAGE_SEG_BYTES = 32768;
 struct Ctx {
   int device = 0;
   uint64_t uuid = 0;
-  std::atomic<uint64_t> next_id{1};
   // handle tables
   std::mutex mu;
   std::unordered_map<uint64_t, Worker*> workers;
   std::unordered_map<uint64_t, Ep*> eps;
-  // submission queue
-  std::atomic<SqNode*> sq_head{nullptr};
-  // completion queue
-  std::mutex cq_mu;
+  // The words that posting threads, the progress thread and a polling consumer hammer on live on
+  // cache lines of their own (no false sharing between the submission and the completion side).
+  alignas(64) std::atomic<uint64_t> next_id{1};  // posting threads
+  // submission queue: written by posting threads, polled by the progress thread
+  alignas(64) std::atomic<SqNode*> sq_head{nullptr};
+  // completion queue: written by the progress thread, polled by the consumer
+  alignas(64) std::atomic<uint32_t> cq_count{0};  // == cq.size(), readable without the lock
+  std::atomic<int> efd_signaled{0};               // the eventfd counter is non-zero
+  alignas(64) std::atomic<int> consumer_polling{0};  // option "consumer_polling": skip the eventfd wake-up
+  std::atomic<int> cq_waiters{0};                    // threads blocked in sw_wait
+  alignas(64) std::mutex cq_mu;
   std::condition_variable cq_cv;
-  std::atomic<uint32_t> cq_count{0};        // == cq.size(), readable without the lock
-  std::atomic<int> cq_waiters{0};           // threads blocked in sw_wait
-  std::atomic<int> consumer_polling{0};     // option "consumer_polling": skip the eventfd wake-up
-  std::atomic<int> efd_signaled{0};         // the eventfd counter is non-zero
   std::deque<sw_completion> cq;
   std::vector<sw_completion> cq_local;  // progress-thread staging
   int efd = -1;
