@@ -30,8 +30,11 @@ typedef int (*poll_fn)(void*, sw_completion*, int);
 enum { SW_OP_RECV = 2 };
 
 /* Pending fast-path operations: op id -> (loop, future, keep-alive), open addressing with linear
- * probing.  The engine hands out sequential op ids, so `op & mask` spreads them perfectly; keeping
- * the entries in C saves a PyLong key, a 5-tuple and a dict insert + delete per operation. */
+ * probing; keeping the entries in C saves a PyLong key, a 5-tuple and a dict insert + delete per
+ * operation.  The engine hands out SEQUENTIAL op ids: hashed by `op & mask` thousands of
+ * pre-posted receives would form one contiguous cluster and every deletion would scan all of it
+ * (measured: 11 us per completion with 19 200 receives outstanding), so the ids are scattered
+ * with a multiplicative (Fibonacci) hash. */
 typedef struct {
   uint64_t op; /* 0: empty */
   PyObject* loop;
@@ -44,6 +47,7 @@ typedef struct {
   OpSlot* tab;
   size_t tab_cap; /* power of two */
   size_t tab_count;
+  unsigned tab_shift; /* 64 - log2(tab_cap) */
   post_send_fn post_send;
   post_recv_fn post_recv;
   poll_fn poll;
@@ -77,17 +81,19 @@ static void tab_clear(Binding* self) {
   self->tab_cap = self->tab_count = 0;
 }
 
+static inline size_t tab_home(uint64_t op, unsigned shift) { return (size_t)((op * 0x9E3779B97F4A7C15ull) >> shift); }
+
 static OpSlot* tab_find(Binding* self, uint64_t op) {
   if (!self->tab_count || !op) return NULL; /* op 0: accept notifications carry no operation */
   const size_t mask = self->tab_cap - 1;
-  for (size_t i = (size_t)op & mask;; i = (i + 1) & mask) {
+  for (size_t i = tab_home(op, self->tab_shift);; i = (i + 1) & mask) {
     if (self->tab[i].op == op) return &self->tab[i];
     if (self->tab[i].op == 0) return NULL;
   }
 }
 
-static void tab_place(OpSlot* tab, size_t mask, OpSlot v) {
-  size_t i = (size_t)v.op & mask;
+static void tab_place(OpSlot* tab, size_t mask, unsigned shift, OpSlot v) {
+  size_t i = tab_home(v.op, shift);
   while (tab[i].op) i = (i + 1) & mask;
   tab[i] = v;
 }
@@ -96,22 +102,25 @@ static void tab_place(OpSlot* tab, size_t mask, OpSlot v) {
 static int tab_insert(Binding* self, uint64_t op, PyObject* loop, PyObject* fut, PyObject* keep) {
   if ((self->tab_count + 1) * 2 > self->tab_cap) {
     const size_t ncap = self->tab_cap ? self->tab_cap * 2 : 1024;
+    unsigned nshift = 64;
+    for (size_t c = ncap; c > 1; c >>= 1) nshift--;
     OpSlot* nt = (OpSlot*)PyMem_Calloc(ncap, sizeof(OpSlot));
     if (!nt) {
       PyErr_NoMemory();
       return -1;
     }
     for (size_t i = 0; i < self->tab_cap; i++)
-      if (self->tab[i].op) tab_place(nt, ncap - 1, self->tab[i]);
+      if (self->tab[i].op) tab_place(nt, ncap - 1, nshift, self->tab[i]);
     PyMem_Free(self->tab);
     self->tab = nt;
     self->tab_cap = ncap;
+    self->tab_shift = nshift;
   }
   OpSlot v = {op, loop, fut, keep};
   Py_INCREF(loop);
   Py_INCREF(fut);
   Py_INCREF(keep);
-  tab_place(self->tab, self->tab_cap - 1, v);
+  tab_place(self->tab, self->tab_cap - 1, self->tab_shift, v);
   self->tab_count++;
   return 0;
 }
@@ -123,7 +132,7 @@ static void tab_remove(Binding* self, OpSlot* s) {
   for (;;) {
     j = (j + 1) & mask;
     if (self->tab[j].op == 0) break;
-    const size_t k = (size_t)self->tab[j].op & mask; /* home position of the entry at j */
+    const size_t k = tab_home(self->tab[j].op, self->tab_shift); /* home position of the entry at j */
     const int stays = (i <= j) ? (i < k && k <= j) : (i < k || k <= j);
     if (stays) continue;
     self->tab[i] = self->tab[j];
@@ -159,6 +168,7 @@ static int Binding_init(Binding* self, PyObject* args, PyObject* kw) {
     return -1;
   self->tab = NULL;
   self->tab_cap = self->tab_count = 0;
+  self->tab_shift = 63;
   self->post_send = (post_send_fn)(uintptr_t)ps;
   self->post_recv = (post_recv_fn)(uintptr_t)pr;
   self->poll = (poll_fn)(uintptr_t)pl;

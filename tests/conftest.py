@@ -65,6 +65,8 @@ def cuda_api():
         get_context=sw.get_context,
         shutdown=sw.shutdown,
         backend_name=sw.backend_name,
+        local_cpus=sw.local_cpus,
+        bind_to_device_numa=sw.bind_to_device_numa,
     )
     yield api
     sw.shutdown()
