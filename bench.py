@@ -293,7 +293,8 @@ def run_ours(args):
         pass
     roofline = {
         "bound": bound, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-        "frac": round(achieved / peak, 4), "traffic": traffic, "kernel": "sw_bulk_tma_kernel",
+        "frac": round(achieved / peak, 4), "traffic": traffic,
+        "kernel": "sw_bulk_tma_kernel / sw_bulk_tma_inline_kernel (same body; <= 96 segments travel as kernel parameters)",
         "launches": st["bulk_event_launches"], "avg_launch_us": round(avg_ms * 1e3, 2),
         "payload_bytes_per_launch": int(payload_per_launch), "peak_source": peak_note,
     }

@@ -1,11 +1,11 @@
 #!/usr/bin/env python
-"""tools/latency_trace.py — where one small-message round trip spends its time.
+"""tests/tools/latency_trace.py — where one small-message round trip spends its time.
 
 Runs the 64 B device-buffer ping-pong (Server + Client on one GPU) with STARWAY_TRACE enabled and
 interleaves the progress thread's pipeline events with time stamps taken in the Python coroutine
 (both are CLOCK_MONOTONIC).  Prints the median gap between consecutive events of a round trip.
 
-  STARWAY_TRACE=/tmp/sw_trace python tools/latency_trace.py [--bytes 64] [--iters 300]
+  STARWAY_TRACE=/tmp/sw_trace python tests/tools/latency_trace.py [--bytes 64] [--iters 300]
 """
 from __future__ import annotations
 
@@ -18,7 +18,7 @@ import statistics
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("STARWAY_QUIET", "1")
 os.environ.setdefault("STARWAY_TRACE", "/tmp/sw_latency_trace")
