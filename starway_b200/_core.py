@@ -28,6 +28,7 @@ import ctypes
 import os
 import threading
 import time
+import weakref
 from collections.abc import Callable
 from types import SimpleNamespace
 from typing import Any
@@ -267,7 +268,8 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
                 raise RuntimeError(_err())
             self._lock = threading.Lock()
             self._ops: dict[int, tuple] = {}
-            self._servers: dict[int, Any] = {}
+            # weak: a Server the caller dropped must be collectable (its __del__ closes the native worker)
+            self._servers: weakref.WeakValueDictionary = weakref.WeakValueDictionary()
             self._efd = lib.sw_event_fd(self._h)
             self._readers: dict[Any, bool] = {}
             self._buf = (SwCompletion * 512)()

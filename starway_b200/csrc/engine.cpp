@@ -354,10 +354,50 @@ struct BulkJob {
   int32_t fail_status = 0;
 };
 
-constexpr uint32_t EP_MAGIC = 0x53574550u, WORKER_MAGIC = 0x5357574Bu;
+constexpr uint32_t EP_MAGIC = 0x53574550u, WORKER_MAGIC = 0x5357574Bu, DEAD_MAGIC = 0x44454144u;
+
+// Worker / endpoint handles are pointers into TYPE-STABLE storage tagged with a 16-bit generation
+// (bits 48-63): the storage of a destroyed object is never returned to malloc, it goes onto a free
+// list and is reused for the next object of the same type with the generation bumped.  A stale
+// handle therefore always dereferences valid memory and fails the magic / generation check,
+// while a process that keeps creating and closing Clients / Servers does not grow (each record is
+// 2-3 KB: two std::deque members alone are 1.2 KB).  Both types start with {magic, gen}.
+constexpr uint64_t HANDLE_PTR_MASK = 0x0000FFFFFFFFFFFFull;
+template <class T>
+struct Slab {
+  static inline std::mutex mu;
+  static inline std::vector<void*> free_list;
+  static T* make() {
+    void* mem = nullptr;
+    uint32_t gen = 1;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (!free_list.empty()) {
+        mem = free_list.back();
+        free_list.pop_back();
+        gen = (static_cast<uint32_t*>(mem)[1] + 1) & 0xFFFFu;
+        if (!gen) gen = 1;
+      }
+    }
+    if (!mem) mem = ::operator new(sizeof(T));
+    T* t = new (mem) T();
+    t->gen = gen;
+    t->id = (uint64_t)(uintptr_t)t | ((uint64_t)gen << 48);
+    return t;
+  }
+  static void recycle(T* t) {
+    const uint32_t gen = t->gen;
+    t->~T();
+    static_cast<uint32_t*>(static_cast<void*>(t))[0] = DEAD_MAGIC;
+    static_cast<uint32_t*>(static_cast<void*>(t))[1] = gen;
+    std::lock_guard<std::mutex> lk(mu);
+    free_list.push_back(t);
+  }
+};
 
 struct Ep {
   uint32_t magic = EP_MAGIC;
+  uint32_t gen = 0;
   uint64_t id = 0;
   Worker* owner = nullptr;
   uint32_t index = 0;  // index of the inbound ring in the owner's match state
@@ -403,6 +443,7 @@ struct Ep {
 
 struct Worker {
   uint32_t magic = WORKER_MAGIC;
+  uint32_t gen = 0;
   uint64_t id = 0;
   int kind = 0;
   Ctx* ctx = nullptr;
@@ -436,6 +477,8 @@ struct Worker {
   int close_phase = 0;
   double close_deadline = 0;
   bool registered = false;
+  std::atomic<bool> register_queued{false};  // an SQ_REGISTER for this worker was pushed
+  std::atomic<bool> retired{false};          // the progress thread has dropped its last reference
   std::thread connector;
   uint32_t bulk_inflight = 0;
 };
@@ -533,6 +576,7 @@ struct Ctx {
   std::thread thr;
   std::atomic<bool> stop{false};
   std::vector<Worker*> active;  // progress-thread private
+  bool need_prune = false;      // progress-thread private: a worker reached close phase 4
   // device resources
   swgpu::stream_t s_put = nullptr, s_match = nullptr, s_bulk = nullptr;
   PutBlock put_blocks[N_PUT_BLOCKS];
@@ -747,8 +791,7 @@ void fill_blob(Ctx* c, Worker* w) {
 }
 
 Ep* ep_new(Ctx* c, Worker* w) {
-  Ep* ep = new Ep();
-  ep->id = (uint64_t)(uintptr_t)ep;
+  Ep* ep = Slab<Ep>::make();
   ep->owner = w;
   memset(&ep->info, 0, sizeof(ep->info));
   return ep;
@@ -982,7 +1025,7 @@ void server_handshake(Ctx* c, Worker* w, int fd, bool tcp) {
       if (ep->peer_ring_mapping) swgpu::ipc_close(ep->peer_ring_mapping);
       if (ep->ring) swgpu::dev_free(ep->ring);
       if (ep->shm) munmap(ep->shm, ep->shm_size);
-      delete ep;
+      Slab<Ep>::recycle(ep);
     }
   }
   close(fd);
@@ -1127,13 +1170,14 @@ void client_connect_thread(Ctx* c, Worker* w, ConnectReq req) {
       c->eps[ep->id] = ep;
     }
     w->status.store(SW_ST_INIT, std::memory_order_release);
+    w->register_queued.store(true, std::memory_order_release);
     sq_push(c, SQ_REGISTER, w, (void*)(uintptr_t)req.op_id);
   } else {
     if (ep) {
       if (ep->peer_ring_mapping) swgpu::ipc_close(ep->peer_ring_mapping);
       if (ep->ring) swgpu::dev_free(ep->ring);
       if (ep->shm) munmap(ep->shm, ep->shm_size);
-      delete ep;
+      Slab<Ep>::recycle(ep);
     }
     if (w->mstate) {
       swgpu::match_state_destroy(w->mstate);
@@ -1949,6 +1993,7 @@ bool progress_close(Ctx* c, Worker* w) {
     if (waiting) return false;
     worker_release(c, w, true);
     w->close_phase = 4;
+    c->need_prune = true;
     w->status.store(SW_ST_CLOSED, std::memory_order_release);
     if (w->close_op) complete(c, w, w->close_op, SW_OP_CLOSE, SW_OK);
     return true;
@@ -2145,10 +2190,13 @@ void progress_main(Ctx* c) {
     active |= poll_bulk(c);
     active |= pump_bulk(c);
     flush_completions(c);
-    // forget fully closed workers
-    if ((iter & 1023) == 0) {
-      c->active.erase(std::remove_if(c->active.begin(), c->active.end(), [](Worker* w) { return w->close_phase >= 4; }),
-                      c->active.end());
+    // forget fully closed workers; `retired` tells sw_worker_destroy that this thread holds no
+    // reference any more and the record may be recycled
+    if (c->need_prune) {
+      c->need_prune = false;
+      auto dead = std::stable_partition(c->active.begin(), c->active.end(), [](Worker* w) { return w->close_phase < 4; });
+      for (auto it = dead; it != c->active.end(); ++it) (*it)->retired.store(true, std::memory_order_release);
+      c->active.erase(dead, c->active.end());
     }
     iter++;
     bool inflight = (c->put_head != c->put_tail) || (c->bulk_head != c->bulk_tail) || !c->post_copies.empty();
@@ -2186,12 +2234,27 @@ void progress_main(Ctx* c) {
 }
 
 Worker* find_worker(Ctx* c, sw_worker_t id) {
-  Worker* w = (Worker*)(uintptr_t)id;
-  return (w && w->magic == WORKER_MAGIC && w->ctx == c) ? w : nullptr;
+  Worker* w = (Worker*)(uintptr_t)(id & HANDLE_PTR_MASK);
+  return (w && w->magic == WORKER_MAGIC && w->gen == (uint32_t)(id >> 48) && w->ctx == c) ? w : nullptr;
 }
 Ep* find_ep(Ctx* c, sw_ep_t id) {
-  Ep* ep = (Ep*)(uintptr_t)id;
-  return (ep && ep->magic == EP_MAGIC && ep->owner && ep->owner->ctx == c) ? ep : nullptr;
+  Ep* ep = (Ep*)(uintptr_t)(id & HANDLE_PTR_MASK);
+  return (ep && ep->magic == EP_MAGIC && ep->gen == (uint32_t)(id >> 48) && ep->owner && ep->owner->ctx == c) ? ep
+                                                                                                              : nullptr;
+}
+
+// returns the records of a closed worker and of its endpoints to their slabs (caller: no other
+// thread references them any more)
+void recycle_worker(Ctx* c, Worker* w) {
+  if (w->connector.joinable()) w->connector.join();
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->workers.erase(w->id);
+    for (Ep* ep : w->eps) c->eps.erase(ep->id);
+  }
+  for (Ep* ep : w->eps) Slab<Ep>::recycle(ep);
+  w->eps.clear();
+  Slab<Worker>::recycle(w);
 }
 
 int classify_mem(const void* ptr, int mem_kind) {
@@ -2313,6 +2376,14 @@ void sw_ctx_destroy(sw_ctx* ctx) {
   for (Worker* w : ws) sw_worker_destroy(ctx, w->id);
   c->stop.store(true, std::memory_order_release);
   if (c->thr.joinable()) c->thr.join();
+  // whatever sw_worker_destroy could not recycle (still closing when it gave up) goes now
+  ws.clear();
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    for (auto& kv : c->workers) ws.push_back(kv.second);
+    c->workers.clear();
+    c->eps.clear();
+  }
   if (c->tracing) {
     if (FILE* f = fopen(c->trace_path.c_str(), "w")) {
       for (auto& r : c->trace) fprintf(f, "%.7f %s %llu %llu\n", r.t, r.what, (unsigned long long)r.a, (unsigned long long)r.b);
@@ -2351,8 +2422,9 @@ void sw_ctx_destroy(sw_ctx* ctx) {
   }
   for (Worker* w : ws) {
     if (w->connector.joinable()) w->connector.join();
-    for (Ep* ep : w->eps) delete ep;
-    delete w;
+    for (Ep* ep : w->eps) Slab<Ep>::recycle(ep);
+    w->eps.clear();
+    Slab<Worker>::recycle(w);
   }
   delete c;
 }
@@ -2404,8 +2476,7 @@ sw_worker_t sw_worker_create(sw_ctx* ctx, int kind) {
     return 0;
   }
   ScopedAffinity numa(c->device);
-  Worker* w = new Worker();
-  w->id = (uint64_t)(uintptr_t)w;
+  Worker* w = Slab<Worker>::make();
   w->kind = kind;
   w->ctx = c;
   std::lock_guard<std::mutex> lk(c->mu);
@@ -2448,6 +2519,7 @@ static int server_start(Ctx* c, Worker* w, const char* addr, uint16_t port, bool
   }
   fill_blob(c, w);
   w->status.store(SW_ST_RUNNING, std::memory_order_release);
+  w->register_queued.store(true, std::memory_order_release);
   sq_push(c, SQ_REGISTER, w, nullptr);
   return 0;
 }
@@ -2555,6 +2627,21 @@ int sw_worker_destroy(sw_ctx* ctx, sw_worker_t wid) {
   while (w->status.load() == SW_ST_CLOSING && now_s() < deadline) {
     struct timespec ts = {0, 100000};
     nanosleep(&ts, nullptr);
+  }
+  // Recycle the record once nothing references it: never handed to the progress thread, or handed
+  // over and already dropped by it.  (A worker stuck in CLOSING keeps its tombstone.)
+  const int st = w->status.load(std::memory_order_acquire);
+  if (st == SW_ST_VOID || st == SW_ST_CLOSED) {
+    bool free_now = !w->register_queued.load(std::memory_order_acquire);
+    if (!free_now) {
+      deadline = now_s() + 0.5;
+      while (!w->retired.load(std::memory_order_acquire) && now_s() < deadline) {
+        struct timespec ts = {0, 50000};
+        nanosleep(&ts, nullptr);
+      }
+      free_now = w->retired.load(std::memory_order_acquire);
+    }
+    if (free_now) recycle_worker(c, w);
   }
   return 0;
 }

@@ -70,3 +70,34 @@ def cuda_api():
     )
     yield api
     sw.shutdown()
+
+
+def _sweep_stale_shm():
+    """Tests kill peer processes on purpose (dead-peer paths); a killed process cannot unlink the POSIX
+    shared-memory segments it created (hostsim 'device memory', control blocks).  Remove the ones whose
+    creating pid no longer exists, so that repeated runs do not fill /dev/shm."""
+    try:
+        names = os.listdir("/dev/shm")
+    except OSError:
+        return
+    for name in names:
+        if not name.startswith(("swsim-", "swb200-")):
+            continue
+        try:
+            pid = int(name.split("-")[1])
+        except (IndexError, ValueError):
+            continue
+        if pid == os.getpid() or os.path.exists(f"/proc/{pid}"):
+            continue
+        try:
+            os.unlink(os.path.join("/dev/shm", name))
+        except OSError:
+            pass
+
+
+def pytest_sessionstart(session):
+    _sweep_stale_shm()
+
+
+def pytest_sessionfinish(session, exitstatus):
+    _sweep_stale_shm()

@@ -145,3 +145,54 @@ def test_completion_detection_modes(sim_api, port, opts):
     finally:
         ctx.set_option("done_flags", 1)
         ctx.set_option("profile", 0)
+
+
+def test_connection_churn_recycles_native_records(sim_api, port):
+    """Creating and dropping Servers / Clients must not grow the process: the native worker and
+    endpoint records are type-stable slabs (handle = pointer | generation << 48) that are reused once
+    the owner is gone, and the context keeps only weak references to Server objects."""
+    import gc
+
+    import numpy as np
+
+    ptr_mask = (1 << 48) - 1
+    seen_server, seen_ep, handles = set(), set(), []
+
+    async def cycle(i):
+        server = sim_api.Server()
+        addr = server.listen_address()
+        clients = [sim_api.Client() for _ in range(2)]
+        for c in clients:
+            await c.aconnect_address(addr)
+        buf = np.zeros(64, dtype=np.uint8)
+        fut = server.arecv(buf, 5, 0xFF)
+        await clients[0].asend(np.full(64, i & 0xFF, dtype=np.uint8), 5)
+        assert await fut == (5, 64) and (buf == (i & 0xFF)).all()
+        for _ in range(200):
+            if len(server.list_clients()) == 2:
+                break
+            await asyncio.sleep(0.005)
+        eps = list(server.list_clients())
+        assert len(eps) == 2
+        seen_server.add(server._w & ptr_mask)
+        handles.append(server._w)
+        for ep in eps:
+            seen_ep.add(ep._id & ptr_mask)
+        for c in clients:
+            await c.aclose()
+        await server.aclose()
+        return eps[0]  # an endpoint object that outlives its server
+
+    stale = None
+    for i in range(40):
+        stale = run(cycle(i))
+        gc.collect()
+    assert len(set(handles)) == len(handles)           # every handle value is unique (generation tag) ...
+    assert len(seen_server) <= 6 and len(seen_ep) <= 12  # ... while the storage behind them is reused
+    # a handle of a recycled record fails the generation check instead of aliasing the new owner
+    lib = sim_api.lib
+    import ctypes
+
+    buf = (ctypes.c_uint64 * 8)()
+    assert lib.sw_list_eps(sim_api.get_context()._h, handles[0], buf, 8) == -1
+    assert stale.name  # metadata was copied at creation; the object stays usable

@@ -68,6 +68,7 @@ async def main():
         assert hist[-1][1] <= hist[1][1] + 2, "shm segments leak"
         if hist[-1][3] is not None:
             assert hist[-1][3] <= hist[1][3] + 64, "device memory leak"
+        assert hist[-1][2] <= hist[1][2] + 16, "resident set grows (records of closed workers / endpoints must be recycled)"
     print("SOAK OK")
 
 
