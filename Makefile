@@ -28,7 +28,7 @@ oracle-core: $(ORACLE)
 hostsim: $(HOSTSIM)
 probe: $(PROBE) $(ABIBENCH)
 
-build/gpu_cuda.o: $(CSRC)/gpu_cuda.cu $(CSRC)/kernels.cuh $(CSRC)/gpu.h $(CSRC)/sw_device.h
+build/gpu_cuda.o: $(CSRC)/gpu_cuda.cu $(CSRC)/kernels.cuh $(CSRC)/gpu.h $(CSRC)/sw_device.h $(CSRC)/bulk_jobs.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 
@@ -59,7 +59,7 @@ build/engine_sim.o: $(ENGINE_SRCS) $(ENGINE_HDRS)
 	@mkdir -p build
 	$(CXX) $(CXXFLAGS) -Iinclude -c $< -o $@
 
-build/gpu_sim.o: tests/hostsim/gpu_sim.cpp $(CSRC)/gpu.h $(CSRC)/sw_device.h oracle/tagmatch.h
+build/gpu_sim.o: tests/hostsim/gpu_sim.cpp $(CSRC)/gpu.h $(CSRC)/sw_device.h $(CSRC)/bulk_jobs.h oracle/tagmatch.h
 	@mkdir -p build
 	$(CXX) $(CXXFLAGS) -c $< -o $@
 

@@ -598,6 +598,9 @@ struct Ctx {
   std::atomic<int64_t> opt_ring_slots{SW_RING_SLOTS_DEFAULT};
   std::atomic<int64_t> opt_bulk_mode{0}, opt_bulk_stages{8}, opt_bulk_stage_bytes{24576}, opt_bulk_ctas{1};
   std::atomic<int64_t> opt_coalesce_us{40}, opt_coalesce_bytes{32 << 20};
+  // 1: launches of <= 96 messages carry the messages as kernel parameters and every CTA copies an equal
+  // byte range (sw_bulk_tma_jobs_kernel); 0: segment list in pinned host memory (sw_bulk_tma_kernel)
+  std::atomic<int64_t> opt_bulk_balance{1};
   // small put / match launches announce completion through a flag in pinned host memory
   // (launch -> seen 7.4 us vs 15.2 us through a timing event on B200, profiles/r01_probe_floor.log)
   std::atomic<int64_t> opt_done_flags{1};
@@ -1342,7 +1345,7 @@ bool pump_sends(Ctx* c) {
   b.timed = c->opt_profile.load() >= 2;
   if (b.timed) swgpu::event_record(b.ev_start, c->s_put);
   if (b.nsegs) {
-    swgpu::BulkTuning up{0, 8, 24576, 1};
+    swgpu::BulkTuning up{0, 8, 24576, 1, 0};
     trace(c, "stage_upload_launch", b.nsegs, staged_bytes);
     if (swgpu::launch_bulk(c->s_put, b.segs, b.nsegs, &up) != 0)
       fprintf(stderr, "starway_b200: staging upload launch failed: %s\n", swgpu::last_error());
@@ -1704,6 +1707,7 @@ bool pump_bulk(Ctx* c) {
   tune.stages = (int)c->opt_bulk_stages.load();
   tune.stage_bytes = (int)c->opt_bulk_stage_bytes.load();
   tune.ctas_per_sm = (int)c->opt_bulk_ctas.load();
+  tune.balance = (int)c->opt_bulk_balance.load();
   const uint64_t sms = (uint64_t)swgpu::sm_count();
   uint64_t target = sms * (uint64_t)std::max(1, tune.ctas_per_sm) * 4;
   uint64_t seg = (b.bytes + target - 1) / target;
@@ -2339,6 +2343,7 @@ sw_ctx* sw_ctx_create(int device) {
   if (const char* e = getenv("STARWAY_BULK_STAGES")) c->opt_bulk_stages = atoll(e);
   if (const char* e = getenv("STARWAY_BULK_STAGE_BYTES")) c->opt_bulk_stage_bytes = atoll(e);
   if (const char* e = getenv("STARWAY_BULK_CTAS")) c->opt_bulk_ctas = atoll(e);
+  if (const char* e = getenv("STARWAY_BULK_BALANCE")) c->opt_bulk_balance = atoll(e);
   if (const char* e = getenv("STARWAY_PINNED_SEND_DIRECT")) c->opt_pinned_send_direct = atoll(e);
   if (const char* e = getenv("STARWAY_TRACE")) {
     c->trace_path = std::string(e) + "." + std::to_string((int)getpid());
@@ -2446,6 +2451,7 @@ int sw_set_option(sw_ctx* ctx, const char* key, int64_t value) {
   else if (k == "coalesce_us") c->opt_coalesce_us = value;
   else if (k == "coalesce_bytes") c->opt_coalesce_bytes = value;
   else if (k == "done_flags") c->opt_done_flags = value;
+  else if (k == "bulk_balance") c->opt_bulk_balance = value;
   else if (k == "consumer_polling") c->consumer_polling.store(value != 0, std::memory_order_seq_cst);
   else {
     set_error("unknown option " + k);

@@ -27,6 +27,7 @@ struct BulkTuning {
   int stages;         // TMA smem stages per CTA (2..8)
   int stage_bytes;    // bytes per stage (multiple of 16)
   int ctas_per_sm;    // resident CTAs per SM targeted
+  int balance;        // TMA mode: 1 = equal byte range per CTA when the launch has <= 96 jobs (see bulk_jobs.h)
 };
 
 const char* backend_name();

@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 
+#include "bulk_jobs.h"
 #include "gpu.h"
 #include "kernels.cuh"
 
@@ -61,6 +62,7 @@ int init(int device) {
   SW_CUDA(cudaFuncGetAttributes(&fa, sw_bulk_tma_kernel));
   g_max_smem_optin -= (int)fa.sharedSizeBytes;   // static mbarrier storage counts against the opt-in limit
   SW_CUDA(cudaFuncSetAttribute(sw_bulk_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem_optin));
+  SW_CUDA(cudaFuncSetAttribute(sw_bulk_tma_jobs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem_optin));
   SW_CUDA(cudaFuncSetAttribute(sw_bulk_tma_inline_kernel<SW_BULK_INLINE_SEGS_SMALL>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem_optin));
   return 0;
@@ -455,6 +457,13 @@ int launch_bulk(stream_t s, const SwSeg* segs, uint32_t nseg, const BulkTuning* 
     const int fit = (int)((size_t)(228 * 1024) / (smem + 1024 + 128));   // CTAs of this size resident per SM
     if (ctas > fit) ctas = fit < 1 ? 1 : fit;
     uint32_t grid = (uint32_t)(g_sms * ctas);
+    SwBulkJobArgs ja;
+    uint32_t jgrid = 0;
+    if (t->balance && bulk_build_jobs(segs, nseg, grid, (uint32_t)sb, (uint32_t)stages, &ja, &jgrid)) {
+      sw_bulk_tma_jobs_kernel<<<jgrid, 32, smem, (cudaStream_t)s>>>(ja);
+      SW_CUDA(cudaGetLastError());
+      return 0;
+    }
     if (grid > nseg) grid = nseg;
     if (nseg <= SW_BULK_INLINE_SEGS_SMALL) {
       SwSegArgs<SW_BULK_INLINE_SEGS_SMALL> a;

@@ -887,9 +887,10 @@ __global__ void __launch_bounds__(256) sw_deliver_kernel(SwMatchState* __restric
 // multiples of 16 B (the host routes anything else to sw_bulk_simt_kernel).
 constexpr int SW_BULK_MAX_STAGES = 8;
 
-// The copy loop, shared by the two entry points below (segment list in memory / in the parameter bank).
-template <class SegAt>
-__device__ __forceinline__ void sw_bulk_tma_body(SegAt seg_at, uint32_t nseg, uint32_t stage_bytes, uint32_t nstages) {
+// The copy pipeline, shared by the entry points below.  `next(src, dst, bytes)` yields this CTA's
+// pieces (each at most stage_bytes, 16-byte aligned) until it returns false.
+template <class Next>
+__device__ __forceinline__ void sw_bulk_tma_pipeline(Next next, uint32_t stage_bytes, uint32_t nstages) {
   extern __shared__ __align__(128) uint8_t sw_smem[];
   __shared__ __align__(8) uint64_t full[SW_BULK_MAX_STAGES];
   if (threadIdx.x != 0) return;
@@ -897,12 +898,6 @@ __device__ __forceinline__ void sw_bulk_tma_body(SegAt seg_at, uint32_t nseg, ui
   sw_fence_mbar_init();
   sw_fence_proxy_async();
 
-  // piece iterator over this CTA's segments
-  uint32_t s = blockIdx.x;
-  uint64_t off = 0;
-  SwSeg cur;
-  cur.src = cur.dst = cur.len = 0;
-  if (s < nseg) cur = seg_at(s);
   uint64_t st_dst[SW_BULK_MAX_STAGES];
   uint32_t st_bytes[SW_BULK_MAX_STAGES];
 
@@ -911,20 +906,14 @@ __device__ __forceinline__ void sw_bulk_tma_body(SegAt seg_at, uint32_t nseg, ui
   bool more = true;
 
   auto issue_load = [&]() -> bool {
-    while (s < nseg && off >= cur.len) {
-      s += gridDim.x;
-      off = 0;
-      if (s < nseg) cur = seg_at(s);
-    }
-    if (s >= nseg) return false;
-    const uint64_t left = cur.len - off;
-    const uint32_t bytes = left < stage_bytes ? static_cast<uint32_t>(left) : stage_bytes;
+    uint64_t src, dst;
+    uint32_t bytes;
+    if (!next(src, dst, bytes)) return false;
     const uint32_t stg = issued % nstages;
     sw_mbar_expect_tx(&full[stg], bytes);
-    sw_bulk_g2s(sw_smem + size_t(stg) * stage_bytes, reinterpret_cast<const void*>(cur.src + off), bytes, &full[stg]);
-    st_dst[stg] = cur.dst + off;
+    sw_bulk_g2s(sw_smem + size_t(stg) * stage_bytes, reinterpret_cast<const void*>(src), bytes, &full[stg]);
+    st_dst[stg] = dst;
     st_bytes[stg] = bytes;
-    off += bytes;
     issued++;
     return true;
   };
@@ -947,6 +936,32 @@ __device__ __forceinline__ void sw_bulk_tma_body(SegAt seg_at, uint32_t nseg, ui
   sw_bulk_wait_all();
 }
 
+// Segment-list source: CTA b walks segments b, b + gridDim.x, ...
+template <class SegAt>
+__device__ __forceinline__ void sw_bulk_tma_body(SegAt seg_at, uint32_t nseg, uint32_t stage_bytes, uint32_t nstages) {
+  uint32_t s = blockIdx.x;
+  uint64_t off = 0;
+  SwSeg cur;
+  cur.src = cur.dst = cur.len = 0;
+  if (threadIdx.x == 0 && s < nseg) cur = seg_at(s);
+  sw_bulk_tma_pipeline(
+      [&](uint64_t& src, uint64_t& dst, uint32_t& bytes) -> bool {
+        while (s < nseg && off >= cur.len) {
+          s += gridDim.x;
+          off = 0;
+          if (s < nseg) cur = seg_at(s);
+        }
+        if (s >= nseg) return false;
+        const uint64_t left = cur.len - off;
+        bytes = left < stage_bytes ? static_cast<uint32_t>(left) : stage_bytes;
+        src = cur.src + off;
+        dst = cur.dst + off;
+        off += bytes;
+        return true;
+      },
+      stage_bytes, nstages);
+}
+
 __global__ void __launch_bounds__(32) sw_bulk_tma_kernel(const SwSeg* __restrict__ segs, uint32_t nseg,
                                                          uint32_t stage_bytes, uint32_t nstages) {
   sw_bulk_tma_body([segs](uint32_t i) { return segs[i]; }, nseg, stage_bytes, nstages);
@@ -966,6 +981,19 @@ struct SwSegArgs {
 template <uint32_t N>
 __global__ void __launch_bounds__(32) sw_bulk_tma_inline_kernel(const __grid_constant__ SwSegArgs<N> a) {
   sw_bulk_tma_body([&a](uint32_t i) { return a.seg[i]; }, a.nseg, a.stage_bytes, a.nstages);
+}
+
+// Balanced variant: the jobs (whole messages) travel as kernel parameters and CTA b copies the byte
+// range [b * share, (b + 1) * share) of their concatenation (SwJobRangeIter, sw_device.h).  Every SM
+// gets the same amount of work whatever the number and size of the messages, and a single 1 MiB
+// message is spread over 32 CTAs instead of 2.
+__global__ void __launch_bounds__(32) sw_bulk_tma_jobs_kernel(const __grid_constant__ SwBulkJobArgs a) {
+  SwJobRangeIter it;
+  it.pos = it.range_end = 0;
+  it.j = 0;
+  if (threadIdx.x == 0) it.init(a, blockIdx.x);
+  sw_bulk_tma_pipeline([&](uint64_t& src, uint64_t& dst, uint32_t& bytes) -> bool { return it.next(a, src, dst, bytes); },
+                       a.stage_bytes, a.nstages);
 }
 
 // ------------------------------------------------------------------ bulk copy, SIMT vectorised

@@ -227,6 +227,48 @@ struct SwSeg {        // one contiguous piece of a rendezvous/loopback copy
   uint64_t pad;
 };
 
+// Balanced bulk copy: the launch carries its jobs (whole messages, at most SW_BULK_INLINE_JOBS of them)
+// in the kernel parameter bank and every CTA takes an equal, contiguous byte range of their
+// concatenation -- no segment list in host memory, no idle SMs when the launch has fewer segments
+// than the GPU has SMs.  The iterator below is the ONLY place that maps (CTA, progress) to addresses;
+// the CPU stand-in backend runs the same code, so every host-logic test exercises it.
+constexpr uint32_t SW_BULK_INLINE_JOBS = 96;
+struct SwBulkJobArgs {
+  uint32_t njobs, stage_bytes, nstages, pad;
+  uint64_t share;                        // bytes per CTA (multiple of 1024)
+  uint64_t end[SW_BULK_INLINE_JOBS];     // end[j] = total bytes of jobs 0..j
+  uint64_t src[SW_BULK_INLINE_JOBS];
+  uint64_t dst[SW_BULK_INLINE_JOBS];
+};
+static_assert(sizeof(SwBulkJobArgs) <= 4096 - 512, "bulk job parameters stay under the classic 4 KiB parameter limit");
+
+struct SwJobRangeIter {
+  uint64_t pos, range_end;
+  uint32_t j;
+  SW_HD void init(const SwBulkJobArgs& a, uint32_t cta) {
+    const uint64_t total = a.njobs ? a.end[a.njobs - 1] : 0;
+    pos = static_cast<uint64_t>(cta) * a.share;
+    if (pos > total) pos = total;
+    range_end = pos + a.share;
+    if (range_end > total) range_end = total;
+    j = 0;
+    while (j < a.njobs && a.end[j] <= pos) j++;
+  }
+  // next piece of at most stage_bytes that stays inside one job and inside this CTA's range
+  SW_HD bool next(const SwBulkJobArgs& a, uint64_t& src, uint64_t& dst, uint32_t& bytes) {
+    if (pos >= range_end) return false;
+    while (a.end[j] <= pos) j++;   // pos < range_end <= end[njobs-1]: terminates inside the array
+    const uint64_t begin = j ? a.end[j - 1] : 0;
+    const uint64_t stop = a.end[j] < range_end ? a.end[j] : range_end;
+    const uint64_t left = stop - pos;
+    bytes = left < a.stage_bytes ? static_cast<uint32_t>(left) : a.stage_bytes;
+    src = a.src[j] + (pos - begin);
+    dst = a.dst[j] + (pos - begin);
+    pos += bytes;
+    return true;
+  }
+};
+
 // Match rule of the UCP tag API as used at reference main.cpp:404,1172:
 // a receive (tag, mask) accepts a message with sender tag `stag` iff
 // ((stag ^ tag) & mask) == 0.

@@ -5,6 +5,7 @@
 //   sw_probe peer                  2-GPU in-process peer pull/push bandwidth, cudaMemcpyPeer ceiling
 //   sw_probe ipc                   2-process CUDA-IPC mapping check + pull bandwidth
 //   sw_probe latency               launch + event-poll latency of the small kernels
+//   sw_probe balance               bulk copy of n x 1 MiB messages: segment-list kernel vs balanced job-range kernel
 //   sw_probe floor                 launch -> completion-seen floor: event vs flag in pinned memory, per-hop cost
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -140,6 +141,7 @@ static void test_bulk_correctness() {
       t.stages = 2 + (int)(rng() % 7);
       t.stage_bytes = 16 * (int)(64 + rng() % 1500);
       t.ctas_per_sm = 1 + (int)(rng() % 3);
+      t.balance = trial & 1;   // odd trials: jobs as kernel parameters, equal byte range per CTA
       REQ(launch_bulk(st, segs, (uint32_t)all.size(), &t) == 0);
       REQ(stream_sync(st) == 0);
       CK(cudaMemcpy(hdst.data(), dst, POOL, cudaMemcpyDeviceToHost));
@@ -794,6 +796,56 @@ static void test_ipc(const char* self) {
 }
 
 
+
+// ------------------------------------------------------------------ segment-list vs balanced job-range launch
+// Launch shapes as the engine produces them for windows of 1 MiB messages: n messages, each cut into
+// segments of ceil(total / (4 * SMs)) rounded to the stage size (pump_bulk), separate allocations.
+static void bench_balance(FILE* json) {
+  stream_t st = stream_create();
+  const size_t MSG = 1u << 20, GAP = 256, MAXN = 96;
+  uint8_t* src = (uint8_t*)dev_alloc(MAXN * (MSG + GAP));
+  uint8_t* dst = (uint8_t*)dev_alloc(MAXN * (MSG + GAP));
+  const size_t FLUSH = 256u << 20;
+  void* flush = dev_alloc(FLUSH);
+  REQ(src && dst && flush);
+  std::vector<uint8_t> h(MAXN * (MSG + GAP));
+  fill_pattern(h, 3);
+  CK(cudaMemcpy(src, h.data(), h.size(), cudaMemcpyHostToDevice));
+  SwSeg* segs = (SwSeg*)host_alloc(sizeof(SwSeg) * 65536);
+  for (int n : {1, 2, 4, 8, 16, 32, 43, 64, 96}) {
+    const uint64_t total = (uint64_t)n * MSG;
+    const uint64_t unit = 24576, target = (uint64_t)sm_count() * 4;
+    uint64_t seg = (total + target - 1) / target;
+    seg = ((seg + unit - 1) / unit) * unit;
+    seg = std::max<uint64_t>(seg, 49152);
+    std::vector<SwSeg> v;
+    for (int m = 0; m < n; m++) {
+      auto p = make_segs((uint64_t)(src + (size_t)m * (MSG + GAP)), (uint64_t)(dst + (size_t)m * (MSG + GAP)), MSG, seg);
+      v.insert(v.end(), p.begin(), p.end());
+    }
+    memcpy(segs, v.data(), v.size() * sizeof(SwSeg));
+    float ms[2];
+    for (int bal = 0; bal < 2; bal++) {
+      CK(cudaMemset(dst, 0, MAXN * (MSG + GAP)));
+      BulkTuning t{0, 8, 24576, 1, bal};
+      ms[bal] = time_bulk(st, segs, (uint32_t)v.size(), t, 7, flush, FLUSH);
+      std::vector<uint8_t> chk((size_t)n * (MSG + GAP));
+      CK(cudaMemcpy(chk.data(), dst, chk.size(), cudaMemcpyDeviceToHost));
+      for (int m = 0; m < n; m++) REQ(memcmp(chk.data() + (size_t)m * (MSG + GAP), h.data() + (size_t)m * (MSG + GAP), MSG) == 0);
+    }
+    printf("[balance] %3d x 1 MiB (%5zu segments of %7llu B): segment list %7.2f us %7.1f GB/s | job ranges %7.2f us %7.1f GB/s\n", n,
+           v.size(), (unsigned long long)seg, ms[0] * 1e3, total / (ms[0] * 1e-3) / 1e9, ms[1] * 1e3, total / (ms[1] * 1e-3) / 1e9);
+    if (json)
+      fprintf(json, "{\"bench\":\"balance\",\"msgs\":%d,\"nseg\":%zu,\"seglist_us\":%.2f,\"jobs_us\":%.2f}\n", n, v.size(), ms[0] * 1e3,
+              ms[1] * 1e3);
+  }
+  host_free(segs);
+  dev_free(src);
+  dev_free(dst);
+  dev_free(flush);
+  stream_destroy(st);
+}
+
 // ------------------------------------------------------------------ launch/completion floor
 // What one launch -> "host knows it finished" costs on this box, by completion mechanism.
 struct FloorArgs {
@@ -965,6 +1017,7 @@ int main(int argc, char** argv) {
   if (cmd == "latency" || cmd == "all") bench_latency(json);
   if (cmd == "bench" || cmd == "all") bench_single(json);
   if (cmd == "floor") bench_floor(json);
+  if (cmd == "balance") bench_balance(json);
   if (cmd == "hostmem") bench_hostmem(json);
   if (cmd == "tune") bench_tune(json);
   if (cmd == "ipc" || cmd == "all") test_ipc(argv[0]);

@@ -21,6 +21,7 @@
 #include <string>
 #include <vector>
 
+#include "../../starway_b200/csrc/bulk_jobs.h"
 #include "../../starway_b200/csrc/gpu.h"
 
 namespace swgpu {
@@ -443,7 +444,35 @@ int launch_match_deliver(stream_t s, SwMatchState* st, const SwMatchIn* in, SwMa
   return 0;
 }
 
-int launch_bulk(stream_t, const SwSeg* segs, uint32_t nseg, const BulkTuning*) {
+int launch_bulk(stream_t, const SwSeg* segs, uint32_t nseg, const BulkTuning* t) {
+  // Balanced launches run the SAME job builder and per-CTA range iterator as the CUDA kernel
+  // (bulk_jobs.h, SwJobRangeIter): one loop iteration per CTA, memcpy in place of the TMA pipeline.
+  SwBulkJobArgs ja;
+  uint32_t grid = 0;
+  if (t && t->mode == 0 && t->balance &&
+      bulk_build_jobs(segs, nseg, 148, (uint32_t)(t->stage_bytes & ~15), (uint32_t)t->stages, &ja, &grid)) {
+    if (getenv("SW_SIM_TRACE_BULK")) fprintf(stderr, "simjobs njobs=%u grid=%u share=%llu total=%llu\n", ja.njobs, grid, (unsigned long long)ja.share, (unsigned long long)ja.end[ja.njobs - 1]);
+    uint64_t copied = 0, want = ja.end[ja.njobs - 1];
+    for (uint32_t cta = 0; cta < grid; cta++) {
+      SwJobRangeIter it;
+      it.init(ja, cta);
+      uint64_t src, dst;
+      uint32_t bytes;
+      while (it.next(ja, src, dst, bytes)) {
+        if (((src | dst | bytes) & 15) || bytes > ja.stage_bytes) {
+          g_err = "bulk job iterator produced a misaligned / oversized piece";
+          return -1;
+        }
+        memcpy((void*)(uintptr_t)dst, (const void*)(uintptr_t)src, bytes);
+        copied += bytes;
+      }
+    }
+    if (copied != want) {
+      g_err = "bulk job iterator did not cover the launch";
+      return -1;
+    }
+    return 0;
+  }
   for (uint32_t i = 0; i < nseg; i++)
     memcpy((void*)(uintptr_t)segs[i].dst, (const void*)(uintptr_t)segs[i].src, segs[i].len);
   return 0;
