@@ -294,7 +294,8 @@ def run_ours(args):
     roofline = {
         "bound": bound, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
         "frac": round(achieved / peak, 4), "traffic": traffic,
-        "kernel": "sw_bulk_tma_kernel / sw_bulk_tma_inline_kernel (same body; <= 96 segments travel as kernel parameters)",
+        "kernel": "sw_bulk_tma_jobs_kernel (<= 96 messages per launch as kernel parameters, equal byte range per CTA; "
+                  "larger launches: sw_bulk_tma_kernel, same cp.async.bulk pipeline)",
         "launches": st["bulk_event_launches"], "avg_launch_us": round(avg_ms * 1e3, 2),
         "payload_bytes_per_launch": int(payload_per_launch), "peak_source": peak_note,
     }
