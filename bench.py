@@ -187,8 +187,9 @@ def run_ours(args):
 
         # the set-up garbage (torch import, buffer lists) goes to the permanent generation: full
         # collections inside the timed region would otherwise walk ~10^6 objects (same in the reference arm)
-        gc.collect()
-        gc.freeze()
+        if not os.environ.get("STARWAY_BENCH_NO_GC_FREEZE"):
+            gc.collect()
+            gc.freeze()
         # warm-up, then bit-exactness of one full window against the sources of the sending rank
         await timed(max(args.warmup, 3), src, dst, torch.cuda.synchronize)
         if world == 1:
