@@ -642,20 +642,20 @@ thread_local bool tls_is_progress = false;
 
 void publish_completions(Ctx* c, const sw_completion* comps, size_t n) {
   if (!n) return;
-  bool was_empty;
   {
     std::lock_guard<std::mutex> lk(c->cq_mu);
-    was_empty = c->cq.empty();
+    const bool was_empty = c->cq.empty();
     for (size_t i = 0; i < n; i++) c->cq.push_back(comps[i]);
     c->cq_count.store((uint32_t)c->cq.size(), std::memory_order_seq_cst);
-  }
-  // A consumer that announced it is busy-polling (option "consumer_polling") needs no wake-up: it
-  // clears the flag and polls once more before it goes back to sleeping on the eventfd.
-  if (was_empty && c->efd >= 0 && !c->consumer_polling.load(std::memory_order_seq_cst)) {
-    c->efd_signaled.store(1, std::memory_order_release);
-    uint64_t one = 1;
-    ssize_t r = write(c->efd, &one, sizeof(one));
-    (void)r;
+    // A consumer that announced it is busy-polling (option "consumer_polling") needs no wake-up: it
+    // clears the flag and polls once more before it goes back to sleeping on the eventfd.  The
+    // eventfd is written and cleared (sw_poll) under cq_mu only: "counter non-zero" <=> efd_signaled.
+    if (was_empty && c->efd >= 0 && !c->consumer_polling.load(std::memory_order_seq_cst)) {
+      c->efd_signaled.store(1, std::memory_order_release);
+      uint64_t one = 1;
+      ssize_t r = write(c->efd, &one, sizeof(one));
+      (void)r;
+    }
   }
   if (c->cq_waiters.load(std::memory_order_seq_cst)) c->cq_cv.notify_one();
   std::lock_guard<std::mutex> lk(c->st_mu);
