@@ -272,7 +272,7 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
             self._servers: weakref.WeakValueDictionary = weakref.WeakValueDictionary()
             self._efd = lib.sw_event_fd(self._h)
             self._readers: dict[Any, bool] = {}
-            self._buf = (SwCompletion * 512)()
+            self._bufs: dict[Any, Any] = {}  # loop -> completion batch buffer (ctypes drain path)
             self._stop = False
             self._wake = threading.Event()
             self._fp = None
@@ -400,11 +400,14 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
 
         def _drain(self, loop) -> int:
             """eventfd reader callback: runs on `loop`'s thread.  Returns the number of completions."""
-            h, buf = self._h, self._buf
+            h = self._h
             if not h:
                 return 0
             if self._fp is not None:
                 return self._fp.drain(loop)
+            buf = self._bufs.get(loop)  # one batch buffer per loop (= per draining thread)
+            if buf is None:
+                buf = self._bufs[loop] = (SwCompletion * 512)()
             total = 0
             while True:
                 n = lib.sw_poll(h, buf, 512)
@@ -483,6 +486,7 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
                     for lp in list(self._readers):
                         if lp.is_closed():
                             self._readers.pop(lp, None)
+                            self._bufs.pop(lp, None)
                     if self._readers:
                         self._wake.wait(0.05)
                         continue

@@ -65,7 +65,6 @@ typedef struct {
   PyObject* str_create_future;
   PyObject* str_set_result;
   PyObject* str_set_exception;
-  sw_completion buf[512];
 } Binding;
 
 static void tab_clear(Binding* self) {
@@ -399,13 +398,17 @@ static int resolve_future(Binding* self, PyObject* fut, const sw_completion* c) 
 
 /* drain(loop): resolve every pending completion; runs on `loop`'s thread (eventfd reader) */
 static PyObject* Binding_drain(Binding* self, PyObject* here) {
+  /* the batch lives on this thread's stack: resolving an entry may run Python code (the shim), which
+   * can release the GIL and let another loop's thread enter drain() on the same Binding */
+  enum { BATCH = 256 };
+  sw_completion batch[BATCH];
   long total = 0;
   for (;;) {
-    int n = self->poll(self->ctx, self->buf, 512);
+    int n = self->poll(self->ctx, batch, BATCH);
     if (n <= 0) break;
     total += n;
     for (int i = 0; i < n; i++) {
-      const sw_completion c = self->buf[i];
+      const sw_completion c = batch[i];
       OpSlot* slot = tab_find(self, c.op_id);
       if (slot) {
         PyObject *loop = slot->loop, *fut = slot->fut, *keep = slot->keep; /* references move to us */
@@ -463,7 +466,7 @@ static PyObject* Binding_drain(Binding* self, PyObject* here) {
       }
       Py_XDECREF(entry);
     }
-    if (n < 512) break;
+    if (n < BATCH) break;
   }
   return PyLong_FromLong(total);
 }
