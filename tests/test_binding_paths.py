@@ -168,3 +168,40 @@ def test_numa_helpers_are_noops_without_topology(sim_api):
     assert sim_api.local_cpus(0) == set()
     assert sim_api.bind_to_device_numa(0) is False
     assert os.sched_getaffinity(0) == before
+
+
+@pytest.mark.parametrize("fast", [True, False], ids=["fastpath", "ctypes"])
+def test_two_loops_in_two_threads_share_one_context(sim_api, ctypes_api, fast):
+    """Either loop may drain completions that belong to the other (one completion queue per context):
+    they are handed over with call_soon_threadsafe; batch buffers are per draining thread."""
+    import threading
+
+    from tests.conftest import free_port
+
+    api = sim_api if fast else ctypes_api
+    errors = []
+
+    async def traffic(port, base):
+        async with cb.gen_server_client(api, port) as (server, client):
+            for rnd in range(30):
+                bufs = [np.zeros(32, dtype=np.uint8) for _ in range(40)]
+                recvs = [server.arecv(b, base + i, (1 << 64) - 1) for i, b in enumerate(bufs)]
+                for i in range(40):
+                    await client.asend(np.full(32, (base + i + rnd) & 0xFF, dtype=np.uint8), base + i)
+                res = await asyncio.gather(*recvs)
+                for i, (r, b) in enumerate(zip(res, bufs)):
+                    assert r == (base + i, 32) and (b == ((base + i + rnd) & 0xFF)).all()
+
+    def worker(base):
+        try:
+            asyncio.run(asyncio.wait_for(traffic(free_port(), base), 120))
+        except BaseException as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(1000 * (k + 1),)) for k in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(180)
+    assert not errors, errors
+    assert not any(t.is_alive() for t in threads)
