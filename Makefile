@@ -67,7 +67,7 @@ build/gpu_sim.o: tests/hostsim/gpu_sim.cpp $(CSRC)/gpu.h $(CSRC)/sw_device.h $(C
 # backend, used only by `pytest -m "not gpu"` to exercise connection/protocol/flush/close
 # logic (world_size 2 on CPU).  Never loaded by the starway_b200 package.
 $(HOSTSIM): build/engine_sim.o build/gpu_sim.o build/tagmatch.o
-	$(CXX) -shared -Wl,-Bsymbolic -Wl,--version-script=$(CSRC)/exports.map -o $@ $^ -lpthread -lrt -ldl
+	$(CXX) -shared -Wl,-Bsymbolic -Wl,--version-script=tests/hostsim/exports_sim.map -o $@ $^ -lpthread -lrt -ldl
 
 $(PROBE): tests/gpu_probe/probe.cu build/gpu_cuda.o build/tagmatch.o
 	$(NVCC) $(NVFLAGS) -o $@ tests/gpu_probe/probe.cu build/gpu_cuda.o build/tagmatch.o

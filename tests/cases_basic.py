@@ -312,6 +312,74 @@ async def case_client_send_with_flush_good(api, port, backend):
     await server.aclose()
 
 
+# ------------------------------------------------------------------ device buffers across two processes (stand-in backend)
+SIMDEV_SIZES = [64, 8128, 8129, (1 << 20) + 16, 3 << 20]
+
+
+def _simdev_pattern(i, n):
+    return ((np.arange(n, dtype=np.uint64) * 2654435761 + i * 97) >> 7).astype(np.uint8)
+
+
+def _proc_simdev_sender(port):
+    """Child: sends from 'device' buffers of the CPU stand-in (eager and rendezvous sizes), flushes,
+    then waits for the parent's verdict so that its buffers stay mapped while the parent pulls."""
+    from tests.hostsim import SimDev
+
+    api = load_api("sim")
+
+    async def inner():
+        client = api.Client()
+        await client.aconnect(SERVER_ADDR, port)
+        bufs = [SimDev.from_np(_simdev_pattern(i, n)) for i, n in enumerate(SIMDEV_SIZES)]
+        verdict = np.zeros(1, dtype=np.uint8)
+        fv = client.arecv(verdict, 0x77, (1 << 64) - 1)
+        for rnd in range(3):  # the same allocations three times: exported-handle / mapping caches hit
+            for i, b in enumerate(bufs):
+                await client.asend(b, 100 * rnd + i)
+            await client.aflush()
+        assert await asyncio.wait_for(fv, 120) == (0x77, 1) and verdict[0] == 1
+        await client.aclose()
+
+    asyncio.run(inner())
+    api.shutdown()
+
+
+async def case_simdev_two_process_device_buffers(api, port):
+    from tests.hostsim import SimDev
+
+    server = api.Server()
+    server.listen(SERVER_ADDR, port)
+    connected = asyncio.Event()
+    loop = asyncio.get_running_loop()
+    server.set_accept_cb(lambda _: loop.call_soon_threadsafe(connected.set))
+    ctx = mp.get_context("spawn")
+    child = ctx.Process(target=_proc_simdev_sender, args=(port,))
+    child.start()
+    try:
+        await asyncio.wait_for(connected.wait(), timeout=120)
+        ep = next(iter(server.list_clients()))
+        for rnd in range(3):
+            dsts = [SimDev.alloc(n + 32) for n in SIMDEV_SIZES]
+            futs = [server.arecv(d, 100 * rnd + i, (1 << 64) - 1) for i, d in enumerate(dsts)]
+            for i, (f, d, n) in enumerate(zip(futs, dsts, SIMDEV_SIZES)):
+                assert await asyncio.wait_for(f, 120) == (100 * rnd + i, n)
+                got = SimDev.to_np(d)
+                np.testing.assert_array_equal(got[:n], _simdev_pattern(i, n))
+                assert (got[n:] == 0xEE).all()
+        await server.asend(ep, np.ones(1, dtype=np.uint8), 0x77)
+        await server.aflush()
+        while child.is_alive():
+            await asyncio.sleep(0.05)
+        child.join()
+        assert child.exitcode == 0
+    finally:
+        if child.is_alive():
+            child.kill()
+        child.join()
+        child.close()
+    await server.aclose()
+
+
 # ------------------------------------------------------------------ state errors
 async def case_client_op_before_connect(api, port):
     # reference :465-473

@@ -479,3 +479,10 @@ int launch_bulk(stream_t, const SwSeg* segs, uint32_t nseg, const BulkTuning* t)
 }
 
 }  // namespace swgpu
+
+// Test-only exports (tests/hostsim/exports_sim.map): "device" buffers for the Python tests, so that the
+// engine's device-buffer paths (zero-copy rendezvous between user buffers, IPC export of user
+// allocations, handle / mapping caches) run on the CPU as well.
+extern "C" void* swsim_dev_alloc(size_t bytes) { return swgpu::dev_alloc(bytes); }
+extern "C" int swsim_dev_free(void* p) { return swgpu::dev_free(p); }
+

@@ -13,3 +13,12 @@ from tests import cases_basic as cb
 @pytest.mark.parametrize("seed", range(int(os.environ.get("CHAOS_SEEDS", "12"))))
 def test_chaos(sim_api, port, seed):
     asyncio.run(asyncio.wait_for(cb.case_chaos(sim_api, port, seed), 120))
+
+
+@pytest.mark.parametrize("seed", range(1000, 1000 + int(os.environ.get("CHAOS_SEEDS", "12")) // 2))
+def test_chaos_device_buffers(sim_api, port, seed):
+    """Same, with the stand-in backend's 'device' buffers: closes and cancellations race with zero-copy
+    rendezvous pulls out of user allocations."""
+    from tests.hostsim import SimDev
+
+    asyncio.run(asyncio.wait_for(cb.case_chaos(sim_api, port, seed, bufs=SimDev), 120))

@@ -196,3 +196,72 @@ def test_connection_churn_recycles_native_records(sim_api, port):
     buf = (ctypes.c_uint64 * 8)()
     assert lib.sw_list_eps(sim_api.get_context()._h, handles[0], buf, 8) == -1
     assert stale.name  # metadata was copied at creation; the object stays usable
+
+
+# ---------------------------------------------------------------- 'device' buffers on the CPU stand-in
+# The stand-in's device allocator hands out memory its pointer query reports as device memory
+# (tests/hostsim SimDev): the engine's device-buffer paths run on the CPU as well — eager payloads read
+# straight from the user buffer, zero-copy rendezvous between user buffers, IPC export of user
+# allocations with its handle cache, truncation into device buffers.
+@pytest.mark.parametrize("seed", [21, 22, 23])
+def test_simdev_random_schedules_vs_oracle(sim_api, port, seed):
+    from tests.hostsim import SimDev
+
+    run(cb.case_random_schedule_vs_oracle(sim_api, port, seed, SimDev))
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_simdev_multi_sender_invariants(sim_api, port, seed):
+    from tests.hostsim import SimDev
+
+    run(cb.case_multi_sender_invariants(sim_api, port, seed, SimDev))
+
+
+@pytest.mark.parametrize("seed", [31, 32, 33])
+def test_simdev_chaos(sim_api, port, seed):
+    from tests.hostsim import SimDev
+
+    run(cb.case_chaos(sim_api, port, seed, bufs=SimDev))
+
+
+@pytest.mark.parametrize("size", [1, 8128, 8129, 65536 + 3, (4 << 20) + 16])
+def test_simdev_mixed_host_and_device_buffers(sim_api, port, size):
+    """device -> host, host -> device and device -> device, same bytes every way."""
+    import numpy as np
+
+    from tests.hostsim import SimDev
+
+    async def go():
+        async with cb.gen_server_client(sim_api, port) as (server, client):
+            ep = next(iter(server.list_clients()))
+            src = np.random.default_rng(size).integers(0, 256, size, dtype=np.uint8)
+            dsrc = SimDev.from_np(src)
+            # device -> host
+            hdst = np.zeros(size + 5, dtype=np.uint8)
+            f = server.arecv(hdst, 1, 0xFF)
+            await client.asend(dsrc, 1)
+            assert await f == (1, size)
+            np.testing.assert_array_equal(hdst[:size], src)
+            assert (hdst[size:] == 0).all()
+            # host -> device
+            ddst = SimDev.alloc(size + 5)
+            f = client.arecv(ddst, 2, 0xFF)
+            await server.asend(ep, src, 2)
+            assert await f == (2, size)
+            np.testing.assert_array_equal(SimDev.to_np(ddst)[:size], src)
+            assert (SimDev.to_np(ddst)[size:] == 0xEE).all()
+            # device -> device
+            ddst2 = SimDev.alloc(size)
+            f = server.arecv(ddst2, 3, 0xFF)
+            await client.asend(dsrc, 3)
+            assert await f == (3, size)
+            np.testing.assert_array_equal(SimDev.to_np(ddst2), src)
+            await asyncio.gather(client.aflush(), server.aflush())
+
+    run(go())
+
+
+def test_simdev_two_process_device_buffers(sim_api, port):
+    """Rendezvous pulls straight out of another process's user 'device' allocation (IPC export by
+    the sender, mapping cache on the receiver), three rounds over the same allocations."""
+    run(cb.case_simdev_two_process_device_buffers(sim_api, port))
