@@ -30,11 +30,13 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <linux/futex.h>
 #include <sys/eventfd.h>
 #include <sys/mman.h>
 #include <sys/prctl.h>
 #include <sys/socket.h>
 #include <sys/stat.h>
+#include <sys/syscall.h>
 #include <sys/un.h>
 #include <time.h>
 #include <unistd.h>
@@ -562,6 +564,7 @@ struct Ctx {
   alignas(64) std::atomic<uint64_t> next_id{1};  // posting threads
   // submission queue: written by posting threads, polled by the progress thread
   alignas(64) std::atomic<SqNode*> sq_head{nullptr};
+  std::atomic<int> sleeping{0};  // the progress thread naps on this word (futex); a submission wakes it
   // completion queue: written by the progress thread, polled by the consumer
   alignas(64) std::atomic<uint32_t> cq_count{0};  // == cq.size(), readable without the lock
   std::atomic<int> efd_signaled{0};               // the eventfd counter is non-zero
@@ -866,6 +869,9 @@ void sq_push(Ctx* c, int kind, Worker* w, void* p, SqNode* n = nullptr) {
   do {
     n->next = head;
   } while (!c->sq_head.compare_exchange_weak(head, n, std::memory_order_release, std::memory_order_relaxed));
+  // an idle progress thread naps between polls of the peers' doorbells: cut the nap short
+  if (c->sleeping.load(std::memory_order_seq_cst) && c->sleeping.exchange(0, std::memory_order_seq_cst))
+    syscall(SYS_futex, reinterpret_cast<int*>(&c->sleeping), FUTEX_WAKE_PRIVATE, 1, nullptr, nullptr, 0);
 }
 
 // ============================================================================ connection: server side
@@ -2223,12 +2229,14 @@ void progress_main(Ctx* c) {
       for (int k = 0; k < 32; k++) __builtin_ia32_pause();
       if (expecting && idle < 0.25) {
         if (idle > 0.002) sched_yield();
-      } else if (idle > 1.0) {
-        struct timespec ts = {0, 300000};
-        nanosleep(&ts, nullptr);
       } else if (idle > 0.02) {
-        struct timespec ts = {0, 30000};
-        nanosleep(&ts, nullptr);
+        // nap: 30 us, 300 us after a second of silence.  Remote doorbells are only seen when the nap
+        // ends; a local submission ends it at once (sq_push -> futex wake).
+        struct timespec ts = {0, idle > 1.0 ? 300000 : 30000};
+        c->sleeping.store(1, std::memory_order_seq_cst);
+        if (c->sq_head.load(std::memory_order_seq_cst) == nullptr)
+          syscall(SYS_futex, reinterpret_cast<int*>(&c->sleeping), FUTEX_WAIT_PRIVATE, 1, &ts, nullptr, 0);
+        c->sleeping.store(0, std::memory_order_seq_cst);
       } else if (idle > 0.002) {
         sched_yield();
       }

@@ -265,3 +265,34 @@ def test_simdev_two_process_device_buffers(sim_api, port):
     """Rendezvous pulls straight out of another process's user 'device' allocation (IPC export by
     the sender, mapping cache on the receiver), three rounds over the same allocations."""
     run(cb.case_simdev_two_process_device_buffers(sim_api, port))
+
+
+def test_round_trip_after_a_long_idle_period(sim_api, port):
+    """After more than a second of silence the progress thread naps (futex, 300 us at a time) and the
+    asyncio loop sleeps in epoll; a submission wakes the former at once.  Functional check: the first
+    round trip after the pause completes promptly (thread wake-ups cost ~0.1-0.3 ms on a busy CI host,
+    so the bound is loose) and carries the right bytes."""
+    import time
+
+    import numpy as np
+
+    async def go():
+        async with cb.gen_server_client(sim_api, port) as (server, client):
+            buf, src = np.zeros(8, dtype=np.uint8), np.arange(8, dtype=np.uint8)
+
+            async def rtt(tag):
+                src[0] = tag
+                t0 = time.perf_counter()
+                f = server.arecv(buf, tag, 0xFF)
+                await client.asend(src, tag)
+                assert await f == (tag, 8)
+                assert (buf == src).all()
+                return time.perf_counter() - t0
+
+            for i in range(20):
+                await rtt(i)
+            for i in range(3):
+                await asyncio.sleep(1.2)
+                assert await rtt(100 + i) < 0.05
+
+    run(go())
