@@ -78,4 +78,16 @@ $(ABIBENCH): tests/gpu_probe/abi_bench.cpp $(LIB) include/starway_b200.h
 clean:
 	rm -rf build $(LIB) $(FASTPATH) $(ORACLE) $(CPUENG) $(HOSTSIM) $(PROBE) $(ABIBENCH)
 
-.PHONY: all lib oracle oracle-core hostsim probe clean
+# Instrumented builds of the host-logic simulator (same sources) for sanitizer runs of the CPU suite:
+#   make hostsim-asan && SW_HOSTSIM_LIB=$PWD/build/asan/libstarway_hostsim.so ASAN_OPTIONS=detect_leaks=0 \
+#     LD_PRELOAD=$(gcc -print-file-name=libasan.so) python -m pytest tests/test_hostlogic_sim.py tests/test_chaos_sim.py
+#   make hostsim-tsan && SW_HOSTSIM_LIB=$PWD/build/tsan/libstarway_hostsim.so \
+#     LD_PRELOAD=$(gcc -print-file-name=libtsan.so) python -m pytest -s tests/test_binding_paths.py tests/test_hostlogic_sim.py
+SAN_CXX ?= /usr/bin/g++
+hostsim-asan hostsim-tsan: hostsim-%:
+	@mkdir -p build/$*
+	$(SAN_CXX) -O1 -g -fsanitize=$(if $(filter asan,$*),address,thread) -fno-omit-frame-pointer -std=c++17 -fPIC -pthread -Iinclude \
+	  -shared -Wl,-Bsymbolic -Wl,--version-script=tests/hostsim/exports_sim.map -o build/$*/libstarway_hostsim.so \
+	  $(CSRC)/engine.cpp tests/hostsim/gpu_sim.cpp -x c oracle/tagmatch.c -lpthread -lrt -ldl
+
+.PHONY: all lib oracle oracle-core hostsim probe clean hostsim-asan hostsim-tsan

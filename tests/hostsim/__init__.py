@@ -10,7 +10,8 @@ import numpy as np
 
 from starway_b200 import _core
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libstarway_hostsim.so")
+# SW_HOSTSIM_LIB: an instrumented build of the same library (AddressSanitizer runs of the CPU suite)
+LIB_PATH = os.environ.get("SW_HOSTSIM_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libstarway_hostsim.so")
 
 
 def load(use_fastpath: bool = True):
