@@ -205,3 +205,16 @@ def test_two_loops_in_two_threads_share_one_context(sim_api, ctypes_api, fast):
         t.join(180)
     assert not errors, errors
     assert not any(t.is_alive() for t in threads)
+
+
+def test_uvloop_event_loop(sim_api):
+    """bench.py and the scenario scripts run on uvloop: eventfd reader, polling callback and the fast
+    path's future handling must behave the same there."""
+    uvloop = pytest.importorskip("uvloop")
+    from tests.conftest import free_port
+    from tests.hostsim import SimDev
+
+    for case in (cb.case_concurrent_send_recv, cb.case_bidirectional_traffic, cb.case_shutdown_with_in_flight_ops):
+        uvloop.run(asyncio.wait_for(case(sim_api, free_port()), 120))
+    uvloop.run(asyncio.wait_for(cb.case_chaos(sim_api, free_port(), 3), 120))
+    uvloop.run(asyncio.wait_for(cb.case_random_schedule_vs_oracle(sim_api, free_port(), 4, SimDev), 120))
