@@ -195,6 +195,22 @@ def run_ours(args):
         if world == 1:
             for s, d in zip(src[0], dst[0]):
                 assert torch.equal(s, d), "payload mismatch"
+            payload_check = "bit-exact vs the sources (loopback)"
+        else:
+            # rank r receives what rank r-1 sent; its sources are a seeded sequence (Philox: seed and
+            # offset only), so they can be regenerated here.  Reported, not asserted: a wrong assumption
+            # about the generator must not be mistaken for a transport error (and vice versa).
+            try:
+                peer = (rank - 1) % world
+                gp = torch.Generator(device=dev).manual_seed(0xB200 + peer)
+                bad = 0
+                for j in range(window):
+                    exp = torch.randint(0, 256, (msg,), dtype=torch.uint8, device=dev, generator=gp)
+                    bad += int(not torch.equal(exp, dst[0][j]))
+                payload_check = (f"bit-exact vs rank {peer}'s regenerated sources ({window} messages)" if bad == 0
+                                 else f"MISMATCH in {bad} of {window} messages vs rank {peer}'s regenerated sources")
+            except Exception as exc:  # noqa: BLE001
+                payload_check = f"not checked ({exc!r})"
         barrier()
         torch.cuda.synchronize()
         ctx.reset_stats()
@@ -273,9 +289,9 @@ def run_ours(args):
         await client.aclose()
         barrier()
         await server.aclose()
-        return value, ms, st, clk, e2e_value, step_bytes, e2e_diag
+        return value, ms, st, clk, e2e_value, step_bytes, e2e_diag, payload_check
 
-    value, ms, st, clk, e2e_value, step_bytes, e2e_diag = new_loop_runner()(main())
+    value, ms, st, clk, e2e_value, step_bytes, e2e_diag, payload_check = new_loop_runner()(main())
 
     # ---- roofline of the dominant kernel (sw_bulk_tma_kernel), from CUDA events recorded on the
     #      stream the kernel is launched on (engine profiling hooks), averaged over the timed region
@@ -324,6 +340,7 @@ def run_ours(args):
             "timing": "wall clock + CUDA events between device-wide synchronisations, max over ranks",
             "api": "public asyncio API (one Future per message, as the reference)",
             "numa": "rank bound to the GPU-local CPUs" if numa_bound else "no CPU binding applied",
+            "payload_check_rank0": payload_check,
         },
         "mmsg_per_s": round(world * window * args.steps / (ms * 1e-3) / 1e6, 4),
         "nvlink_roofline_frac": None if world == 1 else round(value / world / 900.0, 4),
