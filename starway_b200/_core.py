@@ -382,8 +382,14 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
                     except RuntimeError:
                         pass  # loop already closed
 
-        def _slow(self, entry, kind, status, sender_tag, length, worker, ep, here) -> None:
+        def _slow(self, entry, kind, status, sender_tag, length, worker, ep, here, op_id=0) -> None:
             """One completion the C fast path does not handle itself (accept, raw callbacks, other loops)."""
+            if entry is None and op_id:
+                # An operation posted through submit() from another thread: sw_post_* runs with the GIL
+                # released and the entry is registered right after it, both under self._lock.  Taking
+                # the lock here therefore waits for the registration (completions must never be dropped).
+                with self._lock:
+                    entry = self._ops.pop(op_id, None)
             if entry is None:
                 if kind == SW_OP_ACCEPT:
                     srv = self._servers.get(worker)

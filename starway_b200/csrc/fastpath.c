@@ -55,7 +55,7 @@ typedef struct {
   PyObject* ops;            /* dict shared with the Python shim: op id -> ("fut", loop, fut, keep, post_ok) */
   PyObject* resolve;        /* resolve(obj, writable) -> (ptr, nbytes, mem, keep)    [slow path: as_buffer] */
   PyObject* ensure_reader;  /* ensure_reader(loop) */
-  PyObject* slow;           /* slow(entry, kind, status, sender_tag, length, worker, ep, here_loop) */
+  PyObject* slow;           /* slow(entry, kind, status, sender_tag, length, worker, ep, here_loop, op_id) */
   PyObject* last_error;     /* last_error() -> str */
   PyObject* status_string;  /* status_string(code) -> str */
   PyObject* get_running_loop;
@@ -396,6 +396,12 @@ static int resolve_future(Binding* self, PyObject* fut, const sw_completion* c) 
   return 0;
 }
 
+/* A Python error raised while one completion is handed over (user callback, hand-over to another
+ * loop) is reported and the batch goes on: the completions already polled belong to other operations. */
+static void report_and_continue(Binding* self) {
+  if (PyErr_Occurred()) PyErr_WriteUnraisable((PyObject*)self);
+}
+
 /* drain(loop): resolve every pending completion; runs on `loop`'s thread (eventfd reader) */
 static PyObject* Binding_drain(Binding* self, PyObject* here) {
   /* the batch lives on this thread's stack: resolving an entry may run Python code (the shim), which
@@ -419,9 +425,10 @@ static PyObject* Binding_drain(Binding* self, PyObject* here) {
         } else {
           /* a future of another loop: the Python shim hands it over with call_soon_threadsafe */
           PyObject* entry = PyTuple_Pack(5, self->str_fut, loop, fut, keep, Py_None);
-          PyObject* r = entry ? PyObject_CallFunction(self->slow, "OIiKKKKO", entry, (unsigned)c.kind, (int)c.status,
+          PyObject* r = entry ? PyObject_CallFunction(self->slow, "OIiKKKKOK", entry, (unsigned)c.kind, (int)c.status,
                                                       (unsigned long long)c.sender_tag, (unsigned long long)c.length,
-                                                      (unsigned long long)c.worker, (unsigned long long)c.ep, here)
+                                                      (unsigned long long)c.worker, (unsigned long long)c.ep, here,
+                                                      (unsigned long long)c.op_id)
                               : NULL;
           if (!r) rc = -1;
           Py_XDECREF(r);
@@ -430,39 +437,38 @@ static PyObject* Binding_drain(Binding* self, PyObject* here) {
         Py_DECREF(loop);
         Py_DECREF(fut);
         Py_DECREF(keep);
-        if (rc < 0) return NULL;
+        if (rc < 0) report_and_continue(self); /* one failing hand-over must not drop the rest of the batch */
         continue;
       }
       /* not a fast-path operation: the table shared with the Python shim */
       PyObject* key = PyLong_FromUnsignedLongLong(c.op_id);
-      if (!key) return NULL;
+      if (!key) {
+        report_and_continue(self);
+        continue;
+      }
       PyObject* entry = PyDict_GetItemWithError(self->ops, key); /* borrowed */
       if (entry) {
         Py_INCREF(entry);
         PyDict_DelItem(self->ops, key);
       } else if (PyErr_Occurred()) {
-        Py_DECREF(key);
-        return NULL;
+        report_and_continue(self);
       }
       Py_DECREF(key);
       int fast = entry && PyTuple_Check(entry) && PyTuple_GET_SIZE(entry) == 5 &&
                  PyTuple_GET_ITEM(entry, 0) == self->str_fut && PyTuple_GET_ITEM(entry, 1) == here &&
                  PyTuple_GET_ITEM(entry, 4) == Py_None;
       if (fast) {
-        if (resolve_future(self, PyTuple_GET_ITEM(entry, 2), &c) < 0) {
-          Py_XDECREF(entry);
-          return NULL;
-        }
+        if (resolve_future(self, PyTuple_GET_ITEM(entry, 2), &c) < 0) report_and_continue(self);
       } else {
-        /* accept notifications, raw callbacks, other loops, banner callbacks: the Python shim */
-        PyObject* r = PyObject_CallFunction(self->slow, "OIiKKKKO", entry ? entry : Py_None, (unsigned)c.kind, (int)c.status,
+        /* accept notifications, raw callbacks, other loops, banner callbacks -- and operations another
+         * thread posted through the ctypes path (GIL released inside sw_post_*) but has not registered
+         * yet: the Python shim looks those up again under the context lock (op id passed along) */
+        PyObject* r = PyObject_CallFunction(self->slow, "OIiKKKKOK", entry ? entry : Py_None, (unsigned)c.kind, (int)c.status,
                                             (unsigned long long)c.sender_tag, (unsigned long long)c.length,
-                                            (unsigned long long)c.worker, (unsigned long long)c.ep, here);
-        if (!r) {
-          Py_XDECREF(entry);
-          return NULL;
-        }
-        Py_DECREF(r);
+                                            (unsigned long long)c.worker, (unsigned long long)c.ep, here,
+                                            (unsigned long long)c.op_id);
+        if (!r) report_and_continue(self);
+        Py_XDECREF(r);
       }
       Py_XDECREF(entry);
     }

@@ -218,3 +218,61 @@ def test_uvloop_event_loop(sim_api):
         uvloop.run(asyncio.wait_for(case(sim_api, free_port()), 120))
     uvloop.run(asyncio.wait_for(cb.case_chaos(sim_api, free_port(), 3), 120))
     uvloop.run(asyncio.wait_for(cb.case_random_schedule_vs_oracle(sim_api, free_port(), 4, SimDev), 120))
+
+
+@pytest.mark.parametrize("fast", [True, False], ids=["fastpath", "ctypes"])
+def test_second_thread_flush_close_and_raw_callbacks(sim_api, ctypes_api, fast):
+    """Operations posted through the ctypes path (aflush, aflush_ep, aclose, aconnect, the raw callback
+    forms) release the GIL inside sw_post_*: another loop's drain may poll their completion before the
+    posting thread has registered the operation.  The completion must not be dropped (round-1 advisor
+    finding: aflush from a second thread timed out on the fast path)."""
+    import threading
+
+    from tests.conftest import free_port
+
+    api = sim_api if fast else ctypes_api
+    errors = []
+    stop = threading.Event()
+
+    async def traffic(port):
+        async with cb.gen_server_client(api, port) as (server, client):
+            buf = np.zeros(32, dtype=np.uint8)
+            src = np.full(32, 7, dtype=np.uint8)
+            while not stop.is_set():
+                f = server.arecv(buf, 5, (1 << 64) - 1)
+                await client.asend(src, 5)
+                await f
+
+    async def flusher(port):
+        loop = asyncio.get_running_loop()
+        async with cb.gen_server_client(api, port) as (server, client):
+            ep = next(iter(server.list_clients()))
+            for i in range(400):
+                await asyncio.wait_for(client.aflush(), 5)
+                await asyncio.wait_for(server.aflush_ep(ep), 5)
+                done = loop.create_future()
+                client.flush(lambda: loop.call_soon_threadsafe(done.set_result, None),
+                             lambda why: loop.call_soon_threadsafe(done.set_exception, Exception(why)))
+                await asyncio.wait_for(done, 5)
+                if i % 40 == 0:   # connect / close cycles post through the same path
+                    c2 = api.Client()
+                    await asyncio.wait_for(c2.aconnect("127.0.0.1", port), 5)
+                    await asyncio.wait_for(c2.aclose(), 5)
+
+    def worker(fn):
+        try:
+            asyncio.run(asyncio.wait_for(fn(free_port()), 120))
+        except BaseException as e:  # noqa: BLE001
+            errors.append(repr(e))
+        finally:
+            stop.set()
+
+    t1 = threading.Thread(target=worker, args=(traffic,))
+    t2 = threading.Thread(target=worker, args=(flusher,))
+    t1.start()
+    t2.start()
+    t2.join(150)
+    stop.set()
+    t1.join(30)
+    assert not errors, errors
+    assert not t1.is_alive() and not t2.is_alive()

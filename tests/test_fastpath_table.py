@@ -47,7 +47,7 @@ def stub(tmp_path_factory):
 def make_binding(lib, _core, ops, slow_calls):
     addr = lambda f: ctypes.cast(f, ctypes.c_void_p).value  # noqa: E731
 
-    def slow(entry, kind, status, tag, length, worker, ep, here):
+    def slow(entry, kind, status, tag, length, worker, ep, here, op_id=0):
         slow_calls.append((entry, kind, status, tag, length))
 
     return _core._fastpath.Binding(addr(lib.st_post_send), addr(lib.st_post_recv), addr(lib.st_poll), 0, ops,
