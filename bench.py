@@ -192,25 +192,21 @@ def run_ours(args):
             gc.freeze()
         # warm-up, then bit-exactness of one full window against the sources of the sending rank
         await timed(max(args.warmup, 3), src, dst, torch.cuda.synchronize)
-        if world == 1:
-            for s, d in zip(src[0], dst[0]):
-                assert torch.equal(s, d), "payload mismatch"
-            payload_check = "bit-exact vs the sources (loopback)"
-        else:
-            # rank r receives what rank r-1 sent; its sources are a seeded sequence (Philox: seed and
-            # offset only), so they can be regenerated here.  Reported, not asserted: a wrong assumption
-            # about the generator must not be mistaken for a transport error (and vice versa).
-            try:
-                peer = (rank - 1) % world
-                gp = torch.Generator(device=dev).manual_seed(0xB200 + peer)
-                bad = 0
-                for j in range(window):
-                    exp = torch.randint(0, 256, (msg,), dtype=torch.uint8, device=dev, generator=gp)
-                    bad += int(not torch.equal(exp, dst[0][j]))
-                payload_check = (f"bit-exact vs rank {peer}'s regenerated sources ({window} messages)" if bad == 0
-                                 else f"MISMATCH in {bad} of {window} messages vs rank {peer}'s regenerated sources")
-            except Exception as exc:  # noqa: BLE001
-                payload_check = f"not checked ({exc!r})"
+        # Every rank checks the window it received against the sources of the rank that sent it (rank r-1;
+        # its own at N == 1): the sources are a seeded sequence (Philox: seed and offset only), so any rank
+        # can regenerate them.  The mismatch count is summed over ranks and asserted.
+        peer = (rank - 1) % world
+        gp = torch.Generator(device=dev).manual_seed(0xB200 + peer)
+        bad = 0
+        for j in range(window):
+            exp = torch.randint(0, 256, (msg,), dtype=torch.uint8, device=dev, generator=gp)
+            bad += int(not torch.equal(exp, dst[0][j]))
+        if dist is not None:
+            t = torch.tensor([bad], dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            bad = int(t[0])
+        assert bad == 0, f"payload mismatch: {bad} of {world * window} messages differ from the sender's sources"
+        payload_check = (f"asserted on every rank: {world} x {window} messages bit-exact vs the sending rank's regenerated sources")
         barrier()
         torch.cuda.synchronize()
         ctx.reset_stats()
@@ -340,7 +336,7 @@ def run_ours(args):
             "timing": "wall clock + CUDA events between device-wide synchronisations, max over ranks",
             "api": "public asyncio API (one Future per message, as the reference)",
             "numa": "rank bound to the GPU-local CPUs" if numa_bound else "no CPU binding applied",
-            "payload_check_rank0": payload_check,
+            "payload_check_all_ranks": payload_check,
         },
         "mmsg_per_s": round(world * window * args.steps / (ms * 1e-3) / 1e6, 4),
         "nvlink_roofline_frac": None if world == 1 else round(value / world / 900.0, 4),
