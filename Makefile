@@ -28,7 +28,7 @@ oracle-core: $(ORACLE)
 hostsim: $(HOSTSIM)
 probe: $(PROBE) $(ABIBENCH)
 
-build/gpu_cuda.o: $(CSRC)/gpu_cuda.cu $(CSRC)/kernels.cuh $(CSRC)/gpu.h $(CSRC)/sw_device.h $(CSRC)/bulk_jobs.h
+build/gpu_cuda.o: $(CSRC)/gpu_cuda.cu $(CSRC)/kernels.cuh $(CSRC)/progress.cuh $(CSRC)/gpu.h $(CSRC)/sw_device.h $(CSRC)/bulk_jobs.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 

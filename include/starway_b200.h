@@ -98,6 +98,10 @@ typedef struct sw_stats {
   uint64_t put_event_launches;
   double match_event_ms;      /* match + deliver pair */
   uint64_t match_event_launches;
+  /* resident path: control-kernel / pull-kernel launches, and what the pull CTAs copied (bytes) in how much
+   * time (union of the batches' active intervals, device timer) -- the roofline numerator / denominator */
+  uint64_t prog_launches, pull_launches, pull_batches, pull_jobs, pull_bytes;
+  double pull_busy_ms;
 } sw_stats;
 
 /* ---- library / context (reference Context, main.cpp:71-79) */

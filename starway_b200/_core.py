@@ -96,6 +96,12 @@ class SwStats(ctypes.Structure):
         ("put_event_launches", ctypes.c_uint64),
         ("match_event_ms", ctypes.c_double),
         ("match_event_launches", ctypes.c_uint64),
+        ("prog_launches", ctypes.c_uint64),
+        ("pull_launches", ctypes.c_uint64),
+        ("pull_batches", ctypes.c_uint64),
+        ("pull_jobs", ctypes.c_uint64),
+        ("pull_bytes", ctypes.c_uint64),
+        ("pull_busy_ms", ctypes.c_double),
     ]
 
 

@@ -78,7 +78,7 @@ uint64_t rand64() {
 bool pid_alive(uint32_t pid) { return pid == 0 || kill((pid_t)pid, 0) == 0 || errno == EPERM; }
 
 // ============================================================================ shared control block
-constexpr uint32_t SHM_MAGIC = 0x53574332u;  // "SWC2"
+constexpr uint32_t SHM_MAGIC = 0x53574333u;  // "SWC3"
 constexpr uint32_t CTL_RING = 256;
 enum : uint32_t { CTL_FIN = 1, CTL_CLOSE = 2, CTL_CLOSE_ACK = 3, CTL_CANCEL_RTS = 4, CTL_CANCEL_ACK = 5 };
 
@@ -96,6 +96,9 @@ struct alignas(64) ShmDir {  // one direction: sender side X -> receiver side Y
   alignas(64) std::atomic<uint64_t> ctl_head;  // control messages written by X
   alignas(64) std::atomic<uint64_t> ctl_tail;  // control messages consumed by Y
   alignas(64) CtlMsg ctl[CTL_RING];
+  // Rendezvous FIN words, written by Y's pull CTAs (device stores into this page-locked block), read by X:
+  // word [seq % SW_FIN_SLOTS] == (seq << 2) | 1 once rendezvous `seq` of this direction has been pulled.
+  alignas(64) std::atomic<uint64_t> gfin[SW_FIN_SLOTS];
 };
 
 struct ShmCtl {
@@ -314,6 +317,11 @@ struct SendOp {
   void* dev_staging = nullptr;
   size_t staging_size = 0;
   uint64_t rndv_seq = 0;
+  // The put block that carries this send's slot still refers to the record until poll_puts retires it: a
+  // FIN / close that ends the send earlier only notes the outcome here and poll_puts finishes the record.
+  bool in_put = false;
+  bool ended_early = false;
+  int32_t early_status = 0;
 };
 
 constexpr int MEM_PINNED = 3;  // internal: host memory the device can address directly (cudaHostAlloc)
@@ -331,6 +339,7 @@ struct RecvOp {
   void* pinned_bounce = nullptr;  // small host receives land here (device-mapped pinned memory)
   void* dev_staging = nullptr;    // large host receives land here, then D2H
   size_t staging_size = 0;
+  bool rndv_capable = false;      // resident path: counted in Worker::rndv_recvs while posted
 };
 
 struct FlushOp {
@@ -418,6 +427,7 @@ struct Ep {
   uint32_t peer_ring_slots = 0;
   // control block
   ShmCtl* shm = nullptr;
+  uint8_t* shm_dev = nullptr;   // device-visible alias of the control block (nullptr: not page-locked)
   size_t shm_size = 0;
   ShmDir* out = nullptr;  // we are the sender side of this direction
   ShmDir* in = nullptr;   // we are the receiver side of this direction
@@ -434,6 +444,13 @@ struct Ep {
   uint32_t puts_inflight = 0;
   // receive side
   std::set<uint64_t> canceled_rts;  // sender cancelled these rendezvous ids
+  // resident path: withdrawals (CANCEL_RTS) wait here until the control kernel has seen the endpoint's dead bit
+  // and every device-side pull issued before that is complete; then they move to canceled_rts and are acked
+  std::vector<uint64_t> cancel_quiesce;
+  uint64_t cancel_epoch = 0;        // host_epoch value the control kernel has to echo
+  uint64_t cancel_pull_mark = 0;    // device pull jobs that must have completed
+  bool retired = false;             // resources released, ring index reusable (the record stays listed)
+  uint32_t ring_gen = 0;            // generation of `index` (device side: SwMatchState::ring_gen)
   // lifecycle
   bool peer_closed = false;
   bool close_ack_owed = false;
@@ -483,6 +500,29 @@ struct Worker {
   std::atomic<bool> retired{false};          // the progress thread has dropped its last reference
   std::thread connector;
   uint32_t bulk_inflight = 0;
+  // ---- resident path (sw_progress_kernel): host-visible rings and control words of this worker
+  bool resident = false;
+  SwProgCtl* pctl = nullptr;
+  SwPostEnt* post_ring = nullptr;
+  SwCqEnt* cq_ring = nullptr;
+  SwCqEnt* cqr_ring = nullptr;
+  SwHrEnt* hr_ring = nullptr;
+  swgpu::stream_t s_ctl = nullptr;
+  uint64_t prog_seq = 0;          // launches so far
+  bool prog_running = false;
+  bool cfg_dirty = false;         // ring set changed: the running kernel must leave and be relaunched
+  uint64_t posts_written = 0, cq_head = 0, cqr_head = 0, hr_head = 0;
+  uint64_t host_epoch = 0;
+  double last_activity = 0, prog_launched_at = 0;
+  uint32_t prog_spins = 0;
+  // a launch that ended with a ring blocked on the unexpected heap is repeated only when something changed
+  bool prog_stalled = false;
+  uint64_t stall_posts = 0, stall_seen = 0;
+  uint32_t rndv_recvs = 0;        // posted receives that a rendezvous message could land in
+  uint64_t arrivals_seen = 0;
+  std::vector<uint32_t> free_ring_idx;   // ring indices of retired endpoints
+  uint32_t ring_gen_ctr[SW_MAX_EPS] = {};
+  std::vector<Ep*> tombs;                // retired endpoint records whose ring index has been taken over
 };
 
 enum : int { SQ_SEND = 1, SQ_RECV = 2, SQ_FLUSH = 3, SQ_CLOSE = 4, SQ_NEW_EP = 5, SQ_REGISTER = 6 };
@@ -528,6 +568,7 @@ struct Mapping {
   void* base;
   uint32_t refs;
   double last_use;
+  uint64_t uuid, buf_id, remote_base;   // key / value of the device-resident table entry (buf_id 0: none)
 };
 struct MapKey {   // (exporting pid, cudaIpcMemHandle_t bytes)
   uint32_t pid;
@@ -617,6 +658,22 @@ struct Ctx {
   // Measured on B200 (profiles/r01_e2e_staging_variants.md): the copy engine leaves the SMs and more of
   // the PCIe duplex budget to the concurrent download kernel (43.8 vs 37.9 GB/s at N=2).
   std::atomic<int64_t> opt_stage_upload_kernel{0};
+  // ---- resident path
+  // 1: receives are driven by resident control kernels (sw_progress_kernel) and rendezvous copies by the
+  // resident pull CTAs (sw_pull_kernel); 0: one match launch per batch, host-launched bulk copies (round 1)
+  std::atomic<int64_t> opt_resident{1};
+  std::atomic<int64_t> opt_linger_us{150}, opt_max_life_us{2000}, opt_armed_ms{30}, opt_pull_ctas{0};
+  SwPullQueue* pq = nullptr;
+  SwMapEnt* map_tbl = nullptr;
+  SwPullCtl* pull_ctl = nullptr;
+  swgpu::stream_t s_pull = nullptr, s_map = nullptr;
+  swgpu::event_t pull_ev = nullptr;
+  uint64_t pull_seq = 0;
+  bool pull_running = false, pull_stop_sent = false;
+  double pull_launched_at = 0, pull_last_need = 0;
+  uint64_t pull_bytes_seen = 0, pull_busy_seen = 0, pull_batches_seen = 0, pull_jobs_seen = 0;
+  std::atomic<int> stats_flush{0};
+  bool evict_pending = false;   // the mapping cache is waiting for the device-side users to drain
   // stats
   std::mutex st_mu;
   sw_stats stats;
@@ -729,6 +786,7 @@ void send_finished(Ctx* c, SendOp* op, int32_t status) {
 }
 
 void recv_release(Ctx* c, RecvOp* r) {
+  if (r->rndv_capable && r->w && r->w->rndv_recvs) r->w->rndv_recvs--;
   if (r->pinned_bounce) c->host_pool.put(r->pinned_bounce, r->cap);
   if (r->dev_staging) c->staging.put(r->dev_staging, r->staging_size);
   delete r;
@@ -780,7 +838,31 @@ bool worker_alloc_device(Ctx* c, Worker* w) {
     set_error(std::string("worker pinned alloc: ") + swgpu::last_error());
     return false;
   }
+  w->resident = c->opt_resident.load() != 0 && c->pq && c->map_tbl;
+  if (w->resident) {
+    w->pctl = (SwProgCtl*)swgpu::host_alloc(sizeof(SwProgCtl));
+    w->post_ring = (SwPostEnt*)swgpu::host_alloc(sizeof(SwPostEnt) * SW_POST_RING);
+    w->cq_ring = (SwCqEnt*)swgpu::host_alloc(sizeof(SwCqEnt) * SW_CQ_RING);
+    w->cqr_ring = (SwCqEnt*)swgpu::host_alloc(sizeof(SwCqEnt) * SW_CQ_RING);
+    w->hr_ring = (SwHrEnt*)swgpu::host_alloc(sizeof(SwHrEnt) * SW_HR_RING);
+    w->s_ctl = swgpu::stream_create();
+    if (!w->pctl || !w->post_ring || !w->cq_ring || !w->cqr_ring || !w->hr_ring || !w->s_ctl) {
+      set_error(std::string("worker resident-path alloc: ") + swgpu::last_error());
+      return false;
+    }
+    w->last_activity = now_s();
+  }
   return true;
+}
+
+// per-endpoint words the control kernel publishes to: the sender-visible credit word and the FIN words of the
+// inbound direction, through the page-locked alias of the control block
+bool ep_publish_words(Worker* w, Ep* ep) {
+  if (!w->resident) return true;
+  if (!ep->shm_dev) return false;   // sw_ctx_create probed page-locking: this is an error, not a mode switch
+  const size_t off = (uint8_t*)ep->in - (uint8_t*)ep->shm;
+  return swgpu::match_state_set_ep_words(w->mstate, ep->index, ep->shm_dev + off + offsetof(ShmDir, consumed),
+                                         ep->shm_dev + off + offsetof(ShmDir, gfin)) == 0;
 }
 
 void fill_blob(Ctx* c, Worker* w) {
@@ -816,12 +898,37 @@ bool ep_alloc_ring(Ctx* c, Ep* ep) {
   return true;
 }
 
-ShmCtl* shm_create(std::string& name_out, size_t& size_out) {
+// Control blocks are mapped ONCE per process and name (both ends of an in-process connection share the
+// mapping) and page-locked with the CUDA driver, so that kernels can store credits and FIN words into them.
+struct ShmMapping {
+  ShmCtl* host = nullptr;
+  uint8_t* dev = nullptr;   // device-visible alias (nullptr: registration failed, the host forwards instead)
+  size_t size = 0;
+  int refs = 0;
+};
+std::mutex g_shm_mu;
+std::map<std::string, ShmMapping> g_shm;
+
+constexpr size_t shm_bytes() { return (sizeof(ShmCtl) + 4095) & ~(size_t)4095; }
+
+ShmCtl* shm_adopt(const std::string& name, void* p, size_t sz, uint8_t** dev_out) {
+  ShmMapping m;
+  m.host = (ShmCtl*)p;
+  m.size = sz;
+  m.refs = 1;
+  m.dev = (uint8_t*)swgpu::host_register(p, sz);
+  if (!m.dev) fprintf(stderr, "starway_b200: control block not page-locked (%s): receives fall back to host-driven launches\n", swgpu::last_error());
+  g_shm[name] = m;
+  *dev_out = m.dev;
+  return m.host;
+}
+
+ShmCtl* shm_create(std::string& name_out, size_t& size_out, uint8_t** dev_out) {
   char name[64];
   snprintf(name, sizeof(name), "/swb200-%d-%llx", (int)getpid(), (unsigned long long)rand64());
   int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
   if (fd < 0) return nullptr;
-  size_t sz = (sizeof(ShmCtl) + 4095) & ~(size_t)4095;
+  size_t sz = shm_bytes();
   if (ftruncate(fd, (off_t)sz) != 0) {
     close(fd);
     shm_unlink(name);
@@ -839,12 +946,21 @@ ShmCtl* shm_create(std::string& name_out, size_t& size_out) {
   s->version = SW_ABI_VERSION;
   name_out = name;
   size_out = sz;
-  return s;
+  std::lock_guard<std::mutex> lk(g_shm_mu);
+  return shm_adopt(name, p, sz, dev_out);
 }
-ShmCtl* shm_attach(const char* name, size_t& size_out) {
+ShmCtl* shm_attach(const char* name, size_t& size_out, uint8_t** dev_out) {
+  std::lock_guard<std::mutex> lk(g_shm_mu);
+  auto it = g_shm.find(name);
+  if (it != g_shm.end()) {   // the creator lives in this process
+    it->second.refs++;
+    size_out = it->second.size;
+    *dev_out = it->second.dev;
+    return it->second.host;
+  }
   int fd = shm_open(name, O_RDWR, 0600);
   if (fd < 0) return nullptr;
-  size_t sz = (sizeof(ShmCtl) + 4095) & ~(size_t)4095;
+  size_t sz = shm_bytes();
   void* p = mmap(nullptr, sz, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
   close(fd);
   if (p == MAP_FAILED) return nullptr;
@@ -854,7 +970,20 @@ ShmCtl* shm_attach(const char* name, size_t& size_out) {
     return nullptr;
   }
   size_out = sz;
-  return s;
+  return shm_adopt(name, p, sz, dev_out);
+}
+void shm_release(ShmCtl* s) {
+  if (!s) return;
+  std::lock_guard<std::mutex> lk(g_shm_mu);
+  for (auto it = g_shm.begin(); it != g_shm.end(); ++it) {
+    if (it->second.host != s) continue;
+    if (--it->second.refs == 0) {
+      if (it->second.dev) swgpu::host_unregister(it->second.host);
+      munmap(it->second.host, it->second.size);
+      g_shm.erase(it);
+    }
+    return;
+  }
 }
 
 void sq_push(Ctx* c, int kind, Worker* w, void* p, SqNode* n = nullptr) {
@@ -950,18 +1079,20 @@ void server_handshake(Ctx* c, Worker* w, int fd, bool tcp) {
   do {
     if (!read_all(fd, &h, sizeof(h)) || h.magic != WIRE_MAGIC) break;
     h.shm_name[sizeof(h.shm_name) - 1] = 0;
-    if (w->eps.size() >= SW_MAX_EPS) {
-      wl.status = SW_ERR_NO_MEMORY;
+    if (w->eps.size() >= SW_MAX_EPS && w->free_ring_idx.empty()) {
+      wl.status = SW_ERR_NO_MEMORY;   // SW_MAX_EPS connections OPEN at the same time
       break;
     }
     ep = ep_new(c, w);
-    ep->index = (uint32_t)w->eps.size();
+    // ring index: a fresh one, or the index of an endpoint whose connection has ended and drained
+    ep->index = w->free_ring_idx.empty() ? (uint32_t)w->eps.size() : w->free_ring_idx.back();
+    ep->ring_gen = ++w->ring_gen_ctr[ep->index] & SW_EP_GEN_MASK;
     ep->peer_pid = h.pid;
     ep->peer_device = h.device;
     ep->peer_ctx_uuid = h.ctx_uuid;
     ep->peer_worker_id = h.worker_id;
     ep->in_process = (h.pid == (uint32_t)getpid() && h.ctx_uuid == c->uuid);
-    ep->shm = shm_attach(h.shm_name, ep->shm_size);
+    ep->shm = shm_attach(h.shm_name, ep->shm_size, &ep->shm_dev);
     if (!ep->shm) {
       wl.status = SW_ERR_IO_ERROR;
       break;
@@ -990,10 +1121,15 @@ void server_handshake(Ctx* c, Worker* w, int fd, bool tcp) {
       }
     }
     ep->peer_ring_slots = h.ring_slots;
-    if (swgpu::match_state_set_ring(w->mstate, ep->index, ep->ring, ep->ring_slots) != 0) {
+    if (swgpu::match_state_set_ring(w->mstate, ep->index, ep->ring, ep->ring_slots, ep->ring_gen) != 0) {
       wl.status = SW_ERR_IO_ERROR;
       break;
     }
+    if (!ep_publish_words(w, ep)) {
+      wl.status = SW_ERR_IO_ERROR;
+      break;
+    }
+    w->cfg_dirty = true;   // a running control kernel does not know this ring yet
     // endpoint metadata (reference handle_new_endpoint, main.cpp:867-910)
     snprintf(ep->info.name, sizeof(ep->info.name), "starway-ep-%u[pid %u gpu %d]", ep->index, h.pid, h.device);
     if (tcp) {
@@ -1021,7 +1157,15 @@ void server_handshake(Ctx* c, Worker* w, int fd, bool tcp) {
 
   if (wl.status == SW_OK) {
     // the endpoint is visible (list_clients) before the client learns the connect succeeded
-    w->eps.push_back(ep);
+    if (ep->index < w->eps.size()) {
+      w->free_ring_idx.pop_back();
+      w->tombs.push_back(w->eps[ep->index]);   // the retired record stays listed (list_clients never shrinks)
+      w->eps[ep->index] = ep;
+      if (w->pctl)   // the index starts a new life: its requests may go down the device path again
+        __atomic_store_n(&w->pctl->dead_mask, w->pctl->dead_mask & ~(1ull << ep->index), __ATOMIC_RELEASE);
+    } else {
+      w->eps.push_back(ep);
+    }
     {
       std::lock_guard<std::mutex> lk(c->mu);
       c->eps[ep->id] = ep;
@@ -1033,7 +1177,7 @@ void server_handshake(Ctx* c, Worker* w, int fd, bool tcp) {
     if (ep) {
       if (ep->peer_ring_mapping) swgpu::ipc_close(ep->peer_ring_mapping);
       if (ep->ring) swgpu::dev_free(ep->ring);
-      if (ep->shm) munmap(ep->shm, ep->shm_size);
+      if (ep->shm) shm_release(ep->shm);
       Slab<Ep>::recycle(ep);
     }
   }
@@ -1115,7 +1259,7 @@ void client_connect_thread(Ctx* c, Worker* w, ConnectReq req) {
     ep->is_client_side = true;
     if (!ep_alloc_ring(c, ep)) break;
     if (swgpu::match_state_set_ring(w->mstate, 0, ep->ring, ep->ring_slots) != 0) break;
-    ep->shm = shm_create(shm_name, ep->shm_size);
+    ep->shm = shm_create(shm_name, ep->shm_size, &ep->shm_dev);
     if (!ep->shm) {
       status = SW_ERR_IO_ERROR;
       break;
@@ -1123,6 +1267,10 @@ void client_connect_thread(Ctx* c, Worker* w, ConnectReq req) {
     ep->shm->pid[0] = (uint32_t)getpid();
     ep->out = &ep->shm->dir[0];
     ep->in = &ep->shm->dir[1];
+    if (!ep_publish_words(w, ep)) {
+      status = SW_ERR_IO_ERROR;
+      break;
+    }
     // ---- handshake
     WireHello h;
     memset(&h, 0, sizeof(h));
@@ -1185,7 +1333,7 @@ void client_connect_thread(Ctx* c, Worker* w, ConnectReq req) {
     if (ep) {
       if (ep->peer_ring_mapping) swgpu::ipc_close(ep->peer_ring_mapping);
       if (ep->ring) swgpu::dev_free(ep->ring);
-      if (ep->shm) munmap(ep->shm, ep->shm_size);
+      if (ep->shm) shm_release(ep->shm);
       Slab<Ep>::recycle(ep);
     }
     if (w->mstate) {
@@ -1218,6 +1366,8 @@ bool pump_sends(Ctx* c) {
         }
         uint64_t consumed = ep->out->consumed.load(std::memory_order_acquire);
         if (ep->out_sent - consumed >= ep->peer_ring_slots) break;  // no credit
+        // the FIN words of a connection are indexed by the rendezvous sequence number modulo SW_FIN_SLOTS
+        if (op->len > eager_max && ep->rndv_wait.size() >= SW_FIN_SLOTS - 1) break;
         SwPutDesc& d = b.descs[n];
         d.tag = op->tag;
         d.msg_len = op->len;
@@ -1248,7 +1398,7 @@ bool pump_sends(Ctx* c) {
             base = (uint64_t)(uintptr_t)op->ptr;
             size = op->len;
             r.src_ptr = base;
-            r.pad[0] = 1;  // source is pinned host memory
+            r.pad[0] = SW_RTS_PINNED_SRC;
           } else if (op->mem == SW_MEM_HOST) {
             // Staged sends are published batch by batch: keep batches small so that the receiver can
             // start pulling the first payloads while later ones are still being uploaded.
@@ -1286,6 +1436,11 @@ bool pump_sends(Ctx* c) {
             base = (uint64_t)(uintptr_t)op->dev_staging;
             size = op->staging_size;
             r.src_ptr = base;
+            if (!ep->in_process) {
+              swgpu::PtrInfo spi;
+              swgpu::ptr_info(op->dev_staging, &spi);
+              buffer_id = spi.buffer_id;
+            }
           } else {
             r.src_ptr = (uint64_t)(uintptr_t)op->ptr;
             if (!ep->in_process) {
@@ -1324,6 +1479,7 @@ bool pump_sends(Ctx* c) {
           }
           r.alloc_base = base;
           r.alloc_size = size;
+          r.pad[1] = buffer_id;   // key of the receiver's device-resident mapping table
           r.ctx_uuid = c->uuid;
           r.src_pid = (uint32_t)getpid();
           r.src_dev = srcdev;
@@ -1339,6 +1495,7 @@ bool pump_sends(Ctx* c) {
         ep->puts_inflight++;
         ep->sendq.pop_front();
         if (rndv) ep->rndv_wait[op->rndv_seq] = op;
+        op->in_put = true;
         b.items.push_back(PutItem{ep, op, rndv});
         bytes += d.len;
         n++;
@@ -1409,7 +1566,10 @@ bool poll_puts(Ctx* c) {
     }
     for (PutItem& it : b.items) {
       SendOp* op = it.op;
-      if (!it.rndv) {
+      op->in_put = false;
+      if (op->ended_early) {
+        send_finished(c, op, op->early_status);
+      } else if (!it.rndv) {
         send_finished(c, op, q < 0 ? SW_ERR_IO_ERROR : SW_OK);
       } else if (op->dev_staging && !op->user_done) {
         // host buffer has been staged on the device: the caller may reuse it (UCX eager-bcopy semantics)
@@ -1600,7 +1760,19 @@ bool poll_match(Ctx* c, Worker* w) {
 }
 
 // ============================================================================ progress: rendezvous pulls
-void* resolve_mapping(Ctx* c, BulkJob& j) {
+uint64_t pull_outstanding(Ctx* c);
+// device-side users of the mapping table / of mapped addresses: running control kernels, unfinished pulls
+bool mappings_in_use_on_device(Ctx* c) {
+  for (Worker* w : c->active)
+    if (w->prog_running) return true;
+  return pull_outstanding(c) != 0;
+}
+
+// Maps the sender's allocation (cached).  New mappings are also entered into the device-resident table, so
+// that the next rendezvous from that allocation is resolved by the control kernel without the host.
+// *retry: the cache is full and entries can only be dropped while no resident kernel runs -- try again later.
+void* resolve_mapping(Ctx* c, BulkJob& j, bool* retry) {
+  *retry = false;
   MapKey key;
   key.pid = j.rts.src_pid;
   memcpy(key.handle, j.rts.ipc_handle, 64);
@@ -1610,6 +1782,16 @@ void* resolve_mapping(Ctx* c, BulkJob& j) {
     // distinct IPC handles are normal).  Opening/closing a mapping costs ~100s of us, so only
     // the least recently used idle quarter is dropped when the bound is hit.
     if (c->mappings.size() >= MAX_MAPPINGS) {
+      if (c->map_tbl && mappings_in_use_on_device(c)) {
+        // A control kernel may be resolving through the table, a pull may be reading through a mapping:
+        // have the control kernels leave (no relaunch while evict_pending), let the pulls drain, come back.
+        c->evict_pending = true;
+        for (Worker* w : c->active)
+          if (w->prog_running) __atomic_store_n(&w->pctl->stop, 1, __ATOMIC_RELEASE);
+        *retry = true;
+        return nullptr;
+      }
+      c->evict_pending = false;
       std::vector<std::pair<double, MapKey>> idle;
       for (auto& kv : c->mappings)
         if (kv.second.refs == 0) idle.emplace_back(kv.second.last_use, kv.first);
@@ -1620,13 +1802,24 @@ void* resolve_mapping(Ctx* c, BulkJob& j) {
         swgpu::ipc_close(m->second.base);
         c->mappings.erase(m);
       }
+      if (c->map_tbl) {   // rebuild the device table from what is left
+        swgpu::map_table_clear(c->map_tbl);
+        for (auto& kv : c->mappings)
+          if (kv.second.buf_id)
+            swgpu::map_table_insert(c->map_tbl, c->s_map, kv.second.uuid, kv.second.buf_id, kv.second.remote_base,
+                                    (uint64_t)(uintptr_t)kv.second.base);
+      }
     }
     void* base = nullptr;
     if (swgpu::ipc_open(j.rts.ipc_handle, &base) != 0) {
       fprintf(stderr, "starway_b200: cannot map the sender's buffer: %s\n", swgpu::last_error());
       return nullptr;
     }
-    it = c->mappings.emplace(key, Mapping{base, 0, now_s()}).first;
+    Mapping m{base, 0, now_s(), j.rts.ctx_uuid, j.rts.pad[1], j.rts.alloc_base};
+    if (c->map_tbl && m.buf_id &&
+        swgpu::map_table_insert(c->map_tbl, c->s_map, m.uuid, m.buf_id, m.remote_base, (uint64_t)(uintptr_t)base) != 0)
+      m.buf_id = 0;   // probe window full: this allocation keeps going through the host
+    it = c->mappings.emplace(key, m).first;
   }
   it->second.refs++;
   it->second.last_use = now_s();
@@ -1652,7 +1845,10 @@ void bulk_job_done(Ctx* c, BulkJob& j, int32_t status) {
 }
 
 bool pump_bulk(Ctx* c) {
-  if (c->pending_bulk.empty()) return false;
+  if (c->pending_bulk.empty()) {
+    c->evict_pending = false;
+    return false;
+  }
   if ((c->bulk_tail - c->bulk_head) >= (uint32_t)N_BULK_BLOCKS) return false;
   {
     // Coalesce: while more matches are on their way (ops queued, puts or matches in flight), hold the
@@ -1683,7 +1879,13 @@ bool pump_bulk(Ctx* c) {
       if (j.rts.ctx_uuid == c->uuid && j.rts.src_pid == (uint32_t)getpid()) {
         j.src = j.rts.src_ptr;
       } else {
-        void* base = resolve_mapping(c, j);
+        bool retry = false;
+        void* base = resolve_mapping(c, j, &retry);
+        if (retry) {   // the mapping cache has to wait for the resident kernels to leave
+          j.w->bulk_inflight--;
+          c->pending_bulk.push_front(j);
+          break;
+        }
         if (!base) {
           j.failed = true;
           j.fail_status = SW_ERR_UNREACHABLE;
@@ -1799,16 +2001,350 @@ bool poll_bulk(Ctx* c) {
   return any;
 }
 
+// ============================================================================ progress: resident control kernel
+// Replaces pump_match / poll_match when the worker runs on the resident path: the host only feeds the post
+// ring, drains the completion rings and keeps the kernels alive while work is expected.
+uint64_t unseen_arrivals(Worker* w) {
+  uint64_t unseen = 0;
+  for (Ep* ep : w->eps) {
+    if (!ep->in) continue;
+    const uint64_t p = ep->in->produced.load(std::memory_order_acquire);
+    const uint64_t cns = ep->in->consumed.load(std::memory_order_acquire);
+    if (p > cns) unseen += p - cns;
+  }
+  return unseen;
+}
+
+inline bool cq_ready(const SwCqEnt* e, uint64_t idx, int32_t* status) {
+  // status and pass number share one 8-byte word, stored last by the device
+  const uint64_t w = __atomic_load_n(reinterpret_cast<const uint64_t*>(&e->status), __ATOMIC_ACQUIRE);
+  if (static_cast<uint32_t>(w >> 32) != sw_ring_pass(idx, SW_CQ_RING)) return false;
+  *status = static_cast<int32_t>(static_cast<uint32_t>(w));
+  return true;
+}
+
+bool poll_progress_rings(Ctx* c, Worker* w) {
+  bool any = false;
+  // ---- eager completions
+  uint64_t h = w->cq_head;
+  for (;;) {
+    const SwCqEnt* e = &w->cq_ring[h % SW_CQ_RING];
+    int32_t status;
+    if (!cq_ready(e, h, &status)) break;
+    recv_finish(c, w, e->op_id, status, e->tag, e->len);
+    h++;
+  }
+  if (h != w->cq_head) {
+    w->cq_head = h;
+    __atomic_store_n(&w->pctl->cq_head, h, __ATOMIC_RELEASE);
+    any = true;
+  }
+  // ---- rendezvous completions of the pull CTAs (the sender's FIN word has been written by the same CTA)
+  h = w->cqr_head;
+  for (;;) {
+    const SwCqEnt* e = &w->cqr_ring[h % SW_CQ_RING];
+    int32_t status;
+    if (!cq_ready(e, h, &status)) break;
+    trace(c, "pull_done", e->op_id, e->len);
+    recv_finish(c, w, e->op_id, status, e->tag, e->len);
+    h++;
+  }
+  if (h != w->cqr_head) {
+    w->cqr_head = h;
+    __atomic_store_n(&w->pctl->cqr_head, h, __ATOMIC_RELEASE);
+    any = true;
+  }
+  // ---- rendezvous matches the device left to the host (source not mapped yet, host-side or unaligned
+  //      buffers, truncation, withdrawn senders)
+  h = w->hr_head;
+  for (;;) {
+    const SwHrEnt* e = &w->hr_ring[h % SW_HR_RING];
+    if (__atomic_load_n(&e->seq, __ATOMIC_ACQUIRE) != sw_ring_pass(h, SW_HR_RING)) break;
+    const SwRndvRec& r = e->rec;
+    BulkJob j;
+    j.w = w;
+    const uint32_t idx = r.ep & ((1u << SW_EP_IDX_BITS) - 1), gen = r.ep >> SW_EP_IDX_BITS;
+    j.ep = idx < w->eps.size() ? w->eps[idx] : nullptr;
+    j.recv_op = r.op_id;
+    j.dst = r.dst;
+    j.cap = r.cap;
+    j.tag = r.tag;
+    j.len = r.len;
+    j.rts = r.rts;
+    j.t_enq = now_s();
+    {
+      auto rit = w->recvs.find(r.op_id);
+      j.host_side = (r.rts.pad[0] & SW_RTS_PINNED_SRC) != 0 || (rit != w->recvs.end() && rit->second->mem == MEM_PINNED);
+    }
+    if (r.status != SW_OK) {
+      j.failed = true;
+      j.fail_status = r.status;
+    }
+    if (!j.ep || j.ep->retired || j.ep->ring_gen != gen) {
+      // a request parked in the unexpected queue by a connection that has ended since: its source is gone
+      j.ep = nullptr;
+      j.failed = true;
+      j.fail_status = SW_ERR_CONNECTION_RESET;
+    }
+    c->pending_bulk.push_back(j);
+    h++;
+  }
+  if (h != w->hr_head) {
+    w->hr_head = h;
+    __atomic_store_n(&w->pctl->hr_head, h, __ATOMIC_RELEASE);
+    any = true;
+  }
+  if (any) w->last_activity = now_s();
+  return any;
+}
+
+bool pump_progress(Ctx* c, Worker* w) {
+  if (!w->mstate || !w->pctl) return false;
+  const int st = w->status.load(std::memory_order_acquire);
+  if (st != SW_ST_RUNNING && st != SW_ST_CLOSING) return false;
+  bool any = false;
+  // ---- has the last launch ended?
+  if (w->prog_running) {
+    if (__atomic_load_n(&w->pctl->exit_seq, __ATOMIC_ACQUIRE) == w->prog_seq) {
+      w->prog_running = false;
+      trace(c, "prog_exit", w->prog_seq, w->pctl->arrivals);
+      if (w->pctl->err) fprintf(stderr, "starway_b200: device matcher reported inconsistency 0x%llx\n", (unsigned long long)w->pctl->err);
+      w->prog_stalled = w->pctl->stalled != 0;
+      w->stall_posts = w->posts_written;
+      w->stall_seen = unseen_arrivals(w);
+      {
+        const uint64_t arr = w->pctl->arrivals;
+        std::lock_guard<std::mutex> lk(c->st_mu);
+        c->stats.match_arrivals += arr - w->arrivals_seen;
+        w->arrivals_seen = arr;
+      }
+      any = true;
+    } else if ((++w->prog_spins & 0xFFF) == 0 && swgpu::stream_query(w->s_ctl) < 0) {
+      fprintf(stderr, "starway_b200: control kernel failed: %s\n", swgpu::last_error());
+      w->prog_running = false;
+    }
+  }
+  any |= poll_progress_rings(c, w);
+  // ---- new receives -> post ring
+  uint32_t np = 0;
+  if (w->close_phase == 0) {
+    while (!w->new_posts.empty() && w->posts_written - __atomic_load_n(&w->pctl->post_head, __ATOMIC_ACQUIRE) < SW_POST_RING &&
+           w->recvs.size() < SW_PQ_CAP / 2) {
+      RecvOp* r = w->new_posts.front();
+      uint64_t buf = (uint64_t)(uintptr_t)r->ptr;
+      if (r->mem == SW_MEM_HOST && r->cap > HOST_BOUNCE_MAX) {
+        swgpu::PtrInfo pi;
+        swgpu::ptr_info(r->ptr, &pi);
+        if (pi.is_pinned) r->mem = MEM_PINNED;  // a host-launched copy writes the caller's pinned buffer directly
+      }
+      if (r->mem == SW_MEM_HOST) {
+        if (r->cap <= HOST_BOUNCE_MAX) {
+          r->pinned_bounce = c->host_pool.get(r->cap);
+          buf = (uint64_t)(uintptr_t)r->pinned_bounce;
+        } else {
+          r->dev_staging = c->staging.get(r->cap, &r->staging_size);
+          buf = (uint64_t)(uintptr_t)r->dev_staging;
+        }
+        if (!buf) {
+          w->new_posts.pop_front();
+          complete(c, w, r->op_id, SW_OP_RECV, SW_ERR_NO_MEMORY);
+          delete r;
+          continue;
+        }
+      }
+      SwPostEnt& p = w->post_ring[w->posts_written % SW_POST_RING];
+      p.tag = r->tag;
+      p.mask = r->mask;
+      p.buf = buf;
+      p.cap = r->cap;
+      p.op_id = r->op_id;
+      p.flags = r->mem == MEM_PINNED ? (uint32_t)SW_POST_HOSTPATH : 0u;
+      p.pad = 0;
+      if (!p.flags && r->cap > (uint64_t)c->opt_eager_max.load()) {
+        r->rndv_capable = true;   // a rendezvous may land here: keep the pull CTAs of the context resident
+        w->rndv_recvs++;
+      }
+      w->recvs[r->op_id] = r;
+      w->new_posts.pop_front();
+      w->posts_written++;
+      np++;
+    }
+    if (np) {
+      __atomic_store_n(&w->pctl->post_tail, w->posts_written, __ATOMIC_RELEASE);
+      w->last_activity = now_s();
+      std::lock_guard<std::mutex> lk(c->st_mu);
+      c->stats.match_posts += np;
+      any = true;
+    }
+  }
+  if (w->prog_running) {
+    if (w->cfg_dirty || w->close_phase >= 2) __atomic_store_n(&w->pctl->stop, 1, __ATOMIC_RELEASE);
+    return any;
+  }
+  // ---- (re)launch?  Work: receives the kernel has not taken yet, or ring slots it has not consumed (host
+  // doorbell of the peers).  Armed: receives are outstanding and the connection was active recently -- the
+  // kernel then watches the rings itself and a message needs no doorbell, no launch.
+  if (w->close_phase >= 3 || c->evict_pending) return any;
+  const uint64_t unseen = unseen_arrivals(w);
+  const bool posts_pending = w->posts_written != __atomic_load_n(&w->pctl->post_head, __ATOMIC_ACQUIRE);
+  bool work = posts_pending || unseen != 0;
+  if (w->prog_stalled && w->stall_posts == w->posts_written && w->stall_seen == unseen) work = false;
+  const double now = now_s();
+  const bool armed = swgpu::resident_lingers() && w->close_phase == 0 && !w->recvs.empty() &&
+                     now - w->last_activity < (double)c->opt_armed_ms.load() * 1e-3;
+  if (!work && !armed) return any;
+  swgpu::ProgressLaunch a;
+  a.st = w->mstate;
+  a.ctl = w->pctl;
+  a.posts = w->post_ring;
+  a.cq = w->cq_ring;
+  a.cqr = w->cqr_ring;
+  a.hr = w->hr_ring;
+  a.pq = c->pq;
+  a.map = c->map_tbl;
+  a.ctx_uuid = c->uuid;
+  a.launch_seq = ++w->prog_seq;
+  a.pid = (uint32_t)getpid();
+  a.n_eps = (uint32_t)w->eps.size();
+  a.linger_us = (uint32_t)c->opt_linger_us.load();
+  a.max_life_us = (uint32_t)c->opt_max_life_us.load();
+  a.pull_ctas = (uint32_t)c->opt_pull_ctas.load();
+  __atomic_store_n(&w->pctl->stop, 0, __ATOMIC_RELEASE);
+  w->cfg_dirty = false;
+  trace(c, "prog_launch", w->prog_seq, unseen);
+  if (swgpu::launch_progress(w->s_ctl, &a) != 0) {
+    fprintf(stderr, "starway_b200: control kernel launch failed: %s\n", swgpu::last_error());
+    w->prog_seq--;
+    return any;
+  }
+  w->prog_running = true;
+  w->prog_spins = 0;
+  w->prog_launched_at = now;
+  if (work) w->last_activity = now;
+  std::lock_guard<std::mutex> lk(c->st_mu);
+  c->stats.prog_launches++;
+  return true;
+}
+
+// ---- the pull CTAs of the context: alive while device-side rendezvous copies are outstanding or expected
+uint64_t pull_outstanding(Ctx* c) {
+  uint64_t n = 0;
+  for (Worker* w : c->active) {
+    if (!w->pctl) continue;
+    const uint64_t pub = __atomic_load_n(&w->pctl->pull_jobs, __ATOMIC_ACQUIRE);
+    if (pub > w->cqr_head) n += pub - w->cqr_head;
+  }
+  return n;
+}
+
+void pull_collect_stats(Ctx* c) {
+  if (!c->pull_ctl) return;
+  const uint64_t bytes = c->pull_ctl->bytes, busy = c->pull_ctl->busy_ns, batches = c->pull_ctl->batches, jobs = c->pull_ctl->jobs;
+  std::lock_guard<std::mutex> lk(c->st_mu);
+  c->stats.pull_bytes += bytes - c->pull_bytes_seen;
+  c->stats.pull_busy_ms += (double)(busy - c->pull_busy_seen) * 1e-6;
+  c->stats.pull_batches += batches - c->pull_batches_seen;
+  c->stats.pull_jobs += jobs - c->pull_jobs_seen;
+  c->pull_bytes_seen = bytes;
+  c->pull_busy_seen = busy;
+  c->pull_batches_seen = batches;
+  c->pull_jobs_seen = jobs;
+}
+
+bool pump_pull(Ctx* c) {
+  if (!c->pq) return false;
+  bool any = false;
+  if (c->pull_running) {
+    if (__atomic_load_n(&c->pull_ctl->exited, __ATOMIC_ACQUIRE) == c->pull_seq && swgpu::event_query(c->pull_ev) != 1) {
+      c->pull_running = false;
+      c->pull_stop_sent = false;
+      pull_collect_stats(c);
+      trace(c, "pull_exit", c->pull_seq);
+      any = true;
+    }
+  }
+  const uint64_t outstanding = pull_outstanding(c);
+  bool expected = false;   // a running control kernel may hand over a rendezvous match at any moment
+  for (Worker* w : c->active) expected |= w->prog_running && w->rndv_recvs > 0;
+  const double now = now_s();
+  if (outstanding || expected) c->pull_last_need = now;
+  if (c->pull_running) {
+    const bool flush = c->stats_flush.load(std::memory_order_acquire) != 0;
+    if (!c->pull_stop_sent && ((!outstanding && !expected) || flush)) {
+      __atomic_store_n(&c->pull_ctl->stop, 1, __ATOMIC_RELEASE);
+      c->pull_stop_sent = true;
+    }
+    return any;
+  }
+  if (c->stats_flush.load(std::memory_order_acquire)) c->stats_flush.store(0, std::memory_order_release);
+  if (!outstanding && !(expected && swgpu::resident_lingers())) return any;
+  swgpu::BulkTuning tune;
+  tune.mode = 0;
+  tune.stages = (int)c->opt_bulk_stages.load();
+  tune.stage_bytes = (int)c->opt_bulk_stage_bytes.load();
+  tune.ctas_per_sm = 1;
+  tune.balance = 1;
+  __atomic_store_n(&c->pull_ctl->stop, 0, __ATOMIC_RELEASE);
+  c->pull_seq++;
+  trace(c, "pull_launch", c->pull_seq, outstanding);
+  if (swgpu::launch_pull(c->s_pull, c->pq, c->pull_ctl, c->pull_seq, (uint32_t)c->opt_pull_ctas.load(),
+                         (uint32_t)c->opt_linger_us.load() * 2, (uint32_t)c->opt_max_life_us.load(), &tune) != 0) {
+    fprintf(stderr, "starway_b200: pull kernel launch failed: %s\n", swgpu::last_error());
+    c->pull_seq--;
+    return any;
+  }
+  swgpu::event_record(c->pull_ev, c->s_pull);
+  c->pull_running = true;
+  c->pull_stop_sent = false;
+  c->pull_launched_at = now;
+  std::lock_guard<std::mutex> lk(c->st_mu);
+  c->stats.pull_launches++;
+  return true;
+}
+
 // ============================================================================ progress: control ring, flush, close
+// End a rendezvous send that has left the queue.  While the put block that carried its RTS is still in flight
+// the block refers to the record (poll_puts reads it): only note the outcome, poll_puts finishes it.
+void rndv_end(Ctx* c, SendOp* op, int32_t status) {
+  if (op->in_put) {
+    op->ended_early = true;
+    op->early_status = status;
+    return;
+  }
+  send_finished(c, op, status);
+}
+
 void fail_ep_sends(Ctx* c, Ep* ep, int32_t status) {
   while (!ep->sendq.empty()) {
     SendOp* op = ep->sendq.front();
     ep->sendq.pop_front();
     send_finished(c, op, status);
   }
-  for (auto& kv : ep->rndv_wait) send_finished(c, kv.second, status);
+  for (auto& kv : ep->rndv_wait) rndv_end(c, kv.second, status);
   ep->rndv_wait.clear();
   ep->cancel_wait.clear();
+}
+
+// FIN words written by the receiver's pull CTAs (device stores into the page-locked control block)
+bool poll_fin_words(Ctx* c, Ep* ep) {
+  if (!ep->out || ep->rndv_wait.empty()) return false;
+  bool any = false;
+  int looked = 0;
+  for (auto it = ep->rndv_wait.begin(); it != ep->rndv_wait.end() && looked < 64; looked++) {
+    const uint64_t seq = it->first;
+    const uint64_t v = ep->out->gfin[seq % SW_FIN_SLOTS].load(std::memory_order_acquire);
+    if ((v >> 2) != seq) {
+      ++it;
+      continue;
+    }
+    trace(c, "fin_word", seq);
+    SendOp* op = it->second;
+    it = ep->rndv_wait.erase(it);
+    ep->cancel_wait.erase(seq);
+    rndv_end(c, op, (v & 3) == 1 ? SW_OK : SW_ERR_IO_ERROR);
+    any = true;
+  }
+  return any;
 }
 
 bool poll_ctl(Ctx* c, Ep* ep) {
@@ -1831,7 +2367,7 @@ bool poll_ctl(Ctx* c, Ep* ep) {
         if (it != ep->rndv_wait.end()) {
           SendOp* op = it->second;
           ep->rndv_wait.erase(it);
-          send_finished(c, op, m.status);
+          rndv_end(c, op, m.status);
         }
         break;
       }
@@ -1840,6 +2376,19 @@ bool poll_ctl(Ctx* c, Ep* ep) {
         break;
       case CTL_CANCEL_RTS: {
         // the sender is closing and withdraws rendezvous m.a
+        Worker* w = ep->owner;
+        if (w->resident) {
+          // The control kernel may match (and the pull CTAs may copy) this request at any moment: raise the
+          // endpoint's dead bit -- matches of its requests then come to the host -- and acknowledge once
+          // the kernel has seen the bit and every pull it issued before that has completed
+          // (progress_cancels).
+          ep->cancel_quiesce.push_back(m.a);
+          __atomic_store_n(&w->pctl->dead_mask, w->pctl->dead_mask | (1ull << (ep->index & 63)), __ATOMIC_RELEASE);
+          __atomic_store_n(&w->pctl->host_epoch, ++w->host_epoch, __ATOMIC_RELEASE);
+          ep->cancel_epoch = w->host_epoch;
+          ep->cancel_pull_mark = ~0ull;
+          break;
+        }
         bool in_flight = false;
         for (uint32_t k = c->bulk_head; k != c->bulk_tail; k++)
           for (BulkJob& j : c->bulk_blocks[k % N_BULK_BLOCKS].jobs)
@@ -1870,6 +2419,70 @@ bool poll_ctl(Ctx* c, Ep* ep) {
   return any;
 }
 
+// A connection whose peer has closed and whose traffic has drained gives its ring, control block and peer
+// mapping back; the ring index is reused by a later connection (with a new generation).  The record itself
+// stays listed (reference: list_clients never shrinks, tests/test_basic.py:53-56).
+bool retire_eps(Ctx* c, Worker* w) {
+  if (!w->resident || w->kind != SW_WORKER_SERVER || w->close_phase != 0) return false;
+  bool any = false;
+  for (Ep* ep : w->eps) {
+    if (ep->retired || !ep->peer_closed || ep->close_ack_owed || !ep->shm) continue;
+    if (!ep->ctl_backlog.empty() || !ep->sendq.empty() || !ep->rndv_wait.empty() || ep->puts_inflight) continue;
+    if (!ep->cancel_quiesce.empty() || !ep->out_seqs.empty()) continue;
+    if (ep->in->produced.load(std::memory_order_acquire) != ep->in->consumed.load(std::memory_order_acquire)) continue;
+    bool busy = false;
+    for (auto& j : c->pending_bulk) busy |= j.ep == ep;
+    for (uint32_t k = c->bulk_head; k != c->bulk_tail; k++)
+      for (BulkJob& j : c->bulk_blocks[k % N_BULK_BLOCKS].jobs) busy |= j.ep == ep;
+    for (FlushOp* f : w->flushes) busy |= f->marks.count(ep) != 0;
+    if (busy || pull_outstanding(c)) continue;
+    if (w->prog_running) {   // the control kernel polls this ring: have it leave first
+      w->cfg_dirty = true;
+      continue;
+    }
+    swgpu::match_state_set_ring(w->mstate, ep->index, nullptr, 0, 0);
+    swgpu::match_state_set_ep_words(w->mstate, ep->index, nullptr, nullptr);
+    if (ep->peer_ring_mapping) swgpu::ipc_close(ep->peer_ring_mapping);
+    ep->peer_ring_mapping = nullptr;
+    ep->peer_ring = nullptr;
+    if (ep->ring) swgpu::dev_free(ep->ring);   // the peer's CLOSE came after its last put had completed
+    ep->ring = nullptr;
+    shm_release(ep->shm);
+    ep->shm = nullptr;
+    ep->shm_dev = nullptr;
+    ep->in = ep->out = nullptr;
+    ep->retired = true;
+    w->free_ring_idx.push_back(ep->index);
+    trace(c, "ep_retired", ep->index);
+    any = true;
+  }
+  return any;
+}
+
+// resident path: withdrawals wait until the device cannot touch the withdrawn sources any more
+bool progress_cancels(Ctx* c, Worker* w) {
+  bool any = false;
+  for (Ep* ep : w->eps) {
+    if (ep->cancel_quiesce.empty()) continue;
+    const bool seen = !w->prog_running || __atomic_load_n(&w->pctl->dev_epoch, __ATOMIC_ACQUIRE) >= ep->cancel_epoch;
+    if (!seen) continue;
+    if (ep->cancel_pull_mark == ~0ull) ep->cancel_pull_mark = __atomic_load_n(&w->pctl->pull_jobs, __ATOMIC_ACQUIRE);
+    if (w->cqr_head < ep->cancel_pull_mark) continue;   // pulls issued before the dead bit was seen: still copying
+    for (uint64_t seq : ep->cancel_quiesce) {
+      bool in_flight = false;
+      for (uint32_t k = c->bulk_head; k != c->bulk_tail; k++)
+        for (BulkJob& j : c->bulk_blocks[k % N_BULK_BLOCKS].jobs)
+          if (j.ep == ep && j.rts.send_seq == seq) in_flight = true;
+      if (in_flight) continue;   // the FIN of the running host-launched pull acknowledges it
+      ep->canceled_rts.insert(seq);
+      ctl_send(ep, CTL_CANCEL_ACK, SW_OK, seq);
+    }
+    ep->cancel_quiesce.clear();
+    any = true;
+  }
+  return any;
+}
+
 void check_flushes(Ctx* c, Worker* w) {
   for (size_t i = 0; i < w->flushes.size();) {
     FlushOp* f = w->flushes[i];
@@ -1893,6 +2506,7 @@ void check_flushes(Ctx* c, Worker* w) {
 
 void worker_release(Ctx* c, Worker* w, bool leak_rings) {
   for (Ep* ep : w->eps) {
+    if (ep->retired) continue;
     if (ep->peer_ring_mapping) {
       swgpu::ipc_close(ep->peer_ring_mapping);
       ep->peer_ring_mapping = nullptr;
@@ -1902,8 +2516,9 @@ void worker_release(Ctx* c, Worker* w, bool leak_rings) {
     if (ep->ring && safe) swgpu::dev_free(ep->ring);
     ep->ring = nullptr;
     if (ep->shm) {
-      munmap(ep->shm, ep->shm_size);
+      shm_release(ep->shm);
       ep->shm = nullptr;
+      ep->shm_dev = nullptr;
       ep->in = ep->out = nullptr;
     }
   }
@@ -1919,6 +2534,20 @@ void worker_release(Ctx* c, Worker* w, bool leak_rings) {
   if (w->mev_start) swgpu::event_destroy(w->mev_start);
   if (w->mev_fast) swgpu::event_destroy(w->mev_fast);
   w->mev = w->mev_start = w->mev_fast = nullptr;
+  if (w->s_ctl) {
+    swgpu::stream_sync(w->s_ctl);
+    swgpu::stream_destroy(w->s_ctl);
+  }
+  swgpu::host_free(w->pctl);
+  swgpu::host_free(w->post_ring);
+  swgpu::host_free(w->cq_ring);
+  swgpu::host_free(w->cqr_ring);
+  swgpu::host_free(w->hr_ring);
+  w->s_ctl = nullptr;
+  w->pctl = nullptr;
+  w->post_ring = nullptr;
+  w->cq_ring = w->cqr_ring = nullptr;
+  w->hr_ring = nullptr;
   if (w->tcp_fd >= 0) close(w->tcp_fd);
   if (w->unix_fd >= 0) close(w->unix_fd);
   w->tcp_fd = w->unix_fd = -1;
@@ -1961,8 +2590,15 @@ bool progress_close(Ctx* c, Worker* w) {
   if (w->close_phase == 2) {
     // ---- wait for in-flight device work and for the cancel acknowledgements
     bool busy = w->match_inflight || w->bulk_inflight > 0;
+    if (w->resident && w->pctl) {
+      // the control kernel is asked to leave (pump_progress raises `stop` from phase 2 on); rendezvous copies
+      // it handed to the pull CTAs run to completion -- they write into receive buffers of this worker
+      busy |= w->prog_running;
+      busy |= __atomic_load_n(&w->pctl->pull_jobs, __ATOMIC_ACQUIRE) > w->cqr_head;
+    }
     for (Ep* ep : w->eps) {
       if (ep->puts_inflight) busy = true;
+      if (!ep->cancel_quiesce.empty()) busy = true;   // withdrawals of our peers that we still have to acknowledge
       if (!ep->cancel_wait.empty() && !ep->peer_closed && pid_alive(ep->peer_pid) && now_s() < w->close_deadline)
         busy = true;
     }
@@ -1972,7 +2608,7 @@ bool progress_close(Ctx* c, Worker* w) {
       if (pc.op->w == w) busy = true;
     if (busy) return false;
     for (Ep* ep : w->eps) {
-      for (auto& kv : ep->rndv_wait) send_finished(c, kv.second, SW_ERR_CANCELED);
+      for (auto& kv : ep->rndv_wait) rndv_end(c, kv.second, SW_ERR_CANCELED);
       ep->rndv_wait.clear();
       ep->cancel_wait.clear();
     }
@@ -2190,15 +2826,25 @@ void progress_main(Ctx* c) {
     active |= pump_sends(c);
     for (Worker* w : c->active) {
       if (w->close_phase >= 4) continue;
-      for (Ep* ep : w->eps) active |= poll_ctl(c, ep);
-      active |= poll_match(c, w);
-      active |= pump_match(c, w);
+      for (Ep* ep : w->eps) {
+        active |= poll_ctl(c, ep);
+        active |= poll_fin_words(c, ep);
+      }
+      if (w->resident) {
+        active |= pump_progress(c, w);
+        active |= progress_cancels(c, w);
+        if ((iter & 255) == 0) active |= retire_eps(c, w);
+      } else {
+        active |= poll_match(c, w);
+        active |= pump_match(c, w);
+      }
       check_flushes(c, w);
       active |= progress_close(c, w);
       if ((iter & 31) == 0 && w->kind == SW_WORKER_SERVER) poll_listeners(c, w);
     }
     active |= poll_bulk(c);
     active |= pump_bulk(c);
+    active |= pump_pull(c);
     flush_completions(c);
     // forget fully closed workers; `retired` tells sw_worker_destroy that this thread holds no
     // reference any more and the record may be recycled
@@ -2210,9 +2856,10 @@ void progress_main(Ctx* c) {
     }
     iter++;
     bool inflight = (c->put_head != c->put_tail) || (c->bulk_head != c->bulk_tail) || !c->post_copies.empty();
+    inflight |= c->pull_running;
     bool expecting = false;  // operations whose completion depends on a peer's doorbell / FIN
     for (Worker* w : c->active) {
-      inflight |= w->match_inflight;
+      inflight |= w->match_inflight || w->prog_running;
       if (w->close_phase >= 4) continue;
       expecting |= !w->recvs.empty() || !w->flushes.empty() || w->close_phase != 0;
       for (Ep* ep : w->eps) expecting |= !ep->rndv_wait.empty() || !ep->sendq.empty();
@@ -2263,9 +2910,12 @@ void recycle_worker(Ctx* c, Worker* w) {
     std::lock_guard<std::mutex> lk(c->mu);
     c->workers.erase(w->id);
     for (Ep* ep : w->eps) c->eps.erase(ep->id);
+    for (Ep* ep : w->tombs) c->eps.erase(ep->id);
   }
   for (Ep* ep : w->eps) Slab<Ep>::recycle(ep);
+  for (Ep* ep : w->tombs) Slab<Ep>::recycle(ep);
   w->eps.clear();
+  w->tombs.clear();
   Slab<Worker>::recycle(w);
 }
 
@@ -2344,6 +2994,39 @@ sw_ctx* sw_ctx_create(int device) {
     delete c;
     return nullptr;
   }
+  // ---- resident path: pull queue, mapping table; needs page-locking of existing host mappings (control blocks)
+  if (const char* e = getenv("STARWAY_RESIDENT")) c->opt_resident = atoll(e);
+  if (c->opt_resident.load()) {
+    void* probe = mmap(nullptr, 4096, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+    bool can_lock = false;
+    if (probe != MAP_FAILED) {
+      can_lock = swgpu::host_register(probe, 4096) != nullptr;
+      if (can_lock) swgpu::host_unregister(probe);
+      munmap(probe, 4096);
+    }
+    if (!can_lock) {
+      fprintf(stderr, "starway_b200: cannot page-lock shared mappings (%s): using host-driven launches\n", swgpu::last_error());
+      c->opt_resident = 0;
+    }
+  }
+  if (c->opt_resident.load()) {
+    c->pq = swgpu::pull_queue_create();
+    c->map_tbl = swgpu::map_table_create();
+    c->pull_ctl = (SwPullCtl*)swgpu::host_alloc(sizeof(SwPullCtl));
+    c->s_pull = swgpu::stream_create();
+    c->s_map = swgpu::stream_create();
+    c->pull_ev = swgpu::event_create(0);
+    c->opt_pull_ctas = swgpu::pull_default_ctas();
+    if (!c->pq || !c->map_tbl || !c->pull_ctl || !c->s_pull || !c->s_map || !c->pull_ev) {
+      set_error(std::string("sw_ctx_create (resident path): ") + swgpu::last_error());
+      delete c;
+      return nullptr;
+    }
+  }
+  if (const char* e = getenv("STARWAY_LINGER_US")) c->opt_linger_us = std::max<int64_t>(1, atoll(e));
+  if (const char* e = getenv("STARWAY_MAX_LIFE_US")) c->opt_max_life_us = std::max<int64_t>(10, atoll(e));
+  if (const char* e = getenv("STARWAY_ARMED_MS")) c->opt_armed_ms = std::max<int64_t>(0, atoll(e));
+  if (const char* e = getenv("STARWAY_PULL_CTAS")) c->opt_pull_ctas = std::max<int64_t>(0, atoll(e));
   // environment knobs
   if (const char* e = getenv("STARWAY_EAGER_MAX")) c->opt_eager_max = std::min<int64_t>(atoll(e), SW_EAGER_MAX);
   if (const char* e = getenv("STARWAY_RING_SLOTS")) c->opt_ring_slots = std::max<int64_t>(atoll(e), 4);
@@ -2423,6 +3106,20 @@ void sw_ctx_destroy(sw_ctx* ctx) {
     if (b.ev_start) swgpu::event_destroy(b.ev_start);
   }
   for (auto& kv : c->mappings) swgpu::ipc_close(kv.second.base);
+  if (c->s_pull) {
+    // the pull CTAs leave on their own (silence / lifetime); a stop request makes it quick
+    if (c->pull_ctl) __atomic_store_n(&c->pull_ctl->stop, 1, __ATOMIC_RELEASE);
+    swgpu::stream_sync(c->s_pull);
+    swgpu::stream_destroy(c->s_pull);
+  }
+  if (c->s_map) {
+    swgpu::stream_sync(c->s_map);
+    swgpu::stream_destroy(c->s_map);
+  }
+  if (c->pull_ev) swgpu::event_destroy(c->pull_ev);
+  if (c->pq) swgpu::pull_queue_destroy(c->pq);
+  if (c->map_tbl) swgpu::map_table_destroy(c->map_tbl);
+  swgpu::host_free(c->pull_ctl);
   c->host_pool.destroy();
   c->staging.destroy();
   swgpu::stream_destroy(c->s_put);
@@ -2436,7 +3133,9 @@ void sw_ctx_destroy(sw_ctx* ctx) {
   for (Worker* w : ws) {
     if (w->connector.joinable()) w->connector.join();
     for (Ep* ep : w->eps) Slab<Ep>::recycle(ep);
+    for (Ep* ep : w->tombs) Slab<Ep>::recycle(ep);
     w->eps.clear();
+    w->tombs.clear();
     Slab<Worker>::recycle(w);
   }
   delete c;
@@ -2461,6 +3160,11 @@ int sw_set_option(sw_ctx* ctx, const char* key, int64_t value) {
   else if (k == "done_flags") c->opt_done_flags = value;
   else if (k == "bulk_balance") c->opt_bulk_balance = value;
   else if (k == "consumer_polling") c->consumer_polling.store(value != 0, std::memory_order_seq_cst);
+  else if (k == "resident") c->opt_resident = (value != 0 && c->pq) ? 1 : 0;   // applies to workers created afterwards
+  else if (k == "linger_us") c->opt_linger_us = std::max<int64_t>(1, value);
+  else if (k == "max_life_us") c->opt_max_life_us = std::max<int64_t>(10, value);
+  else if (k == "armed_ms") c->opt_armed_ms = std::max<int64_t>(0, value);
+  else if (k == "pull_ctas") c->opt_pull_ctas = std::max<int64_t>(0, value);
   else {
     set_error("unknown option " + k);
     return -1;
@@ -2470,7 +3174,6 @@ int sw_set_option(sw_ctx* ctx, const char* key, int64_t value) {
 int64_t sw_get_option(sw_ctx* ctx, const char* key) {
   Ctx* c = (Ctx*)ctx;
   std::string k(key);
-  if (k == "eager_max") return c->opt_eager_max;
   if (k == "ring_slots") return c->opt_ring_slots;
   if (k == "bulk_mode") return c->opt_bulk_mode;
   if (k == "bulk_stages") return c->opt_bulk_stages;
@@ -2480,6 +3183,12 @@ int64_t sw_get_option(sw_ctx* ctx, const char* key) {
   if (k == "heap_big_blocks") return c->opt_heap_big;
   if (k == "profile") return c->opt_profile;
   if (k == "sm_count") return swgpu::sm_count();
+  if (k == "resident") return c->opt_resident;
+  if (k == "linger_us") return c->opt_linger_us;
+  if (k == "max_life_us") return c->opt_max_life_us;
+  if (k == "armed_ms") return c->opt_armed_ms;
+  if (k == "pull_ctas") return c->opt_pull_ctas;
+  if (k == "eager_max") return c->opt_eager_max;
   return -1;
 }
 
@@ -2832,6 +3541,17 @@ double sw_evaluate_perf(sw_ctx* ctx, sw_worker_t wid, sw_ep_t epid, size_t msg_s
 
 int sw_stats_get(sw_ctx* ctx, sw_stats* out) {
   Ctx* c = (Ctx*)ctx;
+  if (c->pq && !tls_is_progress) {
+    // the pull CTAs publish their byte / busy-time counters when they leave: ask them to (they are relaunched
+    // at once if copies are outstanding), bounded wait
+    c->stats_flush.store(1, std::memory_order_release);
+    sq_push(c, 0, nullptr, nullptr);   // wake a napping progress thread
+    const double deadline = now_s() + 0.25;
+    while (c->stats_flush.load(std::memory_order_acquire) && now_s() < deadline) {
+      struct timespec ts = {0, 20000};
+      nanosleep(&ts, nullptr);
+    }
+  }
   std::lock_guard<std::mutex> lk(c->st_mu);
   *out = c->stats;
   return 0;

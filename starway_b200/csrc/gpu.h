@@ -70,7 +70,7 @@ int upload(void* dst_dev, const void* src_host, size_t n);   // synchronous smal
 // Build/destroy the device-resident queues of one worker.
 SwMatchState* match_state_create(uint32_t heap_small_blocks, uint32_t heap_big_blocks);
 int match_state_destroy(SwMatchState* st);
-int match_state_set_ring(SwMatchState* st, uint32_t ep, void* ring_base, uint32_t slots);
+int match_state_set_ring(SwMatchState* st, uint32_t ep, void* ring_base, uint32_t slots, uint32_t gen = 0);
 
 // Kernel launches (asynchronous on `s`).
 // Completion flag: a word in pinned host memory that a single-CTA launch stores `value` to (system
@@ -89,5 +89,40 @@ int launch_deliver(stream_t s, SwMatchState* st, SwMatchOut* out, uint32_t max_j
 int launch_match_deliver(stream_t s, SwMatchState* st, const SwMatchIn* in, SwMatchOut* out, uint32_t max_jobs,
                          const SwMatchScalars* sc, const DoneFlag* done = nullptr);
 int launch_bulk(stream_t s, const SwSeg* segs, uint32_t nseg, const BulkTuning* tune);
+
+// ---------------------------------------------------------------- resident progress path
+// 1: launch_progress / launch_pull start kernels that stay resident and watch device / host memory on their
+// own (the CUDA backend); 0: each launch performs one pass over what is there and returns (the CPU stand-in).
+int resident_lingers();
+// Page-locks an existing host mapping (the POSIX-shm control block of a connection) and returns the address
+// device code uses for it; nullptr on failure.
+void* host_register(void* p, size_t bytes);
+int host_unregister(void* p);
+// per-endpoint words of a worker's match state the control kernel publishes to (device-visible addresses)
+int match_state_set_ep_words(SwMatchState* st, uint32_t ep, void* credit_word, void* fin_words);
+SwPullQueue* pull_queue_create();
+int pull_queue_destroy(SwPullQueue* q);
+SwMapEnt* map_table_create();
+int map_table_destroy(SwMapEnt* t);
+// insert (exporting context, buffer id) -> (remote base, local mapped base); < 0 when the probe window is full
+int map_table_insert(SwMapEnt* t, stream_t s, uint64_t uuid, uint64_t buf_id, uint64_t remote_base, uint64_t local_base);
+int map_table_clear(SwMapEnt* t);
+
+struct ProgressLaunch {
+  SwMatchState* st;
+  SwProgCtl* ctl;
+  SwPostEnt* posts;
+  SwCqEnt* cq;
+  SwCqEnt* cqr;
+  SwHrEnt* hr;
+  SwPullQueue* pq;
+  SwMapEnt* map;
+  uint64_t ctx_uuid, launch_seq;
+  uint32_t pid, n_eps, linger_us, max_life_us, pull_ctas;
+};
+int launch_progress(stream_t s, const ProgressLaunch* a);
+int launch_pull(stream_t s, SwPullQueue* q, SwPullCtl* ctl, uint64_t launch_seq, uint32_t ctas, uint32_t linger_us,
+                uint32_t max_life_us, const BulkTuning* tune);
+int pull_default_ctas();
 
 }  // namespace swgpu

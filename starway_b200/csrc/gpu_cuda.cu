@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -10,12 +11,14 @@
 #include "bulk_jobs.h"
 #include "gpu.h"
 #include "kernels.cuh"
+#include "progress.cuh"
 
 namespace swgpu {
 
 static thread_local std::string g_err;
 static int g_sms = 148;
 static int g_max_smem_optin = 0;
+static int g_clk_mhz = 1965;
 
 static int fail(cudaError_t e, const char* what) {
   char buf[256];
@@ -58,6 +61,14 @@ int init(int device) {
   SW_CUDA(cudaGetDeviceProperties(&prop, device));
   g_sms = prop.multiProcessorCount;
   g_max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  {
+    int khz = 0;
+    if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device) == cudaSuccess && khz > 0) g_clk_mhz = khz / 1000;
+    cudaFuncAttributes pa;
+    SW_CUDA(cudaFuncGetAttributes(&pa, sw_pull_kernel));
+    SW_CUDA(cudaFuncSetAttribute(sw_pull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)prop.sharedMemPerBlockOptin - (int)pa.sharedSizeBytes));
+  }
   cudaFuncAttributes fa;
   SW_CUDA(cudaFuncGetAttributes(&fa, sw_bulk_tma_kernel));
   g_max_smem_optin -= (int)fa.sharedSizeBytes;   // static mbarrier storage counts against the opt-in limit
@@ -350,10 +361,11 @@ int match_state_destroy(SwMatchState* st) {
   return 0;
 }
 
-int match_state_set_ring(SwMatchState* st, uint32_t ep, void* ring_base, uint32_t slots) {
+int match_state_set_ring(SwMatchState* st, uint32_t ep, void* ring_base, uint32_t slots, uint32_t gen) {
   if (ep >= SW_MAX_EPS) return -1;
   uint64_t base = (uint64_t)(uintptr_t)ring_base;
   uint64_t zero = 0;
+  SW_CUDA(cudaMemcpy(&st->ring_gen[ep], &gen, sizeof(gen), cudaMemcpyHostToDevice));
   SW_CUDA(cudaMemcpy(&st->ring_base[ep], &base, sizeof(base), cudaMemcpyHostToDevice));
   SW_CUDA(cudaMemcpy(&st->ring_slots[ep], &slots, sizeof(slots), cudaMemcpyHostToDevice));
   SW_CUDA(cudaMemcpy(&st->ring_cons[ep], &zero, sizeof(zero), cudaMemcpyHostToDevice));
@@ -481,6 +493,125 @@ int launch_bulk(stream_t s, const SwSeg* segs, uint32_t nseg, const BulkTuning* 
     if (grid > nseg) grid = nseg;
     sw_bulk_simt_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(segs, nseg);
   }
+  SW_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------- resident progress path
+int resident_lingers() { return 1; }
+
+void* host_register(void* p, size_t bytes) {
+  cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped);
+  if (e != cudaSuccess) {
+    fail(e, "cudaHostRegister");
+    return nullptr;
+  }
+  void* d = nullptr;
+  e = cudaHostGetDevicePointer(&d, p, 0);
+  if (e != cudaSuccess) {
+    fail(e, "cudaHostGetDevicePointer");
+    cudaHostUnregister(p);
+    return nullptr;
+  }
+  return d;
+}
+int host_unregister(void* p) {
+  if (p) SW_CUDA(cudaHostUnregister(p));
+  return 0;
+}
+
+int match_state_set_ep_words(SwMatchState* st, uint32_t ep, void* credit_word, void* fin_words) {
+  if (ep >= SW_MAX_EPS) return -1;
+  uint64_t c = (uint64_t)(uintptr_t)credit_word, f = (uint64_t)(uintptr_t)fin_words;
+  SW_CUDA(cudaMemcpy(&st->credit_ptr[ep], &c, sizeof(c), cudaMemcpyHostToDevice));
+  SW_CUDA(cudaMemcpy(&st->fin_ptr[ep], &f, sizeof(f), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+SwPullQueue* pull_queue_create() { return (SwPullQueue*)dev_alloc(sizeof(SwPullQueue)); }
+int pull_queue_destroy(SwPullQueue* q) { return dev_free(q); }
+SwMapEnt* map_table_create() { return (SwMapEnt*)dev_alloc(sizeof(SwMapEnt) * SW_MAP_SLOTS); }
+int map_table_destroy(SwMapEnt* t) { return dev_free(t); }
+static void map_shadow_reset(SwMapEnt* t);
+int map_table_clear(SwMapEnt* t) {
+  SW_CUDA(cudaMemset(t, 0, sizeof(SwMapEnt) * SW_MAP_SLOTS));
+  map_shadow_reset(t);
+  return 0;
+}
+// The host keeps a shadow of the occupied slots; entries are only ever added (or the table is cleared while no
+// control kernel runs).  Body first, then the key the device compares: two stream-ordered copies.
+static std::mutex g_map_mu;
+static std::vector<std::pair<SwMapEnt*, std::vector<uint8_t>>> g_map_shadow;
+int map_table_insert(SwMapEnt* t, stream_t s, uint64_t uuid, uint64_t buf_id, uint64_t remote_base, uint64_t local_base) {
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  std::vector<uint8_t>* used = nullptr;
+  for (auto& kv : g_map_shadow)
+    if (kv.first == t) used = &kv.second;
+  if (!used) {
+    g_map_shadow.emplace_back(t, std::vector<uint8_t>(SW_MAP_SLOTS, 0));
+    used = &g_map_shadow.back().second;
+  }
+  const uint32_t home = sw_map_home(uuid, buf_id);
+  for (uint32_t k = 0; k < SW_MAP_PROBE; k++) {
+    const uint32_t i = (home + k) & (SW_MAP_SLOTS - 1);
+    if ((*used)[i]) continue;
+    (*used)[i] = 1;
+    uint64_t body[2] = {remote_base, local_base}, key[2] = {uuid, buf_id};
+    SW_CUDA(cudaMemcpyAsync(&t[i].remote_base, body, sizeof(body), cudaMemcpyHostToDevice, (cudaStream_t)s));
+    SW_CUDA(cudaMemcpyAsync(&t[i].uuid, key, sizeof(key), cudaMemcpyHostToDevice, (cudaStream_t)s));
+    return 0;
+  }
+  g_err = "mapping table: probe window full";
+  return -1;
+}
+
+static void map_shadow_reset(SwMapEnt* t) {
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  for (auto& kv : g_map_shadow)
+    if (kv.first == t) std::fill(kv.second.begin(), kv.second.end(), 0);
+}
+
+int pull_default_ctas() { return g_sms > 4 ? g_sms - 2 : g_sms; }
+
+int launch_progress(stream_t s, const ProgressLaunch* p) {
+  SwProgArgs a;
+  a.st = p->st;
+  a.ctl = p->ctl;
+  a.posts = p->posts;
+  a.cq = p->cq;
+  a.cqr = p->cqr;
+  a.hr = p->hr;
+  a.pq = p->pq;
+  a.map = p->map;
+  a.ctx_uuid = p->ctx_uuid;
+  a.launch_seq = p->launch_seq;
+  a.pid = p->pid;
+  a.n_eps = p->n_eps;
+  a.linger_us = p->linger_us;
+  a.max_life_us = p->max_life_us;
+  a.pull_ctas = p->pull_ctas;
+  a.clk_mhz = (uint32_t)g_clk_mhz;
+  sw_progress_kernel<<<1, SW_PROG_THREADS, 0, (cudaStream_t)s>>>(a);
+  SW_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_pull(stream_t s, SwPullQueue* q, SwPullCtl* ctl, uint64_t launch_seq, uint32_t ctas, uint32_t linger_us,
+                uint32_t max_life_us, const BulkTuning* t) {
+  int stages = t->stages < 3 ? 3 : (t->stages > SW_BULK_MAX_STAGES ? SW_BULK_MAX_STAGES : t->stages);
+  int sb = t->stage_bytes & ~15;
+  if (sb < 1024) sb = 1024;
+  SwPullArgs a;
+  a.q = q;
+  a.ctl = ctl;
+  a.launch_seq = launch_seq;
+  a.stage_bytes = (uint32_t)sb;
+  a.nstages = (uint32_t)stages;
+  a.linger_us = linger_us;
+  a.max_life_us = max_life_us;
+  a.clk_mhz = (uint32_t)g_clk_mhz;
+  a.pad = 0;
+  sw_pull_kernel<<<ctas, 32, (size_t)stages * sb, (cudaStream_t)s>>>(a);
   SW_CUDA(cudaGetLastError());
   return 0;
 }

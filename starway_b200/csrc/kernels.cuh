@@ -83,7 +83,8 @@ __device__ __forceinline__ void sw_st16(void* p, const int4& v) {
 }
 
 // ------------------------------------------------------------------ cooperative byte copy
-// Copies len bytes with `nthr` cooperating threads (a warp or a CTA).  Uses 16 B
+// Copies len bytes with `nthr` cooperating threads (a warp or a CTA).  Loads never allocate in L1 (a resident
+// kernel reads ring slots that peers rewrite while it runs).  Uses 16 B
 // vectors when src and dst are mutually 16 B aligned, 4 B words when mutually
 // 4 B aligned, bytes otherwise.  Heads/tails are peeled with byte copies.
 __device__ __forceinline__ void sw_copy(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint64_t len,
@@ -93,7 +94,7 @@ __device__ __forceinline__ void sw_copy(uint8_t* __restrict__ dst, const uint8_t
   if (((s ^ d) & 15) == 0) {
     uint64_t head = (16 - (s & 15)) & 15;
     if (head > len) head = len;
-    if (tid < head) dst[tid] = src[tid];
+    if (tid < head) dst[tid] = __ldcg(src + tid);
     const uint64_t body = (len - head) >> 4;
     const int4* s4 = reinterpret_cast<const int4*>(src + head);
     int4* d4 = reinterpret_cast<int4*>(dst + head);
@@ -109,21 +110,37 @@ __device__ __forceinline__ void sw_copy(uint8_t* __restrict__ dst, const uint8_t
     for (; i < body; i += nthr) sw_st16(d4 + i, sw_ld16(s4 + i));
     const uint64_t done = head + (body << 4);
     const uint64_t tail = len - done;
-    if (tid < tail) dst[done + tid] = src[done + tid];
+    if (tid < tail) dst[done + tid] = __ldcg(src + done + tid);
   } else if (((s ^ d) & 3) == 0) {
     uint64_t head = (4 - (s & 3)) & 3;
     if (head > len) head = len;
-    if (tid < head) dst[tid] = src[tid];
+    if (tid < head) dst[tid] = __ldcg(src + tid);
     const uint64_t body = (len - head) >> 2;
     const uint32_t* s1 = reinterpret_cast<const uint32_t*>(src + head);
     uint32_t* d1 = reinterpret_cast<uint32_t*>(dst + head);
-    for (uint64_t i = tid; i < body; i += nthr) d1[i] = s1[i];
+    for (uint64_t i = tid; i < body; i += nthr) d1[i] = __ldcg(s1 + i);
     const uint64_t done = head + (body << 2);
     const uint64_t tail = len - done;
-    if (tid < tail) dst[done + tid] = src[done + tid];
+    if (tid < tail) dst[done + tid] = __ldcg(src + done + tid);
   } else {
-    for (uint64_t i = tid; i < len; i += nthr) dst[i] = src[i];
+    for (uint64_t i = tid; i < len; i += nthr) dst[i] = __ldcg(src + i);
   }
+}
+
+// Slot header: tag / length / kind / magic first, then the sequence word -- the arrival flag -- with release
+// semantics at system scope.  The payload stores of the other lanes are ordered before it by the __syncwarp the
+// callers execute first (release is cumulative), so a receiver that observes the flag with an acquire load
+// (sw_progress_kernel) sees header and payload; a receiver launched after the host doorbell sees them anyway.
+__device__ __forceinline__ void sw_put_header(uint8_t* slot, uint64_t tag, uint64_t msg_len, uint64_t seq, uint32_t kind) {
+  int4 h0;
+  h0.x = static_cast<int>(tag & 0xffffffffu);
+  h0.y = static_cast<int>(tag >> 32);
+  h0.z = static_cast<int>(msg_len & 0xffffffffu);
+  h0.w = static_cast<int>(msg_len >> 32);
+  sw_st16(slot, h0);
+  const uint64_t km = (static_cast<uint64_t>(SW_SLOT_MAGIC) << 32) | kind;
+  asm volatile("st.global.u64 [%0], %1;" ::"l"(slot + 24), "l"(km) : "memory");
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(slot + 16), "l"(seq) : "memory");
 }
 
 // ------------------------------------------------------------------ K1: eager / RTS put
@@ -138,22 +155,8 @@ __global__ void __launch_bounds__(256) sw_put_kernel(const SwPutDesc* __restrict
     const SwPutDesc d = descs[i];
     uint8_t* slot = reinterpret_cast<uint8_t*>(d.dst);
     sw_copy(slot + SW_SLOT_HDR, reinterpret_cast<const uint8_t*>(d.src), d.len, lane, 32);
-    // The slot is consumed only by a kernel launched after the host has seen this launch's CUDA
-    // event and rung the doorbell: the kernel boundary orders payload and header for the consumer.
     __syncwarp();
-    if (lane == 0) {
-      int4 h0, h1;
-      h0.x = static_cast<int>(d.tag & 0xffffffffu);
-      h0.y = static_cast<int>(d.tag >> 32);
-      h0.z = static_cast<int>(d.msg_len & 0xffffffffu);
-      h0.w = static_cast<int>(d.msg_len >> 32);
-      h1.x = static_cast<int>(d.seq & 0xffffffffu);
-      h1.y = static_cast<int>(d.seq >> 32);
-      h1.z = static_cast<int>(d.kind);
-      h1.w = static_cast<int>(SW_SLOT_MAGIC);
-      sw_st16(slot, h0);
-      sw_st16(slot + 16, h1);
-    }
+    if (lane == 0) sw_put_header(slot, d.tag, d.msg_len, d.seq, d.kind);
   }
 }
 
@@ -189,19 +192,7 @@ __global__ void __launch_bounds__(SW_PUT_INLINE * 32) sw_put_inline_kernel(const
       sw_copy(slot + SW_SLOT_HDR, reinterpret_cast<const uint8_t*>(d.src), d.len, lane, 32);
     }
     __syncwarp();
-    if (lane == 0) {
-      int4 h0, h1;
-      h0.x = static_cast<int>(d.tag & 0xffffffffu);
-      h0.y = static_cast<int>(d.tag >> 32);
-      h0.z = static_cast<int>(d.msg_len & 0xffffffffu);
-      h0.w = static_cast<int>(d.msg_len >> 32);
-      h1.x = static_cast<int>(d.seq & 0xffffffffu);
-      h1.y = static_cast<int>(d.seq >> 32);
-      h1.z = static_cast<int>(d.kind);
-      h1.w = static_cast<int>(SW_SLOT_MAGIC);
-      sw_st16(slot, h0);
-      sw_st16(slot + 16, h1);
-    }
+    if (lane == 0) sw_put_header(slot, d.tag, d.msg_len, d.seq, d.kind);
   }
   if (a.done_flag) {
     __syncthreads();

@@ -1,0 +1,1356 @@
+// starway_b200 — resident progress kernels (sm_100a): the receive side without the host on the data path.
+//
+//   sw_progress_kernel  ONE CTA per worker (Client / Server object), resident for a bounded time:
+//                         warp 0   matcher: polls the slot headers of the inbound rings (ld.acquire.sys on the
+//                                  sequence word the peer's put kernel releases last), takes new receives staged
+//                                  by warp 1, runs the tag matching over the device-resident posted / unexpected
+//                                  queues, copies small payloads itself, writes completion records and credits
+//                                  straight to host-visible memory, hands rendezvous matches to the pull queue
+//                         warp 1   host link: polls the worker's control words and the post ring in pinned host
+//                                  memory (PCIe reads off the matcher's critical path), decides when to leave
+//                         warp 2+  helpers: eager payloads above SW_INLINE_DELIVER bytes
+//                       (replaces ucp_worker_progress + the matching inside ucp_tag_recv_nbx,
+//                        reference src/bindings/main.cpp:362,1127 and :404,1172)
+//   sw_pull_kernel      resident pull CTAs of the context (one elected thread each drives the cp.async.bulk
+//                       pipeline): claim chunks of published batches, copy sender buffer -> receive buffer through
+//                       the CUDA-IPC peer mapping, the CTA that completes a batch writes the completion records
+//                       and the FIN words of the senders (replaces the rendezvous leg of ucp_tag_send_nbx,
+//                       reference main.cpp:370,1136)
+//
+// Both kernels leave on their own (linger / maximum lifetime / host request), always with consistent state in
+// device memory; the host relaunches them while work is expected.  Pure data movement and uint64
+// xor/and/compare: no tensor cores, no floating point.
+#pragma once
+#include "kernels.cuh"
+
+// ------------------------------------------------------------------ memory-model helpers
+__device__ __forceinline__ uint64_t sw_ld_acquire_sys(const void* p) {
+  uint64_t v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t sw_ld_relaxed_sys(const void* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sw_st_release_sys(void* p, uint64_t v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void sw_st_relaxed_sys(void* p, uint64_t v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t sw_ld_acquire_gpu(const void* p) {
+  uint64_t v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sw_st_release_gpu(void* p, uint64_t v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t sw_globaltimer() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ int4 sw_ld16_sys(const void* p) {   // host-visible memory: never served from L1
+  int4 r;
+  asm volatile("ld.relaxed.sys.global.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+
+// one completion record: body first, system-scope fence (payload copies of this warp included), then the word
+// that carries status + pass number -- the host reads that word first
+__device__ __forceinline__ void sw_write_cqe(SwCqEnt* ring, uint64_t idx, uint64_t op, uint64_t tag, uint64_t len,
+                                             int32_t status) {
+  SwCqEnt* e = &ring[idx % SW_CQ_RING];
+  e->op_id = op;
+  e->tag = tag;
+  e->len = len;
+  __threadfence_system();
+  const uint64_t w = (static_cast<uint64_t>(sw_ring_pass(idx, SW_CQ_RING)) << 32) | static_cast<uint32_t>(status);
+  sw_st_relaxed_sys(&e->status, w);
+}
+
+// single-thread copy of a small payload (the lane-per-message path of the matcher)
+__device__ __forceinline__ void sw_copy_lane(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t len) {
+  const uint64_t a = reinterpret_cast<uint64_t>(src) | reinterpret_cast<uint64_t>(dst);
+  uint32_t i = 0;
+  if ((a & 15) == 0) {
+    for (; i + 16 <= len; i += 16) sw_st16(dst + i, sw_ld16(src + i));
+  } else if ((a & 3) == 0) {
+    for (; i + 4 <= len; i += 4) *reinterpret_cast<uint32_t*>(dst + i) = *reinterpret_cast<const uint32_t*>(src + i);
+  }
+  for (; i < len; i++) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------ launch parameters
+struct SwProgArgs {
+  SwMatchState* st;
+  SwProgCtl* ctl;            // pinned host
+  const SwPostEnt* posts;    // pinned host, SW_POST_RING entries
+  SwCqEnt* cq;               // pinned host, SW_CQ_RING entries: eager completions (index allocated by the matcher)
+  SwCqEnt* cqr;              // pinned host, SW_CQ_RING entries: rendezvous completions (allocated by pull CTAs)
+  SwHrEnt* hr;               // pinned host, SW_HR_RING entries
+  SwPullQueue* pq;           // device memory (nullptr: every rendezvous goes to the host)
+  const SwMapEnt* map;       // device memory
+  uint64_t ctx_uuid;
+  uint64_t launch_seq;
+  uint32_t pid, n_eps;
+  uint32_t linger_us, max_life_us;
+  uint32_t pull_ctas, clk_mhz;
+};
+
+constexpr uint32_t SW_PROG_THREADS = 256;
+constexpr uint32_t SW_PROG_HELPERS = SW_PROG_THREADS / 32 - 2;
+constexpr uint32_t SW_DJOB_RING = 64;
+constexpr uint32_t SW_SPOST_RING = 64;
+constexpr uint32_t SW_PEND_RING = 128;
+
+struct SwDJob {      // matcher -> helper warp
+  uint64_t src, dst, len, op_id, tag, msg_len, cq_idx;
+  int32_t status;
+  uint32_t pad;
+};
+struct SwPend {      // something that may only be released once helper job `job` has finished
+  uint64_t job;
+  uint64_t cons_after;   // kind 0: ring cursor to publish
+  uint32_t kind;         // 0: ring credit (arg = endpoint), 1: small heap block, 2: big heap block (arg = block)
+  uint32_t arg;
+};
+
+struct SwProgShared {
+  SwPostEnt posts[SW_SPOST_RING];
+  SwDJob jobs[SW_DJOB_RING];
+  SwPend pend[SW_PEND_RING];
+  uint64_t ring_base[SW_MAX_EPS];
+  uint64_t cons[SW_MAX_EPS];
+  uint64_t credit[SW_MAX_EPS];
+  uint32_t ring_mask[SW_MAX_EPS];
+  uint32_t ring_gen[SW_MAX_EPS];
+  uint32_t pend_cnt[SW_MAX_EPS];
+  // rendezvous batch under construction
+  uint64_t pb_end[SW_PULL_JOBS], pb_src[SW_PULL_JOBS], pb_dst[SW_PULL_JOBS];
+  SwPullMeta pb_meta[SW_PULL_JOBS];
+  // cross-warp words
+  volatile uint64_t post_tail;    // staged by the link warp
+  volatile uint64_t post_head;    // consumed by the matcher
+  volatile uint64_t job_tail;     // jobs emitted by the matcher
+  volatile uint64_t cq_head, cqr_head, hr_head, dead_mask, host_epoch;   // copies of the host's words
+  volatile long long active_clk;  // last time the matcher did something
+  volatile uint32_t helper_done[SW_PROG_HELPERS];
+  volatile uint32_t exit_req;     // link warp -> matcher
+  volatile uint32_t helpers_exit; // matcher -> helpers
+};
+
+struct SwResCtx {   // warp-uniform state of the matcher, in registers for the life of the kernel
+  uint64_t p_head, p_tail, u_head, u_tail;
+  uint32_t p_count, u_count, n_free_small, n_free_big;
+  uint64_t cq_alloc, hr_alloc, jobs_emitted, pull_jobs, arrivals, post_head;
+  uint32_t pend_head, pend_tail, pb_n, err;
+  bool stalled;
+};
+
+// ------------------------------------------------------------------ matcher building blocks
+__device__ __forceinline__ uint64_t sw_warp_min64(uint64_t v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const uint64_t x = sw_shfl64(v, (threadIdx.x & 31) ^ o);
+    v = x < v ? x : v;
+  }
+  return v;
+}
+
+// smallest helper-job index that has not finished
+__device__ __forceinline__ uint64_t sw_done_prefix(const SwProgShared& sh, uint32_t lane) {
+  uint64_t v = ~0ull;
+  if (lane < SW_PROG_HELPERS) v = lane + static_cast<uint64_t>(sh.helper_done[lane]) * SW_PROG_HELPERS;
+  return sw_warp_min64(v);
+}
+
+__device__ __forceinline__ void sw_publish_credit(SwMatchState* st, SwProgShared& sh, uint32_t ep, uint64_t cons, uint32_t lane) {
+  if (lane == 0 && cons > sh.credit[ep]) {
+    sh.credit[ep] = cons;
+    if (st->credit_ptr[ep]) sw_st_release_sys(reinterpret_cast<void*>(st->credit_ptr[ep]), cons);
+  }
+}
+
+// releases whose helper job has finished: ring credits, heap blocks
+__device__ __forceinline__ void sw_retire(SwMatchState* st, SwProgShared& sh, SwResCtx& c, uint32_t lane, bool wait_all) {
+  while (c.pend_head != c.pend_tail) {
+    const uint64_t prefix = sw_done_prefix(sh, lane);
+    bool any = false;
+    while (c.pend_head != c.pend_tail) {
+      const SwPend p = sh.pend[c.pend_head % SW_PEND_RING];
+      if (p.job >= prefix) break;
+      if (p.kind == 0) {
+        if (lane == 0) sh.pend_cnt[p.arg]--;
+        __syncwarp();
+        sw_publish_credit(st, sh, p.arg, sh.pend_cnt[p.arg] == 0 ? sh.cons[p.arg] : p.cons_after, lane);
+      } else if (p.kind == 1) {
+        if (lane == 0) st->free_small[c.n_free_small] = p.arg;
+        c.n_free_small++;
+      } else {
+        if (lane == 0) st->free_big[c.n_free_big] = p.arg;
+        c.n_free_big++;
+      }
+      c.pend_head++;
+      any = true;
+    }
+    __syncwarp();
+    if (!wait_all) break;
+    if (!any) __nanosleep(50);
+  }
+}
+
+__device__ __forceinline__ void sw_cq_room(const SwProgShared& sh, const SwResCtx& c, uint32_t n) {
+  while (c.cq_alloc + n - sh.cq_head > SW_CQ_RING) __nanosleep(100);   // the link warp refreshes cq_head
+}
+
+// Complete a receive whose payload (copy_len bytes, already clipped / 0 on error) is at `src`.
+// src_kind 0: ring slot of endpoint `arg` (its cursor after this slot is cons_after), 1 / 2: heap block `arg`.
+// Returns true when the source was released at once (copied by the matcher), false when a helper owns it.
+__device__ __forceinline__ bool sw_res_deliver(SwMatchState* st, SwProgShared& sh, const SwProgArgs& a, SwResCtx& c,
+                                               uint32_t lane, uint64_t src, uint64_t dst, uint64_t copy_len, uint64_t op,
+                                               uint64_t tag, uint64_t msg_len, int32_t status, uint32_t src_kind,
+                                               uint32_t arg, uint64_t cons_after) {
+  sw_cq_room(sh, c, 1);
+  const uint64_t cq_idx = c.cq_alloc++;
+  if (copy_len <= SW_INLINE_DELIVER) {
+    sw_copy(reinterpret_cast<uint8_t*>(dst), reinterpret_cast<const uint8_t*>(src), copy_len, lane, 32);
+    __syncwarp();
+    if (lane == 0) sw_write_cqe(a.cq, cq_idx, op, tag, msg_len, status);
+    if (src_kind == 1) {
+      if (lane == 0) st->free_small[c.n_free_small] = arg;
+      c.n_free_small++;
+    } else if (src_kind == 2) {
+      if (lane == 0) st->free_big[c.n_free_big] = arg;
+      c.n_free_big++;
+    }
+    return true;
+  }
+  // helper job: wait for room in the job ring and in the pending-release ring
+  while (c.jobs_emitted - sw_done_prefix(sh, lane) >= SW_DJOB_RING || c.pend_tail - c.pend_head >= SW_PEND_RING) {
+    sw_retire(st, sh, c, lane, false);
+    __nanosleep(50);
+  }
+  if (lane == 0) {
+    SwDJob* j = &sh.jobs[c.jobs_emitted % SW_DJOB_RING];
+    j->src = src;
+    j->dst = dst;
+    j->len = copy_len;
+    j->op_id = op;
+    j->tag = tag;
+    j->msg_len = msg_len;
+    j->cq_idx = cq_idx;
+    j->status = status;
+    SwPend* p = &sh.pend[c.pend_tail % SW_PEND_RING];
+    p->job = c.jobs_emitted;
+    p->cons_after = cons_after;
+    p->kind = src_kind;
+    p->arg = arg;
+    if (src_kind == 0) sh.pend_cnt[arg]++;
+    __threadfence_block();
+    sh.job_tail = c.jobs_emitted + 1;
+  }
+  c.jobs_emitted++;
+  c.pend_tail++;
+  __syncwarp();
+  return false;
+}
+
+// publish the rendezvous batch under construction to the pull CTAs of the context
+__device__ __forceinline__ void sw_res_flush_pull(SwMatchState* st, SwProgShared& sh, const SwProgArgs& a, SwResCtx& c,
+                                                  uint32_t lane) {
+  if (c.pb_n == 0) return;
+  SwPullQueue* q = a.pq;
+  uint64_t ticket = 0;
+  if (lane == 0) ticket = atomicAdd(reinterpret_cast<unsigned long long*>(&q->alloc), 1ull);
+  ticket = sw_shfl64(ticket, 0);
+  SwPullSlot* s = &q->slot[ticket % SW_PULL_SLOTS];
+  const uint64_t want = ticket >= SW_PULL_SLOTS ? ticket - SW_PULL_SLOTS + 1 : 0;
+  while (sw_ld_acquire_gpu(&s->free_seq) != want) __nanosleep(100);   // the previous occupant has been retired
+  const uint32_t n = c.pb_n;
+  for (uint32_t j = lane; j < n; j += 32) {
+    s->end[j] = sh.pb_end[j];
+    s->src[j] = sh.pb_src[j];
+    s->dst[j] = sh.pb_dst[j];
+    s->meta[j] = sh.pb_meta[j];
+  }
+  if (lane == 0) {
+    const uint64_t total = sh.pb_end[n - 1];
+    // chunk: about two per pull CTA, 8 KiB .. 256 KiB, a multiple of 1 KiB
+    uint64_t chunk = total / (2ull * (a.pull_ctas ? a.pull_ctas : 1)) + 1023;
+    chunk &= ~1023ull;
+    if (chunk < 8192) chunk = 8192;
+    if (chunk > 262144) chunk = 262144;
+    uint64_t nch = (total + chunk - 1) / chunk;
+    if (nch == 0) nch = 1;
+    s->njobs = n;
+    s->nchunks = static_cast<uint32_t>(nch);
+    s->exit = 0;
+    s->chunk_bytes = chunk;
+    s->total = total;
+    s->next_chunk = 0;
+    s->done_chunks = 0;
+    s->retire = 0;
+    s->t_first = 0;
+    s->cqr_ring = reinterpret_cast<uint64_t>(a.cqr);
+    s->cqr_alloc = reinterpret_cast<uint64_t>(&st->cqr_alloc);
+    s->cqr_head_dev = reinterpret_cast<uint64_t>(&st->cqr_head);
+    s->cqr_head_host = reinterpret_cast<uint64_t>(&a.ctl->cqr_head);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence();
+    sw_st_release_gpu(&s->seq, ticket + 1);
+    a.ctl->pull_jobs = c.pull_jobs;   // the host keeps the pull kernel alive while jobs are outstanding
+  }
+  c.pb_n = 0;
+  __syncwarp();
+}
+
+// warp-wide probe of the (exporter, allocation) -> mapped base table; 0: not mapped here (yet)
+__device__ __forceinline__ uint64_t sw_map_lookup(const SwMapEnt* map, uint64_t uuid, uint64_t buf_id, uint64_t remote_base,
+                                                  uint32_t lane) {
+  if (!map || !buf_id) return 0;
+  const SwMapEnt* e = &map[(sw_map_home(uuid, buf_id) + lane) & (SW_MAP_SLOTS - 1)];
+  const int4 k = sw_ld16(e);
+  const uint64_t e_uuid = (static_cast<uint64_t>(static_cast<uint32_t>(k.y)) << 32) | static_cast<uint32_t>(k.x);
+  const uint64_t e_buf = (static_cast<uint64_t>(static_cast<uint32_t>(k.w)) << 32) | static_cast<uint32_t>(k.z);
+  const uint32_t hit = __ballot_sync(0xffffffffu, e_uuid == uuid && e_buf == buf_id);
+  if (!hit) return 0;
+  const int L = __ffs(hit) - 1;
+  uint64_t rb = 0, lb = 0;
+  if (static_cast<int>(lane) == L) {
+    rb = e->remote_base;
+    lb = e->local_base;
+  }
+  rb = sw_shfl64(rb, L);
+  lb = sw_shfl64(lb, L);
+  return rb == remote_base ? lb : 0;
+}
+
+// A rendezvous request (the 128 B SwRts at `payload`: ring slot or heap copy) met the receive (buf, cap, op).
+__device__ __forceinline__ void sw_res_rts(SwMatchState* st, SwProgShared& sh, const SwProgArgs& a, SwResCtx& c,
+                                           uint32_t lane, uint64_t payload, uint64_t stag, uint64_t msg_len, uint32_t epf,
+                                           uint64_t buf, uint64_t cap, uint64_t op, uint32_t pflags) {
+  const uint32_t w = reinterpret_cast<const volatile uint32_t*>(payload)[lane];   // 128 B descriptor, 4 B per lane, not from L1
+  auto f64 = [&](int word) {
+    const uint32_t lo = __shfl_sync(0xffffffffu, w, word), hi = __shfl_sync(0xffffffffu, w, word + 1);
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+  };
+  const uint64_t alloc_base = f64(16), alloc_size = f64(18), src_ptr = f64(20), send_seq = f64(22);
+  const uint64_t uuid = f64(24), rflags = f64(28), buf_id = f64(30);
+  const uint32_t src_pid = __shfl_sync(0xffffffffu, w, 26);
+  const bool trunc = msg_len > cap;
+  uint64_t src = 0;
+  const uint32_t ep = epf & ((1u << SW_EP_IDX_BITS) - 1);   // ring index; the rest of the field is its generation
+  bool device_path = a.pq != nullptr && a.pull_ctas != 0 && !trunc && !(pflags & SW_POST_HOSTPATH) &&
+                     !(rflags & SW_RTS_PINNED_SRC) && !((sh.dead_mask >> ep) & 1) && st->fin_ptr[ep] != 0 &&
+                     (epf >> SW_EP_IDX_BITS) == sh.ring_gen[ep];
+  if (device_path) {
+    if (uuid == a.ctx_uuid && src_pid == a.pid) {
+      src = src_ptr;   // same process, same context: the sender's pointer is ours
+    } else {
+      const uint64_t local = sw_map_lookup(a.map, uuid, buf_id, alloc_base, lane);
+      if (local && src_ptr >= alloc_base && src_ptr - alloc_base + msg_len <= alloc_size) src = local + (src_ptr - alloc_base);
+    }
+    if (!src || ((src | buf) & 15)) device_path = false;   // not mapped yet / generic alignment: the host copies
+  }
+  if (device_path) {
+    if (lane == 0) {
+      const uint32_t j = c.pb_n;
+      const uint64_t body = msg_len & ~15ull;
+      sh.pb_end[j] = (j ? sh.pb_end[j - 1] : 0) + body;
+      sh.pb_src[j] = src;
+      sh.pb_dst[j] = buf;
+      SwPullMeta m;
+      m.op_id = op;
+      m.tag = stag;
+      m.len = msg_len;
+      m.fin_addr = st->fin_ptr[ep] + 8ull * (send_seq % SW_FIN_SLOTS);
+      m.fin_val = (send_seq << 2) | 1;
+      sh.pb_meta[j] = m;
+    }
+    c.pb_n++;
+    c.pull_jobs++;
+    __syncwarp();
+    if (c.pb_n == SW_PULL_JOBS) sw_res_flush_pull(st, sh, a, c, lane);
+    return;
+  }
+  // host path: the record travels to the host, which maps the source / launches the generic copy
+  while (c.hr_alloc + 1 - sh.hr_head > SW_HR_RING) __nanosleep(100);
+  SwHrEnt* h = &a.hr[c.hr_alloc % SW_HR_RING];
+  reinterpret_cast<uint32_t*>(&h->rec.rts)[lane] = w;
+  if (lane == 0) {
+    h->rec.op_id = op;
+    h->rec.dst = buf;
+    h->rec.cap = cap;
+    h->rec.tag = stag;
+    h->rec.len = msg_len;
+    h->rec.ep = epf;
+    h->rec.status = trunc ? SW_ERR_MESSAGE_TRUNCATED : SW_OK;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence_system();
+    sw_st_relaxed_sys(&h->pad, static_cast<uint64_t>(sw_ring_pass(c.hr_alloc, SW_HR_RING)) << 32);
+  }
+  c.hr_alloc++;
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------ phase 1: new receives (n <= 32, staged in shared memory)
+__device__ __forceinline__ void sw_res_posts(SwMatchState* __restrict__ st, SwProgShared& sh, const SwProgArgs& a,
+                                             SwResCtx& c, const uint32_t lane, const uint32_t n) {
+  const uint64_t PQM = SW_PQ_CAP - 1, UQM = SW_UQ_CAP - 1;
+  SwPostEnt mine;
+  mine.tag = mine.mask = mine.buf = mine.cap = mine.op_id = 0;
+  mine.flags = 0;
+  if (lane < n) mine = sh.posts[(c.post_head + lane) % SW_SPOST_RING];
+  if (c.u_count == 0 && SW_PQ_CAP - (c.p_tail - c.p_head) >= n) {
+    // nothing is waiting in the unexpected queue: every receive is simply appended, one lane each
+    if (lane < n) {
+      const uint64_t s = (c.p_tail + lane) & PQM;
+      st->p_tag[s] = mine.tag;
+      st->p_mask[s] = mine.mask;
+      st->p_buf[s] = mine.buf;
+      st->p_cap[s] = mine.cap;
+      st->p_op[s] = mine.op_id;
+      st->p_valid[s] = 1u | (mine.flags << 8);
+    }
+    c.p_tail += n;
+    c.p_count += n;
+    __syncwarp();
+    return;
+  }
+  // register window over the unexpected queue: lane L caches entry (wb + L)
+  uint64_t wb = c.u_head;
+  uint64_t w_tag = 0, w_len = 0, w_data = 0;
+  uint32_t w_meta = 0, w_blk = 0;
+  auto load_uwin = [&]() {
+    const uint64_t idx = wb + lane;
+    w_meta = 0;
+    if (idx < c.u_tail) {
+      const uint64_t s = idx & UQM;
+      w_meta = st->u_meta[s];
+      w_tag = st->u_tag[s];
+      w_len = st->u_len[s];
+      w_data = st->u_data[s];
+      w_blk = st->u_blk[s];
+    }
+  };
+  load_uwin();
+  for (uint32_t j = 0; j < n; j++) {
+    const uint64_t tag = sw_shfl64(mine.tag, j), mask = sw_shfl64(mine.mask, j);
+    const uint64_t buf = sw_shfl64(mine.buf, j), cap = sw_shfl64(mine.cap, j);
+    const uint64_t op = sw_shfl64(mine.op_id, j);
+    const uint32_t pflags = __shfl_sync(0xffffffffu, mine.flags, j);
+    bool found = false;
+    uint64_t f_tag = 0, f_len = 0, f_data = 0;
+    uint32_t f_meta = 0, f_blk = 0;
+    if (c.u_count) {
+      while (__ballot_sync(0xffffffffu, (w_meta & SW_UMETA_VALID) != 0) == 0 && wb + 32 <= c.u_tail) {
+        wb += 32;
+        load_uwin();
+      }
+      const bool hit = (w_meta & SW_UMETA_VALID) && sw_tag_match(w_tag, tag, mask);
+      uint32_t bal = __ballot_sync(0xffffffffu, hit);
+      if (bal) {
+        const int L = __ffs(bal) - 1;
+        f_tag = sw_shfl64(w_tag, L);
+        f_len = sw_shfl64(w_len, L);
+        f_data = sw_shfl64(w_data, L);
+        f_meta = __shfl_sync(0xffffffffu, w_meta, L);
+        f_blk = __shfl_sync(0xffffffffu, w_blk, L);
+        if (static_cast<int>(lane) == L) {
+          w_meta = 0;
+          st->u_meta[(wb + L) & UQM] = 0;
+        }
+        found = true;
+      } else {
+        for (uint64_t b = wb + 32; b < c.u_tail && !found; b += 32) {
+          const uint64_t idx = b + lane;
+          uint32_t meta = 0;
+          uint64_t t = 0;
+          if (idx < c.u_tail) {
+            meta = st->u_meta[idx & UQM];
+            t = st->u_tag[idx & UQM];
+          }
+          const bool h2 = (meta & SW_UMETA_VALID) && sw_tag_match(t, tag, mask);
+          bal = __ballot_sync(0xffffffffu, h2);
+          if (bal) {
+            const int L = __ffs(bal) - 1;
+            uint64_t l = 0, dta = 0;
+            uint32_t blk = 0;
+            if (static_cast<int>(lane) == L) {
+              l = st->u_len[idx & UQM];
+              dta = st->u_data[idx & UQM];
+              blk = st->u_blk[idx & UQM];
+              st->u_meta[idx & UQM] = 0;
+            }
+            f_tag = sw_shfl64(t, L);
+            f_len = sw_shfl64(l, L);
+            f_data = sw_shfl64(dta, L);
+            f_meta = __shfl_sync(0xffffffffu, meta, L);
+            f_blk = __shfl_sync(0xffffffffu, blk, L);
+            found = true;
+          }
+        }
+      }
+    }
+    if (found) {
+      c.u_count--;
+      const bool big = (f_meta & SW_UMETA_BIG) != 0;
+      if (f_meta & SW_UMETA_RTS) {
+        sw_res_rts(st, sh, a, c, lane, f_data, f_tag, f_len, f_meta & SW_UMETA_EPMASK, buf, cap, op, pflags);
+        // the descriptor has been read: its heap block is free again
+        if (lane == 0) (big ? st->free_big[c.n_free_big] : st->free_small[c.n_free_small]) = f_blk;
+        if (big)
+          c.n_free_big++;
+        else
+          c.n_free_small++;
+      } else {
+        const bool trunc = f_len > cap;
+        sw_res_deliver(st, sh, a, c, lane, f_data, buf, trunc ? 0 : f_len, op, f_tag, f_len,
+                       trunc ? SW_ERR_MESSAGE_TRUNCATED : SW_OK, big ? 2u : 1u, f_blk, 0);
+      }
+    } else if (c.p_tail - c.p_head >= SW_PQ_CAP) {
+      c.err |= 2;   // posted queue overflow (the host throttles before this can happen)
+      sw_cq_room(sh, c, 1);
+      if (lane == 0) sw_write_cqe(a.cq, c.cq_alloc, op, 0, 0, SW_ERR_NO_MEMORY);
+      c.cq_alloc++;
+    } else {
+      if (lane == 0) {
+        const uint64_t s = c.p_tail & PQM;
+        st->p_tag[s] = tag;
+        st->p_mask[s] = mask;
+        st->p_buf[s] = buf;
+        st->p_cap[s] = cap;
+        st->p_op[s] = op;
+        st->p_valid[s] = 1u | (pflags << 8);
+      }
+      c.p_tail++;
+      c.p_count++;
+    }
+  }
+  while (__ballot_sync(0xffffffffu, (w_meta & SW_UMETA_VALID) != 0) == 0 && wb + 32 <= c.u_tail) {
+    wb += 32;
+    load_uwin();
+  }
+  c.u_head = wb;
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------ phase 2: arrivals on one ring
+// Looks at up to 32 slots from the ring cursor; a slot has arrived when its header carries the expected
+// sequence number (written last, with release semantics, by the peer's put kernel).  Returns the number of
+// slots consumed.
+__device__ __forceinline__ uint32_t sw_res_arrivals(SwMatchState* __restrict__ st, SwProgShared& sh, const SwProgArgs& a,
+                                                    SwResCtx& c, const uint32_t lane, const uint32_t ep) {
+  const uint64_t PQM = SW_PQ_CAP - 1, UQM = SW_UQ_CAP - 1;
+  uint64_t cons = sh.cons[ep];
+  const uint32_t epf = ep | (sh.ring_gen[ep] << SW_EP_IDX_BITS);
+  const uint64_t ring = sh.ring_base[ep];
+  const uint64_t smask = sh.ring_mask[ep];
+  const uint64_t my_slot = ring + ((cons + lane) & smask) * SW_SLOT_BYTES;
+  const uint64_t seqw = sw_ld_acquire_sys(reinterpret_cast<const void*>(my_slot + 16));
+  const uint32_t okb = __ballot_sync(0xffffffffu, seqw == cons + lane + 1);
+  const uint32_t chunk = okb == 0xffffffffu ? 32u : static_cast<uint32_t>(__ffs(~okb) - 1);
+  if (!chunk) return 0;
+  uint64_t h_tag = 0, h_len = 0;
+  uint32_t h_kind = 0, h_magic = 0;
+  if (lane < chunk) {
+    const int4 h0 = sw_ld16(reinterpret_cast<const void*>(my_slot));
+    const uint64_t km = *reinterpret_cast<const volatile uint64_t*>(my_slot + 24);
+    h_tag = (static_cast<uint64_t>(static_cast<uint32_t>(h0.y)) << 32) | static_cast<uint32_t>(h0.x);
+    h_len = (static_cast<uint64_t>(static_cast<uint32_t>(h0.w)) << 32) | static_cast<uint32_t>(h0.z);
+    h_kind = static_cast<uint32_t>(km);
+    h_magic = static_cast<uint32_t>(km >> 32);
+  }
+  if (__ballot_sync(0xffffffffu, lane < chunk && h_magic != SW_SLOT_MAGIC)) c.err |= 1;
+
+  // register window over the posted queue
+  uint64_t wb = c.p_head;
+  uint64_t w_tag = 0, w_mask = 0, w_buf = 0, w_cap = 0, w_op = 0;
+  uint32_t w_valid = 0;
+  auto load_pwin = [&]() {
+    const uint64_t idx = wb + lane;
+    w_valid = 0;
+    if (idx < c.p_tail) {
+      const uint64_t s = idx & PQM;
+      w_valid = st->p_valid[s];
+      w_tag = st->p_tag[s];
+      w_mask = st->p_mask[s];
+      w_buf = st->p_buf[s];
+      w_cap = st->p_cap[s];
+      w_op = st->p_op[s];
+    }
+  };
+  if (c.p_count) load_pwin();
+  const uint64_t cons0 = cons;
+  bool blocked = false;
+  uint32_t j0 = 0;
+  // ---- pairing step: when the first k valid receives of the window accept every one of the next k arrivals
+  // (all wildcard masks, or one common tag they all accept) arrival j goes to the j-th of them -- exactly what
+  // the sequential rule (earliest-posted matching receive) yields.
+  while (j0 < chunk && c.p_count) {
+    while (__ballot_sync(0xffffffffu, w_valid != 0) == 0 && wb + 32 <= c.p_tail) {
+      wb += 32;
+      load_pwin();
+    }
+    const uint32_t V = __ballot_sync(0xffffffffu, w_valid != 0);
+    if (!V) break;
+    const uint32_t lt = (1u << lane) - 1;
+    const uint32_t k = min(chunk - j0, static_cast<uint32_t>(__popc(V)));
+    const uint32_t rnk = __popc(V & lt);
+    const bool in_k = w_valid && rnk < k;
+    bool compat = __ballot_sync(0xffffffffu, in_k && w_mask != 0) == 0;
+    if (!compat) {
+      const uint64_t T = sw_shfl64(h_tag, j0);
+      const bool same = __ballot_sync(0xffffffffu, lane >= j0 && lane < j0 + k && h_tag != T) == 0;
+      if (same) compat = __ballot_sync(0xffffffffu, in_k && !sw_tag_match(T, w_tag, w_mask)) == 0;
+    }
+    if (!compat) break;
+    const int srcl = static_cast<int>(min(j0 + rnk, 31u));
+    const uint64_t a_tag = sw_shfl64(h_tag, srcl), a_len = sw_shfl64(h_len, srcl);
+    const uint64_t a_slot = sw_shfl64(my_slot, srcl);
+    const uint32_t a_kind = __shfl_sync(0xffffffffu, h_kind, srcl);
+    const bool a_rts = a_kind == SW_KIND_RTS;
+    const bool trunc = a_len > w_cap;
+    const uint64_t copy_len = trunc ? 0 : a_len;
+    const bool small = in_k && !a_rts && copy_len <= SW_INLINE_DELIVER;
+    const uint32_t small_m = __ballot_sync(0xffffffffu, small);
+    const uint32_t other_m = __ballot_sync(0xffffffffu, in_k && !small);
+    // small eager payloads: one lane per message, completion records in pairing order
+    const uint32_t n_small = __popc(small_m);
+    if (n_small) {
+      sw_cq_room(sh, c, n_small);
+      if (small) {
+        sw_copy_lane(reinterpret_cast<uint8_t*>(w_buf), reinterpret_cast<const uint8_t*>(a_slot + SW_SLOT_HDR),
+                     static_cast<uint32_t>(copy_len));
+        sw_write_cqe(a.cq, c.cq_alloc + __popc(small_m & lt), w_op, a_tag, a_len, trunc ? SW_ERR_MESSAGE_TRUNCATED : SW_OK);
+      }
+      c.cq_alloc += n_small;
+    }
+    if (in_k) {
+      st->p_valid[(wb + lane) & PQM] = 0;
+    }
+    // everything else (larger eager payloads, rendezvous requests) one after the other, in pairing order
+    uint32_t rest = other_m;
+    while (rest) {
+      const int L = __ffs(rest) - 1;
+      rest &= rest - 1;
+      const uint64_t o_tag = sw_shfl64(a_tag, L), o_len = sw_shfl64(a_len, L), o_slot = sw_shfl64(a_slot, L);
+      const uint64_t o_buf = sw_shfl64(w_buf, L), o_cap = sw_shfl64(w_cap, L), o_op = sw_shfl64(w_op, L);
+      const uint32_t o_valid = __shfl_sync(0xffffffffu, w_valid, L);
+      const bool o_rts = __shfl_sync(0xffffffffu, static_cast<uint32_t>(a_rts), L) != 0;
+      const uint32_t o_rank = __shfl_sync(0xffffffffu, rnk, L);
+      if (o_rts) {
+        sw_res_rts(st, sh, a, c, lane, o_slot + SW_SLOT_HDR, o_tag, o_len, epf, o_buf, o_cap, o_op, o_valid >> 8);
+      } else {
+        const bool t2 = o_len > o_cap;
+        sw_res_deliver(st, sh, a, c, lane, o_slot + SW_SLOT_HDR, o_buf, t2 ? 0 : o_len, o_op, o_tag, o_len,
+                       t2 ? SW_ERR_MESSAGE_TRUNCATED : SW_OK, 0, ep, cons + o_rank + 1);
+      }
+    }
+    if (in_k) w_valid = 0;
+    c.p_count -= k;
+    j0 += k;
+    cons += k;
+  }
+  // ---- one arrival at a time
+  for (uint32_t j = j0; j < chunk && !blocked; j++) {
+    const uint64_t stag = sw_shfl64(h_tag, j), mlen = sw_shfl64(h_len, j);
+    const uint32_t kind = __shfl_sync(0xffffffffu, h_kind, j);
+    const uint64_t slot = sw_shfl64(my_slot, j);
+    const uint64_t payload = slot + SW_SLOT_HDR;
+    const bool is_rts = kind == SW_KIND_RTS;
+    bool found = false;
+    uint64_t f_buf = 0, f_cap = 0, f_op = 0;
+    uint32_t f_valid = 0;
+    if (c.p_count) {
+      while (__ballot_sync(0xffffffffu, w_valid != 0) == 0 && wb + 32 <= c.p_tail) {
+        wb += 32;
+        load_pwin();
+      }
+      const bool hit = w_valid && sw_tag_match(stag, w_tag, w_mask);
+      uint32_t bal = __ballot_sync(0xffffffffu, hit);
+      if (bal) {
+        const int L = __ffs(bal) - 1;
+        f_buf = sw_shfl64(w_buf, L);
+        f_cap = sw_shfl64(w_cap, L);
+        f_op = sw_shfl64(w_op, L);
+        f_valid = __shfl_sync(0xffffffffu, w_valid, L);
+        if (static_cast<int>(lane) == L) {
+          w_valid = 0;
+          st->p_valid[(wb + L) & PQM] = 0;
+        }
+        found = true;
+      } else {
+        for (uint64_t b = wb + 32; b < c.p_tail && !found; b += 32) {
+          const uint64_t idx = b + lane;
+          uint32_t v = 0;
+          uint64_t t = 0, m = 0;
+          if (idx < c.p_tail) {
+            v = st->p_valid[idx & PQM];
+            t = st->p_tag[idx & PQM];
+            m = st->p_mask[idx & PQM];
+          }
+          const bool h2 = v && sw_tag_match(stag, t, m);
+          bal = __ballot_sync(0xffffffffu, h2);
+          if (bal) {
+            const int L = __ffs(bal) - 1;
+            uint64_t bf = 0, cp = 0, op = 0;
+            if (static_cast<int>(lane) == L) {
+              bf = st->p_buf[idx & PQM];
+              cp = st->p_cap[idx & PQM];
+              op = st->p_op[idx & PQM];
+              st->p_valid[idx & PQM] = 0;
+            }
+            f_buf = sw_shfl64(bf, L);
+            f_cap = sw_shfl64(cp, L);
+            f_op = sw_shfl64(op, L);
+            f_valid = __shfl_sync(0xffffffffu, v, L);
+            found = true;
+          }
+        }
+      }
+    }
+    if (found) {
+      c.p_count--;
+      if (is_rts) {
+        sw_res_rts(st, sh, a, c, lane, payload, stag, mlen, epf, f_buf, f_cap, f_op, f_valid >> 8);
+      } else {
+        const bool trunc = mlen > f_cap;
+        sw_res_deliver(st, sh, a, c, lane, payload, f_buf, trunc ? 0 : mlen, f_op, stag, mlen,
+                       trunc ? SW_ERR_MESSAGE_TRUNCATED : SW_OK, 0, ep, cons + 1);
+      }
+    } else {
+      // unexpected: park the payload (or the RTS descriptor) on the heap -- copied by this warp at once, so the
+      // slot is free again and a later receive finds the bytes in place
+      const uint64_t need = is_rts ? sizeof(SwRts) : mlen;
+      const bool big = need > SW_HEAP_SMALL_BYTES;
+      const bool have = big ? (c.n_free_big > 0) : (c.n_free_small > 0);
+      if (!have || c.u_tail - c.u_head >= SW_UQ_CAP) {
+        blocked = true;   // back-pressure: the message stays in its ring slot until receives free the heap
+        c.stalled = true;
+        break;
+      }
+      uint32_t blk = 0;
+      if (lane == 0) blk = big ? st->free_big[c.n_free_big - 1] : st->free_small[c.n_free_small - 1];
+      blk = __shfl_sync(0xffffffffu, blk, 0);
+      if (big)
+        c.n_free_big--;
+      else
+        c.n_free_small--;
+      const uint64_t haddr = big ? reinterpret_cast<uint64_t>(st->heap_big) + uint64_t(blk) * SW_HEAP_BIG_BYTES
+                                 : reinterpret_cast<uint64_t>(st->heap_small) + uint64_t(blk) * SW_HEAP_SMALL_BYTES;
+      sw_copy(reinterpret_cast<uint8_t*>(haddr), reinterpret_cast<const uint8_t*>(payload), need, lane, 32);
+      if (lane == 0) {
+        const uint64_t s = c.u_tail & UQM;
+        st->u_tag[s] = stag;
+        st->u_len[s] = mlen;
+        st->u_data[s] = haddr;
+        st->u_blk[s] = blk;
+        st->u_meta[s] = SW_UMETA_VALID | (big ? SW_UMETA_BIG : 0) | (is_rts ? SW_UMETA_RTS : 0) | (epf & SW_UMETA_EPMASK);
+      }
+      c.u_tail++;
+      c.u_count++;
+      __syncwarp();
+    }
+    cons++;
+  }
+  if (c.p_count) {
+    while (__ballot_sync(0xffffffffu, w_valid != 0) == 0 && wb + 32 <= c.p_tail) {
+      wb += 32;
+      load_pwin();
+    }
+    c.p_head = wb;
+  } else {
+    c.p_head = c.p_tail;
+  }
+  const uint32_t used = static_cast<uint32_t>(cons - cons0);
+  if (used) {
+    if (lane == 0) sh.cons[ep] = cons;
+    __syncwarp();
+    c.arrivals += used;
+    // slots whose payload a helper still reads stay owned until that job retires
+    if (sh.pend_cnt[ep] == 0) sw_publish_credit(st, sh, ep, cons, lane);
+  }
+  return used;
+}
+
+// compaction of the queues when tombstones dominate (same procedure as sw_match_body)
+__device__ __forceinline__ void sw_res_compact(SwMatchState* __restrict__ st, SwResCtx& c, const uint32_t lane) {
+  const uint64_t PQM = SW_PQ_CAP - 1, UQM = SW_UQ_CAP - 1;
+  if (c.p_tail - c.p_head > SW_PQ_CAP / 2) {
+    uint64_t j = c.p_head;
+    for (uint64_t b = c.p_head; b < c.p_tail; b += 32) {
+      const uint64_t idx = b + lane;
+      uint32_t v = 0;
+      uint64_t t = 0, m = 0, bf = 0, cp = 0, op = 0;
+      if (idx < c.p_tail) {
+        const uint64_t s = idx & PQM;
+        v = st->p_valid[s];
+        if (v) {
+          t = st->p_tag[s];
+          m = st->p_mask[s];
+          bf = st->p_buf[s];
+          cp = st->p_cap[s];
+          op = st->p_op[s];
+        }
+      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, v != 0);
+      const uint64_t pos = j + __popc(bal & ((1u << lane) - 1));
+      __syncwarp();
+      if (v) {
+        const uint64_t s = pos & PQM;
+        st->p_tag[s] = t;
+        st->p_mask[s] = m;
+        st->p_buf[s] = bf;
+        st->p_cap[s] = cp;
+        st->p_op[s] = op;
+        st->p_valid[s] = v;
+      }
+      j += __popc(bal);
+      __syncwarp();
+    }
+    for (uint64_t idx = j + lane; idx < c.p_tail; idx += 32) st->p_valid[idx & PQM] = 0;
+    c.p_tail = j;
+    __syncwarp();
+  }
+  if (c.u_tail - c.u_head > SW_UQ_CAP / 2) {
+    uint64_t j = c.u_head;
+    for (uint64_t b = c.u_head; b < c.u_tail; b += 32) {
+      const uint64_t idx = b + lane;
+      uint32_t meta = 0, blk = 0;
+      uint64_t t = 0, l = 0, dta = 0;
+      if (idx < c.u_tail) {
+        const uint64_t s = idx & UQM;
+        meta = st->u_meta[s];
+        if (meta & SW_UMETA_VALID) {
+          t = st->u_tag[s];
+          l = st->u_len[s];
+          dta = st->u_data[s];
+          blk = st->u_blk[s];
+        }
+      }
+      const bool v = (meta & SW_UMETA_VALID) != 0;
+      const uint32_t bal = __ballot_sync(0xffffffffu, v);
+      const uint64_t pos = j + __popc(bal & ((1u << lane) - 1));
+      __syncwarp();
+      if (v) {
+        const uint64_t s = pos & UQM;
+        st->u_tag[s] = t;
+        st->u_len[s] = l;
+        st->u_data[s] = dta;
+        st->u_blk[s] = blk;
+        st->u_meta[s] = meta;
+      }
+      j += __popc(bal);
+      __syncwarp();
+    }
+    for (uint64_t idx = j + lane; idx < c.u_tail; idx += 32) st->u_meta[idx & UQM] = 0;
+    c.u_tail = j;
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ the control kernel
+__global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const __grid_constant__ SwProgArgs a) {
+  __shared__ SwProgShared sh;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  SwMatchState* st = a.st;
+  const long long clk0 = clock64();
+  // ---- set-up: ring geometry and cursors from the match state
+  for (uint32_t e = threadIdx.x; e < SW_MAX_EPS; e += blockDim.x) {
+    sh.ring_base[e] = st->ring_base[e];
+    sh.ring_mask[e] = st->ring_slots[e] ? st->ring_slots[e] - 1 : 0;
+    sh.ring_gen[e] = st->ring_gen[e] & SW_EP_GEN_MASK;
+    sh.cons[e] = st->ring_cons[e];
+    sh.credit[e] = st->ring_cons[e];
+    sh.pend_cnt[e] = 0;
+  }
+  if (threadIdx.x == 0) {
+    sh.post_tail = sh.post_head = st->post_consumed;
+    sh.job_tail = 0;
+    sh.cq_head = a.ctl->cq_head;
+    sh.cqr_head = a.ctl->cqr_head;
+    sh.hr_head = a.ctl->hr_head;
+    sh.dead_mask = a.ctl->dead_mask;
+    sh.host_epoch = a.ctl->host_epoch;
+    sh.active_clk = clk0;
+    sh.exit_req = 0;
+    sh.helpers_exit = 0;
+    for (uint32_t h = 0; h < SW_PROG_HELPERS; h++) sh.helper_done[h] = 0;
+  }
+  __syncthreads();
+
+  if (warp == 0) {
+    // ================================================================ matcher
+    SwResCtx c;
+    c.p_head = st->p_head;
+    c.p_tail = st->p_tail;
+    c.u_head = st->u_head;
+    c.u_tail = st->u_tail;
+    c.p_count = st->p_count;
+    c.u_count = st->u_count;
+    c.n_free_small = st->n_free_small;
+    c.n_free_big = st->n_free_big;
+    c.cq_alloc = st->cq_alloc;
+    c.hr_alloc = st->hr_alloc;
+    c.pull_jobs = st->pull_jobs;
+    c.arrivals = st->arrivals;
+    c.post_head = st->post_consumed;
+    c.jobs_emitted = 0;
+    c.pend_head = c.pend_tail = 0;
+    c.pb_n = 0;
+    c.err = 0;
+    uint64_t echoed = ~0ull, iters = 0;
+    uint32_t rr = st->rr_ep;
+    const uint32_t n_eps = a.n_eps;
+    for (;;) {
+      bool did = false;
+      c.stalled = false;
+      // The host bumps host_epoch AFTER changing dead_mask and waits for the echo: read the epoch before anything
+      // of this iteration looks at dead_mask, echo it once the iteration (and what it handed on) is done.
+      const uint64_t he = sh.host_epoch;
+      __threadfence_block();
+      sw_res_compact(st, c, lane);
+      // ---- new receives staged by the link warp
+      for (;;) {
+        const uint64_t pt = sh.post_tail;
+        if (c.post_head >= pt) break;
+        __threadfence_block();
+        const uint32_t n = static_cast<uint32_t>(min(static_cast<uint64_t>(32), pt - c.post_head));
+        sw_res_posts(st, sh, a, c, lane, n);
+        c.post_head += n;
+        if (lane == 0) sh.post_head = c.post_head;
+        did = true;
+      }
+      const bool leaving = sh.exit_req != 0;
+      // ---- arrivals: every ring, round robin; a busy ring is drained in a few steps before the next one
+      if (!leaving) {
+        for (uint32_t e = 0; e < n_eps; e++) {
+          const uint32_t ep = (rr + e) % n_eps;
+          if (!sh.ring_base[ep]) continue;
+          for (int rep = 0; rep < 4; rep++) {
+            const uint32_t used = sw_res_arrivals(st, sh, a, c, lane, ep);
+            did |= used != 0;
+            if (used < 32) break;
+          }
+        }
+        rr++;
+      }
+      if (c.pb_n) sw_res_flush_pull(st, sh, a, c, lane);
+      if (c.pend_head != c.pend_tail) sw_retire(st, sh, c, lane, false);
+      if (he != echoed) {   // nothing matched under an older dead_mask is left in this warp
+        echoed = he;
+        if (lane == 0) {
+          __threadfence_system();
+          a.ctl->dev_epoch = he;
+        }
+      }
+      iters++;
+      if (leaving) {
+        // the link warp stops staging before it raises exit_req: once nothing staged is left, leave
+        if (c.post_head >= sh.post_tail) break;
+        continue;
+      }
+      if (did) {
+        if (lane == 0) sh.active_clk = clock64();
+      } else {
+        __nanosleep(40);
+      }
+    }
+    // ---- wind down: helpers finish, every deferred release happens, state goes back to device memory
+    sw_res_flush_pull(st, sh, a, c, lane);
+    sw_retire(st, sh, c, lane, true);
+    for (uint32_t e = lane; e < SW_MAX_EPS; e += 32)
+      if (sh.ring_base[e]) st->ring_cons[e] = sh.cons[e];   // (a ring attached while this launch ran is not ours to touch)
+    if (lane == 0) {
+      st->p_head = c.p_head;
+      st->p_tail = c.p_tail;
+      st->u_head = c.u_head;
+      st->u_tail = c.u_tail;
+      st->p_count = c.p_count;
+      st->u_count = c.u_count;
+      st->n_free_small = c.n_free_small;
+      st->n_free_big = c.n_free_big;
+      st->cq_alloc = c.cq_alloc;
+      st->hr_alloc = c.hr_alloc;
+      st->pull_jobs = c.pull_jobs;
+      st->arrivals = c.arrivals;
+      st->post_consumed = c.post_head;
+      st->rr_ep = rr;
+      a.ctl->pull_jobs = c.pull_jobs;
+      a.ctl->arrivals = c.arrivals;
+      a.ctl->n_posted = c.p_count;
+      a.ctl->n_unexp = c.u_count;
+      a.ctl->err = a.ctl->err | c.err;
+      a.ctl->stalled = c.stalled ? 1 : 0;
+      a.ctl->iterations = a.ctl->iterations + iters;
+      __threadfence_block();
+      sh.helpers_exit = 1;
+    }
+  } else if (warp == 1) {
+    // ================================================================ host link
+    const long long linger_clk = static_cast<long long>(a.linger_us) * a.clk_mhz;
+    const long long life_clk = static_cast<long long>(a.max_life_us) * a.clk_mhz;
+    uint64_t staged = sh.post_tail;
+    uint64_t he_prev = sh.host_epoch;
+    bool leaving = false;
+    for (;;) {
+      uint64_t host_tail = 0, stop = 0;
+      if (lane == 0) {
+        const int4 w0 = sw_ld16_sys(const_cast<const uint64_t*>(&a.ctl->post_tail));   // post_tail, cq_head
+        const int4 w1 = sw_ld16_sys(const_cast<const uint64_t*>(&a.ctl->cqr_head));    // cqr_head, hr_head
+        const int4 w2 = sw_ld16_sys(const_cast<const uint64_t*>(&a.ctl->stop));        // stop, dead_mask
+        const uint64_t he = sw_ld_relaxed_sys(const_cast<const uint64_t*>(&a.ctl->host_epoch));
+        auto u64of = [](int lo, int hi) { return (static_cast<uint64_t>(static_cast<uint32_t>(hi)) << 32) | static_cast<uint32_t>(lo); };
+        host_tail = u64of(w0.x, w0.y);
+        sh.cq_head = u64of(w0.z, w0.w);
+        const uint64_t cqrh = u64of(w1.x, w1.y);
+        if (cqrh != sh.cqr_head) {
+          sh.cqr_head = cqrh;
+          st->cqr_head = cqrh;   // the pull CTAs read the device copy
+        }
+        sh.hr_head = u64of(w1.z, w1.w);
+        stop = u64of(w2.x, w2.y);
+        sh.dead_mask = u64of(w2.z, w2.w);
+        // The epoch handed to the matcher is the one read in the PREVIOUS round: this round's dead_mask was
+        // requested after that read had returned, so it is at least as new as the epoch that vouches for it.
+        __threadfence_block();
+        sh.host_epoch = he_prev;
+        he_prev = he;
+      }
+      host_tail = sw_shfl64(host_tail, 0);
+      stop = sw_shfl64(stop, 0);
+      if (leaving) {
+        // the matcher winds down (it may still need room in the completion rings): keep the host's cursors fresh
+        if (sh.helpers_exit) break;
+        continue;
+      }
+      // stage new receives: lane L copies entry (staged + L)
+      const uint64_t consumed = sh.post_head;
+      const uint64_t room = SW_SPOST_RING - (staged - consumed);
+      uint64_t n = host_tail - staged;
+      if (n > room) n = room;
+      if (n > 32) n = 32;
+      if (lane < n) {
+        const SwPostEnt* src = &a.posts[(staged + lane) % SW_POST_RING];
+        int4* dst = reinterpret_cast<int4*>(&sh.posts[(staged + lane) % SW_SPOST_RING]);
+        dst[0] = sw_ld16_sys(reinterpret_cast<const int4*>(src));
+        dst[1] = sw_ld16_sys(reinterpret_cast<const int4*>(src) + 1);
+        dst[2] = sw_ld16_sys(reinterpret_cast<const int4*>(src) + 2);
+      }
+      __syncwarp();
+      if (n) {
+        staged += n;
+        if (lane == 0) {
+          __threadfence_block();
+          sh.post_tail = staged;
+          a.ctl->post_head = staged;   // the host may reuse these ring entries
+        }
+      }
+      const long long now = clock64();
+      const bool idle = n == 0 && host_tail == staged && staged == sh.post_head && now - sh.active_clk > linger_clk;
+      if (stop || idle || now - clk0 > life_clk) {
+        if (lane == 0) {
+          __threadfence_block();
+          sh.exit_req = 1;   // after the last staging store: the matcher drains what is staged and leaves
+        }
+        leaving = true;
+      }
+    }
+  } else {
+    // ================================================================ helpers: larger eager payloads
+    const uint32_t h = warp - 2;
+    uint64_t i = h;
+    uint32_t done = 0;
+    for (;;) {
+      while (sh.job_tail <= i) {
+        if (sh.helpers_exit) goto out;
+        __nanosleep(30);
+      }
+      __threadfence_block();
+      {
+        const SwDJob j = sh.jobs[i % SW_DJOB_RING];
+        sw_copy(reinterpret_cast<uint8_t*>(j.dst), reinterpret_cast<const uint8_t*>(j.src), j.len, lane, 32);
+        __syncwarp();
+        if (lane == 0) {
+          sw_write_cqe(a.cq, j.cq_idx, j.op_id, j.tag, j.msg_len, j.status);
+          sh.helper_done[h] = ++done;
+        }
+        __syncwarp();
+      }
+      i += SW_PROG_HELPERS;
+    }
+  }
+out:
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    a.ctl->exit_seq = a.launch_seq;
+  }
+}
+
+// ------------------------------------------------------------------ the pull kernel
+struct SwPullArgs {
+  SwPullQueue* q;
+  SwPullCtl* ctl;          // pinned host
+  uint64_t launch_seq;
+  uint32_t stage_bytes, nstages;
+  uint32_t linger_us, max_life_us, clk_mhz, pad;
+};
+
+// the CTA that completed the last chunk of a batch: tails, completion records, FIN words, statistics
+__device__ __forceinline__ void sw_pull_finalize(SwPullQueue* q, SwPullSlot* s) {
+  const uint32_t n = s->njobs;
+  for (uint32_t j = 0; j < n; j++) {
+    const uint64_t len = s->meta[j].len, body = len & ~15ull;
+    for (uint64_t k = body; k < len; k++)
+      reinterpret_cast<uint8_t*>(s->dst[j])[k] = reinterpret_cast<const volatile uint8_t*>(s->src[j])[k];
+  }
+  __threadfence_system();   // every chunk of the batch (released by its CTA's atomic) and the tails, before the records
+  if (n) {
+    SwCqEnt* ring = reinterpret_cast<SwCqEnt*>(s->cqr_ring);
+    const uint64_t base = atomicAdd(reinterpret_cast<unsigned long long*>(s->cqr_alloc), static_cast<unsigned long long>(n));
+    // room: the device copy of the host's cursor is refreshed by the worker's control kernel; when that one is
+    // not running, read the host's word itself
+    while (base + n - sw_ld_relaxed_sys(reinterpret_cast<const void*>(s->cqr_head_dev)) > SW_CQ_RING) {
+      const uint64_t hh = sw_ld_relaxed_sys(reinterpret_cast<const void*>(s->cqr_head_host));
+      if (base + n - hh <= SW_CQ_RING) break;
+      __nanosleep(500);
+    }
+    for (uint32_t j = 0; j < n; j++) {
+      SwCqEnt* e = &ring[(base + j) % SW_CQ_RING];
+      e->op_id = s->meta[j].op_id;
+      e->tag = s->meta[j].tag;
+      e->len = s->meta[j].len;
+    }
+    __threadfence_system();
+    for (uint32_t j = 0; j < n; j++) {
+      const uint64_t idx = base + j;
+      sw_st_relaxed_sys(&ring[idx % SW_CQ_RING].status, static_cast<uint64_t>(sw_ring_pass(idx, SW_CQ_RING)) << 32);
+      if (s->meta[j].fin_addr) sw_st_relaxed_sys(reinterpret_cast<void*>(s->meta[j].fin_addr), s->meta[j].fin_val);
+    }
+  }
+  // statistics: bytes and the union of the batches' active intervals
+  const uint64_t t1 = sw_globaltimer(), t0 = s->t_first ? s->t_first : t1;
+  const uint64_t prev = atomicMax(reinterpret_cast<unsigned long long*>(&q->last_end), static_cast<unsigned long long>(t1));
+  if (t1 > prev) atomicAdd(reinterpret_cast<unsigned long long*>(&q->busy_ns), static_cast<unsigned long long>(t1 - (t0 > prev ? t0 : prev)));
+  atomicAdd(reinterpret_cast<unsigned long long*>(&q->bytes), static_cast<unsigned long long>(s->total));
+  atomicAdd(reinterpret_cast<unsigned long long*>(&q->batches), 1ull);
+  atomicAdd(reinterpret_cast<unsigned long long*>(&q->jobs), static_cast<unsigned long long>(n));
+}
+
+// every CTA leaves a batch once (no more chunks for it), the finalizer once more: the last of them frees the slot
+__device__ __forceinline__ void sw_pull_retire(SwPullSlot* s, uint64_t ticket) {
+  __threadfence();
+  const uint32_t r = atomicAdd(&s->retire, 1u) + 1;
+  if (r == gridDim.x + 1) sw_st_release_gpu(&s->free_seq, ticket + 1);
+}
+
+__global__ void __launch_bounds__(32) sw_pull_kernel(const __grid_constant__ SwPullArgs a) {
+  extern __shared__ __align__(128) uint8_t sw_smem[];
+  __shared__ __align__(8) uint64_t full[SW_BULK_MAX_STAGES];
+  __shared__ uint64_t s_end[SW_PULL_JOBS], s_src[SW_PULL_JOBS], s_dst[SW_PULL_JOBS];
+  if (threadIdx.x != 0) return;
+  SwPullQueue* q = a.q;
+  const uint32_t nstages = a.nstages, stage_bytes = a.stage_bytes;
+  for (uint32_t i = 0; i < nstages; i++) sw_mbar_init(&full[i], 1);
+  sw_fence_mbar_init();
+  sw_fence_proxy_async();
+
+  constexpr uint32_t TRK = 16;   // pieces tracked between load issue and accounted completion (> stages + lag)
+  constexpr uint32_t LAG = 2;    // store groups allowed to be outstanding when completions are accounted
+  uint64_t st_dst[SW_BULK_MAX_STAGES];
+  uint32_t st_bytes[SW_BULK_MAX_STAGES];
+  SwPullSlot* tr_slot[TRK];      // != nullptr: this piece is the last of a chunk of that slot
+  uint64_t tr_ticket[TRK];
+  for (uint32_t i = 0; i < TRK; i++) {
+    tr_slot[i] = nullptr;
+    tr_ticket[i] = 0;
+  }
+  const uint32_t lookahead = nstages - 2;
+  uint64_t issued = 0, stored = 0, retired = 0;
+
+  // generator state
+  uint64_t b = sw_ld_acquire_gpu(&q->start);   // ticket looked at next
+  SwPullSlot* cur = nullptr;                   // batch being worked on
+  uint32_t njobs = 0, nchunks = 0, j = 0;
+  uint64_t chunk_bytes = 0, total = 0, pos = 0, cend = 0;
+  bool have_chunk = false, leave = false;
+  const long long clk0 = clock64();
+  long long last_work = clk0;
+  const long long linger_clk = static_cast<long long>(a.linger_us) * a.clk_mhz;
+  const long long life_clk = static_cast<long long>(a.max_life_us) * a.clk_mhz;
+  bool exit_published = false, exit_taken = false;
+  uint64_t exit_ticket = 0;
+  uint32_t polls = 0;
+
+  auto chunk_done = [&](SwPullSlot* s, uint64_t ticket) {
+    __threadfence();
+    const uint32_t d = atomicAdd(&s->done_chunks, 1u) + 1;
+    if (d == s->nchunks) {
+      __threadfence();
+      sw_pull_finalize(q, s);
+      sw_pull_retire(s, ticket);
+    }
+  };
+  // next piece of work, without blocking: 1 = piece, 0 = nothing right now
+  auto try_next = [&](uint64_t& src, uint64_t& dst, uint32_t& bytes, bool& last) -> int {
+    for (;;) {
+      if (have_chunk) {
+        if (pos < cend) {
+          while (s_end[j] <= pos) j++;
+          const uint64_t begin = j ? s_end[j - 1] : 0;
+          const uint64_t stop = s_end[j] < cend ? s_end[j] : cend;
+          const uint64_t left = stop - pos;
+          bytes = left < stage_bytes ? static_cast<uint32_t>(left) : stage_bytes;
+          src = s_src[j] + (pos - begin);
+          dst = s_dst[j] + (pos - begin);
+          pos += bytes;
+          last = pos >= cend;
+          if (last) have_chunk = false;
+          return 1;
+        }
+        have_chunk = false;
+        chunk_done(cur, b);   // an empty chunk (a batch of tails only)
+      }
+      if (!cur) {
+        SwPullSlot* s = &q->slot[b % SW_PULL_SLOTS];
+        if (sw_ld_acquire_gpu(&s->seq) != b + 1) {
+          // nothing published: CTA 0 decides when the whole grid leaves (host request, silence, lifetime).  It
+          // takes a ticket from the counter the matchers use -- every batch before it is still served by this
+          // grid, every batch after it by the next launch -- and publishes the EXIT batch as soon as that
+          // ticket's slot is free, without ever blocking (it keeps copying meanwhile).
+          if (blockIdx.x == 0 && !exit_published && (++polls & 7) == 0) {
+            if (!exit_taken) {
+              const long long now = clock64();
+              const bool stop = sw_ld_relaxed_sys(const_cast<const uint64_t*>(&a.ctl->stop)) != 0;
+              if (stop || now - last_work > linger_clk || now - clk0 > life_clk) {
+                exit_ticket = atomicAdd(reinterpret_cast<unsigned long long*>(&q->alloc), 1ull);
+                exit_taken = true;
+              }
+            }
+            if (exit_taken) {
+              SwPullSlot* xs = &q->slot[exit_ticket % SW_PULL_SLOTS];
+              const uint64_t want = exit_ticket >= SW_PULL_SLOTS ? exit_ticket - SW_PULL_SLOTS + 1 : 0;
+              if (sw_ld_acquire_gpu(&xs->free_seq) == want) {
+                xs->njobs = 0;
+                xs->nchunks = 0;
+                xs->exit = 1;
+                xs->total = 0;
+                xs->next_chunk = xs->done_chunks = xs->retire = 0;
+                __threadfence();
+                sw_st_release_gpu(&xs->seq, exit_ticket + 1);
+                exit_published = true;
+              }
+            }
+          }
+          return 0;
+        }
+        if (s->exit) {
+          leave = true;
+          return 0;
+        }
+        cur = s;
+        last_work = clock64();   // CTA 0 decides about leaving: a batch it got no chunk of is activity all the same
+        njobs = s->njobs;
+        nchunks = s->nchunks;
+        chunk_bytes = s->chunk_bytes;
+        total = s->total;
+        for (uint32_t k = 0; k < njobs; k++) {
+          s_end[k] = s->end[k];
+          s_src[k] = s->src[k];
+          s_dst[k] = s->dst[k];
+        }
+      }
+      const uint32_t cidx = atomicAdd(&cur->next_chunk, 1u);
+      if (cidx >= nchunks) {
+        sw_pull_retire(cur, b);   // nothing left for this CTA in batch b
+        cur = nullptr;
+        b++;
+        continue;
+      }
+      if (cidx == 0) cur->t_first = sw_globaltimer();
+      pos = static_cast<uint64_t>(cidx) * chunk_bytes;
+      cend = pos + chunk_bytes < total ? pos + chunk_bytes : total;
+      j = 0;
+      have_chunk = true;
+      last_work = clock64();
+    }
+  };
+  auto account = [&](uint64_t piece) {
+    SwPullSlot* s = tr_slot[piece % TRK];
+    if (s) chunk_done(s, tr_ticket[piece % TRK]);
+  };
+
+  for (;;) {
+    // ---- issue loads up to the look-ahead
+    bool idle = false;
+    while (issued - stored < lookahead && issued - retired < TRK - 1) {
+      uint64_t src, dst;
+      uint32_t bytes;
+      bool last;
+      if (!try_next(src, dst, bytes, last)) {
+        idle = true;
+        break;
+      }
+      // (try_next may have moved on to a later batch before it yielded: `cur` / `b` describe the piece's batch)
+      if (issued >= nstages) sw_bulk_wait_read<1>();   // the store that last used this stage has read it
+      const uint32_t stg = issued % nstages;
+      sw_mbar_expect_tx(&full[stg], bytes);
+      sw_bulk_g2s(sw_smem + size_t(stg) * stage_bytes, reinterpret_cast<const void*>(src), bytes, &full[stg]);
+      st_dst[stg] = dst;
+      st_bytes[stg] = bytes;
+      tr_slot[issued % TRK] = last ? cur : nullptr;
+      tr_ticket[issued % TRK] = b;
+      issued++;
+    }
+    // ---- store the oldest loaded piece
+    if (stored < issued) {
+      const uint32_t stg = stored % nstages;
+      sw_mbar_wait(&full[stg], (stored / nstages) & 1);
+      sw_bulk_s2g(reinterpret_cast<void*>(st_dst[stg]), sw_smem + size_t(stg) * stage_bytes, st_bytes[stg]);
+      sw_bulk_commit();
+      stored++;
+    }
+    // ---- account completions: all but the LAG most recent store groups have been written
+    if (stored - retired > LAG) {
+      asm volatile("cp.async.bulk.wait_group %0;" ::"n"(LAG) : "memory");
+      while (retired + LAG < stored) account(retired++);
+    }
+    if (idle && stored == issued) {
+      sw_bulk_wait_all();
+      while (retired < stored) account(retired++);
+      if (leave) break;
+      __nanosleep(200);
+    }
+  }
+  // the EXIT batch: every CTA passes it once; the last one hands the next launch its first ticket
+  {
+    SwPullSlot* s = &q->slot[b % SW_PULL_SLOTS];
+    __threadfence();
+    const uint32_t r = atomicAdd(&s->retire, 1u) + 1;
+    if (r == gridDim.x) {
+      s->exit = 0;
+      q->start = b + 1;
+      __threadfence();
+      sw_st_release_gpu(&s->free_seq, b + 1);
+      a.ctl->bytes = q->bytes;
+      a.ctl->busy_ns = q->busy_ns;
+      a.ctl->batches = q->batches;
+      a.ctl->jobs = q->jobs;
+      __threadfence_system();
+      a.ctl->exited = a.launch_seq;
+    }
+  }
+}

@@ -27,10 +27,11 @@ constexpr uint32_t SW_RING_SLOTS_DEFAULT = 1024;                // 8 MiB per end
 
 enum : uint32_t { SW_KIND_EAGER = 1, SW_KIND_RTS = 2 };
 
-struct SwSlotHdr {     // 64 B, 16 B aligned, written last by the put kernel
+struct SwSlotHdr {     // 64 B, 16 B aligned, written after the payload by the put kernel
   uint64_t tag;        // sender tag (full uint64)
   uint64_t len;        // message length in bytes (for RTS: length of the remote payload)
-  uint64_t seq;        // 1-based slot sequence number on this ring (sanity flag)
+  uint64_t seq;        // 1-based slot sequence number on this ring: the ARRIVAL FLAG, stored last with release
+                       // semantics at system scope; the receiver's control kernel polls it with ld.acquire.sys
   uint32_t kind;       // SW_KIND_*
   uint32_t magic;      // SW_SLOT_MAGIC
   uint64_t pad[4];
@@ -48,7 +49,8 @@ struct SwRts {            // 128 B
   uint64_t ctx_uuid;       // sender context id (same value => same process => direct ptr)
   uint32_t src_pid;
   int32_t src_dev;         // CUDA ordinal of the source memory (-1: unknown)
-  uint64_t pad[2];
+  uint64_t pad[2];         // [0]: SW_RTS_* flags; [1]: CUDA buffer id of the source allocation (key of the receiver's
+                           //      device-resident mapping table; 0: unknown)
 };
 static_assert(sizeof(SwRts) == 128, "SwRts layout");
 static_assert(sizeof(SwSlotHdr) == 64, "SwSlotHdr layout");
@@ -203,6 +205,10 @@ struct SwMatchState {   // device memory, one per worker
   uint64_t ring_base[SW_MAX_EPS];
   uint32_t ring_slots[SW_MAX_EPS];   // power of two
   uint64_t ring_cons[SW_MAX_EPS];    // slots consumed so far
+  uint64_t credit_ptr[SW_MAX_EPS];   // resident path: device-visible address of the sender-visible `consumed` word
+  uint64_t fin_ptr[SW_MAX_EPS];      // resident path: device-visible address of the FIN words of that connection
+  uint32_t ring_gen[SW_MAX_EPS];     // generation of the ring index (a retired endpoint's index is reused): travels
+                                     // with unexpected rendezvous requests so that a stale one is never pulled
   // unexpected heap: two size classes, index stacks; frees are deferred one launch
   uint8_t* heap_small;  uint32_t* free_small;  uint32_t n_free_small;  uint32_t cap_small;
   uint8_t* heap_big;    uint32_t* free_big;    uint32_t n_free_big;    uint32_t cap_big;
@@ -212,12 +218,127 @@ struct SwMatchState {   // device memory, one per worker
   SwJob* jobs;
   uint32_t n_jobs;
   uint32_t rr_ep;        // round-robin start endpoint
+  // resident path: cursors that survive from one launch of the control kernel to the next
+  uint64_t cq_alloc;       // eager completion records written so far
+  uint64_t hr_alloc;       // host-path rendezvous records written so far
+  uint64_t pull_jobs;      // rendezvous jobs handed to the pull queue so far
+  uint64_t arrivals;       // ring slots consumed so far
+  uint64_t post_consumed;  // receives taken from the post ring so far
+  uint64_t cqr_alloc;      // rendezvous completion records allocated by pull CTAs (atomic)
+  uint64_t cqr_head;       // device copy of the host's cursor into the rendezvous completion ring
 };
 
 constexpr uint32_t SW_UMETA_VALID = 1u << 31;
 constexpr uint32_t SW_UMETA_BIG = 1u << 30;
 constexpr uint32_t SW_UMETA_RTS = 1u << 29;
-constexpr uint32_t SW_UMETA_EPMASK = 0xFFFFu;
+constexpr uint32_t SW_UMETA_EPMASK = 0xFFFFu;   // bits 0-5: ring index, bits 6-15: generation of that index
+constexpr uint32_t SW_EP_IDX_BITS = 6, SW_EP_GEN_MASK = 0x3FFu;
+static_assert(SW_MAX_EPS <= (1u << SW_EP_IDX_BITS), "ring index field");
+
+// ---------------------------------------------------------------- resident progress path
+// The receive side of a worker is driven by a RESIDENT (bounded-lifetime) control kernel instead of
+// one match launch per batch: it polls the slot headers of the inbound rings in device memory
+// (release/acquire on the header's sequence word -- no host doorbell on the data path), takes new
+// receives from a ring in pinned host memory, matches, delivers eager payloads, publishes credits and
+// completion records straight to host-visible memory, and hands rendezvous matches to a pool of
+// resident pull CTAs (sw_pull_kernel) through a queue in device memory.  The kernels exit on their own
+// after `linger` of silence or `max_life`, so device-wide synchronisations of the application
+// (cudaFree, cudaDeviceSynchronize) never wait long; the host relaunches them while work is expected.
+constexpr uint32_t SW_POST_RING = 4096;     // host -> device: new receives (pinned host memory)
+constexpr uint32_t SW_CQ_RING = 16384;      // device -> host: completion records (pinned host memory)
+constexpr uint32_t SW_HR_RING = 2048;       // device -> host: rendezvous matches the host must copy
+constexpr uint32_t SW_FIN_SLOTS = 1024;     // rendezvous FIN words per direction (control block)
+constexpr uint32_t SW_PULL_SLOTS = 8;       // pull batches in flight per context
+constexpr uint32_t SW_PULL_JOBS = 64;       // messages per pull batch
+constexpr uint32_t SW_MAP_SLOTS = 8192;     // device-resident (exporter, allocation) -> mapped base table
+constexpr uint32_t SW_MAP_PROBE = 32;       // one warp-wide probe
+constexpr uint32_t SW_INLINE_DELIVER = 256; // eager payloads up to this size are copied by the matcher warp itself
+
+enum : uint32_t { SW_POST_HOSTPATH = 1 };   // a rendezvous into this receive is copied by a host-launched kernel
+enum : uint64_t { SW_RTS_PINNED_SRC = 1 };  // SwRts::pad[0]: the source is pinned host memory
+
+struct SwPostEnt {   // pinned host: one posted receive on its way to the control kernel
+  uint64_t tag, mask, buf, cap, op_id;
+  uint32_t flags, pad;
+};
+static_assert(sizeof(SwPostEnt) == 48, "SwPostEnt layout");
+
+struct SwCqEnt {     // pinned host: `seq` (pass number of the ring, never 0) is written last
+  uint64_t op_id, tag, len;
+  int32_t status;
+  uint32_t seq;
+};
+static_assert(sizeof(SwCqEnt) == 32, "SwCqEnt layout");
+SW_HD static inline uint32_t sw_ring_pass(uint64_t idx, uint32_t cap) { return static_cast<uint32_t>(idx / cap) + 1; }
+
+struct SwHrEnt {     // pinned host: a rendezvous match handed to the host (`seq` written last)
+  SwRndvRec rec;
+  uint32_t pad;
+  uint32_t seq;
+};
+
+struct SwMapEnt {    // device memory: key = (exporting context, CUDA buffer id of the allocation)
+  uint64_t uuid, buf_id;   // buf_id == 0: empty
+  uint64_t remote_base, local_base;
+};
+SW_HD static inline uint32_t sw_map_home(uint64_t uuid, uint64_t buf_id) {
+  uint64_t h = (uuid ^ (buf_id * 0x9E3779B97F4A7C15ull)) * 0xD6E8FEB86659FD93ull;
+  return static_cast<uint32_t>(h >> 40) & (SW_MAP_SLOTS - 1);
+}
+
+// Words shared between the host engine and the control kernel of one worker (pinned host memory).
+struct SwProgCtl {
+  // host -> kernel
+  alignas(64) volatile uint64_t post_tail;   // receives written into the post ring so far
+  volatile uint64_t cq_head;                 // eager completion records consumed by the host
+  volatile uint64_t cqr_head;                // rendezvous completion records consumed by the host
+  volatile uint64_t hr_head;                 // host-path rendezvous records consumed by the host
+  alignas(64) volatile uint64_t stop;        // != 0: leave as soon as the state is consistent
+  volatile uint64_t dead_mask;               // endpoints (bit = ring index) whose rendezvous go to the host
+  volatile uint64_t host_epoch;              // bumped by the host; echoed in dev_epoch by a later iteration
+  volatile uint64_t pad0;
+  // kernel -> host
+  alignas(64) volatile uint64_t post_head;   // receives taken from the post ring
+  volatile uint64_t dev_epoch;
+  volatile uint64_t exit_seq;                // launch number of the last launch that has ended
+  volatile uint64_t pull_jobs;               // rendezvous jobs handed to the pull queue so far
+  volatile uint64_t arrivals;                // ring slots consumed so far
+  volatile uint64_t n_posted, n_unexp;       // queue depths at exit
+  volatile uint64_t err;                     // consistency errors seen by the matcher
+  volatile uint64_t stalled;                 // a ring is blocked on the unexpected heap (needs new receives)
+  volatile uint64_t iterations;
+};
+
+// ---- pull queue: rendezvous copies executed by the resident pull CTAs of the context
+struct SwPullMeta {       // completion of one pulled message
+  uint64_t op_id, tag, len;
+  uint64_t fin_addr;      // word in the sender-visible control block (0: none)
+  uint64_t fin_val;
+};
+struct SwPullSlot {
+  uint64_t seq;           // ticket + 1 once published (release); compared by the workers
+  uint64_t free_seq;      // ticket + 1 of the last batch retired from this slot
+  uint32_t njobs, nchunks, exit, pad;
+  uint64_t chunk_bytes, total;
+  uint32_t next_chunk, done_chunks, retire, pad2;
+  uint64_t t_first;       // globaltimer of the first claim
+  // where the completion records of this batch go (the receiving worker's rendezvous CQ)
+  uint64_t cqr_ring, cqr_alloc, cqr_head_dev, cqr_head_host;
+  uint64_t end[SW_PULL_JOBS], src[SW_PULL_JOBS], dst[SW_PULL_JOBS];
+  SwPullMeta meta[SW_PULL_JOBS];
+};
+struct SwPullQueue {      // device memory, one per context
+  uint64_t alloc;         // next ticket (atomic)
+  uint64_t start;         // first ticket the next pull launch looks at
+  uint64_t bytes, busy_ns, last_end, batches, jobs;   // statistics (roofline: bytes / busy_ns)
+  uint64_t pad;
+  SwPullSlot slot[SW_PULL_SLOTS];
+};
+struct SwPullCtl {        // pinned host, one per context
+  alignas(64) volatile uint64_t stop;     // host -> kernel: publish an EXIT batch
+  alignas(64) volatile uint64_t exited;   // kernel -> host: launch number of the last launch whose CTA 0 left
+  volatile uint64_t bytes, busy_ns, batches, jobs;   // copies of the queue statistics at exit
+};
 
 // ---------------------------------------------------------------- bulk copy input
 struct SwSeg {        // one contiguous piece of a rendezvous/loopback copy

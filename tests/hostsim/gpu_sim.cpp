@@ -240,11 +240,12 @@ int match_state_destroy(SwMatchState* st) {
   free(st);
   return 0;
 }
-int match_state_set_ring(SwMatchState* st, uint32_t ep, void* ring_base, uint32_t slots) {
+int match_state_set_ring(SwMatchState* st, uint32_t ep, void* ring_base, uint32_t slots, uint32_t gen) {
   if (ep >= SW_MAX_EPS) return -1;
   st->ring_base[ep] = (uint64_t)(uintptr_t)ring_base;
   st->ring_slots[ep] = slots;
   st->ring_cons[ep] = 0;
+  st->ring_gen[ep] = gen;
   return 0;
 }
 
@@ -261,8 +262,11 @@ int launch_put(stream_t, const SwPutDesc* descs, uint32_t n, const DoneFlag* don
     h.seq = d.seq;
     h.kind = d.kind;
     h.magic = SW_SLOT_MAGIC;
-    __atomic_thread_fence(__ATOMIC_RELEASE);
-    memcpy(slot, &h, 32);
+    // same order as sw_put_header: tag / length / kind / magic, then the sequence word (the arrival flag) with
+    // release semantics
+    memcpy(slot, &h, 16);
+    memcpy(slot + 24, &h.kind, 8);
+    __atomic_store_n(reinterpret_cast<uint64_t*>(slot + 16), h.seq, __ATOMIC_RELEASE);
   }
   // same split as the CUDA backend: only the small (single-CTA) variant announces itself by flag
   uint32_t n_rts = 0;
@@ -475,6 +479,253 @@ int launch_bulk(stream_t, const SwSeg* segs, uint32_t nseg, const BulkTuning* t)
   }
   for (uint32_t i = 0; i < nseg; i++)
     memcpy((void*)(uintptr_t)segs[i].dst, (const void*)(uintptr_t)segs[i].src, segs[i].len);
+  return 0;
+}
+
+// ---------------------------------------------------------------- resident progress path (one pass per launch)
+// The CUDA backend keeps sw_progress_kernel / sw_pull_kernel resident; this stand-in performs ONE pass of the
+// same protocol per launch, synchronously: post ring -> matching -> eager delivery / rendezvous copy through the
+// mapping table -> completion rings, credit words and FIN words -> exit word.  The host engine cannot tell the
+// difference except that nothing happens between launches (resident_lingers() == 0).
+int resident_lingers() { return 0; }
+void* host_register(void* p, size_t) { return p; }
+int host_unregister(void*) { return 0; }
+int match_state_set_ep_words(SwMatchState* st, uint32_t ep, void* credit_word, void* fin_words) {
+  if (ep >= SW_MAX_EPS) return -1;
+  st->credit_ptr[ep] = (uint64_t)(uintptr_t)credit_word;
+  st->fin_ptr[ep] = (uint64_t)(uintptr_t)fin_words;
+  return 0;
+}
+SwPullQueue* pull_queue_create() { return (SwPullQueue*)calloc(1, sizeof(SwPullQueue)); }
+int pull_queue_destroy(SwPullQueue* q) {
+  free(q);
+  return 0;
+}
+SwMapEnt* map_table_create() { return (SwMapEnt*)calloc(SW_MAP_SLOTS, sizeof(SwMapEnt)); }
+int map_table_destroy(SwMapEnt* t) {
+  free(t);
+  return 0;
+}
+int map_table_clear(SwMapEnt* t) {
+  memset(t, 0, sizeof(SwMapEnt) * SW_MAP_SLOTS);
+  return 0;
+}
+int map_table_insert(SwMapEnt* t, stream_t, uint64_t uuid, uint64_t buf_id, uint64_t remote_base, uint64_t local_base) {
+  const uint32_t home = sw_map_home(uuid, buf_id);
+  for (uint32_t k = 0; k < SW_MAP_PROBE; k++) {
+    SwMapEnt& e = t[(home + k) & (SW_MAP_SLOTS - 1)];
+    if (e.buf_id) continue;
+    e.remote_base = remote_base;
+    e.local_base = local_base;
+    e.uuid = uuid;
+    __atomic_store_n(&e.buf_id, buf_id, __ATOMIC_RELEASE);
+    return 0;
+  }
+  g_err = "mapping table: probe window full";
+  return -1;
+}
+int pull_default_ctas() { return 8; }
+
+namespace {
+struct Pass {
+  const ProgressLaunch* a;
+  SwMatchState* st;
+  SwProgCtl* ctl;
+  bool rings_full() const {
+    return st->cq_alloc - ctl->cq_head + 8 > SW_CQ_RING || st->cqr_alloc - ctl->cqr_head + 8 > SW_CQ_RING ||
+           st->hr_alloc - ctl->hr_head + 8 > SW_HR_RING;
+  }
+  static void cqe(SwCqEnt* ring, uint64_t idx, uint64_t op, uint64_t tag, uint64_t len, int32_t status) {
+    SwCqEnt* e = &ring[idx % SW_CQ_RING];
+    e->op_id = op;
+    e->tag = tag;
+    e->len = len;
+    const uint64_t w = ((uint64_t)sw_ring_pass(idx, SW_CQ_RING) << 32) | (uint32_t)status;
+    __atomic_store_n(reinterpret_cast<uint64_t*>(&e->status), w, __ATOMIC_RELEASE);
+  }
+  void deliver(uint64_t src, uint64_t dst, uint64_t msg_len, uint64_t cap, uint64_t op, uint64_t tag) {
+    const bool trunc = msg_len > cap;
+    if (!trunc && msg_len) memcpy((void*)(uintptr_t)dst, (const void*)(uintptr_t)src, msg_len);
+    cqe(a->cq, st->cq_alloc++, op, tag, msg_len, trunc ? SW_ERR_MESSAGE_TRUNCATED : SW_OK);
+  }
+  uint64_t map_lookup(uint64_t uuid, uint64_t buf_id, uint64_t remote_base) const {
+    if (!a->map || !buf_id) return 0;
+    const uint32_t home = sw_map_home(uuid, buf_id);
+    for (uint32_t k = 0; k < SW_MAP_PROBE; k++) {
+      const SwMapEnt& e = a->map[(home + k) & (SW_MAP_SLOTS - 1)];
+      if (__atomic_load_n(&e.buf_id, __ATOMIC_ACQUIRE) == buf_id && e.uuid == uuid) return e.remote_base == remote_base ? e.local_base : 0;
+    }
+    return 0;
+  }
+  // same decision as sw_res_rts
+  void rts(uint64_t payload, uint64_t stag, uint64_t msg_len, uint32_t epf, uint64_t buf, uint64_t cap, uint64_t op, uint32_t pflags) {
+    SwRts r;
+    memcpy(&r, (const void*)(uintptr_t)payload, sizeof(r));
+    const uint32_t ep = epf & ((1u << SW_EP_IDX_BITS) - 1);
+    const bool trunc = msg_len > cap;
+    bool device_path = a->pq && a->pull_ctas && !trunc && !(pflags & SW_POST_HOSTPATH) && !(r.pad[0] & SW_RTS_PINNED_SRC) &&
+                       !((ctl->dead_mask >> ep) & 1) && st->fin_ptr[ep] && (epf >> SW_EP_IDX_BITS) == (st->ring_gen[ep] & SW_EP_GEN_MASK);
+    uint64_t src = 0;
+    if (device_path) {
+      if (r.ctx_uuid == a->ctx_uuid && r.src_pid == a->pid) {
+        src = r.src_ptr;
+      } else {
+        const uint64_t local = map_lookup(r.ctx_uuid, r.pad[1], r.alloc_base);
+        if (local && r.src_ptr >= r.alloc_base && r.src_ptr - r.alloc_base + msg_len <= r.alloc_size) src = local + (r.src_ptr - r.alloc_base);
+      }
+      if (!src || ((src | buf) & 15)) device_path = false;
+    }
+    if (device_path) {
+      // what the pull CTAs do: copy, completion record, FIN word of the sender, statistics
+      if (msg_len) memcpy((void*)(uintptr_t)buf, (const void*)(uintptr_t)src, msg_len);
+      cqe(a->cqr, st->cqr_alloc++, op, stag, msg_len, SW_OK);
+      __atomic_store_n(reinterpret_cast<uint64_t*>(st->fin_ptr[ep] + 8ull * (r.send_seq % SW_FIN_SLOTS)), (r.send_seq << 2) | 1, __ATOMIC_RELEASE);
+      st->pull_jobs++;
+      a->pq->bytes += msg_len & ~15ull;
+      a->pq->busy_ns += 1000;
+      a->pq->batches++;
+      a->pq->jobs++;
+      return;
+    }
+    SwHrEnt* h = &a->hr[st->hr_alloc % SW_HR_RING];
+    h->rec.rts = r;
+    h->rec.op_id = op;
+    h->rec.dst = buf;
+    h->rec.cap = cap;
+    h->rec.tag = stag;
+    h->rec.len = msg_len;
+    h->rec.ep = epf;
+    h->rec.status = trunc ? SW_ERR_MESSAGE_TRUNCATED : SW_OK;
+    h->pad = 0;
+    __atomic_store_n(&h->seq, sw_ring_pass(st->hr_alloc, SW_HR_RING), __ATOMIC_RELEASE);
+    st->hr_alloc++;
+  }
+};
+}  // namespace
+
+int launch_progress(stream_t, const ProgressLaunch* a) {
+  const uint64_t PQM = SW_PQ_CAP - 1, UQM = SW_UQ_CAP - 1;
+  Pass p{a, a->st, a->ctl};
+  SwMatchState* st = a->st;
+  SwProgCtl* ctl = a->ctl;
+  const uint64_t epoch = __atomic_load_n(&ctl->host_epoch, __ATOMIC_ACQUIRE);
+  bool stalled = false;
+  // ---- new receives, in post order, against the unexpected queue (earliest arrival first)
+  while (st->post_consumed < __atomic_load_n(&ctl->post_tail, __ATOMIC_ACQUIRE) && !p.rings_full()) {
+    const SwPostEnt e = a->posts[st->post_consumed % SW_POST_RING];
+    st->post_consumed++;
+    bool found = false;
+    for (uint64_t idx = st->u_head; idx < st->u_tail; idx++) {
+      const uint64_t s = idx & UQM;
+      const uint32_t meta = st->u_meta[s];
+      if (!(meta & SW_UMETA_VALID) || !sw_tag_match(st->u_tag[s], e.tag, e.mask)) continue;
+      st->u_meta[s] = 0;
+      st->u_count--;
+      if (meta & SW_UMETA_RTS)
+        p.rts(st->u_data[s], st->u_tag[s], st->u_len[s], meta & SW_UMETA_EPMASK, e.buf, e.cap, e.op_id, e.flags);
+      else
+        p.deliver(st->u_data[s], e.buf, st->u_len[s], e.cap, e.op_id, st->u_tag[s]);
+      if (meta & SW_UMETA_BIG)
+        st->free_big[st->n_free_big++] = st->u_blk[s];
+      else
+        st->free_small[st->n_free_small++] = st->u_blk[s];
+      found = true;
+      break;
+    }
+    while (st->u_head < st->u_tail && !(st->u_meta[st->u_head & UQM] & SW_UMETA_VALID)) st->u_head++;
+    if (found) continue;
+    if (st->p_tail - st->p_head >= SW_PQ_CAP) {
+      Pass::cqe(a->cq, st->cq_alloc++, e.op_id, 0, 0, SW_ERR_NO_MEMORY);
+      continue;
+    }
+    const uint64_t s = st->p_tail & PQM;
+    st->p_tag[s] = e.tag;
+    st->p_mask[s] = e.mask;
+    st->p_buf[s] = e.buf;
+    st->p_cap[s] = e.cap;
+    st->p_op[s] = e.op_id;
+    st->p_valid[s] = 1u | (e.flags << 8);
+    st->p_tail++;
+    st->p_count++;
+  }
+  __atomic_store_n(&ctl->post_head, st->post_consumed, __ATOMIC_RELEASE);
+  // ---- arrivals: a slot has arrived when its header carries the expected sequence number
+  for (uint32_t k = 0; k < a->n_eps; k++) {
+    const uint32_t ep = (st->rr_ep + k) % a->n_eps;
+    if (!st->ring_base[ep]) continue;
+    const uint32_t epf = ep | ((st->ring_gen[ep] & SW_EP_GEN_MASK) << SW_EP_IDX_BITS);
+    uint64_t cons = st->ring_cons[ep];
+    for (;;) {
+      if (p.rings_full()) break;
+      const uint8_t* slot = (const uint8_t*)(uintptr_t)(st->ring_base[ep] + (cons & (st->ring_slots[ep] - 1)) * SW_SLOT_BYTES);
+      if (__atomic_load_n(reinterpret_cast<const uint64_t*>(slot + 16), __ATOMIC_ACQUIRE) != cons + 1) break;
+      SwSlotHdr h;
+      memcpy(&h, slot, 32);
+      if (h.magic != SW_SLOT_MAGIC) ctl->err |= 1;
+      const bool is_rts = h.kind == SW_KIND_RTS;
+      const uint64_t payload = (uint64_t)(uintptr_t)(slot + SW_SLOT_HDR);
+      bool found = false;
+      for (uint64_t idx = st->p_head; idx < st->p_tail; idx++) {
+        const uint64_t s = idx & PQM;
+        if (!st->p_valid[s] || !sw_tag_match(h.tag, st->p_tag[s], st->p_mask[s])) continue;
+        const uint32_t pflags = st->p_valid[s] >> 8;
+        st->p_valid[s] = 0;
+        st->p_count--;
+        if (is_rts)
+          p.rts(payload, h.tag, h.len, epf, st->p_buf[s], st->p_cap[s], st->p_op[s], pflags);
+        else
+          p.deliver(payload, st->p_buf[s], h.len, st->p_cap[s], st->p_op[s], h.tag);
+        found = true;
+        break;
+      }
+      while (st->p_head < st->p_tail && !st->p_valid[st->p_head & PQM]) st->p_head++;
+      if (!found) {
+        const uint64_t need = is_rts ? sizeof(SwRts) : h.len;
+        const bool big = need > SW_HEAP_SMALL_BYTES;
+        if ((big ? st->n_free_big : st->n_free_small) == 0 || st->u_tail - st->u_head >= SW_UQ_CAP) {
+          stalled = true;   // back-pressure: the message stays in its ring slot
+          break;
+        }
+        const uint32_t blk = big ? st->free_big[--st->n_free_big] : st->free_small[--st->n_free_small];
+        const uint64_t haddr = big ? (uint64_t)(uintptr_t)st->heap_big + (uint64_t)blk * SW_HEAP_BIG_BYTES
+                                   : (uint64_t)(uintptr_t)st->heap_small + (uint64_t)blk * SW_HEAP_SMALL_BYTES;
+        if (need) memcpy((void*)(uintptr_t)haddr, (const void*)(uintptr_t)payload, need);
+        const uint64_t s = st->u_tail & UQM;
+        st->u_tag[s] = h.tag;
+        st->u_len[s] = h.len;
+        st->u_data[s] = haddr;
+        st->u_blk[s] = blk;
+        st->u_meta[s] = SW_UMETA_VALID | (big ? SW_UMETA_BIG : 0) | (is_rts ? SW_UMETA_RTS : 0) | (epf & SW_UMETA_EPMASK);
+        st->u_tail++;
+        st->u_count++;
+      }
+      cons++;
+      st->arrivals++;
+    }
+    if (cons != st->ring_cons[ep]) {
+      st->ring_cons[ep] = cons;
+      if (st->credit_ptr[ep]) __atomic_store_n(reinterpret_cast<uint64_t*>(st->credit_ptr[ep]), cons, __ATOMIC_RELEASE);
+    }
+  }
+  st->rr_ep++;
+  ctl->pull_jobs = st->pull_jobs;
+  ctl->arrivals = st->arrivals;
+  ctl->n_posted = st->p_count;
+  ctl->n_unexp = st->u_count;
+  ctl->stalled = stalled ? 1 : 0;
+  ctl->iterations = ctl->iterations + 1;
+  __atomic_store_n(&ctl->dev_epoch, epoch, __ATOMIC_RELEASE);
+  __atomic_store_n(&ctl->exit_seq, a->launch_seq, __ATOMIC_RELEASE);
+  return 0;
+}
+
+// the copies were made by the pass that matched them: the "pull kernel" only reports and leaves
+int launch_pull(stream_t, SwPullQueue* q, SwPullCtl* ctl, uint64_t launch_seq, uint32_t, uint32_t, uint32_t, const BulkTuning*) {
+  ctl->bytes = q->bytes;
+  ctl->busy_ns = q->busy_ns;
+  ctl->batches = q->batches;
+  ctl->jobs = q->jobs;
+  __atomic_store_n(&ctl->exited, launch_seq, __ATOMIC_RELEASE);
   return 0;
 }
 
