@@ -38,7 +38,7 @@ WINDOW = 64
 POOL_SETS = 4  # 4 x 64 MiB sources + 4 x 64 MiB destinations = 512 MiB > 126 MB L2
 TAG, MASK = 1, 0xFFFF
 METRIC = "tagged send/recv GB/s & Mmsg/s vs size, 1/2/4/8 B200; NVLink roofline %"
-NVLINK_MEASURED_GBS = 770.0  # /opt/skills/guides/B200_PROFILING.md: measured peer copy per direction (900 nominal)
+NVLINK_NOMINAL_GBS = 900.0  # score NVLink against the nominal 900 GB/s per direction (measured peer copy: 770)
 
 
 def new_loop_runner():
@@ -277,8 +277,9 @@ def run_ours(args):
                     f.write(f"{t:.7f} {name} 0 0\n")
         st2 = ctx.stats()
         e2e_diag = {"ms_per_step": round(e2e_ms / e2e_steps, 3),
-                    "bulk_kernel_ms_per_step": round(st2["bulk_event_ms"] / e2e_steps, 3),
+                    "copy_kernel_ms_per_step": round((st2["bulk_event_ms"] + st2["pull_busy_ms"]) / e2e_steps, 3),
                     "bulk_launches_per_step": round((st2["bulk_tma_launches"] + st2["bulk_simt_launches"]) / e2e_steps, 1),
+                    "pull_batches_per_step": round(st2["pull_batches"] / e2e_steps, 1),
                     "staged_h2d_bytes_per_step": int(st2["h2d_bytes"] / e2e_steps),
                     "staged_d2h_bytes_per_step": int(st2["d2h_bytes"] / e2e_steps)}
 
@@ -289,17 +290,31 @@ def run_ours(args):
 
     value, ms, st, clk, e2e_value, step_bytes, e2e_diag, payload_check = new_loop_runner()(main())
 
-    # ---- roofline of the dominant kernel (sw_bulk_tma_kernel), from CUDA events recorded on the
-    #      stream the kernel is launched on (engine profiling hooks), averaged over the timed region
-    launches = max(1, st["bulk_event_launches"])
-    avg_ms = st["bulk_event_ms"] / launches
-    payload_per_launch = st["bulk_event_bytes"] / launches
+    # ---- roofline of the dominant kernel: the rendezvous copy.  On the resident path the copies are made by the
+    #      pull CTAs (sw_pull_kernel), which stay on the GPU across many batches: the time base is the union of the
+    #      batches' active intervals (first chunk claimed -> batch completed, device timer), accumulated by the
+    #      kernel itself over the timed region.  Host-launched copies (sw_bulk_tma_*_kernel; resident=0, or sources
+    #      the control kernel cannot resolve) are timed with CUDA events on their stream.
+    if st["pull_bytes"] > 0:
+        launches = max(1, st["pull_batches"])
+        avg_ms = st["pull_busy_ms"] / launches
+        payload_per_launch = st["pull_bytes"] / launches
+        kernel = ("sw_pull_kernel (resident pull CTAs, one elected thread each: cp.async.bulk global->smem->global, "
+                  "8 x 24 KiB stages; a 'launch' here is one published batch of matched messages)")
+        n_launches = st["pull_batches"]
+    else:
+        launches = max(1, st["bulk_event_launches"])
+        avg_ms = st["bulk_event_ms"] / launches
+        payload_per_launch = st["bulk_event_bytes"] / launches
+        kernel = ("sw_bulk_tma_jobs_kernel (<= 96 messages per launch as kernel parameters, equal byte range per CTA; "
+                  "larger launches: sw_bulk_tma_kernel, same cp.async.bulk pipeline)")
+        n_launches = st["bulk_event_launches"]
     if world == 1:
         algo_bytes = 2 * payload_per_launch  # loopback: read N + write N bytes of HBM
         peak, bound, peak_note = float(peaks["hbm_gbs"]), "hbm", f"HBM copy, {peaks_src}"
     else:
         algo_bytes = payload_per_launch  # N payload bytes cross NVLink in one direction
-        peak, bound, peak_note = NVLINK_MEASURED_GBS, "nvlink", "NVLink per direction: measured peer copy 770 GB/s (B200_PROFILING.md; 900 nominal)"
+        peak, bound, peak_note = NVLINK_NOMINAL_GBS, "nvlink", "NVLink 5 per direction, nominal 900 GB/s (BASELINE.md; measured peer copy on this pool: 770 GB/s)"
     achieved = algo_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
     traffic = None
     try:
@@ -312,13 +327,12 @@ def run_ours(args):
     roofline = {
         "bound": bound, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
         "frac": round(achieved / peak, 4), "traffic": traffic,
-        "kernel": "sw_bulk_tma_jobs_kernel (<= 96 messages per launch as kernel parameters, equal byte range per CTA; "
-                  "larger launches: sw_bulk_tma_kernel, same cp.async.bulk pipeline)",
-        "launches": st["bulk_event_launches"], "avg_launch_us": round(avg_ms * 1e3, 2),
+        "kernel": kernel,
+        "launches": n_launches, "avg_launch_us": round(avg_ms * 1e3, 2),
         "payload_bytes_per_launch": int(payload_per_launch), "peak_source": peak_note,
     }
-    gpu_launches = int(st["put_launches"] + st["match_launches"] + st["deliver_launches"]
-                       + st["bulk_tma_launches"] + st["bulk_simt_launches"])
+    gpu_launches = int(st["put_launches"] + st["prog_launches"] + st["pull_launches"] + st["match_launches"]
+                       + st["deliver_launches"] + st["bulk_tma_launches"] + st["bulk_simt_launches"])
     if rank != 0:
         sw.shutdown()
         return

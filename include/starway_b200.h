@@ -102,6 +102,9 @@ typedef struct sw_stats {
    * time (union of the batches' active intervals, device timer) -- the roofline numerator / denominator */
   uint64_t prog_launches, pull_launches, pull_batches, pull_jobs, pull_bytes;
   double pull_busy_ms;
+  uint64_t prog_exit_stop, prog_exit_idle, prog_exit_life; /* why control-kernel launches ended */
+  double prog_life_ms;                                     /* total time control kernels were resident */
+  uint64_t put_resident;                                   /* put batches executed by a resident control kernel (no launch) */
 } sw_stats;
 
 /* ---- library / context (reference Context, main.cpp:71-79) */

@@ -102,6 +102,11 @@ class SwStats(ctypes.Structure):
         ("pull_jobs", ctypes.c_uint64),
         ("pull_bytes", ctypes.c_uint64),
         ("pull_busy_ms", ctypes.c_double),
+        ("prog_exit_stop", ctypes.c_uint64),
+        ("prog_exit_idle", ctypes.c_uint64),
+        ("prog_exit_life", ctypes.c_uint64),
+        ("prog_life_ms", ctypes.c_double),
+        ("put_resident", ctypes.c_uint64),
     ]
 
 

@@ -507,6 +507,8 @@ struct Worker {
   SwCqEnt* cq_ring = nullptr;
   SwCqEnt* cqr_ring = nullptr;
   SwHrEnt* hr_ring = nullptr;
+  SwPutDesc* send_ring = nullptr;   // put descriptors executed by the resident kernel (small batches, no launch)
+  uint64_t sends_written = 0;
   swgpu::stream_t s_ctl = nullptr;
   uint64_t prog_seq = 0;          // launches so far
   bool prog_running = false;
@@ -546,6 +548,10 @@ struct PutBlock {
   uint32_t spins = 0;
   bool flag_mode = false, timed = false;
   bool busy = false;
+  // executed by the sending worker's resident control kernel instead of a launch: done when the kernel's
+  // send_done counter has passed res_end
+  Worker* res_worker = nullptr;
+  uint64_t res_end = 0;
   std::vector<PutItem> items;
 };
 struct BulkBlock {
@@ -663,6 +669,9 @@ struct Ctx {
   // resident pull CTAs (sw_pull_kernel); 0: one match launch per batch, host-launched bulk copies (round 1)
   std::atomic<int64_t> opt_resident{1};
   std::atomic<int64_t> opt_linger_us{150}, opt_max_life_us{2000}, opt_armed_ms{30}, opt_pull_ctas{0};
+  // batches of at most this many sends of ONE worker whose control kernel is resident are executed by that
+  // kernel (descriptor ring in pinned memory) instead of a put launch; 0: always launch
+  std::atomic<int64_t> opt_resident_puts{8};
   SwPullQueue* pq = nullptr;
   SwMapEnt* map_tbl = nullptr;
   SwPullCtl* pull_ctl = nullptr;
@@ -845,8 +854,9 @@ bool worker_alloc_device(Ctx* c, Worker* w) {
     w->cq_ring = (SwCqEnt*)swgpu::host_alloc(sizeof(SwCqEnt) * SW_CQ_RING);
     w->cqr_ring = (SwCqEnt*)swgpu::host_alloc(sizeof(SwCqEnt) * SW_CQ_RING);
     w->hr_ring = (SwHrEnt*)swgpu::host_alloc(sizeof(SwHrEnt) * SW_HR_RING);
+    w->send_ring = (SwPutDesc*)swgpu::host_alloc(sizeof(SwPutDesc) * SW_SEND_RING);
     w->s_ctl = swgpu::stream_create();
-    if (!w->pctl || !w->post_ring || !w->cq_ring || !w->cqr_ring || !w->hr_ring || !w->s_ctl) {
+    if (!w->pctl || !w->post_ring || !w->cq_ring || !w->cqr_ring || !w->hr_ring || !w->send_ring || !w->s_ctl) {
       set_error(std::string("worker resident-path alloc: ") + swgpu::last_error());
       return false;
     }
@@ -1351,10 +1361,11 @@ bool pump_sends(Ctx* c) {
   PutBlock& b = c->put_blocks[c->put_tail % N_PUT_BLOCKS];
   uint32_t n = 0;
   uint64_t bytes = 0, h2d = 0, staged_bytes = 0;
-  bool batch_full = false;
+  bool batch_full = false, stream_ordered = false;
   const uint64_t eager_max = (uint64_t)std::min<int64_t>(c->opt_eager_max.load(), SW_EAGER_MAX);
   b.items.clear();
   b.nsegs = 0;
+  b.res_worker = nullptr;
   for (Worker* w : c->active) {
     for (Ep* ep : w->eps) {
       while (!ep->sendq.empty() && n < PUT_BATCH) {
@@ -1425,11 +1436,13 @@ bool pump_sends(Ctx* c) {
                 for (uint64_t off = 0; off < body; off += STAGE_SEG_BYTES)
                   b.segs[b.nsegs++] = SwSeg{(uint64_t)(uintptr_t)op->ptr + off, (uint64_t)(uintptr_t)op->dev_staging + off,
                                             std::min<uint64_t>(STAGE_SEG_BYTES, body - off), 0};
+                stream_ordered = true;
                 if (op->len > body)
                   swgpu::memcpy_h2d((uint8_t*)op->dev_staging + body, op->ptr + body, op->len - body, c->s_put);
               } else {
                 trace(c, "h2d_enqueue", op->len);
                 swgpu::memcpy_h2d(op->dev_staging, op->ptr, op->len, c->s_put);
+                stream_ordered = true;   // the RTS may only become visible after this copy: needs the put launch behind it
               }
               h2d += op->len;
             }
@@ -1505,6 +1518,32 @@ bool pump_sends(Ctx* c) {
     if (n >= PUT_BATCH || batch_full) break;
   }
   if (!n) return false;
+  // ---- small batch of one worker whose control kernel is resident: hand the descriptors to that kernel
+  if (n <= (uint32_t)c->opt_resident_puts.load() && !stream_ordered && b.nsegs == 0 && swgpu::resident_lingers()) {
+    Worker* w0 = b.items[0].op->w;
+    bool one = w0->resident && w0->prog_running && w0->send_ring && c->opt_profile.load() < 2 &&
+               w0->sends_written + n - __atomic_load_n(&w0->pctl->send_done, __ATOMIC_ACQUIRE) <= SW_SEND_RING;
+    for (uint32_t i = 1; one && i < n; i++) one = b.items[i].op->w == w0;
+    if (one) {
+      for (uint32_t i = 0; i < n; i++) w0->send_ring[(w0->sends_written + i) % SW_SEND_RING] = b.descs[i];
+      w0->sends_written += n;
+      __atomic_store_n(&w0->pctl->send_tail, w0->sends_written, __ATOMIC_RELEASE);
+      trace(c, "put_resident", n, bytes + h2d);
+      b.res_worker = w0;
+      b.res_end = w0->sends_written;
+      b.flag_mode = false;
+      b.timed = false;
+      b.busy = true;
+      c->put_tail++;
+      w0->last_activity = now_s();
+      std::lock_guard<std::mutex> lk(c->st_mu);
+      c->stats.put_resident++;
+      c->stats.put_msgs += n;
+      c->stats.put_bytes += bytes;
+      c->stats.h2d_bytes += h2d;
+      return true;
+    }
+  }
   b.timed = c->opt_profile.load() >= 2;
   if (b.timed) swgpu::event_record(b.ev_start, c->s_put);
   if (b.nsegs) {
@@ -1536,7 +1575,10 @@ bool poll_puts(Ctx* c) {
   while (c->put_head != c->put_tail) {
     PutBlock& b = c->put_blocks[c->put_head % N_PUT_BLOCKS];
     int q;
-    if (b.flag_mode) {
+    if (b.res_worker) {
+      // the resident kernel of the sending worker executes these puts (if it left first, the relaunch does)
+      q = __atomic_load_n(&b.res_worker->pctl->send_done, __ATOMIC_ACQUIRE) >= b.res_end ? 0 : 1;
+    } else if (b.flag_mode) {
       q = __atomic_load_n(b.done, __ATOMIC_ACQUIRE) == b.done_seq ? 0 : 1;
       // a faulted launch never writes its flag: look at the stream now and then
       if (q == 1 && (++b.spins & 0x3FF) == 0 && swgpu::stream_query(c->s_put) < 0) q = -1;
@@ -2113,10 +2155,12 @@ bool pump_progress(Ctx* c, Worker* w) {
       w->stall_posts = w->posts_written;
       w->stall_seen = unseen_arrivals(w);
       {
-        const uint64_t arr = w->pctl->arrivals;
+        const uint64_t arr = w->pctl->arrivals, why = w->pctl->exit_reason, life = w->pctl->life_us;
         std::lock_guard<std::mutex> lk(c->st_mu);
         c->stats.match_arrivals += arr - w->arrivals_seen;
         w->arrivals_seen = arr;
+        (why == 1 ? c->stats.prog_exit_stop : why == 2 ? c->stats.prog_exit_idle : c->stats.prog_exit_life)++;
+        c->stats.prog_life_ms += (double)life * 1e-3;
       }
       any = true;
     } else if ((++w->prog_spins & 0xFFF) == 0 && swgpu::stream_query(w->s_ctl) < 0) {
@@ -2187,8 +2231,10 @@ bool pump_progress(Ctx* c, Worker* w) {
   if (w->close_phase >= 3 || c->evict_pending) return any;
   const uint64_t unseen = unseen_arrivals(w);
   const bool posts_pending = w->posts_written != __atomic_load_n(&w->pctl->post_head, __ATOMIC_ACQUIRE);
+  const bool sends_pending = w->sends_written != __atomic_load_n(&w->pctl->send_done, __ATOMIC_ACQUIRE);
   bool work = posts_pending || unseen != 0;
   if (w->prog_stalled && w->stall_posts == w->posts_written && w->stall_seen == unseen) work = false;
+  work |= sends_pending;   // puts handed to a kernel that left before it took them
   const double now = now_s();
   const bool armed = swgpu::resident_lingers() && w->close_phase == 0 && !w->recvs.empty() &&
                      now - w->last_activity < (double)c->opt_armed_ms.load() * 1e-3;
@@ -2200,6 +2246,7 @@ bool pump_progress(Ctx* c, Worker* w) {
   a.cq = w->cq_ring;
   a.cqr = w->cqr_ring;
   a.hr = w->hr_ring;
+  a.sends = w->send_ring;
   a.pq = c->pq;
   a.map = c->map_tbl;
   a.ctx_uuid = c->uuid;
@@ -2543,6 +2590,8 @@ void worker_release(Ctx* c, Worker* w, bool leak_rings) {
   swgpu::host_free(w->cq_ring);
   swgpu::host_free(w->cqr_ring);
   swgpu::host_free(w->hr_ring);
+  swgpu::host_free(w->send_ring);
+  w->send_ring = nullptr;
   w->s_ctl = nullptr;
   w->pctl = nullptr;
   w->post_ring = nullptr;
@@ -3165,6 +3214,7 @@ int sw_set_option(sw_ctx* ctx, const char* key, int64_t value) {
   else if (k == "max_life_us") c->opt_max_life_us = std::max<int64_t>(10, value);
   else if (k == "armed_ms") c->opt_armed_ms = std::max<int64_t>(0, value);
   else if (k == "pull_ctas") c->opt_pull_ctas = std::max<int64_t>(0, value);
+  else if (k == "resident_puts") c->opt_resident_puts = std::max<int64_t>(0, value);
   else {
     set_error("unknown option " + k);
     return -1;

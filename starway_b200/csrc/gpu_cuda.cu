@@ -581,6 +581,7 @@ int launch_progress(stream_t s, const ProgressLaunch* p) {
   a.cq = p->cq;
   a.cqr = p->cqr;
   a.hr = p->hr;
+  a.sends = p->sends;
   a.pq = p->pq;
   a.map = p->map;
   a.ctx_uuid = p->ctx_uuid;

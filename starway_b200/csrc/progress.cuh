@@ -8,7 +8,9 @@
 //                                  straight to host-visible memory, hands rendezvous matches to the pull queue
 //                         warp 1   host link: polls the worker's control words and the post ring in pinned host
 //                                  memory (PCIe reads off the matcher's critical path), decides when to leave
-//                         warp 2+  helpers: eager payloads above SW_INLINE_DELIVER bytes
+//                         warp 2   puts: small batches of sends the host hands over while the kernel is resident
+//                                  (payload + released header into the peer's ring, no launch on the sender side)
+//                         warp 3+  helpers: eager payloads above SW_INLINE_DELIVER bytes
 //                       (replaces ucp_worker_progress + the matching inside ucp_tag_recv_nbx,
 //                        reference src/bindings/main.cpp:362,1127 and :404,1172)
 //   sw_pull_kernel      resident pull CTAs of the context (one elected thread each drives the cp.async.bulk
@@ -95,6 +97,7 @@ struct SwProgArgs {
   SwCqEnt* cq;               // pinned host, SW_CQ_RING entries: eager completions (index allocated by the matcher)
   SwCqEnt* cqr;              // pinned host, SW_CQ_RING entries: rendezvous completions (allocated by pull CTAs)
   SwHrEnt* hr;               // pinned host, SW_HR_RING entries
+  const SwPutDesc* sends;    // pinned host, SW_SEND_RING entries (payload sources / RTS descriptors they point at: pinned or device)
   SwPullQueue* pq;           // device memory (nullptr: every rendezvous goes to the host)
   const SwMapEnt* map;       // device memory
   uint64_t ctx_uuid;
@@ -105,7 +108,8 @@ struct SwProgArgs {
 };
 
 constexpr uint32_t SW_PROG_THREADS = 256;
-constexpr uint32_t SW_PROG_HELPERS = SW_PROG_THREADS / 32 - 2;
+constexpr uint32_t SW_PROG_HELPERS = SW_PROG_THREADS / 32 - 3;
+constexpr uint32_t SW_SSEND_RING = 16;
 constexpr uint32_t SW_DJOB_RING = 64;
 constexpr uint32_t SW_SPOST_RING = 64;
 constexpr uint32_t SW_PEND_RING = 128;
@@ -124,6 +128,7 @@ struct SwPend {      // something that may only be released once helper job `job
 
 struct SwProgShared {
   SwPostEnt posts[SW_SPOST_RING];
+  SwPutDesc sends[SW_SSEND_RING];
   SwDJob jobs[SW_DJOB_RING];
   SwPend pend[SW_PEND_RING];
   uint64_t ring_base[SW_MAX_EPS];
@@ -139,6 +144,8 @@ struct SwProgShared {
   volatile uint64_t post_tail;    // staged by the link warp
   volatile uint64_t post_head;    // consumed by the matcher
   volatile uint64_t job_tail;     // jobs emitted by the matcher
+  volatile uint64_t send_tail;    // put descriptors staged by the link warp
+  volatile uint64_t send_done;    // put descriptors executed by the put warp
   volatile uint64_t cq_head, cqr_head, hr_head, dead_mask, host_epoch;   // copies of the host's words
   volatile long long active_clk;  // last time the matcher did something
   volatile uint32_t helper_done[SW_PROG_HELPERS];
@@ -878,6 +885,7 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
   }
   if (threadIdx.x == 0) {
     sh.post_tail = sh.post_head = st->post_consumed;
+    sh.send_tail = sh.send_done = st->send_consumed;
     sh.job_tail = 0;
     sh.cq_head = a.ctl->cq_head;
     sh.cqr_head = a.ctl->cqr_head;
@@ -1002,14 +1010,15 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
     // ================================================================ host link
     const long long linger_clk = static_cast<long long>(a.linger_us) * a.clk_mhz;
     const long long life_clk = static_cast<long long>(a.max_life_us) * a.clk_mhz;
-    uint64_t staged = sh.post_tail;
+    uint64_t staged = sh.post_tail, sstaged = sh.send_tail;
     uint64_t he_prev = sh.host_epoch;
     bool leaving = false;
     for (;;) {
-      uint64_t host_tail = 0, stop = 0;
+      uint64_t host_tail = 0, stop = 0, host_stail = 0;
       if (lane == 0) {
         const int4 w0 = sw_ld16_sys(const_cast<const uint64_t*>(&a.ctl->post_tail));   // post_tail, cq_head
         const int4 w1 = sw_ld16_sys(const_cast<const uint64_t*>(&a.ctl->cqr_head));    // cqr_head, hr_head
+        host_stail = sw_ld_relaxed_sys(const_cast<const uint64_t*>(&a.ctl->send_tail));
         const int4 w2 = sw_ld16_sys(const_cast<const uint64_t*>(&a.ctl->stop));        // stop, dead_mask
         const uint64_t he = sw_ld_relaxed_sys(const_cast<const uint64_t*>(&a.ctl->host_epoch));
         auto u64of = [](int lo, int hi) { return (static_cast<uint64_t>(static_cast<uint32_t>(hi)) << 32) | static_cast<uint32_t>(lo); };
@@ -1030,6 +1039,7 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
         he_prev = he;
       }
       host_tail = sw_shfl64(host_tail, 0);
+      host_stail = sw_shfl64(host_stail, 0);
       stop = sw_shfl64(stop, 0);
       if (leaving) {
         // the matcher winds down (it may still need room in the completion rings): keep the host's cursors fresh
@@ -1058,19 +1068,65 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
           a.ctl->post_head = staged;   // the host may reuse these ring entries
         }
       }
+      // put descriptors for the put warp: lane L copies descriptor (sstaged + L)
+      uint64_t ns = host_stail - sstaged;
+      const uint64_t sroom = SW_SSEND_RING - (sstaged - sh.send_done);
+      if (ns > sroom) ns = sroom;
+      if (lane < ns) {
+        const SwPutDesc* src = &a.sends[(sstaged + lane) % SW_SEND_RING];
+        int4* dst = reinterpret_cast<int4*>(&sh.sends[(sstaged + lane) % SW_SSEND_RING]);
+        dst[0] = sw_ld16_sys(reinterpret_cast<const int4*>(src));
+        dst[1] = sw_ld16_sys(reinterpret_cast<const int4*>(src) + 1);
+        dst[2] = sw_ld16_sys(reinterpret_cast<const int4*>(src) + 2);
+      }
+      __syncwarp();
+      if (ns) {
+        sstaged += ns;
+        if (lane == 0) {
+          __threadfence_block();
+          sh.send_tail = sstaged;
+          a.ctl->send_head = sstaged;
+          sh.active_clk = clock64();
+        }
+      }
       const long long now = clock64();
-      const bool idle = n == 0 && host_tail == staged && staged == sh.post_head && now - sh.active_clk > linger_clk;
+      const bool idle = n == 0 && ns == 0 && host_tail == staged && staged == sh.post_head && host_stail == sstaged &&
+                        sstaged == sh.send_done && now - sh.active_clk > linger_clk;
       if (stop || idle || now - clk0 > life_clk) {
         if (lane == 0) {
+          a.ctl->exit_reason = stop ? 1 : (idle ? 2 : 3);
+          a.ctl->life_us = static_cast<uint64_t>(now - clk0) / (a.clk_mhz ? a.clk_mhz : 1);
           __threadfence_block();
           sh.exit_req = 1;   // after the last staging store: the matcher drains what is staged and leaves
         }
         leaving = true;
       }
     }
+  } else if (warp == 2) {
+    // ================================================================ puts handed over by the host
+    // (the sender side of ucp_tag_send_nbx for small batches while this kernel is resident: no launch)
+    uint64_t i = sh.send_tail;
+    for (;;) {
+      while (sh.send_tail <= i) {
+        if (sh.helpers_exit) goto out;   // raised after the link warp has stopped staging: nothing is left behind
+        __nanosleep(20);
+      }
+      __threadfence_block();
+      const SwPutDesc d = sh.sends[i % SW_SSEND_RING];
+      uint8_t* slot = reinterpret_cast<uint8_t*>(d.dst);
+      sw_copy(slot + SW_SLOT_HDR, reinterpret_cast<const uint8_t*>(d.src), d.len, lane, 32);
+      __syncwarp();
+      if (lane == 0) {
+        sw_put_header(slot, d.tag, d.msg_len, d.seq, d.kind);
+        i++;
+        sh.send_done = i;
+        sw_st_release_sys(const_cast<uint64_t*>(&a.ctl->send_done), i);   // after the header: the host rings the doorbell on it
+      }
+      i = sw_shfl64(i, 0);
+    }
   } else {
     // ================================================================ helpers: larger eager payloads
-    const uint32_t h = warp - 2;
+    const uint32_t h = warp - 3;
     uint64_t i = h;
     uint32_t done = 0;
     for (;;) {
@@ -1095,6 +1151,7 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
 out:
   __syncthreads();
   if (threadIdx.x == 0) {
+    st->send_consumed = sh.send_done;
     __threadfence_system();
     a.ctl->exit_seq = a.launch_seq;
   }

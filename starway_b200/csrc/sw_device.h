@@ -226,6 +226,7 @@ struct SwMatchState {   // device memory, one per worker
   uint64_t post_consumed;  // receives taken from the post ring so far
   uint64_t cqr_alloc;      // rendezvous completion records allocated by pull CTAs (atomic)
   uint64_t cqr_head;       // device copy of the host's cursor into the rendezvous completion ring
+  uint64_t send_consumed;  // put descriptors taken from the send ring so far
 };
 
 constexpr uint32_t SW_UMETA_VALID = 1u << 31;
@@ -253,6 +254,7 @@ constexpr uint32_t SW_PULL_JOBS = 64;       // messages per pull batch
 constexpr uint32_t SW_MAP_SLOTS = 8192;     // device-resident (exporter, allocation) -> mapped base table
 constexpr uint32_t SW_MAP_PROBE = 32;       // one warp-wide probe
 constexpr uint32_t SW_INLINE_DELIVER = 256; // eager payloads up to this size are copied by the matcher warp itself
+constexpr uint32_t SW_SEND_RING = 64;       // host -> device: put descriptors executed by the resident control kernel
 
 enum : uint32_t { SW_POST_HOSTPATH = 1 };   // a rendezvous into this receive is copied by a host-launched kernel
 enum : uint64_t { SW_RTS_PINNED_SRC = 1 };  // SwRts::pad[0]: the source is pinned host memory
@@ -293,6 +295,8 @@ struct SwProgCtl {
   volatile uint64_t cq_head;                 // eager completion records consumed by the host
   volatile uint64_t cqr_head;                // rendezvous completion records consumed by the host
   volatile uint64_t hr_head;                 // host-path rendezvous records consumed by the host
+  volatile uint64_t send_tail;               // put descriptors written into the send ring so far
+  volatile uint64_t pad_s;
   alignas(64) volatile uint64_t stop;        // != 0: leave as soon as the state is consistent
   volatile uint64_t dead_mask;               // endpoints (bit = ring index) whose rendezvous go to the host
   volatile uint64_t host_epoch;              // bumped by the host; echoed in dev_epoch by a later iteration
@@ -307,6 +311,10 @@ struct SwProgCtl {
   volatile uint64_t err;                     // consistency errors seen by the matcher
   volatile uint64_t stalled;                 // a ring is blocked on the unexpected heap (needs new receives)
   volatile uint64_t iterations;
+  volatile uint64_t send_head;               // put descriptors taken from the send ring
+  volatile uint64_t send_done;               // put descriptors executed (slot written, header released)
+  volatile uint64_t exit_reason;             // why the last launch left: 1 host request, 2 silence (linger), 3 lifetime
+  volatile uint64_t life_us;                 // how long it ran
 };
 
 // ---- pull queue: rendezvous copies executed by the resident pull CTAs of the context

@@ -714,6 +714,8 @@ int launch_progress(stream_t, const ProgressLaunch* a) {
   ctl->n_unexp = st->u_count;
   ctl->stalled = stalled ? 1 : 0;
   ctl->iterations = ctl->iterations + 1;
+  ctl->exit_reason = 2;
+  ctl->life_us = 1;
   __atomic_store_n(&ctl->dev_epoch, epoch, __ATOMIC_RELEASE);
   __atomic_store_n(&ctl->exit_seq, a->launch_seq, __ATOMIC_RELEASE);
   return 0;

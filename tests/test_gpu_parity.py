@@ -415,7 +415,10 @@ def test_c_abi_direct_device_pointers(cuda_api, port):
     torch.cuda.synchronize()
     assert torch.equal(dst, src)
     st = ctx.stats()
-    assert st["bulk_tma_launches"] > 0 and st["put_launches"] > 0 and st["match_launches"] > 0
+    # the product kernels moved the data: puts (launched or executed by the resident control kernel), the
+    # control kernel (or, with resident=0, match launches), rendezvous copies by the pull CTAs or a bulk launch
+    assert st["put_launches"] + st["put_resident"] > 0 and st["prog_launches"] + st["match_launches"] > 0
+    assert st["pull_jobs"] + st["bulk_tma_launches"] > 0
 
 
 @pytest.mark.parametrize("size", [70000, (1 << 20) + 3, 32 << 20])
