@@ -209,6 +209,7 @@ def run_ours(args):
         payload_check = (f"asserted on every rank: {world} x {window} messages bit-exact vs the sending rank's regenerated sources")
         barrier()
         torch.cuda.synchronize()
+        warm_batches = ctx.stats()["pull_batches"]
         ctx.reset_stats()
         clocks = ClockSampler(local_rank)
         clocks.start()
@@ -251,7 +252,7 @@ def run_ours(args):
             await client.aclose()
             barrier()
             await server.aclose()
-            return value, ms, st, clk, float("nan"), step_bytes, {}
+            return value, ms, st, clk, float("nan"), step_bytes, {}, payload_check, warm_batches
         await timed_host(3)
         if world == 1:
             for s, d in zip(hsrc[0], hdst[0]):
@@ -286,9 +287,9 @@ def run_ours(args):
         await client.aclose()
         barrier()
         await server.aclose()
-        return value, ms, st, clk, e2e_value, step_bytes, e2e_diag, payload_check
+        return value, ms, st, clk, e2e_value, step_bytes, e2e_diag, payload_check, warm_batches
 
-    value, ms, st, clk, e2e_value, step_bytes, e2e_diag, payload_check = new_loop_runner()(main())
+    value, ms, st, clk, e2e_value, step_bytes, e2e_diag, payload_check, st0_batches = new_loop_runner()(main())
 
     # ---- roofline of the dominant kernel: the rendezvous copy.  On the resident path the copies are made by the
     #      pull CTAs (sw_pull_kernel), which stay on the GPU across many batches: the time base is the union of the
@@ -331,6 +332,12 @@ def run_ours(args):
         "launches": n_launches, "avg_launch_us": round(avg_ms * 1e3, 2),
         "payload_bytes_per_launch": int(payload_per_launch), "peak_source": peak_note,
     }
+    if st["pull_batches"]:
+        # per-batch phases of the pull CTAs (device timer; averages over the life of the context)
+        tot = max(1, st0_batches + st["pull_batches"])
+        roofline["batch_phases_us"] = {"published_to_first_claim": round(st["pull_pickup_ms"] * 1e3 / tot, 2),
+                                       "first_claim_to_last_chunk": round(st["pull_copy_ms"] * 1e3 / tot, 2),
+                                       "records_and_fin_words": round(st["pull_fin_ms"] * 1e3 / tot, 2)}
     gpu_launches = int(st["put_launches"] + st["prog_launches"] + st["pull_launches"] + st["match_launches"]
                        + st["deliver_launches"] + st["bulk_tma_launches"] + st["bulk_simt_launches"])
     if rank != 0:

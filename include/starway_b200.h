@@ -105,6 +105,8 @@ typedef struct sw_stats {
   uint64_t prog_exit_stop, prog_exit_idle, prog_exit_life; /* why control-kernel launches ended */
   double prog_life_ms;                                     /* total time control kernels were resident */
   uint64_t put_resident;                                   /* put batches executed by a resident control kernel (no launch) */
+  double pull_pickup_ms, pull_copy_ms, pull_fin_ms;        /* pull batches, summed since context creation: published -> first
+                                                              chunk claimed -> last chunk written -> records and FIN words out */
 } sw_stats;
 
 /* ---- library / context (reference Context, main.cpp:71-79) */

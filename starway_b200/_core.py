@@ -107,6 +107,9 @@ class SwStats(ctypes.Structure):
         ("prog_exit_life", ctypes.c_uint64),
         ("prog_life_ms", ctypes.c_double),
         ("put_resident", ctypes.c_uint64),
+        ("pull_pickup_ms", ctypes.c_double),
+        ("pull_copy_ms", ctypes.c_double),
+        ("pull_fin_ms", ctypes.c_double),
     ]
 
 

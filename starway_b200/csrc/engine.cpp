@@ -507,7 +507,7 @@ struct Worker {
   SwCqEnt* cq_ring = nullptr;
   SwCqEnt* cqr_ring = nullptr;
   SwHrEnt* hr_ring = nullptr;
-  SwPutDesc* send_ring = nullptr;   // put descriptors executed by the resident kernel (small batches, no launch)
+  SwSendEnt* send_ring = nullptr;   // puts executed by the resident kernel (small batches, no launch)
   uint64_t sends_written = 0;
   swgpu::stream_t s_ctl = nullptr;
   uint64_t prog_seq = 0;          // launches so far
@@ -671,7 +671,7 @@ struct Ctx {
   std::atomic<int64_t> opt_linger_us{150}, opt_max_life_us{2000}, opt_armed_ms{30}, opt_pull_ctas{0};
   // batches of at most this many sends of ONE worker whose control kernel is resident are executed by that
   // kernel (descriptor ring in pinned memory) instead of a put launch; 0: always launch
-  std::atomic<int64_t> opt_resident_puts{8};
+  std::atomic<int64_t> opt_resident_puts{24};
   SwPullQueue* pq = nullptr;
   SwMapEnt* map_tbl = nullptr;
   SwPullCtl* pull_ctl = nullptr;
@@ -854,7 +854,7 @@ bool worker_alloc_device(Ctx* c, Worker* w) {
     w->cq_ring = (SwCqEnt*)swgpu::host_alloc(sizeof(SwCqEnt) * SW_CQ_RING);
     w->cqr_ring = (SwCqEnt*)swgpu::host_alloc(sizeof(SwCqEnt) * SW_CQ_RING);
     w->hr_ring = (SwHrEnt*)swgpu::host_alloc(sizeof(SwHrEnt) * SW_HR_RING);
-    w->send_ring = (SwPutDesc*)swgpu::host_alloc(sizeof(SwPutDesc) * SW_SEND_RING);
+    w->send_ring = (SwSendEnt*)swgpu::host_alloc(sizeof(SwSendEnt) * SW_SEND_RING);
     w->s_ctl = swgpu::stream_create();
     if (!w->pctl || !w->post_ring || !w->cq_ring || !w->cqr_ring || !w->hr_ring || !w->send_ring || !w->s_ctl) {
       set_error(std::string("worker resident-path alloc: ") + swgpu::last_error());
@@ -1525,7 +1525,17 @@ bool pump_sends(Ctx* c) {
                w0->sends_written + n - __atomic_load_n(&w0->pctl->send_done, __ATOMIC_ACQUIRE) <= SW_SEND_RING;
     for (uint32_t i = 1; one && i < n; i++) one = b.items[i].op->w == w0;
     if (one) {
-      for (uint32_t i = 0; i < n; i++) w0->send_ring[(w0->sends_written + i) % SW_SEND_RING] = b.descs[i];
+      for (uint32_t i = 0; i < n; i++) {
+        SwSendEnt& e = w0->send_ring[(w0->sends_written + i) % SW_SEND_RING];
+        e.d = b.descs[i];
+        // RTS descriptors and small host payloads travel inside the entry: the kernel fetches descriptor and
+        // payload in one PCIe round trip
+        const bool staged_payload = e.d.src >= (uint64_t)(uintptr_t)b.stage && e.d.src < (uint64_t)(uintptr_t)b.stage + (uint64_t)PUT_BATCH * SW_SLOT_BYTES;
+        if (e.d.kind == SW_KIND_RTS || (staged_payload && e.d.len <= sizeof(e.inl))) {
+          memcpy(e.inl, (const void*)(uintptr_t)e.d.src, e.d.len);
+          e.d.src = 0;
+        }
+      }
       w0->sends_written += n;
       __atomic_store_n(&w0->pctl->send_tail, w0->sends_written, __ATOMIC_RELEASE);
       trace(c, "put_resident", n, bytes + h2d);
@@ -2288,6 +2298,9 @@ void pull_collect_stats(Ctx* c) {
   if (!c->pull_ctl) return;
   const uint64_t bytes = c->pull_ctl->bytes, busy = c->pull_ctl->busy_ns, batches = c->pull_ctl->batches, jobs = c->pull_ctl->jobs;
   std::lock_guard<std::mutex> lk(c->st_mu);
+  c->stats.pull_pickup_ms = (double)c->pull_ctl->pickup_ns * 1e-6;   // totals since the context was created
+  c->stats.pull_copy_ms = (double)c->pull_ctl->copy_ns * 1e-6;
+  c->stats.pull_fin_ms = (double)c->pull_ctl->fin_ns * 1e-6;
   c->stats.pull_bytes += bytes - c->pull_bytes_seen;
   c->stats.pull_busy_ms += (double)(busy - c->pull_busy_seen) * 1e-6;
   c->stats.pull_batches += batches - c->pull_batches_seen;

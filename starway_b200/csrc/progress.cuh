@@ -8,9 +8,9 @@
 //                                  straight to host-visible memory, hands rendezvous matches to the pull queue
 //                         warp 1   host link: polls the worker's control words and the post ring in pinned host
 //                                  memory (PCIe reads off the matcher's critical path), decides when to leave
-//                         warp 2   puts: small batches of sends the host hands over while the kernel is resident
+//                         warp 2-3 puts: small batches of sends the host hands over while the kernel is resident
 //                                  (payload + released header into the peer's ring, no launch on the sender side)
-//                         warp 3+  helpers: eager payloads above SW_INLINE_DELIVER bytes
+//                         warp 4+  helpers: eager payloads above SW_INLINE_DELIVER bytes
 //                       (replaces ucp_worker_progress + the matching inside ucp_tag_recv_nbx,
 //                        reference src/bindings/main.cpp:362,1127 and :404,1172)
 //   sw_pull_kernel      resident pull CTAs of the context (one elected thread each drives the cp.async.bulk
@@ -97,7 +97,7 @@ struct SwProgArgs {
   SwCqEnt* cq;               // pinned host, SW_CQ_RING entries: eager completions (index allocated by the matcher)
   SwCqEnt* cqr;              // pinned host, SW_CQ_RING entries: rendezvous completions (allocated by pull CTAs)
   SwHrEnt* hr;               // pinned host, SW_HR_RING entries
-  const SwPutDesc* sends;    // pinned host, SW_SEND_RING entries (payload sources / RTS descriptors they point at: pinned or device)
+  const SwSendEnt* sends;    // pinned host, SW_SEND_RING entries
   SwPullQueue* pq;           // device memory (nullptr: every rendezvous goes to the host)
   const SwMapEnt* map;       // device memory
   uint64_t ctx_uuid;
@@ -108,8 +108,9 @@ struct SwProgArgs {
 };
 
 constexpr uint32_t SW_PROG_THREADS = 256;
-constexpr uint32_t SW_PROG_HELPERS = SW_PROG_THREADS / 32 - 3;
-constexpr uint32_t SW_SSEND_RING = 16;
+constexpr uint32_t SW_PROG_PUTTERS = 2;
+constexpr uint32_t SW_PROG_HELPERS = SW_PROG_THREADS / 32 - 2 - SW_PROG_PUTTERS;
+constexpr uint32_t SW_SSEND_RING = 32;
 constexpr uint32_t SW_DJOB_RING = 64;
 constexpr uint32_t SW_SPOST_RING = 64;
 constexpr uint32_t SW_PEND_RING = 128;
@@ -128,7 +129,8 @@ struct SwPend {      // something that may only be released once helper job `job
 
 struct SwProgShared {
   SwPostEnt posts[SW_SPOST_RING];
-  SwPutDesc sends[SW_SSEND_RING];
+  SwSendEnt sends[SW_SSEND_RING];
+  uint64_t fin_ptr[SW_MAX_EPS];
   SwDJob jobs[SW_DJOB_RING];
   SwPend pend[SW_PEND_RING];
   uint64_t ring_base[SW_MAX_EPS];
@@ -145,7 +147,9 @@ struct SwProgShared {
   volatile uint64_t post_head;    // consumed by the matcher
   volatile uint64_t job_tail;     // jobs emitted by the matcher
   volatile uint64_t send_tail;    // put descriptors staged by the link warp
-  volatile uint64_t send_done;    // put descriptors executed by the put warp
+  volatile uint64_t send_done;    // every put below this index has been executed (published by the link warp)
+  volatile uint64_t send_base;    // index of the first put of this launch
+  volatile uint32_t put_done[SW_PROG_PUTTERS];   // puts executed by each put warp in this launch
   volatile uint64_t cq_head, cqr_head, hr_head, dead_mask, host_epoch;   // copies of the host's words
   volatile long long active_clk;  // last time the matcher did something
   volatile uint32_t helper_done[SW_PROG_HELPERS];
@@ -305,6 +309,7 @@ __device__ __forceinline__ void sw_res_flush_pull(SwMatchState* st, SwProgShared
     s->done_chunks = 0;
     s->retire = 0;
     s->t_first = 0;
+    s->t_pub = sw_globaltimer();
     s->cqr_ring = reinterpret_cast<uint64_t>(a.cqr);
     s->cqr_alloc = reinterpret_cast<uint64_t>(&st->cqr_alloc);
     s->cqr_head_dev = reinterpret_cast<uint64_t>(&st->cqr_head);
@@ -357,7 +362,7 @@ __device__ __forceinline__ void sw_res_rts(SwMatchState* st, SwProgShared& sh, c
   uint64_t src = 0;
   const uint32_t ep = epf & ((1u << SW_EP_IDX_BITS) - 1);   // ring index; the rest of the field is its generation
   bool device_path = a.pq != nullptr && a.pull_ctas != 0 && !trunc && !(pflags & SW_POST_HOSTPATH) &&
-                     !(rflags & SW_RTS_PINNED_SRC) && !((sh.dead_mask >> ep) & 1) && st->fin_ptr[ep] != 0 &&
+                     !(rflags & SW_RTS_PINNED_SRC) && !((sh.dead_mask >> ep) & 1) && sh.fin_ptr[ep] != 0 &&
                      (epf >> SW_EP_IDX_BITS) == sh.ring_gen[ep];
   if (device_path) {
     if (uuid == a.ctx_uuid && src_pid == a.pid) {
@@ -379,7 +384,7 @@ __device__ __forceinline__ void sw_res_rts(SwMatchState* st, SwProgShared& sh, c
       m.op_id = op;
       m.tag = stag;
       m.len = msg_len;
-      m.fin_addr = st->fin_ptr[ep] + 8ull * (send_seq % SW_FIN_SLOTS);
+      m.fin_addr = sh.fin_ptr[ep] + 8ull * (send_seq % SW_FIN_SLOTS);
       m.fin_val = (send_seq << 2) | 1;
       sh.pb_meta[j] = m;
     }
@@ -632,7 +637,73 @@ __device__ __forceinline__ uint32_t sw_res_arrivals(SwMatchState* __restrict__ s
     const uint64_t copy_len = trunc ? 0 : a_len;
     const bool small = in_k && !a_rts && copy_len <= SW_INLINE_DELIVER;
     const uint32_t small_m = __ballot_sync(0xffffffffu, small);
-    const uint32_t other_m = __ballot_sync(0xffffffffu, in_k && !small);
+    // rendezvous requests the pull CTAs can serve (source in this process or already in the mapping table, 16 B
+    // alignment): one lane per request builds its entry of the pull batch
+    bool rfast = false;
+    uint64_t r_src = 0, r_seq = 0;
+    if (in_k && a_rts && !trunc && a.pq != nullptr && a.pull_ctas != 0 && !((w_valid >> 8) & SW_POST_HOSTPATH) &&
+        !((sh.dead_mask >> ep) & 1) && sh.fin_ptr[ep] != 0) {
+      const uint64_t rp = a_slot + SW_SLOT_HDR;   // the SwRts in the slot
+      const int4 q0 = sw_ld16(reinterpret_cast<const void*>(rp + 64));    // alloc_base, alloc_size
+      const int4 q1 = sw_ld16(reinterpret_cast<const void*>(rp + 80));    // src_ptr, send_seq
+      const int4 q2 = sw_ld16(reinterpret_cast<const void*>(rp + 96));    // ctx_uuid, src_pid | src_dev
+      const int4 q3 = sw_ld16(reinterpret_cast<const void*>(rp + 112));   // flags, buffer id
+      auto u64of = [](int lo, int hi) { return (static_cast<uint64_t>(static_cast<uint32_t>(hi)) << 32) | static_cast<uint32_t>(lo); };
+      const uint64_t alloc_base = u64of(q0.x, q0.y), alloc_size = u64of(q0.z, q0.w), src_ptr = u64of(q1.x, q1.y);
+      const uint64_t uuid = u64of(q2.x, q2.y), rflags = u64of(q3.x, q3.y), buf_id = u64of(q3.z, q3.w);
+      r_seq = u64of(q1.z, q1.w);
+      if (!(rflags & SW_RTS_PINNED_SRC)) {
+        if (uuid == a.ctx_uuid && static_cast<uint32_t>(q2.z) == a.pid) {
+          r_src = src_ptr;
+        } else if (a.map && buf_id && src_ptr >= alloc_base && src_ptr - alloc_base + a_len <= alloc_size) {
+          const uint32_t home = sw_map_home(uuid, buf_id);
+          for (uint32_t k = 0; k < SW_MAP_PROBE; k++) {
+            const SwMapEnt* me = &a.map[(home + k) & (SW_MAP_SLOTS - 1)];
+            const int4 key = sw_ld16(me);
+            const uint64_t e_buf = u64of(key.z, key.w);
+            if (!e_buf) break;   // entries are only ever added: an empty slot ends the probe
+            if (e_buf == buf_id && u64of(key.x, key.y) == uuid) {
+              const int4 val = sw_ld16(reinterpret_cast<const int4*>(me) + 1);
+              if (u64of(val.x, val.y) == alloc_base) r_src = u64of(val.z, val.w) + (src_ptr - alloc_base);
+              break;
+            }
+          }
+        }
+      }
+      rfast = r_src != 0 && ((r_src | w_buf) & 15) == 0;
+    }
+    const uint32_t rfast_m = __ballot_sync(0xffffffffu, rfast);
+    if (rfast_m) {
+      const uint32_t cnt = __popc(rfast_m);
+      if (c.pb_n + cnt > SW_PULL_JOBS) sw_res_flush_pull(st, sh, a, c, lane);
+      // cumulative body bytes: inclusive scan over the participating lanes
+      const uint64_t body = rfast ? (a_len & ~15ull) : 0;
+      uint64_t scan = body;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t up = sw_shfl64(scan, static_cast<int>(lane) - o < 0 ? static_cast<int>(lane) : static_cast<int>(lane) - o);
+        if (static_cast<int>(lane) >= o) scan += up;
+      }
+      const uint64_t base_end = c.pb_n ? sh.pb_end[c.pb_n - 1] : 0;
+      __syncwarp();
+      if (rfast) {
+        const uint32_t j = c.pb_n + __popc(rfast_m & lt);
+        sh.pb_end[j] = base_end + scan;
+        sh.pb_src[j] = r_src;
+        sh.pb_dst[j] = w_buf;
+        SwPullMeta m;
+        m.op_id = w_op;
+        m.tag = a_tag;
+        m.len = a_len;
+        m.fin_addr = sh.fin_ptr[ep] + 8ull * (r_seq % SW_FIN_SLOTS);
+        m.fin_val = (r_seq << 2) | 1;
+        sh.pb_meta[j] = m;
+      }
+      c.pb_n += cnt;
+      c.pull_jobs += cnt;
+      __syncwarp();
+    }
+    const uint32_t other_m = __ballot_sync(0xffffffffu, in_k && !small && !rfast);
     // small eager payloads: one lane per message, completion records in pairing order
     const uint32_t n_small = __popc(small_m);
     if (n_small) {
@@ -879,13 +950,15 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
     sh.ring_base[e] = st->ring_base[e];
     sh.ring_mask[e] = st->ring_slots[e] ? st->ring_slots[e] - 1 : 0;
     sh.ring_gen[e] = st->ring_gen[e] & SW_EP_GEN_MASK;
+    sh.fin_ptr[e] = st->fin_ptr[e];
     sh.cons[e] = st->ring_cons[e];
     sh.credit[e] = st->ring_cons[e];
     sh.pend_cnt[e] = 0;
   }
   if (threadIdx.x == 0) {
     sh.post_tail = sh.post_head = st->post_consumed;
-    sh.send_tail = sh.send_done = st->send_consumed;
+    sh.send_tail = sh.send_done = sh.send_base = st->send_consumed;
+    for (uint32_t k = 0; k < SW_PROG_PUTTERS; k++) sh.put_done[k] = 0;
     sh.job_tail = 0;
     sh.cq_head = a.ctl->cq_head;
     sh.cqr_head = a.ctl->cqr_head;
@@ -1042,8 +1115,19 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
       host_stail = sw_shfl64(host_stail, 0);
       stop = sw_shfl64(stop, 0);
       if (leaving) {
-        // the matcher winds down (it may still need room in the completion rings): keep the host's cursors fresh
-        if (sh.helpers_exit) break;
+        // the matcher winds down (it may still need room in the completion rings): keep the host's cursors fresh;
+        // the put warps finish what is staged
+        uint64_t v = ~0ull;
+        for (uint32_t k = 0; k < SW_PROG_PUTTERS; k++) {
+          const uint64_t nxt = sh.send_base + k + static_cast<uint64_t>(sh.put_done[k]) * SW_PROG_PUTTERS;
+          v = nxt < v ? nxt : v;
+        }
+        if (v > sstaged) v = sstaged;
+        if (v != sh.send_done && lane == 0) {
+          sh.send_done = v;
+          sw_st_release_sys(const_cast<uint64_t*>(&a.ctl->send_done), v);
+        }
+        if (sh.helpers_exit && v == sstaged) break;
         continue;
       }
       // stage new receives: lane L copies entry (staged + L)
@@ -1068,16 +1152,29 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
           a.ctl->post_head = staged;   // the host may reuse these ring entries
         }
       }
-      // put descriptors for the put warp: lane L copies descriptor (sstaged + L)
+      // puts for the put warps: lane L copies entry (sstaged + L), descriptor and inline payload in one round trip
+      uint64_t sdone = sh.send_base;
+      {
+        uint64_t v = ~0ull;
+        for (uint32_t k = 0; k < SW_PROG_PUTTERS; k++) {
+          const uint64_t nxt = sh.send_base + k + static_cast<uint64_t>(sh.put_done[k]) * SW_PROG_PUTTERS;
+          v = nxt < v ? nxt : v;
+        }
+        sdone = v < sstaged ? v : sstaged;   // first put that has not been executed
+      }
+      if (sdone != sh.send_done && lane == 0) {
+        sh.send_done = sdone;
+        sw_st_release_sys(const_cast<uint64_t*>(&a.ctl->send_done), sdone);   // headers released before: the host rings the doorbell on it
+        sh.active_clk = clock64();
+      }
       uint64_t ns = host_stail - sstaged;
-      const uint64_t sroom = SW_SSEND_RING - (sstaged - sh.send_done);
+      const uint64_t sroom = SW_SSEND_RING - (sstaged - sdone);
       if (ns > sroom) ns = sroom;
       if (lane < ns) {
-        const SwPutDesc* src = &a.sends[(sstaged + lane) % SW_SEND_RING];
+        const int4* src = reinterpret_cast<const int4*>(&a.sends[(sstaged + lane) % SW_SEND_RING]);
         int4* dst = reinterpret_cast<int4*>(&sh.sends[(sstaged + lane) % SW_SSEND_RING]);
-        dst[0] = sw_ld16_sys(reinterpret_cast<const int4*>(src));
-        dst[1] = sw_ld16_sys(reinterpret_cast<const int4*>(src) + 1);
-        dst[2] = sw_ld16_sys(reinterpret_cast<const int4*>(src) + 2);
+#pragma unroll
+        for (int q = 0; q < static_cast<int>(sizeof(SwSendEnt) / 16); q++) dst[q] = sw_ld16_sys(src + q);
       }
       __syncwarp();
       if (ns) {
@@ -1091,7 +1188,7 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
       }
       const long long now = clock64();
       const bool idle = n == 0 && ns == 0 && host_tail == staged && staged == sh.post_head && host_stail == sstaged &&
-                        sstaged == sh.send_done && now - sh.active_clk > linger_clk;
+                        sstaged == sdone && now - sh.active_clk > linger_clk;
       if (stop || idle || now - clk0 > life_clk) {
         if (lane == 0) {
           a.ctl->exit_reason = stop ? 1 : (idle ? 2 : 3);
@@ -1102,31 +1199,39 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
         leaving = true;
       }
     }
-  } else if (warp == 2) {
+  } else if (warp < 2 + SW_PROG_PUTTERS) {
     // ================================================================ puts handed over by the host
     // (the sender side of ucp_tag_send_nbx for small batches while this kernel is resident: no launch)
-    uint64_t i = sh.send_tail;
+    const uint32_t pw = warp - 2;
+    uint64_t i = sh.send_base + pw;
+    uint32_t done = 0;
     for (;;) {
       while (sh.send_tail <= i) {
         if (sh.helpers_exit) goto out;   // raised after the link warp has stopped staging: nothing is left behind
         __nanosleep(20);
       }
       __threadfence_block();
-      const SwPutDesc d = sh.sends[i % SW_SSEND_RING];
+      const SwSendEnt* e = &sh.sends[i % SW_SSEND_RING];
+      const SwPutDesc d = e->d;
       uint8_t* slot = reinterpret_cast<uint8_t*>(d.dst);
-      sw_copy(slot + SW_SLOT_HDR, reinterpret_cast<const uint8_t*>(d.src), d.len, lane, 32);
+      if (d.src) {
+        sw_copy(slot + SW_SLOT_HDR, reinterpret_cast<const uint8_t*>(d.src), d.len, lane, 32);
+      } else if (lane * 16 < d.len) {
+        // inline payload (<= 128 B, staged in shared memory): whole 16 B units, the slot has room for the round-up
+        sw_st16(slot + SW_SLOT_HDR + 16 * lane, reinterpret_cast<const int4*>(e->inl)[lane]);
+      }
       __syncwarp();
       if (lane == 0) {
         sw_put_header(slot, d.tag, d.msg_len, d.seq, d.kind);
-        i++;
-        sh.send_done = i;
-        sw_st_release_sys(const_cast<uint64_t*>(&a.ctl->send_done), i);   // after the header: the host rings the doorbell on it
+        __threadfence_block();
+        sh.put_done[pw] = ++done;
       }
-      i = sw_shfl64(i, 0);
+      __syncwarp();
+      i += SW_PROG_PUTTERS;
     }
   } else {
     // ================================================================ helpers: larger eager payloads
-    const uint32_t h = warp - 3;
+    const uint32_t h = warp - 2 - SW_PROG_PUTTERS;
     uint64_t i = h;
     uint32_t done = 0;
     for (;;) {
@@ -1169,6 +1274,7 @@ struct SwPullArgs {
 // the CTA that completed the last chunk of a batch: tails, completion records, FIN words, statistics
 __device__ __forceinline__ void sw_pull_finalize(SwPullQueue* q, SwPullSlot* s) {
   const uint32_t n = s->njobs;
+  const uint64_t t_copied = sw_globaltimer();
   for (uint32_t j = 0; j < n; j++) {
     const uint64_t len = s->meta[j].len, body = len & ~15ull;
     for (uint64_t k = body; k < len; k++)
@@ -1205,6 +1311,9 @@ __device__ __forceinline__ void sw_pull_finalize(SwPullQueue* q, SwPullSlot* s) 
   atomicAdd(reinterpret_cast<unsigned long long*>(&q->bytes), static_cast<unsigned long long>(s->total));
   atomicAdd(reinterpret_cast<unsigned long long*>(&q->batches), 1ull);
   atomicAdd(reinterpret_cast<unsigned long long*>(&q->jobs), static_cast<unsigned long long>(n));
+  if (s->t_pub && t0 >= s->t_pub) atomicAdd(reinterpret_cast<unsigned long long*>(&q->pickup_ns), static_cast<unsigned long long>(t0 - s->t_pub));
+  if (t_copied >= t0) atomicAdd(reinterpret_cast<unsigned long long*>(&q->copy_ns), static_cast<unsigned long long>(t_copied - t0));
+  atomicAdd(reinterpret_cast<unsigned long long*>(&q->fin_ns), static_cast<unsigned long long>(sw_globaltimer() - t_copied));
 }
 
 // every CTA leaves a batch once (no more chunks for it), the finalizer once more: the last of them frees the slot
@@ -1406,6 +1515,9 @@ __global__ void __launch_bounds__(32) sw_pull_kernel(const __grid_constant__ SwP
       a.ctl->busy_ns = q->busy_ns;
       a.ctl->batches = q->batches;
       a.ctl->jobs = q->jobs;
+      a.ctl->pickup_ns = q->pickup_ns;
+      a.ctl->copy_ns = q->copy_ns;
+      a.ctl->fin_ns = q->fin_ns;
       __threadfence_system();
       a.ctl->exited = a.launch_seq;
     }

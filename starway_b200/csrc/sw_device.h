@@ -259,6 +259,12 @@ constexpr uint32_t SW_SEND_RING = 64;       // host -> device: put descriptors e
 enum : uint32_t { SW_POST_HOSTPATH = 1 };   // a rendezvous into this receive is copied by a host-launched kernel
 enum : uint64_t { SW_RTS_PINNED_SRC = 1 };  // SwRts::pad[0]: the source is pinned host memory
 
+struct SwSendEnt {   // pinned host: one put for the resident control kernel of the sending worker
+  SwPutDesc d;       // d.src == 0: the payload (<= 128 B: an RTS descriptor, a small host payload) is in `inl`
+  uint8_t inl[128];
+};
+static_assert(sizeof(SwSendEnt) == 176, "SwSendEnt layout");
+
 struct SwPostEnt {   // pinned host: one posted receive on its way to the control kernel
   uint64_t tag, mask, buf, cap, op_id;
   uint32_t flags, pad;
@@ -330,6 +336,7 @@ struct SwPullSlot {
   uint64_t chunk_bytes, total;
   uint32_t next_chunk, done_chunks, retire, pad2;
   uint64_t t_first;       // globaltimer of the first claim
+  uint64_t t_pub;         // globaltimer when the matcher published the batch
   // where the completion records of this batch go (the receiving worker's rendezvous CQ)
   uint64_t cqr_ring, cqr_alloc, cqr_head_dev, cqr_head_host;
   uint64_t end[SW_PULL_JOBS], src[SW_PULL_JOBS], dst[SW_PULL_JOBS];
@@ -339,13 +346,14 @@ struct SwPullQueue {      // device memory, one per context
   uint64_t alloc;         // next ticket (atomic)
   uint64_t start;         // first ticket the next pull launch looks at
   uint64_t bytes, busy_ns, last_end, batches, jobs;   // statistics (roofline: bytes / busy_ns)
-  uint64_t pad;
+  uint64_t pickup_ns, copy_ns, fin_ns;                // per-batch phases: published -> first claim -> last chunk -> records out
   SwPullSlot slot[SW_PULL_SLOTS];
 };
 struct SwPullCtl {        // pinned host, one per context
   alignas(64) volatile uint64_t stop;     // host -> kernel: publish an EXIT batch
   alignas(64) volatile uint64_t exited;   // kernel -> host: launch number of the last launch whose CTA 0 left
   volatile uint64_t bytes, busy_ns, batches, jobs;   // copies of the queue statistics at exit
+  volatile uint64_t pickup_ns, copy_ns, fin_ns;
 };
 
 // ---------------------------------------------------------------- bulk copy input
