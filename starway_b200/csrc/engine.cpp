@@ -515,7 +515,7 @@ struct Worker {
   bool cfg_dirty = false;         // ring set changed: the running kernel must leave and be relaunched
   uint64_t posts_written = 0, cq_head = 0, cqr_head = 0, hr_head = 0;
   uint64_t host_epoch = 0;
-  double last_activity = 0, prog_launched_at = 0;
+  double last_activity = 0, prog_launched_at = 0, last_send = -1;
   uint32_t prog_spins = 0;
   // a launch that ended with a ring blocked on the unexpected heap is repeated only when something changed
   bool prog_stalled = false;
@@ -552,6 +552,9 @@ struct PutBlock {
   // send_done counter has passed res_end
   Worker* res_worker = nullptr;
   uint64_t res_end = 0;
+  // every block launches on a stream of its own: put kernels are latency-bound (a handful of stores behind a
+  // launch), so consecutive batches overlap instead of queueing behind each other; blocks still retire in order
+  swgpu::stream_t s = nullptr;
   std::vector<PutItem> items;
 };
 struct BulkBlock {
@@ -1438,10 +1441,10 @@ bool pump_sends(Ctx* c) {
                                             std::min<uint64_t>(STAGE_SEG_BYTES, body - off), 0};
                 stream_ordered = true;
                 if (op->len > body)
-                  swgpu::memcpy_h2d((uint8_t*)op->dev_staging + body, op->ptr + body, op->len - body, c->s_put);
+                  swgpu::memcpy_h2d((uint8_t*)op->dev_staging + body, op->ptr + body, op->len - body, b.s);
               } else {
                 trace(c, "h2d_enqueue", op->len);
-                swgpu::memcpy_h2d(op->dev_staging, op->ptr, op->len, c->s_put);
+                swgpu::memcpy_h2d(op->dev_staging, op->ptr, op->len, b.s);
                 stream_ordered = true;   // the RTS may only become visible after this copy: needs the put launch behind it
               }
               h2d += op->len;
@@ -1555,21 +1558,21 @@ bool pump_sends(Ctx* c) {
     }
   }
   b.timed = c->opt_profile.load() >= 2;
-  if (b.timed) swgpu::event_record(b.ev_start, c->s_put);
+  if (b.timed) swgpu::event_record(b.ev_start, b.s);
   if (b.nsegs) {
     swgpu::BulkTuning up{0, 8, 24576, 1, 0};
     trace(c, "stage_upload_launch", b.nsegs, staged_bytes);
-    if (swgpu::launch_bulk(c->s_put, b.segs, b.nsegs, &up) != 0)
+    if (swgpu::launch_bulk(b.s, b.segs, b.nsegs, &up) != 0)
       fprintf(stderr, "starway_b200: staging upload launch failed: %s\n", swgpu::last_error());
   }
   trace(c, "put_launch", n, bytes + h2d);
   swgpu::DoneFlag df{b.done, ++c->flag_seq};
-  const int lr = swgpu::launch_put(c->s_put, b.descs, n, (b.timed || !c->opt_done_flags.load()) ? nullptr : &df);
+  const int lr = swgpu::launch_put(b.s, b.descs, n, (b.timed || !c->opt_done_flags.load()) ? nullptr : &df);
   if (lr < 0) fprintf(stderr, "starway_b200: put launch failed: %s\n", swgpu::last_error());
   b.flag_mode = lr == 1;
   b.done_seq = df.value;
   b.spins = 0;
-  if (!b.flag_mode) swgpu::event_record(b.timed ? b.ev : b.ev_fast, c->s_put);
+  if (!b.flag_mode) swgpu::event_record(b.timed ? b.ev : b.ev_fast, b.s);
   b.busy = true;
   c->put_tail++;
   std::lock_guard<std::mutex> lk(c->st_mu);
@@ -1591,7 +1594,7 @@ bool poll_puts(Ctx* c) {
     } else if (b.flag_mode) {
       q = __atomic_load_n(b.done, __ATOMIC_ACQUIRE) == b.done_seq ? 0 : 1;
       // a faulted launch never writes its flag: look at the stream now and then
-      if (q == 1 && (++b.spins & 0x3FF) == 0 && swgpu::stream_query(c->s_put) < 0) q = -1;
+      if (q == 1 && (++b.spins & 0x3FF) == 0 && swgpu::stream_query(b.s) < 0) q = -1;
     } else {
       q = swgpu::event_query(b.timed ? b.ev : b.ev_fast);
     }
@@ -2246,8 +2249,12 @@ bool pump_progress(Ctx* c, Worker* w) {
   if (w->prog_stalled && w->stall_posts == w->posts_written && w->stall_seen == unseen) work = false;
   work |= sends_pending;   // puts handed to a kernel that left before it took them
   const double now = now_s();
-  const bool armed = swgpu::resident_lingers() && w->close_phase == 0 && !w->recvs.empty() &&
-                     now - w->last_activity < (double)c->opt_armed_ms.load() * 1e-3;
+  if (w->last_send == 0) w->last_send = now;   // a send was queued since the last look
+  // armed: receives are outstanding and the connection was active recently, or the worker has been sending within
+  // the last millisecond (its next small batch of puts then needs no launch)
+  const bool armed = swgpu::resident_lingers() && w->close_phase == 0 &&
+                     ((!w->recvs.empty() && now - w->last_activity < (double)c->opt_armed_ms.load() * 1e-3) ||
+                      (c->opt_resident_puts.load() > 0 && now - w->last_send < 1e-3));
   if (!work && !armed) return any;
   swgpu::ProgressLaunch a;
   a.st = w->mstate;
@@ -2759,6 +2766,7 @@ void drain_sq(Ctx* c) {
         op->sseq = op->ep->next_sseq++;
         op->ep->out_seqs.insert(op->sseq);
         op->ep->sendq.push_back(op);
+        w->last_send = 0;   // stamped by pump_progress (one clock read per loop, not per op)
         break;
       }
       case SQ_RECV: {
@@ -3041,7 +3049,8 @@ sw_ctx* sw_ctx_create(int device) {
     b.ev_fast = swgpu::event_create(0);
     b.done = (uint64_t*)swgpu::host_alloc(64);
     if (b.done) *b.done = 0;
-    ok = b.descs && b.rts && b.stage && b.segs && b.ev && b.ev_start && b.ev_fast && b.done;
+    b.s = i == 0 ? c->s_put : swgpu::stream_create();
+    ok = b.descs && b.rts && b.stage && b.segs && b.ev && b.ev_start && b.ev_fast && b.done && b.s;
   }
   for (int i = 0; ok && i < N_BULK_BLOCKS; i++) {
     BulkBlock& b = c->bulk_blocks[i];
@@ -3156,6 +3165,7 @@ void sw_ctx_destroy(sw_ctx* ctx) {
     swgpu::host_free(b.stage);
     swgpu::host_free(b.segs);
     swgpu::host_free(b.done);
+    if (i > 0 && b.s) swgpu::stream_destroy(b.s);
     if (b.ev) swgpu::event_destroy(b.ev);
     if (b.ev_start) swgpu::event_destroy(b.ev_start);
     if (b.ev_fast) swgpu::event_destroy(b.ev_fast);

@@ -1271,64 +1271,179 @@ struct SwPullArgs {
   uint32_t linger_us, max_life_us, clk_mhz, pad;
 };
 
-// the CTA that completed the last chunk of a batch: tails, completion records, FIN words, statistics
-__device__ __forceinline__ void sw_pull_finalize(SwPullQueue* q, SwPullSlot* s) {
+// ---- completion of a batch (CTA 0 of the pull kernel, a full warp, no copy traffic of its own): tails, completion
+// records into the receiving worker's rendezvous CQ, FIN words into the senders' control blocks, statistics.
+// The copy CTAs signal with plain atomics (their bulk stores have completed when they do); the fences are here.
+__device__ __forceinline__ void sw_pull_finalize(SwPullQueue* q, SwPullSlot* sp, uint32_t lane) {
+  volatile SwPullSlot* s = sp;   // written by a matcher on another SM: never from this SM's L1
   const uint32_t n = s->njobs;
   const uint64_t t_copied = sw_globaltimer();
-  for (uint32_t j = 0; j < n; j++) {
+  for (uint32_t j = lane; j < n; j += 32) {
     const uint64_t len = s->meta[j].len, body = len & ~15ull;
     for (uint64_t k = body; k < len; k++)
       reinterpret_cast<uint8_t*>(s->dst[j])[k] = reinterpret_cast<const volatile uint8_t*>(s->src[j])[k];
   }
-  __threadfence_system();   // every chunk of the batch (released by its CTA's atomic) and the tails, before the records
+  __threadfence_system();   // the chunks of the batch (complete before their CTAs counted them) and the tails, before the records
+  __syncwarp();
   if (n) {
     SwCqEnt* ring = reinterpret_cast<SwCqEnt*>(s->cqr_ring);
-    const uint64_t base = atomicAdd(reinterpret_cast<unsigned long long*>(s->cqr_alloc), static_cast<unsigned long long>(n));
-    // room: the device copy of the host's cursor is refreshed by the worker's control kernel; when that one is
-    // not running, read the host's word itself
-    while (base + n - sw_ld_relaxed_sys(reinterpret_cast<const void*>(s->cqr_head_dev)) > SW_CQ_RING) {
-      const uint64_t hh = sw_ld_relaxed_sys(reinterpret_cast<const void*>(s->cqr_head_host));
-      if (base + n - hh <= SW_CQ_RING) break;
-      __nanosleep(500);
+    uint64_t base = 0;
+    if (lane == 0) {
+      base = atomicAdd(reinterpret_cast<unsigned long long*>(s->cqr_alloc), static_cast<unsigned long long>(n));
+      // room: the device copy of the host's cursor is refreshed by the worker's control kernel; when that one is
+      // not running, read the host's word itself
+      while (base + n - sw_ld_relaxed_sys(reinterpret_cast<const void*>(s->cqr_head_dev)) > SW_CQ_RING) {
+        const uint64_t hh = sw_ld_relaxed_sys(reinterpret_cast<const void*>(s->cqr_head_host));
+        if (base + n - hh <= SW_CQ_RING) break;
+        __nanosleep(500);
+      }
     }
-    for (uint32_t j = 0; j < n; j++) {
+    base = sw_shfl64(base, 0);
+    for (uint32_t j = lane; j < n; j += 32) {
       SwCqEnt* e = &ring[(base + j) % SW_CQ_RING];
       e->op_id = s->meta[j].op_id;
       e->tag = s->meta[j].tag;
       e->len = s->meta[j].len;
     }
     __threadfence_system();
-    for (uint32_t j = 0; j < n; j++) {
+    for (uint32_t j = lane; j < n; j += 32) {
       const uint64_t idx = base + j;
       sw_st_relaxed_sys(&ring[idx % SW_CQ_RING].status, static_cast<uint64_t>(sw_ring_pass(idx, SW_CQ_RING)) << 32);
       if (s->meta[j].fin_addr) sw_st_relaxed_sys(reinterpret_cast<void*>(s->meta[j].fin_addr), s->meta[j].fin_val);
     }
   }
-  // statistics: bytes and the union of the batches' active intervals
-  const uint64_t t1 = sw_globaltimer(), t0 = s->t_first ? s->t_first : t1;
-  const uint64_t prev = atomicMax(reinterpret_cast<unsigned long long*>(&q->last_end), static_cast<unsigned long long>(t1));
-  if (t1 > prev) atomicAdd(reinterpret_cast<unsigned long long*>(&q->busy_ns), static_cast<unsigned long long>(t1 - (t0 > prev ? t0 : prev)));
-  atomicAdd(reinterpret_cast<unsigned long long*>(&q->bytes), static_cast<unsigned long long>(s->total));
-  atomicAdd(reinterpret_cast<unsigned long long*>(&q->batches), 1ull);
-  atomicAdd(reinterpret_cast<unsigned long long*>(&q->jobs), static_cast<unsigned long long>(n));
-  if (s->t_pub && t0 >= s->t_pub) atomicAdd(reinterpret_cast<unsigned long long*>(&q->pickup_ns), static_cast<unsigned long long>(t0 - s->t_pub));
-  if (t_copied >= t0) atomicAdd(reinterpret_cast<unsigned long long*>(&q->copy_ns), static_cast<unsigned long long>(t_copied - t0));
-  atomicAdd(reinterpret_cast<unsigned long long*>(&q->fin_ns), static_cast<unsigned long long>(sw_globaltimer() - t_copied));
+  __syncwarp();
+  if (lane == 0) {
+    // statistics: bytes and the union of the batches' active intervals
+    const uint64_t t1 = sw_globaltimer(), t0 = s->t_first ? s->t_first : t_copied;
+    if (t1 > q->last_end) {   // (only this warp writes the statistics)
+      q->busy_ns += t1 - (t0 > q->last_end ? t0 : q->last_end);
+      q->last_end = t1;
+    }
+    q->bytes += s->total;
+    q->batches += 1;
+    q->jobs += n;
+    if (s->t_pub && t0 >= s->t_pub) q->pickup_ns += t0 - s->t_pub;
+    if (t_copied >= t0) q->copy_ns += t_copied - t0;
+    q->fin_ns += t1 - t_copied;
+  }
 }
 
-// every CTA leaves a batch once (no more chunks for it), the finalizer once more: the last of them frees the slot
+// A slot is free again when every copy CTA has left the batch (no more chunks for it) and CTA 0 has completed it.
 __device__ __forceinline__ void sw_pull_retire(SwPullSlot* s, uint64_t ticket) {
-  __threadfence();
   const uint32_t r = atomicAdd(&s->retire, 1u) + 1;
-  if (r == gridDim.x + 1) sw_st_release_gpu(&s->free_seq, ticket + 1);
+  if (r == gridDim.x) sw_st_release_gpu(&s->free_seq, ticket + 1);
 }
 
 __global__ void __launch_bounds__(32) sw_pull_kernel(const __grid_constant__ SwPullArgs a) {
   extern __shared__ __align__(128) uint8_t sw_smem[];
   __shared__ __align__(8) uint64_t full[SW_BULK_MAX_STAGES];
   __shared__ uint64_t s_end[SW_PULL_JOBS], s_src[SW_PULL_JOBS], s_dst[SW_PULL_JOBS];
-  if (threadIdx.x != 0) return;
   SwPullQueue* q = a.q;
+  const uint64_t first = sw_ld_acquire_gpu(&q->start);   // first ticket of this launch
+  const long long clk0 = clock64();
+  const long long linger_clk = static_cast<long long>(a.linger_us) * a.clk_mhz;
+  const long long life_clk = static_cast<long long>(a.max_life_us) * a.clk_mhz;
+
+  if (blockIdx.x == 0) {
+    // ================================================================ CTA 0: completions, and when the grid leaves
+    const uint32_t lane = threadIdx.x;
+    uint64_t finalized = 0;        // batches of this launch completed so far
+    uint64_t exit_ticket = 0;
+    bool exit_taken = false, exit_published = false;
+    long long last_work = clk0;
+    uint32_t polls = 0;
+    for (;;) {
+      // ---- a batch is complete when every chunk has been counted
+      bool did = false;
+      for (uint32_t k = 0; k < SW_PULL_SLOTS; k++) {
+        SwPullSlot* s = &q->slot[k];
+        uint32_t ready = 0;
+        if (lane == 0) {
+          const uint64_t seq = sw_ld_acquire_gpu(&s->seq);
+          // published, of this launch, not an EXIT marker, not completed yet, all chunks counted
+          if (seq > first && !s->exit && s->fin_seq != seq && (!exit_taken || seq - 1 < exit_ticket) &&
+              *reinterpret_cast<volatile uint32_t*>(&s->done_chunks) == *reinterpret_cast<volatile uint32_t*>(&s->nchunks))
+            ready = 1;
+        }
+        ready = __shfl_sync(0xffffffffu, ready, 0);
+        if (!ready) continue;
+        sw_pull_finalize(q, s, lane);
+        if (lane == 0) {
+          s->fin_seq = s->seq;
+          sw_pull_retire(s, s->seq - 1);
+        }
+        __syncwarp();
+        finalized++;
+        did = true;
+      }
+      const long long now = clock64();
+      if (did) last_work = now;
+      // ---- leaving: take a ticket from the counter the matchers use -- every batch before it is served by this
+      // grid, every batch after it by the next launch -- and publish the EXIT batch as soon as that ticket's
+      // slot is free; the copy CTAs leave when they reach it, this CTA when everything before it is completed
+      if (!exit_published && (++polls & 3) == 0) {
+        uint32_t go = 0;
+        if (lane == 0) {
+          if (!exit_taken) {
+            const bool stop = sw_ld_relaxed_sys(const_cast<const uint64_t*>(&a.ctl->stop)) != 0;
+            const uint64_t alloc = *reinterpret_cast<volatile uint64_t*>(&q->alloc);
+            const bool quiet = alloc == first + finalized;   // nothing allocated that is not completed
+            if (stop || (quiet && now - last_work > linger_clk) || now - clk0 > life_clk) {
+              exit_ticket = atomicAdd(reinterpret_cast<unsigned long long*>(&q->alloc), 1ull);
+              exit_taken = true;
+            }
+          }
+          if (exit_taken) {
+            SwPullSlot* xs = &q->slot[exit_ticket % SW_PULL_SLOTS];
+            const uint64_t want = exit_ticket >= SW_PULL_SLOTS ? exit_ticket - SW_PULL_SLOTS + 1 : 0;
+            if (sw_ld_acquire_gpu(&xs->free_seq) == want) {
+              xs->njobs = 0;
+              xs->nchunks = 0;
+              xs->exit = 1;
+              xs->total = 0;
+              xs->next_chunk = xs->done_chunks = xs->retire = 0;
+              __threadfence();
+              sw_st_release_gpu(&xs->seq, exit_ticket + 1);
+              go = 2;
+            } else {
+              go = 1;
+            }
+          }
+        }
+        go = __shfl_sync(0xffffffffu, go, 0);
+        exit_taken = go != 0;
+        exit_published = go == 2;
+        exit_ticket = sw_shfl64(exit_ticket, 0);
+      }
+      if (exit_published && first + finalized == exit_ticket) break;
+      if (!did) __nanosleep(100);
+    }
+    // the EXIT batch: every CTA passes it once; the last one hands the next launch its first ticket
+    if (lane == 0) {
+      SwPullSlot* s = &q->slot[exit_ticket % SW_PULL_SLOTS];
+      a.ctl->bytes = q->bytes;
+      a.ctl->busy_ns = q->busy_ns;
+      a.ctl->batches = q->batches;
+      a.ctl->jobs = q->jobs;
+      a.ctl->pickup_ns = q->pickup_ns;
+      a.ctl->copy_ns = q->copy_ns;
+      a.ctl->fin_ns = q->fin_ns;
+      __threadfence_system();
+      const uint32_t r = atomicAdd(&s->retire, 1u) + 1;
+      if (r == gridDim.x) {
+        s->exit = 0;
+        q->start = exit_ticket + 1;
+        __threadfence();
+        sw_st_release_gpu(&s->free_seq, exit_ticket + 1);
+      }
+      a.ctl->exited = a.launch_seq;   // (the host also waits for the stream: the other CTAs may still be leaving)
+    }
+    return;
+  }
+
+  // ================================================================ copy CTAs: one elected thread drives the TMA pipeline
+  if (threadIdx.x != 0) return;
   const uint32_t nstages = a.nstages, stage_bytes = a.stage_bytes;
   for (uint32_t i = 0; i < nstages; i++) sw_mbar_init(&full[i], 1);
   sw_fence_mbar_init();
@@ -1339,37 +1454,20 @@ __global__ void __launch_bounds__(32) sw_pull_kernel(const __grid_constant__ SwP
   uint64_t st_dst[SW_BULK_MAX_STAGES];
   uint32_t st_bytes[SW_BULK_MAX_STAGES];
   SwPullSlot* tr_slot[TRK];      // != nullptr: this piece is the last of a chunk of that slot
-  uint64_t tr_ticket[TRK];
-  for (uint32_t i = 0; i < TRK; i++) {
-    tr_slot[i] = nullptr;
-    tr_ticket[i] = 0;
-  }
+  for (uint32_t i = 0; i < TRK; i++) tr_slot[i] = nullptr;
   const uint32_t lookahead = nstages - 2;
   uint64_t issued = 0, stored = 0, retired = 0;
 
   // generator state
-  uint64_t b = sw_ld_acquire_gpu(&q->start);   // ticket looked at next
+  uint64_t b = first;                          // ticket looked at next
   SwPullSlot* cur = nullptr;                   // batch being worked on
   uint32_t njobs = 0, nchunks = 0, j = 0;
   uint64_t chunk_bytes = 0, total = 0, pos = 0, cend = 0;
   bool have_chunk = false, leave = false;
-  const long long clk0 = clock64();
-  long long last_work = clk0;
-  const long long linger_clk = static_cast<long long>(a.linger_us) * a.clk_mhz;
-  const long long life_clk = static_cast<long long>(a.max_life_us) * a.clk_mhz;
-  bool exit_published = false, exit_taken = false;
-  uint64_t exit_ticket = 0;
-  uint32_t polls = 0;
 
-  auto chunk_done = [&](SwPullSlot* s, uint64_t ticket) {
-    __threadfence();
-    const uint32_t d = atomicAdd(&s->done_chunks, 1u) + 1;
-    if (d == s->nchunks) {
-      __threadfence();
-      sw_pull_finalize(q, s);
-      sw_pull_retire(s, ticket);
-    }
-  };
+  // a chunk is counted once its bulk stores have completed (cp.async.bulk.wait_group): plain atomic, no fence --
+  // CTA 0 fences once per batch before it publishes the completion records
+  auto chunk_done = [&](SwPullSlot* s) { atomicAdd(&s->done_chunks, 1u); };
   // next piece of work, without blocking: 1 = piece, 0 = nothing right now
   auto try_next = [&](uint64_t& src, uint64_t& dst, uint32_t& bytes, bool& last) -> int {
     for (;;) {
@@ -1388,47 +1486,16 @@ __global__ void __launch_bounds__(32) sw_pull_kernel(const __grid_constant__ SwP
           return 1;
         }
         have_chunk = false;
-        chunk_done(cur, b);   // an empty chunk (a batch of tails only)
+        chunk_done(cur);   // an empty chunk (a batch of tails only)
       }
       if (!cur) {
         SwPullSlot* s = &q->slot[b % SW_PULL_SLOTS];
-        if (sw_ld_acquire_gpu(&s->seq) != b + 1) {
-          // nothing published: CTA 0 decides when the whole grid leaves (host request, silence, lifetime).  It
-          // takes a ticket from the counter the matchers use -- every batch before it is still served by this
-          // grid, every batch after it by the next launch -- and publishes the EXIT batch as soon as that
-          // ticket's slot is free, without ever blocking (it keeps copying meanwhile).
-          if (blockIdx.x == 0 && !exit_published && (++polls & 7) == 0) {
-            if (!exit_taken) {
-              const long long now = clock64();
-              const bool stop = sw_ld_relaxed_sys(const_cast<const uint64_t*>(&a.ctl->stop)) != 0;
-              if (stop || now - last_work > linger_clk || now - clk0 > life_clk) {
-                exit_ticket = atomicAdd(reinterpret_cast<unsigned long long*>(&q->alloc), 1ull);
-                exit_taken = true;
-              }
-            }
-            if (exit_taken) {
-              SwPullSlot* xs = &q->slot[exit_ticket % SW_PULL_SLOTS];
-              const uint64_t want = exit_ticket >= SW_PULL_SLOTS ? exit_ticket - SW_PULL_SLOTS + 1 : 0;
-              if (sw_ld_acquire_gpu(&xs->free_seq) == want) {
-                xs->njobs = 0;
-                xs->nchunks = 0;
-                xs->exit = 1;
-                xs->total = 0;
-                xs->next_chunk = xs->done_chunks = xs->retire = 0;
-                __threadfence();
-                sw_st_release_gpu(&xs->seq, exit_ticket + 1);
-                exit_published = true;
-              }
-            }
-          }
-          return 0;
-        }
+        if (sw_ld_acquire_gpu(&s->seq) != b + 1) return 0;   // not published yet
         if (s->exit) {
           leave = true;
           return 0;
         }
         cur = s;
-        last_work = clock64();   // CTA 0 decides about leaving: a batch it got no chunk of is activity all the same
         njobs = s->njobs;
         nchunks = s->nchunks;
         chunk_bytes = s->chunk_bytes;
@@ -1451,12 +1518,11 @@ __global__ void __launch_bounds__(32) sw_pull_kernel(const __grid_constant__ SwP
       cend = pos + chunk_bytes < total ? pos + chunk_bytes : total;
       j = 0;
       have_chunk = true;
-      last_work = clock64();
     }
   };
   auto account = [&](uint64_t piece) {
     SwPullSlot* s = tr_slot[piece % TRK];
-    if (s) chunk_done(s, tr_ticket[piece % TRK]);
+    if (s) chunk_done(s);
   };
 
   for (;;) {
@@ -1470,15 +1536,13 @@ __global__ void __launch_bounds__(32) sw_pull_kernel(const __grid_constant__ SwP
         idle = true;
         break;
       }
-      // (try_next may have moved on to a later batch before it yielded: `cur` / `b` describe the piece's batch)
       if (issued >= nstages) sw_bulk_wait_read<1>();   // the store that last used this stage has read it
       const uint32_t stg = issued % nstages;
       sw_mbar_expect_tx(&full[stg], bytes);
       sw_bulk_g2s(sw_smem + size_t(stg) * stage_bytes, reinterpret_cast<const void*>(src), bytes, &full[stg]);
       st_dst[stg] = dst;
       st_bytes[stg] = bytes;
-      tr_slot[issued % TRK] = last ? cur : nullptr;
-      tr_ticket[issued % TRK] = b;
+      tr_slot[issued % TRK] = last ? cur : nullptr;   // (`cur` is the batch the piece belongs to)
       issued++;
     }
     // ---- store the oldest loaded piece
@@ -1495,31 +1559,23 @@ __global__ void __launch_bounds__(32) sw_pull_kernel(const __grid_constant__ SwP
       while (retired + LAG < stored) account(retired++);
     }
     if (idle && stored == issued) {
-      sw_bulk_wait_all();
-      while (retired < stored) account(retired++);
+      if (retired < stored) {
+        sw_bulk_wait_all();
+        while (retired < stored) account(retired++);
+      }
       if (leave) break;
-      __nanosleep(200);
+      __nanosleep(100);
     }
   }
   // the EXIT batch: every CTA passes it once; the last one hands the next launch its first ticket
   {
     SwPullSlot* s = &q->slot[b % SW_PULL_SLOTS];
-    __threadfence();
     const uint32_t r = atomicAdd(&s->retire, 1u) + 1;
     if (r == gridDim.x) {
       s->exit = 0;
       q->start = b + 1;
       __threadfence();
       sw_st_release_gpu(&s->free_seq, b + 1);
-      a.ctl->bytes = q->bytes;
-      a.ctl->busy_ns = q->busy_ns;
-      a.ctl->batches = q->batches;
-      a.ctl->jobs = q->jobs;
-      a.ctl->pickup_ns = q->pickup_ns;
-      a.ctl->copy_ns = q->copy_ns;
-      a.ctl->fin_ns = q->fin_ns;
-      __threadfence_system();
-      a.ctl->exited = a.launch_seq;
     }
   }
 }

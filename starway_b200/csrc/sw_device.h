@@ -332,6 +332,7 @@ struct SwPullMeta {       // completion of one pulled message
 struct SwPullSlot {
   uint64_t seq;           // ticket + 1 once published (release); compared by the workers
   uint64_t free_seq;      // ticket + 1 of the last batch retired from this slot
+  uint64_t fin_seq;       // == seq once CTA 0 of the pull kernel has completed the batch
   uint32_t njobs, nchunks, exit, pad;
   uint64_t chunk_bytes, total;
   uint32_t next_chunk, done_chunks, retire, pad2;

@@ -14,6 +14,9 @@ import starway_b200 as sw  # noqa: E402
 
 
 async def main():
+    for kv in filter(None, os.environ.get("RS_OPTS", "").split(",")):
+        k, v = kv.split("=")
+        sw.get_context().set_option(k, int(v))
     server, client = sw.Server(), sw.Client()
     await client.aconnect_address(server.listen_address())
     for _ in range(400):
