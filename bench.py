@@ -4,7 +4,8 @@
   python bench.py --gpus N --steps K --warmup W            our arm (CUDA, sm_100a)
   python bench.py --impl reference --gpus N ...            reference arm: the reference's CPU path
                                                            (restated, oracle/cpu_engine.cpp) on host cores
-  python bench.py --sweep                                  size sweep 64 B - 1 GiB (BASELINE config 3) -> JSON lines
+Every line also carries `sweep`: BASELINE config 3 sampled at 64 B ... 1 GiB in the same run (--no-sweep skips it;
+the full 25-size sweep, uni- and bidirectional, is `bench_scenarios.py sweep`).
 
 Workload (BASELINE.json configs[1]): point-to-point asend/arecv of 1 MiB buffers, tag=1,
 tag_mask=0xFFFF.  One step = a window of WINDOW messages: the receiver posts WINDOW receives,
@@ -108,6 +109,66 @@ class ClockSampler:
             "sm_max_mhz": self.max_mhz,
             "reasons": sorted(self.reasons),
         }
+
+
+SWEEP_SIZES = [64, 4096, 65536, 1 << 20, 16 << 20, 256 << 20, 1 << 30]   # config 3, sampled
+
+
+def sweep_plan(n):
+    """(window, iterations) of one sweep point: SURVEY 8d shape (window = min(64, max(1, 2^28 / n)) sends in flight,
+    then aflush), bounded so that the whole sweep adds a fraction of a second to the run."""
+    window = min(64, max(1, (1 << 28) // n))
+    iters = max(3, min(100, (1 << 31) // (window * n)))
+    return window, iters
+
+
+async def run_sweep(torch, dev, server, client, rank, world, barrier, allreduce_max, allreduce_sum, sizes):
+    """BASELINE config 3, sampled: for every size a stream of `window` messages per iteration (receives pre-posted,
+    sends in flight, aflush), device buffers, public asyncio API; GB/s and Mmsg/s per direction per GPU, the
+    fraction of the payload roofline, and a bit-exact check of the last window against the SENDER's pattern."""
+    pool_bytes = max(sizes)
+    def pattern(r):
+        t = torch.arange(pool_bytes // 8, device=dev, dtype=torch.int64)
+        t.mul_(2654435761).add_(r * 0x9E3779B1)
+        return t.view(torch.uint8)
+    src_pool = pattern(rank)
+    exp_pool = src_pool if world == 1 else pattern((rank - 1) % world)
+    dst_pool = torch.empty(pool_bytes, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    out = []
+    for n in sizes:
+        window, iters = sweep_plan(n)
+        offs = [(j * n) % (pool_bytes - n + 1) for j in range(window)]
+        srcs = [src_pool[o:o + n] for o in offs]
+        dsts = [dst_pool[o:o + n] for o in offs]
+        dst_pool[: min(pool_bytes, window * n)].fill_(0xEE)
+        torch.cuda.synchronize()
+
+        async def one():
+            recvs = [server.arecv(d, TAG, MASK) for d in dsts]
+            sends = [client.asend(x, TAG) for x in srcs]
+            for f in sends:
+                await f
+            await client.aflush()
+            for f in recvs:
+                await f
+
+        await one()   # warm-up (mappings, pools)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            await one()
+        torch.cuda.synchronize()
+        el = allreduce_max(time.perf_counter() - t0)
+        bad = allreduce_sum(sum(int(not torch.equal(dst_pool[o:o + n], exp_pool[o:o + n])) for o in offs))
+        gbs = window * iters * n / el / 1e9
+        out.append({"bytes": n, "window": window, "iters": iters, "gbs_per_gpu": round(gbs, 3),
+                    "mmsg_per_s_per_gpu": round(window * iters / el / 1e6, 4), "bit_exact": bad == 0, "_gbs": gbs})
+        barrier()
+    del src_pool, dst_pool, exp_pool
+    torch.cuda.empty_cache()
+    return out
 
 
 # ----------------------------------------------------------------------------------------- our arm
@@ -233,63 +294,92 @@ def run_ours(args):
         step_bytes = window * msg
         value = world * step_bytes * args.steps / (ms * 1e-3) / 1e9
 
-        # ---- e2e: same steps, pinned HOST buffers through the public API (H2D + D2H inside)
-        hsrc = [[torch.from_numpy(np.random.default_rng(rank * 1000 + k * 100 + j).integers(0, 256, msg, dtype=np.uint8)).pin_memory().numpy()
-                 for j in range(window)] for k in range(2)]
-        hdst = [[torch.empty(msg, dtype=torch.uint8).pin_memory().numpy() for _ in range(window)] for k in range(2)]
+        # ---- the metric's "vs size" half: sampled sweep (config 3) at this N, same run
+        def allreduce_max(x):
+            if dist is None:
+                return x
+            t = torch.tensor([x], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t[0])
+
+        def allreduce_sum(x):
+            if dist is None:
+                return x
+            t = torch.tensor([x], dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return int(t[0])
+
+        sweep = []
+        if not args.no_sweep:
+            del src, dst
+            torch.cuda.empty_cache()
+            sweep = await run_sweep(torch, dev, server, client, rank, world, barrier, allreduce_max, allreduce_sum,
+                                    [n for n in SWEEP_SIZES if n <= args.sweep_max_bytes])
+
+        # ---- e2e: same steps with HOST buffers through the public API (H2D + D2H inside the timed region):
+        #      page-locked NumPy arrays (the headline e2e) and ordinary pageable NumPy arrays (what a caller of the
+        #      reference passes)
+        def host_bufs(pinned):
+            mk = (lambda a: a.pin_memory().numpy()) if pinned else (lambda a: a.numpy().copy())
+            hs = [[mk(torch.from_numpy(np.random.default_rng(rank * 1000 + k * 100 + j).integers(0, 256, msg, dtype=np.uint8)))
+                   for j in range(window)] for k in range(2)]
+            hd = [[mk(torch.empty(msg, dtype=torch.uint8)) for _ in range(window)] for k in range(2)]
+            return hs, hd
 
         marks = []
 
-        async def timed_host(nsteps):
-            for i in range(nsteps):
-                k = i % 2
-                marks.append(("e2e_step_begin", time.monotonic()))
-                res = await window_step(server, client, eps, hsrc[k], hdst[k])
-                marks.append(("e2e_step_end", time.monotonic()))
-                assert all(r == (TAG, msg) for r in res)
+        async def e2e_leg(pinned):
+            hsrc, hdst = host_bufs(pinned)
+
+            async def timed_host(nsteps):
+                for i in range(nsteps):
+                    k = i % 2
+                    marks.append(("e2e_step_begin", time.monotonic()))
+                    res = await window_step(server, client, eps, hsrc[k], hdst[k])
+                    marks.append(("e2e_step_end", time.monotonic()))
+                    assert all(r == (TAG, msg) for r in res)
+
+            await timed_host(3)
+            if world == 1:
+                for s_, d_ in zip(hsrc[0], hdst[0]):
+                    assert np.array_equal(s_, d_), "host payload mismatch"
+            barrier()
+            torch.cuda.synchronize()
+            steps = max(3, min(args.steps, 40))
+            ctx.reset_stats()
+            t0 = time.perf_counter()
+            await timed_host(steps)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            barrier()
+            ms_ = allreduce_max((t1 - t0) * 1e3)
+            return world * step_bytes * steps / (ms_ * 1e-3) / 1e9, ms_, steps, ctx.stats()
 
         if args.no_e2e:
             await client.aclose()
             barrier()
             await server.aclose()
-            return value, ms, st, clk, float("nan"), step_bytes, {}, payload_check, warm_batches
-        await timed_host(3)
-        if world == 1:
-            for s, d in zip(hsrc[0], hdst[0]):
-                assert np.array_equal(s, d), "host payload mismatch"
-        barrier()
-        torch.cuda.synchronize()
-        e2e_steps = max(3, min(args.steps, 40))
-        ctx.reset_stats()
-        t0 = time.perf_counter()
-        await timed_host(e2e_steps)
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        barrier()
-        e2e_ms = (t1 - t0) * 1e3
-        if dist is not None:
-            t = torch.tensor([e2e_ms], dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_ms = float(t[0])
-        e2e_value = world * step_bytes * e2e_steps / (e2e_ms * 1e-3) / 1e9
+            return value, ms, st, clk, float("nan"), step_bytes, {}, payload_check, warm_batches, sweep
+        e2e_value, e2e_ms, e2e_steps, st2 = await e2e_leg(True)
+        e2e_pageable, pg_ms, pg_steps, _ = await e2e_leg(False)
         if os.environ.get("STARWAY_TRACE"):
             with open(os.environ["STARWAY_TRACE"] + f".py.{os.getpid()}", "w") as f:
                 for name, t in marks:
                     f.write(f"{t:.7f} {name} 0 0\n")
-        st2 = ctx.stats()
         e2e_diag = {"ms_per_step": round(e2e_ms / e2e_steps, 3),
                     "copy_kernel_ms_per_step": round((st2["bulk_event_ms"] + st2["pull_busy_ms"]) / e2e_steps, 3),
                     "bulk_launches_per_step": round((st2["bulk_tma_launches"] + st2["bulk_simt_launches"]) / e2e_steps, 1),
                     "pull_batches_per_step": round(st2["pull_batches"] / e2e_steps, 1),
                     "staged_h2d_bytes_per_step": int(st2["h2d_bytes"] / e2e_steps),
-                    "staged_d2h_bytes_per_step": int(st2["d2h_bytes"] / e2e_steps)}
+                    "staged_d2h_bytes_per_step": int(st2["d2h_bytes"] / e2e_steps),
+                    "pageable_value": round(e2e_pageable, 2), "pageable_ms_per_step": round(pg_ms / pg_steps, 3)}
 
         await client.aclose()
         barrier()
         await server.aclose()
-        return value, ms, st, clk, e2e_value, step_bytes, e2e_diag, payload_check, warm_batches
+        return value, ms, st, clk, e2e_value, step_bytes, e2e_diag, payload_check, warm_batches, sweep
 
-    value, ms, st, clk, e2e_value, step_bytes, e2e_diag, payload_check, st0_batches = new_loop_runner()(main())
+    value, ms, st, clk, e2e_value, step_bytes, e2e_diag, payload_check, st0_batches, sweep = new_loop_runner()(main())
 
     # ---- roofline of the dominant kernel: the rendezvous copy.  On the resident path the copies are made by the
     #      pull CTAs (sw_pull_kernel), which stay on the GPU across many batches: the time base is the union of the
@@ -343,7 +433,13 @@ def run_ours(args):
     if rank != 0:
         sw.shutdown()
         return
-    cpu = cpu_baseline_run(args.msg_bytes, args.window, budget_s=12.0) if (world == 1 and not args.no_cpu_baseline) else None
+    cpu = cpu_baseline_run(args.msg_bytes, args.window, budget_s=10.0) if (world == 1 and not args.no_cpu_baseline) else None
+    per_gpu_peak = float(peaks["hbm_gbs"]) / 2 if world == 1 else NVLINK_NOMINAL_GBS
+    for pt in sweep:
+        pt["frac_of_roofline"] = round(pt.pop("_gbs") / per_gpu_peak, 4)
+    if cpu is not None and sweep:
+        # the reference-shaped CPU path at the same sizes ("reference CPU path beside it")
+        cpu["sweep"] = cpu_sweep([pt["bytes"] for pt in sweep])
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
@@ -360,10 +456,18 @@ def run_ours(args):
             "payload_check_all_ranks": payload_check,
         },
         "mmsg_per_s": round(world * window * args.steps / (ms * 1e-3) / 1e6, 4),
+        "sweep": {"what": "BASELINE config 3, sampled: per size, `window` messages in flight then aflush, device buffers, "
+                          "per direction per GPU" + ("" if world == 1 else f"; every rank streams to rank+1 at once ({world}-GPU ring)"),
+                  "roofline_gbs_per_gpu": round(per_gpu_peak, 1),
+                  "roofline": "HBM copy / 2 (loopback: every payload byte is read and written)" if world == 1 else "NVLink 5, 900 GB/s per direction (nominal)",
+                  "points": sweep},
         "nvlink_roofline_frac": None if world == 1 else round(value / world / 900.0, 4),
         "clocks": clk,
         "e2e": {"value": None if args.no_e2e else round(e2e_value, 2), "unit": "GB/s", "h2d_bytes_per_step": step_bytes, "d2h_bytes_per_step": step_bytes,
-                "buffers": "pinned host NumPy arrays through Client.asend/Server.arecv", "rank0_breakdown": e2e_diag},
+                "buffers": "page-locked host NumPy arrays through Client.asend/Server.arecv", "rank0_breakdown": e2e_diag},
+        "e2e_pageable": {"value": e2e_diag.get("pageable_value"), "unit": "GB/s",
+                         "buffers": "ordinary (pageable) NumPy arrays through the same calls"},
+        "reference_arm_note": "the reference arm (--impl reference) is ONE in-process CPU pair on rank 0 whatever N is: compare per GPU",
         "gpu_launches": gpu_launches,
         "roofline": roofline,
     }
@@ -424,6 +528,49 @@ def cpu_baseline_run(msg, window, budget_s=12.0, steps=None, warmup=2):
     }
 
 
+def cpu_sweep(sizes, budget_s=1.2):
+    """The restated reference on host cores at the sweep sizes (host NumPy buffers, same window shape)."""
+    import numpy as np
+
+    from oracle import starway_cpu as cpu
+
+    async def main():
+        port = 41000 + (os.getpid() % 20000)
+        s, c = cpu.make_pair(port)
+        await c.aconnect("127.0.0.1", port)
+        pool = np.random.default_rng(7).integers(0, 256, max(sizes), dtype=np.uint8)
+        dpool = np.zeros(max(sizes), dtype=np.uint8)
+        out = []
+        for n in sizes:
+            window, _ = sweep_plan(n)
+            offs = [(j * n) % (len(pool) - n + 1) for j in range(window)]
+            srcs, dsts = [pool[o:o + n] for o in offs], [dpool[o:o + n] for o in offs]
+
+            async def one():
+                recvs = [s.arecv(d, TAG, MASK) for d in dsts]
+                sends = [c.asend(x, TAG) for x in srcs]
+                await asyncio.gather(*sends)
+                await c.aflush()
+                await asyncio.gather(*recvs)
+
+            await one()
+            it, t0 = 0, time.perf_counter()
+            while True:
+                await one()
+                it += 1
+                el = time.perf_counter() - t0
+                if el > budget_s or it >= 100:
+                    break
+            ok = all(np.array_equal(a, b) for a, b in zip(srcs, dsts))
+            out.append({"bytes": n, "window": window, "iters": it, "gbs": round(window * it * n / el / 1e9, 3),
+                        "mmsg_per_s": round(window * it / el / 1e6, 4), "bit_exact": bool(ok)})
+        await c.aclose()
+        await s.aclose()
+        return out
+
+    return new_loop_runner()(main())
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -437,6 +584,8 @@ def run_reference(args):
                                f"window {args.window} msgs/step + aflush, Server+Client in one process",
                    "msg_bytes": args.msg_bytes, "window": args.window},
         "cpu_baseline": cpu,
+        "sweep": {"what": "the same CPU pair at the sweep sizes (host NumPy buffers)",
+                  "points": [] if args.no_sweep else cpu_sweep([n for n in SWEEP_SIZES if n <= args.sweep_max_bytes])},
         "e2e": {"value": cpu["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -453,6 +602,8 @@ def main():
     ap.add_argument("--window", type=int, default=WINDOW)
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (ncu launch lists of the device-resident steps)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the sampled size sweep (config 3)")
+    ap.add_argument("--sweep-max-bytes", type=int, default=1 << 30)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -2086,6 +2086,7 @@ bool poll_progress_rings(Ctx* c, Worker* w) {
     const SwCqEnt* e = &w->cq_ring[h % SW_CQ_RING];
     int32_t status;
     if (!cq_ready(e, h, &status)) break;
+    trace(c, "cqe_eager", e->op_id, e->len);
     recv_finish(c, w, e->op_id, status, e->tag, e->len);
     h++;
   }

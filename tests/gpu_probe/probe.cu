@@ -999,6 +999,107 @@ static void bench_floor(FILE* json) {
   CK(cudaStreamDestroy(st));
 }
 
+// ------------------------------------------------------------------ hostlat: what device <-> host-memory hops cost
+// One CTA, two warps.  Warp 1 (optional) keeps PCIe reads of pinned host memory in flight, like the link warp of
+// sw_progress_kernel.  Warp 0 lane 0 measures with clock64:
+//   mode 0: latency of one ld.relaxed.sys from pinned host memory
+//   mode 1: store to pinned host memory + fence.sys (the completion-record pattern)
+//   mode 2: store to device memory + fence.sys
+//   mode 3: store to device memory + fence.gpu
+//   mode 4: host -> device signalling through pinned memory: the host bumps a word, the kernel echoes it (RTT seen by the host)
+__global__ void hostlat_kernel(volatile uint64_t* host_words, uint64_t* dev_words, int mode, int iters, int bg, uint64_t* out,
+                               volatile uint64_t* stop) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 1) {
+    if (!bg || lane) return;
+    uint64_t acc = 0;
+    while (*reinterpret_cast<volatile uint64_t*>(dev_words + 64) == 0) {
+      uint64_t v;
+      asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(host_words + 32) : "memory");
+      acc += v;
+    }
+    out[63] = acc;
+    return;
+  }
+  if (lane) return;
+  long long total = 0, worst = 0;
+  if (mode == 4) {
+    uint64_t seen = 0;
+    while (!*stop) {
+      uint64_t v;
+      asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(host_words) : "memory");
+      if (v != seen) {
+        seen = v;
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(host_words + 8), "l"(v) : "memory");
+      }
+    }
+  } else {
+    for (int i = 0; i < iters; i++) {
+      const long long t0 = clock64();
+      if (mode == 0) {
+        uint64_t v;
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(host_words + (i & 7)) : "memory");
+        total += (v & 1);
+      } else if (mode == 1) {
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(host_words + 16 + (i & 7)), "l"((uint64_t)i) : "memory");
+        __threadfence_system();
+      } else if (mode == 2) {
+        dev_words[i & 7] = i;
+        __threadfence_system();
+      } else {
+        dev_words[i & 7] = i;
+        __threadfence();
+      }
+      const long long dt = clock64() - t0;
+      total += dt;
+      worst = dt > worst ? dt : worst;
+    }
+  }
+  out[0] = (uint64_t)total;
+  out[1] = (uint64_t)worst;
+  __threadfence();
+  *reinterpret_cast<volatile uint64_t*>(dev_words + 64) = 1;
+}
+
+static void bench_hostlat(FILE* json) {
+  uint64_t* host = (uint64_t*)host_alloc(4096);
+  uint64_t* dev = (uint64_t*)dev_alloc(4096);
+  uint64_t* out = (uint64_t*)host_alloc(4096);
+  int khz = 0;
+  CK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0));
+  const double mhz = khz / 1000.0;
+  const char* names[] = {"ld.sys of pinned host memory", "st pinned host + fence.sys", "st device + fence.sys", "st device + fence.gpu"};
+  for (int bg = 0; bg < 2; bg++)
+    for (int mode = 0; mode < 4; mode++) {
+      CK(cudaMemset(dev, 0, 4096));
+      const int iters = 2000;
+      hostlat_kernel<<<1, 64>>>(host, dev, mode, iters, bg, out, host + 40);
+      CK(cudaDeviceSynchronize());
+      printf("hostlat %-32s background PCIe reads %d: mean %.2f us  worst %.2f us\n", names[mode], bg, out[0] / mhz / iters, out[1] / mhz);
+      if (json) fprintf(json, "{\"probe\":\"hostlat\",\"what\":\"%s\",\"bg_reads\":%d,\"mean_us\":%.3f,\"worst_us\":%.3f}\n", names[mode], bg, out[0] / mhz / iters, out[1] / mhz);
+    }
+  // host -> device -> host echo through pinned memory (the post-ring / completion-ring hop pair)
+  CK(cudaMemset(dev, 0, 4096));
+  host[0] = host[8] = host[40] = 0;
+  hostlat_kernel<<<1, 64>>>(host, dev, 4, 0, 0, out, host + 40);
+  std::vector<double> rtt;
+  for (int i = 1; i <= 2000; i++) {
+    const double t0 = now_s();
+    __atomic_store_n(&host[0], (uint64_t)i, __ATOMIC_RELEASE);
+    while (__atomic_load_n(&host[8], __ATOMIC_ACQUIRE) != (uint64_t)i) {
+    }
+    rtt.push_back((now_s() - t0) * 1e6);
+  }
+  __atomic_store_n(&host[40], 1, __ATOMIC_RELEASE);
+  CK(cudaDeviceSynchronize());
+  std::sort(rtt.begin(), rtt.end());
+  printf("hostlat host word -> kernel poll -> echo word -> host: median %.2f us  p10 %.2f  p90 %.2f\n", rtt[rtt.size() / 2], rtt[rtt.size() / 10], rtt[rtt.size() * 9 / 10]);
+  if (json) fprintf(json, "{\"probe\":\"hostlat\",\"what\":\"host->kernel->host echo\",\"median_us\":%.3f}\n", rtt[rtt.size() / 2]);
+  host_free(host);
+  host_free(out);
+  dev_free(dev);
+}
+
 int main(int argc, char** argv) {
   std::string cmd = argc > 1 ? argv[1] : "correctness";
   if (cmd == "ipc-child") return ipc_child(argv[2]);
@@ -1019,6 +1120,7 @@ int main(int argc, char** argv) {
   if (cmd == "floor") bench_floor(json);
   if (cmd == "balance") bench_balance(json);
   if (cmd == "hostmem") bench_hostmem(json);
+  if (cmd == "hostlat") bench_hostlat(json);
   if (cmd == "tune") bench_tune(json);
   if (cmd == "ipc" || cmd == "all") test_ipc(argv[0]);
   if (cmd == "peer" || cmd == "all") bench_peer(json);

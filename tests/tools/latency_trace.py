@@ -50,6 +50,9 @@ def main():
     marks = []
 
     async def run():
+        for kv in filter(None, os.environ.get("SW_OPTS", "").split(",")):   # e.g. SW_OPTS=resident_puts=0,linger_us=300
+            k, v = kv.split("=")
+            sw.get_context().set_option(k, int(v))
         server, client = sw.Server(), sw.Client()
         await client.aconnect_address(server.listen_address())
         while not server.list_clients():
