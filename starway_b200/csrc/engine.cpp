@@ -2573,6 +2573,12 @@ void check_flushes(Ctx* c, Worker* w) {
 }
 
 void worker_release(Ctx* c, Worker* w, bool leak_rings) {
+  if (c->tracing && w->pctl && w->pctl->dbg[0]) {
+    const double mhz = 1965.0, n = (double)w->pctl->dbg[0];
+    fprintf(stderr, "starway_b200 resident puts (worker %llx): %llu; seen->staged %.2f us, staged->released %.2f us, released->published %.2f us; link round %.2f us\n",
+            (unsigned long long)w->id, (unsigned long long)w->pctl->dbg[0], w->pctl->dbg[1] / n / mhz, w->pctl->dbg[2] / n / mhz,
+            w->pctl->dbg[3] / n / mhz, w->pctl->dbg[4] ? w->pctl->dbg[5] / (double)w->pctl->dbg[4] / mhz : 0.0);
+  }
   for (Ep* ep : w->eps) {
     if (ep->retired) continue;
     if (ep->peer_ring_mapping) {

@@ -8,9 +8,9 @@
 //                                  straight to host-visible memory, hands rendezvous matches to the pull queue
 //                         warp 1   host link: polls the worker's control words and the post ring in pinned host
 //                                  memory (PCIe reads off the matcher's critical path), decides when to leave
-//                         warp 2-3 puts: small batches of sends the host hands over while the kernel is resident
+//                         warp 2   puts: small batches of sends the host hands over while the kernel is resident
 //                                  (payload + released header into the peer's ring, no launch on the sender side)
-//                         warp 4+  helpers: eager payloads above SW_INLINE_DELIVER bytes
+//                         warp 3+  helpers: eager payloads above SW_INLINE_DELIVER bytes
 //                       (replaces ucp_worker_progress + the matching inside ucp_tag_recv_nbx,
 //                        reference src/bindings/main.cpp:362,1127 and :404,1172)
 //   sw_pull_kernel      resident pull CTAs of the context (one elected thread each drives the cp.async.bulk
@@ -108,7 +108,7 @@ struct SwProgArgs {
 };
 
 constexpr uint32_t SW_PROG_THREADS = 256;
-constexpr uint32_t SW_PROG_PUTTERS = 2;
+constexpr uint32_t SW_PROG_PUTTERS = 1;
 constexpr uint32_t SW_PROG_HELPERS = SW_PROG_THREADS / 32 - 2 - SW_PROG_PUTTERS;
 constexpr uint32_t SW_SSEND_RING = 32;
 constexpr uint32_t SW_DJOB_RING = 64;
@@ -147,9 +147,9 @@ struct SwProgShared {
   volatile uint64_t post_head;    // consumed by the matcher
   volatile uint64_t job_tail;     // jobs emitted by the matcher
   volatile uint64_t send_tail;    // put descriptors staged by the link warp
-  volatile uint64_t send_done;    // every put below this index has been executed (published by the link warp)
+  volatile uint64_t send_done;    // every put below this index has been executed (and published to the host)
   volatile uint64_t send_base;    // index of the first put of this launch
-  volatile uint32_t put_done[SW_PROG_PUTTERS];   // puts executed by each put warp in this launch
+  volatile long long t_staged, t_released;   // latency budget of resident puts (last put)
   volatile uint64_t cq_head, cqr_head, hr_head, dead_mask, host_epoch;   // copies of the host's words
   volatile long long active_clk;  // last time the matcher did something
   volatile uint32_t helper_done[SW_PROG_HELPERS];
@@ -958,7 +958,6 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
   if (threadIdx.x == 0) {
     sh.post_tail = sh.post_head = st->post_consumed;
     sh.send_tail = sh.send_done = sh.send_base = st->send_consumed;
-    for (uint32_t k = 0; k < SW_PROG_PUTTERS; k++) sh.put_done[k] = 0;
     sh.job_tail = 0;
     sh.cq_head = a.ctl->cq_head;
     sh.cqr_head = a.ctl->cqr_head;
@@ -1081,67 +1080,64 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
     }
   } else if (warp == 1) {
     // ================================================================ host link
+    // Every look at host memory costs a PCIe round trip (~1 us) and a thread's system-scope loads do not overlap:
+    // each round is ONE warp-wide load instruction (a lane per 16-byte unit), then one more for the entries.
     const long long linger_clk = static_cast<long long>(a.linger_us) * a.clk_mhz;
     const long long life_clk = static_cast<long long>(a.max_life_us) * a.clk_mhz;
     uint64_t staged = sh.post_tail, sstaged = sh.send_tail;
     uint64_t he_prev = sh.host_epoch;
+    uint64_t dbg_n = 0, dbg_stage = 0, dbg_rounds = 0;
     bool leaving = false;
+    const uint8_t* ctl_bytes = reinterpret_cast<const uint8_t*>(const_cast<const SwProgCtl*>(a.ctl));
+    auto u64of = [](int lo, int hi) { return (static_cast<uint64_t>(static_cast<uint32_t>(hi)) << 32) | static_cast<uint32_t>(lo); };
     for (;;) {
-      uint64_t host_tail = 0, stop = 0, host_stail = 0;
+      // units of the two host->kernel lines: 0 {post_tail, cq_head} 1 {cqr_head, hr_head} 2 {send_tail, -}
+      //                                      4 {stop, dead_mask} 5 {host_epoch, -}
+      int4 v = make_int4(0, 0, 0, 0);
+      if (lane < 6) v = sw_ld16_sys(ctl_bytes + 16 * lane);
+      auto unit_lo = [&](int u) { return u64of(__shfl_sync(0xffffffffu, v.x, u), __shfl_sync(0xffffffffu, v.y, u)); };
+      auto unit_hi = [&](int u) { return u64of(__shfl_sync(0xffffffffu, v.z, u), __shfl_sync(0xffffffffu, v.w, u)); };
+      const uint64_t host_tail = unit_lo(0), cq_head = unit_hi(0), cqr_head = unit_lo(1), hr_head = unit_hi(1);
+      const uint64_t host_stail = unit_lo(2), stop = unit_lo(4), dead_mask = unit_hi(4), he = unit_lo(5);
       if (lane == 0) {
-        const int4 w0 = sw_ld16_sys(const_cast<const uint64_t*>(&a.ctl->post_tail));   // post_tail, cq_head
-        const int4 w1 = sw_ld16_sys(const_cast<const uint64_t*>(&a.ctl->cqr_head));    // cqr_head, hr_head
-        host_stail = sw_ld_relaxed_sys(const_cast<const uint64_t*>(&a.ctl->send_tail));
-        const int4 w2 = sw_ld16_sys(const_cast<const uint64_t*>(&a.ctl->stop));        // stop, dead_mask
-        const uint64_t he = sw_ld_relaxed_sys(const_cast<const uint64_t*>(&a.ctl->host_epoch));
-        auto u64of = [](int lo, int hi) { return (static_cast<uint64_t>(static_cast<uint32_t>(hi)) << 32) | static_cast<uint32_t>(lo); };
-        host_tail = u64of(w0.x, w0.y);
-        sh.cq_head = u64of(w0.z, w0.w);
-        const uint64_t cqrh = u64of(w1.x, w1.y);
-        if (cqrh != sh.cqr_head) {
-          sh.cqr_head = cqrh;
-          st->cqr_head = cqrh;   // the pull CTAs read the device copy
+        sh.cq_head = cq_head;
+        if (cqr_head != sh.cqr_head) {
+          sh.cqr_head = cqr_head;
+          st->cqr_head = cqr_head;   // the pull CTAs read the device copy
         }
-        sh.hr_head = u64of(w1.z, w1.w);
-        stop = u64of(w2.x, w2.y);
-        sh.dead_mask = u64of(w2.z, w2.w);
+        sh.hr_head = hr_head;
+        sh.dead_mask = dead_mask;
         // The epoch handed to the matcher is the one read in the PREVIOUS round: this round's dead_mask was
         // requested after that read had returned, so it is at least as new as the epoch that vouches for it.
         __threadfence_block();
         sh.host_epoch = he_prev;
-        he_prev = he;
       }
-      host_tail = sw_shfl64(host_tail, 0);
-      host_stail = sw_shfl64(host_stail, 0);
-      stop = sw_shfl64(stop, 0);
+      he_prev = he;
+      dbg_rounds++;
       if (leaving) {
         // the matcher winds down (it may still need room in the completion rings): keep the host's cursors fresh;
-        // the put warps finish what is staged
-        uint64_t v = ~0ull;
-        for (uint32_t k = 0; k < SW_PROG_PUTTERS; k++) {
-          const uint64_t nxt = sh.send_base + k + static_cast<uint64_t>(sh.put_done[k]) * SW_PROG_PUTTERS;
-          v = nxt < v ? nxt : v;
+        // the put warp finishes what is staged
+        if (sh.helpers_exit && sh.send_done == sstaged) {
+          if (lane == 0) {
+            a.ctl->dbg[0] = a.ctl->dbg[0] + dbg_n;
+            a.ctl->dbg[1] = a.ctl->dbg[1] + dbg_stage;
+            a.ctl->dbg[4] = a.ctl->dbg[4] + dbg_rounds;
+            a.ctl->dbg[5] = a.ctl->dbg[5] + static_cast<uint64_t>(clock64() - clk0);
+          }
+          break;
         }
-        if (v > sstaged) v = sstaged;
-        if (v != sh.send_done && lane == 0) {
-          sh.send_done = v;
-          sw_st_release_sys(const_cast<uint64_t*>(&a.ctl->send_done), v);
-        }
-        if (sh.helpers_exit && v == sstaged) break;
         continue;
       }
-      // stage new receives: lane L copies entry (staged + L)
+      // ---- stage new receives: up to 10 per round, a lane per 16-byte unit (3 units per entry)
       const uint64_t consumed = sh.post_head;
       const uint64_t room = SW_SPOST_RING - (staged - consumed);
       uint64_t n = host_tail - staged;
       if (n > room) n = room;
-      if (n > 32) n = 32;
-      if (lane < n) {
-        const SwPostEnt* src = &a.posts[(staged + lane) % SW_POST_RING];
-        int4* dst = reinterpret_cast<int4*>(&sh.posts[(staged + lane) % SW_SPOST_RING]);
-        dst[0] = sw_ld16_sys(reinterpret_cast<const int4*>(src));
-        dst[1] = sw_ld16_sys(reinterpret_cast<const int4*>(src) + 1);
-        dst[2] = sw_ld16_sys(reinterpret_cast<const int4*>(src) + 2);
+      if (n > 10) n = 10;
+      if (lane < 3 * n) {
+        const uint32_t e = lane / 3, u = lane % 3;
+        const int4* src = reinterpret_cast<const int4*>(&a.posts[(staged + e) % SW_POST_RING]);
+        reinterpret_cast<int4*>(&sh.posts[(staged + e) % SW_SPOST_RING])[u] = sw_ld16_sys(src + u);
       }
       __syncwarp();
       if (n) {
@@ -1152,29 +1148,19 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
           a.ctl->post_head = staged;   // the host may reuse these ring entries
         }
       }
-      // puts for the put warps: lane L copies entry (sstaged + L), descriptor and inline payload in one round trip
-      uint64_t sdone = sh.send_base;
-      {
-        uint64_t v = ~0ull;
-        for (uint32_t k = 0; k < SW_PROG_PUTTERS; k++) {
-          const uint64_t nxt = sh.send_base + k + static_cast<uint64_t>(sh.put_done[k]) * SW_PROG_PUTTERS;
-          v = nxt < v ? nxt : v;
-        }
-        sdone = v < sstaged ? v : sstaged;   // first put that has not been executed
-      }
-      if (sdone != sh.send_done && lane == 0) {
-        sh.send_done = sdone;
-        sw_st_release_sys(const_cast<uint64_t*>(&a.ctl->send_done), sdone);   // headers released before: the host rings the doorbell on it
-        sh.active_clk = clock64();
-      }
+      // ---- stage puts for the put warp: two entries per load instruction (11 units each)
+      const uint64_t sdone = sh.send_done;
       uint64_t ns = host_stail - sstaged;
       const uint64_t sroom = SW_SSEND_RING - (sstaged - sdone);
       if (ns > sroom) ns = sroom;
-      if (lane < ns) {
-        const int4* src = reinterpret_cast<const int4*>(&a.sends[(sstaged + lane) % SW_SEND_RING]);
-        int4* dst = reinterpret_cast<int4*>(&sh.sends[(sstaged + lane) % SW_SSEND_RING]);
-#pragma unroll
-        for (int q = 0; q < static_cast<int>(sizeof(SwSendEnt) / 16); q++) dst[q] = sw_ld16_sys(src + q);
+      const long long t_seen = clock64();
+      constexpr uint32_t UNITS = sizeof(SwSendEnt) / 16;
+      for (uint64_t base = 0; base < ns; base += 2) {
+        const uint32_t e = lane / UNITS, u = lane % UNITS;
+        if (e < 2 && base + e < ns) {
+          const int4* src = reinterpret_cast<const int4*>(&a.sends[(sstaged + base + e) % SW_SEND_RING]);
+          reinterpret_cast<int4*>(&sh.sends[(sstaged + base + e) % SW_SSEND_RING])[u] = sw_ld16_sys(src + u);
+        }
       }
       __syncwarp();
       if (ns) {
@@ -1183,12 +1169,16 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
           __threadfence_block();
           sh.send_tail = sstaged;
           a.ctl->send_head = sstaged;
-          sh.active_clk = clock64();
+          const long long ts = clock64();
+          sh.active_clk = ts;
+          sh.t_staged = ts;
+          dbg_stage += ts - t_seen;
+          dbg_n += ns;
         }
       }
       const long long now = clock64();
       const bool idle = n == 0 && ns == 0 && host_tail == staged && staged == sh.post_head && host_stail == sstaged &&
-                        sstaged == sdone && now - sh.active_clk > linger_clk;
+                        sstaged == sh.send_done && now - sh.active_clk > linger_clk;
       if (stop || idle || now - clk0 > life_clk) {
         if (lane == 0) {
           a.ctl->exit_reason = stop ? 1 : (idle ? 2 : 3);
@@ -1199,35 +1189,66 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
         leaving = true;
       }
     }
-  } else if (warp < 2 + SW_PROG_PUTTERS) {
+  } else if (warp == 2) {
     // ================================================================ puts handed over by the host
     // (the sender side of ucp_tag_send_nbx for small batches while this kernel is resident: no launch)
-    const uint32_t pw = warp - 2;
-    uint64_t i = sh.send_base + pw;
-    uint32_t done = 0;
+    uint64_t i = sh.send_base;
+    uint64_t dbg_put = 0, dbg_pub = 0;
     for (;;) {
-      while (sh.send_tail <= i) {
-        if (sh.helpers_exit) goto out;   // raised after the link warp has stopped staging: nothing is left behind
+      uint64_t tail;
+      while ((tail = sh.send_tail) <= i) {
+        if (sh.helpers_exit) {   // raised after the link warp has stopped staging: nothing is left behind
+          if (lane == 0) {
+            a.ctl->dbg[2] = a.ctl->dbg[2] + dbg_put;
+            a.ctl->dbg[3] = a.ctl->dbg[3] + dbg_pub;
+          }
+          goto out;
+        }
         __nanosleep(20);
       }
       __threadfence_block();
-      const SwSendEnt* e = &sh.sends[i % SW_SSEND_RING];
-      const SwPutDesc d = e->d;
-      uint8_t* slot = reinterpret_cast<uint8_t*>(d.dst);
-      if (d.src) {
-        sw_copy(slot + SW_SLOT_HDR, reinterpret_cast<const uint8_t*>(d.src), d.len, lane, 32);
-      } else if (lane * 16 < d.len) {
-        // inline payload (<= 128 B, staged in shared memory): whole 16 B units, the slot has room for the round-up
-        sw_st16(slot + SW_SLOT_HDR + 16 * lane, reinterpret_cast<const int4*>(e->inl)[lane]);
-      }
-      __syncwarp();
-      if (lane == 0) {
+      const uint32_t n = static_cast<uint32_t>(tail - i < 32 ? tail - i : 32);
+      // a lane per put when the payload is small (inline in the entry, or <= 256 B): payload, then the header
+      // with release semantics; larger payloads by the whole warp, one after the other
+      const SwSendEnt* e = &sh.sends[(i + lane) % SW_SSEND_RING];
+      SwPutDesc d;
+      d.src = d.dst = d.tag = d.seq = d.msg_len = 0;
+      d.len = d.kind = 0;
+      if (lane < n) d = e->d;
+      const bool mine = lane < n && (d.src == 0 || d.len <= 256);
+      if (mine) {
+        uint8_t* slot = reinterpret_cast<uint8_t*>(d.dst);
+        if (d.src) {
+          sw_copy_lane(slot + SW_SLOT_HDR, reinterpret_cast<const uint8_t*>(d.src), d.len);
+        } else {
+          for (uint32_t k = 0; k * 16 < d.len; k++) sw_st16(slot + SW_SLOT_HDR + 16 * k, reinterpret_cast<const int4*>(e->inl)[k]);
+        }
         sw_put_header(slot, d.tag, d.msg_len, d.seq, d.kind);
-        __threadfence_block();
-        sh.put_done[pw] = ++done;
+      }
+      const uint32_t big = __ballot_sync(0xffffffffu, lane < n && !mine);
+      uint32_t rest = big;
+      while (rest) {
+        const int L = __ffs(rest) - 1;
+        rest &= rest - 1;
+        const uint64_t src = sw_shfl64(d.src, L), dst = sw_shfl64(d.dst, L);
+        const uint32_t len = __shfl_sync(0xffffffffu, d.len, L);
+        sw_copy(reinterpret_cast<uint8_t*>(dst) + SW_SLOT_HDR, reinterpret_cast<const uint8_t*>(src), len, lane, 32);
+        __syncwarp();
+        if (static_cast<int>(lane) == L) sw_put_header(reinterpret_cast<uint8_t*>(dst), d.tag, d.msg_len, d.seq, d.kind);
       }
       __syncwarp();
-      i += SW_PROG_PUTTERS;
+      i += n;
+      if (lane == 0) {
+        const long long t1 = clock64();
+        sw_st_release_sys(const_cast<uint64_t*>(&a.ctl->send_done), i);   // every header before it: the host rings the doorbell on it
+        __threadfence_block();
+        sh.send_done = i;
+        const long long t2 = clock64();
+        sh.active_clk = t2;
+        dbg_put += t1 - sh.t_staged;
+        dbg_pub += t2 - t1;
+      }
+      __syncwarp();
     }
   } else {
     // ================================================================ helpers: larger eager payloads

@@ -321,6 +321,10 @@ struct SwProgCtl {
   volatile uint64_t send_done;               // put descriptors executed (slot written, header released)
   volatile uint64_t exit_reason;             // why the last launch left: 1 host request, 2 silence (linger), 3 lifetime
   volatile uint64_t life_us;                 // how long it ran
+  // clock sums for the latency budget of resident puts (SM clocks; [0] count, [1] first sight of a new descriptor
+  // -> staged in shared memory, [2] staged -> slot written and header released, [3] released -> send_done
+  // published, [4] link-warp rounds, [5] link-warp clocks)
+  volatile uint64_t dbg[8];
 };
 
 // ---- pull queue: rendezvous copies executed by the resident pull CTAs of the context
