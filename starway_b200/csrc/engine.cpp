@@ -1527,6 +1527,11 @@ bool pump_sends(Ctx* c) {
     bool one = w0->resident && w0->prog_running && w0->send_ring && c->opt_profile.load() < 2 &&
                w0->sends_written + n - __atomic_load_n(&w0->pctl->send_done, __ATOMIC_ACQUIRE) <= SW_SEND_RING;
     for (uint32_t i = 1; one && i < n; i++) one = b.items[i].op->w == w0;
+    // the put warp takes a lane per put for RTS descriptors and payloads up to 256 B; larger eager payloads are
+    // copied by the whole warp one after the other -- a launch (a warp per message) is faster for more than two
+    uint32_t large = 0;
+    for (uint32_t i = 0; i < n; i++) large += b.descs[i].kind == SW_KIND_EAGER && b.descs[i].len > 256;
+    one = one && large <= 2;
     if (one) {
       for (uint32_t i = 0; i < n; i++) {
         SwSendEnt& e = w0->send_ring[(w0->sends_written + i) % SW_SEND_RING];
@@ -2217,6 +2222,7 @@ bool pump_progress(Ctx* c, Worker* w) {
       p.cap = r->cap;
       p.op_id = r->op_id;
       p.flags = r->mem == MEM_PINNED ? (uint32_t)SW_POST_HOSTPATH : 0u;
+      if (r->pinned_bounce) p.flags |= SW_POST_HOSTBUF;
       p.pad = 0;
       if (!p.flags && r->cap > (uint64_t)c->opt_eager_max.load()) {
         r->rndv_capable = true;   // a rendezvous may land here: keep the pull CTAs of the context resident

@@ -66,13 +66,20 @@ __device__ __forceinline__ int4 sw_ld16_sys(const void* p) {   // host-visible m
 
 // one completion record: body first, system-scope fence (payload copies of this warp included), then the word
 // that carries status + pass number -- the host reads that word first
+// `host_dst`: the payload went to host memory: payload and record travel the same way and get a system-scope
+// fence between them (~1.5 us, `sw_probe hostlat`).  A payload in device memory only has to be performed at gpu
+// scope before the record leaves (L2 is where every later reader of that buffer looks; 0.3 us); the fence also
+// keeps the record's body ahead of its pass word on the way out (posted writes of one requester stay in order).
 __device__ __forceinline__ void sw_write_cqe(SwCqEnt* ring, uint64_t idx, uint64_t op, uint64_t tag, uint64_t len,
-                                             int32_t status) {
+                                             int32_t status, bool host_dst = true) {
   SwCqEnt* e = &ring[idx % SW_CQ_RING];
   e->op_id = op;
   e->tag = tag;
   e->len = len;
-  __threadfence_system();
+  if (host_dst)
+    __threadfence_system();
+  else
+    __threadfence();
   const uint64_t w = (static_cast<uint64_t>(sw_ring_pass(idx, SW_CQ_RING)) << 32) | static_cast<uint32_t>(status);
   sw_st_relaxed_sys(&e->status, w);
 }
@@ -227,13 +234,13 @@ __device__ __forceinline__ void sw_cq_room(const SwProgShared& sh, const SwResCt
 __device__ __forceinline__ bool sw_res_deliver(SwMatchState* st, SwProgShared& sh, const SwProgArgs& a, SwResCtx& c,
                                                uint32_t lane, uint64_t src, uint64_t dst, uint64_t copy_len, uint64_t op,
                                                uint64_t tag, uint64_t msg_len, int32_t status, uint32_t src_kind,
-                                               uint32_t arg, uint64_t cons_after) {
+                                               uint32_t arg, uint64_t cons_after, uint32_t pflags) {
   sw_cq_room(sh, c, 1);
   const uint64_t cq_idx = c.cq_alloc++;
   if (copy_len <= SW_INLINE_DELIVER) {
     sw_copy(reinterpret_cast<uint8_t*>(dst), reinterpret_cast<const uint8_t*>(src), copy_len, lane, 32);
     __syncwarp();
-    if (lane == 0) sw_write_cqe(a.cq, cq_idx, op, tag, msg_len, status);
+    if (lane == 0) sw_write_cqe(a.cq, cq_idx, op, tag, msg_len, status, (pflags & SW_POST_HOSTBUF) != 0);
     if (src_kind == 1) {
       if (lane == 0) st->free_small[c.n_free_small] = arg;
       c.n_free_small++;
@@ -258,6 +265,7 @@ __device__ __forceinline__ bool sw_res_deliver(SwMatchState* st, SwProgShared& s
     j->msg_len = msg_len;
     j->cq_idx = cq_idx;
     j->status = status;
+    j->pad = pflags;
     SwPend* p = &sh.pend[c.pend_tail % SW_PEND_RING];
     p->job = c.jobs_emitted;
     p->cons_after = cons_after;
@@ -529,7 +537,7 @@ __device__ __forceinline__ void sw_res_posts(SwMatchState* __restrict__ st, SwPr
       } else {
         const bool trunc = f_len > cap;
         sw_res_deliver(st, sh, a, c, lane, f_data, buf, trunc ? 0 : f_len, op, f_tag, f_len,
-                       trunc ? SW_ERR_MESSAGE_TRUNCATED : SW_OK, big ? 2u : 1u, f_blk, 0);
+                       trunc ? SW_ERR_MESSAGE_TRUNCATED : SW_OK, big ? 2u : 1u, f_blk, 0, pflags);
       }
     } else if (c.p_tail - c.p_head >= SW_PQ_CAP) {
       c.err |= 2;   // posted queue overflow (the host throttles before this can happen)
@@ -711,7 +719,8 @@ __device__ __forceinline__ uint32_t sw_res_arrivals(SwMatchState* __restrict__ s
       if (small) {
         sw_copy_lane(reinterpret_cast<uint8_t*>(w_buf), reinterpret_cast<const uint8_t*>(a_slot + SW_SLOT_HDR),
                      static_cast<uint32_t>(copy_len));
-        sw_write_cqe(a.cq, c.cq_alloc + __popc(small_m & lt), w_op, a_tag, a_len, trunc ? SW_ERR_MESSAGE_TRUNCATED : SW_OK);
+        sw_write_cqe(a.cq, c.cq_alloc + __popc(small_m & lt), w_op, a_tag, a_len, trunc ? SW_ERR_MESSAGE_TRUNCATED : SW_OK,
+                     ((w_valid >> 8) & SW_POST_HOSTBUF) != 0);
       }
       c.cq_alloc += n_small;
     }
@@ -733,7 +742,7 @@ __device__ __forceinline__ uint32_t sw_res_arrivals(SwMatchState* __restrict__ s
       } else {
         const bool t2 = o_len > o_cap;
         sw_res_deliver(st, sh, a, c, lane, o_slot + SW_SLOT_HDR, o_buf, t2 ? 0 : o_len, o_op, o_tag, o_len,
-                       t2 ? SW_ERR_MESSAGE_TRUNCATED : SW_OK, 0, ep, cons + o_rank + 1);
+                       t2 ? SW_ERR_MESSAGE_TRUNCATED : SW_OK, 0, ep, cons + o_rank + 1, o_valid >> 8);
       }
     }
     if (in_k) w_valid = 0;
@@ -806,7 +815,7 @@ __device__ __forceinline__ uint32_t sw_res_arrivals(SwMatchState* __restrict__ s
       } else {
         const bool trunc = mlen > f_cap;
         sw_res_deliver(st, sh, a, c, lane, payload, f_buf, trunc ? 0 : mlen, f_op, stag, mlen,
-                       trunc ? SW_ERR_MESSAGE_TRUNCATED : SW_OK, 0, ep, cons + 1);
+                       trunc ? SW_ERR_MESSAGE_TRUNCATED : SW_OK, 0, ep, cons + 1, f_valid >> 8);
       }
     } else {
       // unexpected: park the payload (or the RTS descriptor) on the heap -- copied by this warp at once, so the
@@ -857,8 +866,10 @@ __device__ __forceinline__ uint32_t sw_res_arrivals(SwMatchState* __restrict__ s
     if (lane == 0) sh.cons[ep] = cons;
     __syncwarp();
     c.arrivals += used;
-    // slots whose payload a helper still reads stay owned until that job retires
-    if (sh.pend_cnt[ep] == 0) sw_publish_credit(st, sh, ep, cons, lane);
+    // Credits cost a system-scope release (~1.5 us): while messages keep coming they are returned a quarter of
+    // the ring at a time; the matcher's main loop returns the rest as soon as an iteration finds nothing new.
+    // Slots whose payload a helper still reads stay owned until that job retires.
+    if (sh.pend_cnt[ep] == 0 && cons - sh.credit[ep] >= (smask + 1) / 4) sw_publish_credit(st, sh, ep, cons, lane);
   }
   return used;
 }
@@ -1045,12 +1056,18 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
       if (did) {
         if (lane == 0) sh.active_clk = clock64();
       } else {
+        // quiet: return the credits that were held back
+        for (uint32_t e = 0; e < n_eps; e++)
+          if (sh.ring_base[e] && sh.pend_cnt[e] == 0 && sh.cons[e] != sh.credit[e]) sw_publish_credit(st, sh, e, sh.cons[e], lane);
         __nanosleep(40);
       }
     }
     // ---- wind down: helpers finish, every deferred release happens, state goes back to device memory
     sw_res_flush_pull(st, sh, a, c, lane);
     sw_retire(st, sh, c, lane, true);
+    for (uint32_t e = 0; e < n_eps; e++)
+      if (sh.ring_base[e]) sw_publish_credit(st, sh, e, sh.cons[e], lane);
+    __syncwarp();
     for (uint32_t e = lane; e < SW_MAX_EPS; e += 32)
       if (sh.ring_base[e]) st->ring_cons[e] = sh.cons[e];   // (a ring attached while this launch ran is not ours to touch)
     if (lane == 0) {
@@ -1128,14 +1145,14 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
         }
         continue;
       }
-      // ---- stage new receives: up to 10 per round, a lane per 16-byte unit (3 units per entry)
+      // ---- stage new receives: up to 32 per round, 16-byte units spread over the lanes (3 units per entry)
       const uint64_t consumed = sh.post_head;
       const uint64_t room = SW_SPOST_RING - (staged - consumed);
       uint64_t n = host_tail - staged;
       if (n > room) n = room;
-      if (n > 10) n = 10;
-      if (lane < 3 * n) {
-        const uint32_t e = lane / 3, u = lane % 3;
+      if (n > 32) n = 32;
+      for (uint32_t x = lane; x < 3 * n; x += 32) {
+        const uint32_t e = x / 3, u = x % 3;
         const int4* src = reinterpret_cast<const int4*>(&a.posts[(staged + e) % SW_POST_RING]);
         reinterpret_cast<int4*>(&sh.posts[(staged + e) % SW_SPOST_RING])[u] = sw_ld16_sys(src + u);
       }
@@ -1266,7 +1283,7 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
         sw_copy(reinterpret_cast<uint8_t*>(j.dst), reinterpret_cast<const uint8_t*>(j.src), j.len, lane, 32);
         __syncwarp();
         if (lane == 0) {
-          sw_write_cqe(a.cq, j.cq_idx, j.op_id, j.tag, j.msg_len, j.status);
+          sw_write_cqe(a.cq, j.cq_idx, j.op_id, j.tag, j.msg_len, j.status, (j.pad & SW_POST_HOSTBUF) != 0);
           sh.helper_done[h] = ++done;
         }
         __syncwarp();

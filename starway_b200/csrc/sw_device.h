@@ -256,7 +256,10 @@ constexpr uint32_t SW_MAP_PROBE = 32;       // one warp-wide probe
 constexpr uint32_t SW_INLINE_DELIVER = 256; // eager payloads up to this size are copied by the matcher warp itself
 constexpr uint32_t SW_SEND_RING = 64;       // host -> device: put descriptors executed by the resident control kernel
 
-enum : uint32_t { SW_POST_HOSTPATH = 1 };   // a rendezvous into this receive is copied by a host-launched kernel
+enum : uint32_t {
+  SW_POST_HOSTPATH = 1,   // a rendezvous into this receive is copied by a host-launched kernel
+  SW_POST_HOSTBUF = 2,    // the landing buffer is host memory (pinned bounce): payload and record need a system-scope fence
+};
 enum : uint64_t { SW_RTS_PINNED_SRC = 1 };  // SwRts::pad[0]: the source is pinned host memory
 
 struct SwSendEnt {   // pinned host: one put for the resident control kernel of the sending worker

@@ -92,8 +92,14 @@ int main(int argc, char** argv) {
     uint64_t launches = s1.put_launches - s0.put_launches + s1.match_launches - s0.match_launches +
                         s1.deliver_launches - s0.deliver_launches + s1.bulk_tma_launches - s0.bulk_tma_launches +
                         s1.bulk_simt_launches - s0.bulk_simt_launches;
-    printf("[c-abi loopback] %10zu B window=%4zu: %9.3f GB/s  %8.4f Mmsg/s  %8.2f us/msg  (%llu launches/step)\n", n, window,
+    launches += s1.prog_launches - s0.prog_launches + s1.pull_launches - s0.pull_launches;
+    const double pb = (double)(s1.pull_batches - s0.pull_batches), pbusy = s1.pull_busy_ms - s0.pull_busy_ms;
+    printf("[c-abi loopback] %10zu B window=%4zu: %9.3f GB/s  %8.4f Mmsg/s  %8.2f us/msg  (%llu launches/step)", n, window,
            gbs, msgs / best / 1e6, best / msgs * 1e6, (unsigned long long)(launches / steps));
+    if (pb > 0)
+      printf("  pull: %.0f batches of %.2f MB, %.1f us each, %.0f GB/s while active", pb, (double)(s1.pull_bytes - s0.pull_bytes) / pb / 1e6,
+             pbusy * 1e3 / pb, (double)(s1.pull_bytes - s0.pull_bytes) / (pbusy * 1e-3) / 1e9);
+    printf("\n");
     if (out)
       fprintf(out, "{\"bench\":\"c_abi_loopback\",\"msg_bytes\":%zu,\"window\":%zu,\"gbs\":%.3f,\"mmsg_s\":%.4f,\"us_per_msg\":%.3f}\n",
               n, window, gbs, msgs / best / 1e6, best / msgs * 1e6);
