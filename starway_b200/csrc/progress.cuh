@@ -142,7 +142,8 @@ struct SwProgShared {
   SwPend pend[SW_PEND_RING];
   uint64_t ring_base[SW_MAX_EPS];
   uint64_t cons[SW_MAX_EPS];
-  uint64_t credit[SW_MAX_EPS];
+  uint64_t credit[SW_MAX_EPS];       // cursor published to the sender so far
+  uint64_t releasable[SW_MAX_EPS];   // cursor that may be published (no helper still reads a slot below it)
   uint32_t ring_mask[SW_MAX_EPS];
   uint32_t ring_gen[SW_MAX_EPS];
   uint32_t pend_cnt[SW_MAX_EPS];
@@ -205,9 +206,13 @@ __device__ __forceinline__ void sw_retire(SwMatchState* st, SwProgShared& sh, Sw
       const SwPend p = sh.pend[c.pend_head % SW_PEND_RING];
       if (p.job >= prefix) break;
       if (p.kind == 0) {
-        if (lane == 0) sh.pend_cnt[p.arg]--;
+        // the slots up to this job's are free again (published lazily: a release costs a system-scope fence)
+        if (lane == 0) {
+          sh.pend_cnt[p.arg]--;
+          const uint64_t r = sh.pend_cnt[p.arg] == 0 ? sh.cons[p.arg] : p.cons_after;
+          if (r > sh.releasable[p.arg]) sh.releasable[p.arg] = r;
+        }
         __syncwarp();
-        sw_publish_credit(st, sh, p.arg, sh.pend_cnt[p.arg] == 0 ? sh.cons[p.arg] : p.cons_after, lane);
       } else if (p.kind == 1) {
         if (lane == 0) st->free_small[c.n_free_small] = p.arg;
         c.n_free_small++;
@@ -869,7 +874,9 @@ __device__ __forceinline__ uint32_t sw_res_arrivals(SwMatchState* __restrict__ s
     // Credits cost a system-scope release (~1.5 us): while messages keep coming they are returned a quarter of
     // the ring at a time; the matcher's main loop returns the rest as soon as an iteration finds nothing new.
     // Slots whose payload a helper still reads stay owned until that job retires.
-    if (sh.pend_cnt[ep] == 0 && cons - sh.credit[ep] >= (smask + 1) / 4) sw_publish_credit(st, sh, ep, cons, lane);
+    if (sh.pend_cnt[ep] == 0 && lane == 0) sh.releasable[ep] = cons;
+    __syncwarp();
+    if (sh.releasable[ep] - sh.credit[ep] >= (smask + 1) / 4) sw_publish_credit(st, sh, ep, sh.releasable[ep], lane);
   }
   return used;
 }
@@ -964,6 +971,7 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
     sh.fin_ptr[e] = st->fin_ptr[e];
     sh.cons[e] = st->ring_cons[e];
     sh.credit[e] = st->ring_cons[e];
+    sh.releasable[e] = st->ring_cons[e];
     sh.pend_cnt[e] = 0;
   }
   if (threadIdx.x == 0) {
@@ -1058,7 +1066,7 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
       } else {
         // quiet: return the credits that were held back
         for (uint32_t e = 0; e < n_eps; e++)
-          if (sh.ring_base[e] && sh.pend_cnt[e] == 0 && sh.cons[e] != sh.credit[e]) sw_publish_credit(st, sh, e, sh.cons[e], lane);
+          if (sh.ring_base[e] && sh.releasable[e] != sh.credit[e]) sw_publish_credit(st, sh, e, sh.releasable[e], lane);
         __nanosleep(40);
       }
     }
@@ -1066,7 +1074,7 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
     sw_res_flush_pull(st, sh, a, c, lane);
     sw_retire(st, sh, c, lane, true);
     for (uint32_t e = 0; e < n_eps; e++)
-      if (sh.ring_base[e]) sw_publish_credit(st, sh, e, sh.cons[e], lane);
+      if (sh.ring_base[e]) sw_publish_credit(st, sh, e, sh.cons[e], lane);   // every helper has finished
     __syncwarp();
     for (uint32_t e = lane; e < SW_MAX_EPS; e += 32)
       if (sh.ring_base[e]) st->ring_cons[e] = sh.cons[e];   // (a ring attached while this launch ran is not ours to touch)

@@ -97,8 +97,9 @@ int main(int argc, char** argv) {
     printf("[c-abi loopback] %10zu B window=%4zu: %9.3f GB/s  %8.4f Mmsg/s  %8.2f us/msg  (%llu launches/step)", n, window,
            gbs, msgs / best / 1e6, best / msgs * 1e6, (unsigned long long)(launches / steps));
     if (pb > 0)
-      printf("  pull: %.0f batches of %.2f MB, %.1f us each, %.0f GB/s while active", pb, (double)(s1.pull_bytes - s0.pull_bytes) / pb / 1e6,
-             pbusy * 1e3 / pb, (double)(s1.pull_bytes - s0.pull_bytes) / (pbusy * 1e-3) / 1e9);
+      printf("  pull: %.0f batches of %.2f MB, %.1f us each, %.0f GB/s while active; phases %.1f / %.1f / %.1f us", pb,
+             (double)(s1.pull_bytes - s0.pull_bytes) / pb / 1e6, pbusy * 1e3 / pb, (double)(s1.pull_bytes - s0.pull_bytes) / (pbusy * 1e-3) / 1e9,
+             (s1.pull_pickup_ms - s0.pull_pickup_ms) * 1e3 / pb, (s1.pull_copy_ms - s0.pull_copy_ms) * 1e3 / pb, (s1.pull_fin_ms - s0.pull_fin_ms) * 1e3 / pb);
     printf("\n");
     if (out)
       fprintf(out, "{\"bench\":\"c_abi_loopback\",\"msg_bytes\":%zu,\"window\":%zu,\"gbs\":%.3f,\"mmsg_s\":%.4f,\"us_per_msg\":%.3f}\n",
