@@ -85,8 +85,9 @@ async def large_array_client(client, cfg, bufs):
             durations.append(time.perf_counter() - t0)
     total = sum(durations)
     per = [n / d / 1e9 for d in durations]
+    # metric keys and samples as the reference's scenario reports them (benchmarks/scenarios.py:109-120)
     return {"total_seconds": total, "avg_seconds_per_iter": total / iters, "avg_gbps": n * iters / total / 1e9,
-            "best_gbps": max(per), "worst_gbps": min(per)}
+            "best_gbps": max(per), "worst_gbps": min(per)}, {"duration_seconds": durations, "per_iter_gbps": per}
 
 
 async def large_array_server(server, ep, cfg, bufs):
@@ -108,9 +109,12 @@ async def small_messages_client(client, cfg, bufs):
         if b >= warm:
             durations.append(time.perf_counter() - t0)
     total = sum(durations)
-    lat = np.array(durations) / conc * 1e6
-    return {"total_seconds": total, "messages_per_second": iters * conc / total, "bandwidth_gbps": n * iters * conc / total / 1e9,
-            "latency_p50_us": float(np.percentile(lat, 50)), "latency_p95_us": float(np.percentile(lat, 95))}
+    per_msg = [d / conc for d in durations]
+    lat = np.array(per_msg) * 1e6
+    # reference benchmarks/scenarios.py:184-196
+    return ({"total_seconds": total, "messages_per_second": iters * conc / total, "bandwidth_gbps": n * iters * conc / total / 1e9,
+             "latency_p50_us": float(np.percentile(lat, 50)), "latency_p95_us": float(np.percentile(lat, 95))},
+            {"batch_duration_seconds": durations, "avg_latency_seconds": per_msg})
 
 
 async def small_messages_server(server, ep, cfg, bufs):
@@ -132,8 +136,10 @@ async def pingpong_client(client, cfg, bufs):
         if i >= cfg["warmup"]:
             rtts.append(time.perf_counter() - t0)
     us = np.array(rtts) * 1e6
-    return {"rtt_avg_us": float(us.mean()), "rtt_p50_us": float(np.percentile(us, 50)), "rtt_p95_us": float(np.percentile(us, 95)),
-            "rtt_min_us": float(us.min())}
+    # reference benchmarks/scenarios.py:261-272 (plus the 95th percentile)
+    return ({"avg_rtt_us": float(us.mean()), "median_rtt_us": float(np.median(us)), "min_rtt_us": float(us.min()),
+             "max_rtt_us": float(us.max()), "avg_one_way_us": float(us.mean()) / 2.0, "p95_rtt_us": float(np.percentile(us, 95))},
+            {"rtt_seconds": rtts})
 
 
 async def pingpong_server(server, ep, cfg, bufs):
@@ -154,8 +160,10 @@ async def streaming_client(client, cfg, bufs):
         if i >= warm:
             durations.append(time.perf_counter() - t0)
     total = sum(durations)
-    return {"total_seconds": total, "aggregate_gbps": 2 * n * iters / total / 1e9, "per_direction_gbps": n * iters / total / 1e9,
-            "avg_iter_us": total / iters * 1e6}
+    # reference benchmarks/scenarios.py:319-336
+    return ({"total_seconds": total, "avg_seconds_per_iter": total / iters, "client_to_server_gbps": n * iters / total / 1e9,
+             "server_to_client_gbps": n * iters / total / 1e9, "aggregate_gbps": 2 * n * iters / total / 1e9},
+            {"iteration_seconds": durations})
 
 
 async def streaming_server(server, ep, cfg, bufs):
@@ -196,9 +204,10 @@ async def run_client_side(client, plan, bufs):
     results = []
     for name, cfg in plan:
         await _recv_frame(client, READY_TAG)
-        metrics = await SCENARIOS[name][0](client, cfg, bufs)
+        metrics, samples = await SCENARIOS[name][0](client, cfg, bufs)
         await client.asend(_frame({"scenario": name, "done": True}), DONE_TAG)
-        results.append({"name": name, "metrics": metrics, "config": cfg})
+        # one entry = the reference's ScenarioResult.to_dict() (benchmarks/scenarios.py:49-57)
+        results.append({"name": name, "metrics": metrics, "config": cfg, "samples": samples})
     return results
 
 
@@ -267,14 +276,22 @@ async def amain(args):
         results = await run_client_side(client, plan, bufs)
         await client.aclose()
     if results is not None:
-        report = {"backend": sw.backend_name(), "buffers": kind, "role": args.role, "results": results}
+        # the reference's report (src/starway/bench.py:383-405): timestamp, transport, scenarios[]; `transport` is the
+        # UCX_TLS variable there -- here the backend and where the buffers live
+        report = {"timestamp": time.time(), "transport": f"{sw.backend_name()}:{kind}", "role": args.role,
+                  "scenarios": [dict(r) if args.store_trace else {k: v for k, v in r.items() if k != "samples"} for r in results]}
+        print("\n=== Benchmark Results ===")
         for r in results:
-            print(f"[{r['name']}]")
+            print(f"\n[{r['name']}]")
             for k, v in r["metrics"].items():
                 print(f"  {k}: {v:.6f}" if isinstance(v, float) else f"  {k}: {v}")
         if args.output:
+            import os
+
+            os.makedirs(os.path.dirname(os.path.abspath(args.output)), exist_ok=True)
             with open(args.output, "w") as f:
                 json.dump(report, f, indent=2)
+            print(f"\nJSON results written to {args.output}")
     sw.shutdown()
 
 
@@ -287,6 +304,7 @@ def main(argv=None):
     ap.add_argument("--buffers", choices=["auto", "device", "host"], default="auto")
     ap.add_argument("--scenario", dest="scenarios", action="append", help="repeatable; default: all")
     ap.add_argument("--output", default=None, help="write a JSON report here")
+    ap.add_argument("--store-trace", action="store_true", help="keep the per-iteration samples in the JSON report")
     ap.add_argument("--large-bytes", type=parse_size)
     ap.add_argument("--large-iterations", type=int)
     ap.add_argument("--large-warmup", type=int)

@@ -34,10 +34,38 @@ def test_scenarios_loopback_on_sim(sim_api):
     assert [r["name"] for r in results] == [p[0] for p in plan]
     assert results[0]["metrics"]["avg_gbps"] > 0
     assert results[1]["metrics"]["messages_per_second"] > 0
-    assert results[2]["metrics"]["rtt_p50_us"] > 0
+    assert results[2]["metrics"]["median_rtt_us"] > 0
     assert results[3]["metrics"]["aggregate_gbps"] > 0
 
 
 def test_cli_parsing():
     assert bc.parse_size("4MiB") == 4 << 20 and bc.parse_size("1g") == 1 << 30 and bc.parse_size("512") == 512
     assert bc.list_scenarios() == ["large-array", "small-messages", "pingpong-flag", "streaming-duplex"]
+
+
+# the keys of the reference's JSON report (reference src/starway/bench.py:383-405, benchmarks/scenarios.py:49-57,
+# 109-120, 184-196, 261-272, 319-336)
+REFERENCE_METRICS = {
+    "large-array": {"total_seconds", "avg_seconds_per_iter", "avg_gbps", "best_gbps", "worst_gbps"},
+    "small-messages": {"total_seconds", "messages_per_second", "bandwidth_gbps", "latency_p50_us", "latency_p95_us"},
+    "pingpong-flag": {"avg_rtt_us", "median_rtt_us", "min_rtt_us", "max_rtt_us", "avg_one_way_us"},
+    "streaming-duplex": {"total_seconds", "avg_seconds_per_iter", "client_to_server_gbps", "server_to_client_gbps", "aggregate_gbps"},
+}
+REFERENCE_SAMPLES = {
+    "large-array": {"duration_seconds", "per_iter_gbps"},
+    "small-messages": {"batch_duration_seconds", "avg_latency_seconds"},
+    "pingpong-flag": {"rtt_seconds"},
+    "streaming-duplex": {"iteration_seconds"},
+}
+
+
+def check_report(report, with_samples):
+    assert {"timestamp", "transport", "scenarios"} <= set(report)
+    assert [s["name"] for s in report["scenarios"]] == list(REFERENCE_METRICS)
+    for s in report["scenarios"]:
+        assert {"name", "metrics", "config"} <= set(s)
+        assert REFERENCE_METRICS[s["name"]] <= set(s["metrics"]), (s["name"], sorted(s["metrics"]))
+        assert all(isinstance(v, float) and v >= 0 for v in s["metrics"].values())
+        assert ("samples" in s) == with_samples
+        if with_samples:
+            assert REFERENCE_SAMPLES[s["name"]] == set(s["samples"])

@@ -543,3 +543,31 @@ def test_numa_local_cpus(cuda_api):
         assert (now == (cpus & allowed)) if changed else True
     finally:
         os.sched_setaffinity(0, allowed)
+
+
+# ------------------------------------------------------------------ the reference's benchmark CLI on the GPU
+@pytest.mark.parametrize("buffers", ["device", "host"])
+def test_bench_cli_loopback_all_scenarios(tmp_path, buffers):
+    """`python -m starway_b200.bench_cli --role loopback`: the four scenarios of the reference's harness through
+    the product library, device and host buffers, and the JSON report with the reference's schema
+    (reference src/starway/bench.py:125-201, 383-405; benchmarks/scenarios.py:96-108, 159-177, 238-266, 305-331)."""
+    import json
+    import subprocess
+    import sys
+
+    from tests.test_bench_cli_sim import check_report
+
+    torch_cuda()
+    out = tmp_path / f"report_{buffers}.json"
+    cmd = [sys.executable, "-m", "starway_b200.bench_cli", "--role", "loopback", "--buffers", buffers, "--output", str(out),
+           "--store-trace", "--large-bytes", "256MiB", "--large-iterations", "2", "--flag-iterations", "200", "--flag-warmup", "20",
+           "--stream-iterations", "16", "--stream-warmup", "2"]
+    env = dict(os.environ, STARWAY_QUIET="1", PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=280, env=env)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    report = json.loads(out.read_text())
+    check_report(report, with_samples=True)
+    assert report["transport"] == f"cuda-sm_100a:{buffers}"
+    m = {s["name"]: s["metrics"] for s in report["scenarios"]}
+    assert m["large-array"]["avg_gbps"] > 1.0 and m["small-messages"]["messages_per_second"] > 1e4
+    assert 0 < m["pingpong-flag"]["median_rtt_us"] < 5000 and m["streaming-duplex"]["aggregate_gbps"] > 1.0
