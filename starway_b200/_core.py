@@ -712,6 +712,12 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
                 raise RuntimeError(_err())
             return buf.raw[:n]
 
+        def close(self, callback: Callable[[], None]):
+            """Binding-level close (reference ``_bindings.pyi:31,69``, bound at ``main.cpp:1538-1581``): returns at
+            once, ``callback()`` fires when the worker has shut down.  Raises RuntimeError when not running."""
+            h, w = self._ctx._h, self._w
+            self._ctx.submit(lambda: lib.sw_close(h, w), ("cb", callback, None, None))
+
         def _aclose(self, loop, banner):
             loop, fut = self._future(loop)
             h, w = self._ctx._h, self._w

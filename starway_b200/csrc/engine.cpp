@@ -319,6 +319,8 @@ struct SendOp {
   uint64_t rndv_seq = 0;
   // The put block that carries this send's slot still refers to the record until poll_puts retires it: a
   // FIN / close that ends the send earlier only notes the outcome here and poll_puts finishes the record.
+  bool stage_d2d = false;   // device source that CUDA IPC cannot export (cuMemCreate / expandable segments):
+                            // copied into an exportable staging buffer first
   bool in_put = false;
   bool ended_early = false;
   int32_t early_status = 0;
@@ -644,6 +646,7 @@ struct Ctx {
   struct HandleEnt {
     uint64_t base;
     uint8_t handle[64];
+    bool exportable = true;   // false: cudaIpcGetMemHandle refuses this allocation (virtual-memory-management API)
   };
   std::unordered_map<uint64_t, HandleEnt> handle_cache;  // CUDA buffer id -> exported IPC handle
   // options
@@ -1413,9 +1416,38 @@ bool pump_sends(Ctx* c) {
             size = op->len;
             r.src_ptr = base;
             r.pad[0] = SW_RTS_PINNED_SRC;
-          } else if (op->mem == SW_MEM_HOST) {
+          } else if (op->mem != SW_MEM_HOST && !ep->in_process && !op->stage_d2d && !op->dev_staging) {
+            // device source, peer in another process: can the allocation be exported?  (answer cached per allocation)
+            swgpu::PtrInfo pi;
+            swgpu::ptr_info(op->ptr, &pi);
+            if (!pi.is_device || pi.base == 0) {
+              ep->sendq.pop_front();
+              set_error("rendezvous source is not a CUDA device allocation");
+              send_finished(c, op, SW_ERR_INVALID_PARAM);
+              continue;
+            }
+            auto hit = pi.buffer_id ? c->handle_cache.find(pi.buffer_id) : c->handle_cache.end();
+            if (hit != c->handle_cache.end() && hit->second.base == pi.base) {
+              op->stage_d2d = !hit->second.exportable;
+            } else {
+              Ctx::HandleEnt he;
+              he.base = pi.base;
+              he.exportable = swgpu::ipc_get((void*)(uintptr_t)pi.base, he.handle) == 0;
+              if (pi.buffer_id) {
+                if (c->handle_cache.size() > 8192) c->handle_cache.clear();
+                c->handle_cache[pi.buffer_id] = he;
+              }
+              op->stage_d2d = !he.exportable;
+            }
+          }
+          if (op->mem == MEM_PINNED) {
+            // (handled above)
+          } else if (op->mem == SW_MEM_HOST || op->stage_d2d) {
             // Staged sends are published batch by batch: keep batches small so that the receiver can
             // start pulling the first payloads while later ones are still being uploaded.
+            // (Host memory; or device memory from the CUDA virtual-memory-management API -- PyTorch's expandable
+            // segments -- which cudaIpcGetMemHandle cannot export: one device-to-device copy into an exportable
+            // staging buffer, at HBM speed, keeps such tensors usable as rendezvous sources.)
             if (!op->dev_staging && n > 0 && staged_bytes + op->len > STAGE_BATCH_BYTES) {
               batch_full = true;
               break;
@@ -1428,6 +1460,11 @@ bool pump_sends(Ctx* c) {
                 send_finished(c, op, SW_ERR_NO_MEMORY);
                 continue;
               }
+              if (op->stage_d2d) {
+                trace(c, "d2d_stage", op->len);
+                swgpu::memcpy_d2d(op->dev_staging, op->ptr, op->len, b.s);
+                stream_ordered = true;
+              } else {
               swgpu::PtrInfo hpi;
               swgpu::ptr_info(op->ptr, &hpi);
               const uint64_t pieces = (op->len + STAGE_SEG_BYTES - 1) / STAGE_SEG_BYTES;
@@ -1448,6 +1485,7 @@ bool pump_sends(Ctx* c) {
                 stream_ordered = true;   // the RTS may only become visible after this copy: needs the put launch behind it
               }
               h2d += op->len;
+              }
             }
             base = (uint64_t)(uintptr_t)op->dev_staging;
             size = op->staging_size;
@@ -1467,12 +1505,6 @@ bool pump_sends(Ctx* c) {
               size = pi.size;
               srcdev = pi.device;
               buffer_id = pi.buffer_id;
-              if (!pi.is_device || base == 0) {
-                ep->sendq.pop_front();
-                set_error("rendezvous source is not a CUDA device allocation");
-                send_finished(c, op, SW_ERR_INVALID_PARAM);
-                continue;
-              }
             }
           }
           if (!ep->in_process) {

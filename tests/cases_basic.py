@@ -16,10 +16,10 @@ Not portable, and why:
 from __future__ import annotations
 
 import asyncio
+import os
 import contextlib
 import gc
 import multiprocessing as mp
-import os
 
 import numpy as np
 
@@ -217,7 +217,18 @@ async def case_evaluate_perf(api, port):
 
 
 # ------------------------------------------------------------------ flush-then-exit delivery (2 processes)
-SIZE_FLUSH = {"sim": 48 * 1024 * 1024, "cuda": 1024 * 1024 * 1024}
+class _SizeFlush(dict):
+    """Payload of the flush-then-exit tests (the reference sends 8 GiB of host memory, tests/test_basic.py:280-309,
+    396-415).  The GPU default is 1 GiB; STARWAY_FLUSH_BYTES (inherited by the spawned peer) selects the multi-GiB
+    shape."""
+
+    def __getitem__(self, backend):
+        if backend == "cuda" and os.environ.get("STARWAY_FLUSH_BYTES"):
+            return int(os.environ["STARWAY_FLUSH_BYTES"])
+        return dict.__getitem__(self, backend)
+
+
+SIZE_FLUSH = _SizeFlush({"sim": 48 * 1024 * 1024, "cuda": 1024 * 1024 * 1024})
 
 
 def _proc_server_send(backend, port, mode):
@@ -320,9 +331,11 @@ def _simdev_pattern(i, n):
     return ((np.arange(n, dtype=np.uint64) * 2654435761 + i * 97) >> 7).astype(np.uint8)
 
 
-def _proc_simdev_sender(port):
+def _proc_simdev_sender(port, exportable=True):
     """Child: sends from 'device' buffers of the CPU stand-in (eager and rendezvous sizes), flushes,
-    then waits for the parent's verdict so that its buffers stay mapped while the parent pulls."""
+    then waits for the parent's verdict so that its buffers stay mapped while the parent pulls.
+    exportable=False: buffers the IPC export refuses (the stand-in's version of cuMemCreate / expandable-segment
+    memory): the engine stages them through an exportable buffer."""
     from tests.hostsim import SimDev
 
     api = load_api("sim")
@@ -330,7 +343,7 @@ def _proc_simdev_sender(port):
     async def inner():
         client = api.Client()
         await client.aconnect(SERVER_ADDR, port)
-        bufs = [SimDev.from_np(_simdev_pattern(i, n)) for i, n in enumerate(SIMDEV_SIZES)]
+        bufs = [SimDev.from_np(_simdev_pattern(i, n), exportable) for i, n in enumerate(SIMDEV_SIZES)]
         verdict = np.zeros(1, dtype=np.uint8)
         fv = client.arecv(verdict, 0x77, (1 << 64) - 1)
         for rnd in range(3):  # the same allocations three times: exported-handle / mapping caches hit
@@ -344,7 +357,7 @@ def _proc_simdev_sender(port):
     api.shutdown()
 
 
-async def case_simdev_two_process_device_buffers(api, port):
+async def case_simdev_two_process_device_buffers(api, port, exportable=True):
     from tests.hostsim import SimDev
 
     server = api.Server()
@@ -353,7 +366,7 @@ async def case_simdev_two_process_device_buffers(api, port):
     loop = asyncio.get_running_loop()
     server.set_accept_cb(lambda _: loop.call_soon_threadsafe(connected.set))
     ctx = mp.get_context("spawn")
-    child = ctx.Process(target=_proc_simdev_sender, args=(port,))
+    child = ctx.Process(target=_proc_simdev_sender, args=(port, exportable))
     child.start()
     try:
         await asyncio.wait_for(connected.wait(), timeout=120)
@@ -864,8 +877,53 @@ async def case_chaos(api, port, seed, n_ops=120, bufs=None):
 
 
 
+# ------------------------------------------------------------------ the binding-level (callback) surface, close included
+async def case_binding_level_callbacks(api, port):
+    """The reference's `_bindings` classes take callbacks (reference _bindings.pyi:23-88); a maintainer who swaps the
+    extension module calls these, `close(callback)` included (main.cpp:594-601, 1375-1382)."""
+    loop = asyncio.get_running_loop()
+
+    def waiter():
+        fut = loop.create_future()
+        return fut, (lambda *a: loop.call_soon_threadsafe(fut.set_result, a)), (lambda why: loop.call_soon_threadsafe(fut.set_exception, Exception(why)))
+
+    server, client = api.Server(), api.Client()
+    server.listen(SERVER_ADDR, port)
+    f, ok, _ = waiter()
+    client.connect(SERVER_ADDR, port, ok)
+    assert await asyncio.wait_for(f, 30) == ("",)
+    for _ in range(200):
+        if server.list_clients():
+            break
+        await asyncio.sleep(0.005)
+    ep = next(iter(server.list_clients()))
+    buf = np.zeros(16, dtype=np.uint8)
+    fr, ok_r, fail_r = waiter()
+    server.recv(buf, 3, 0xFF, ok_r, fail_r)
+    fs, ok_s, fail_s = waiter()
+    client.send(np.arange(16, dtype=np.uint8), 0x103, ok_s, fail_s)
+    assert await asyncio.wait_for(fs, 30) == ()
+    assert await asyncio.wait_for(fr, 30) == (0x103, 16)
+    np.testing.assert_array_equal(buf, np.arange(16, dtype=np.uint8))
+    ff, ok_f, fail_f = waiter()
+    server.flush_ep(ep, ok_f, fail_f)
+    assert await asyncio.wait_for(ff, 30) == ()
+    fc, ok_c, _ = waiter()
+    client.close(ok_c)
+    assert await asyncio.wait_for(fc, 30) == ()
+    fc2, ok_c2, _ = waiter()
+    server.close(ok_c2)
+    assert await asyncio.wait_for(fc2, 30) == ()
+    try:
+        client.close(lambda: None)   # reference: "You can only close once" -> RuntimeError
+        raise AssertionError("second close must raise")
+    except RuntimeError as e:
+        assert "not running" in str(e)
+
+
 SINGLE_PROCESS_CASES = [
     case_server_listen_client_connect_close,
+    case_binding_level_callbacks,
     case_worker_address_connection_roundtrip,
     case_worker_address_accept_callback_invoked,
     case_worker_address_multiple_clients,

@@ -29,10 +29,10 @@ class SimDev:
     _lib = None
 
     class Buf:
-        def __init__(self, lib, nbytes):
+        def __init__(self, lib, nbytes, exportable=True):
             self.nbytes = int(nbytes)
             self._lib = lib
-            self.ptr = lib.swsim_dev_alloc(max(self.nbytes, 1))
+            self.ptr = (lib.swsim_dev_alloc if exportable else lib.swsim_dev_alloc_noexport)(max(self.nbytes, 1))
             if not self.ptr:
                 raise MemoryError("swsim_dev_alloc failed")
             self.np = np.ctypeslib.as_array((ctypes.c_uint8 * max(self.nbytes, 1)).from_address(self.ptr))[: self.nbytes]
@@ -56,6 +56,8 @@ class SimDev:
             lib = ctypes.CDLL(LIB_PATH)
             lib.swsim_dev_alloc.restype = ctypes.c_void_p
             lib.swsim_dev_alloc.argtypes = [ctypes.c_size_t]
+            lib.swsim_dev_alloc_noexport.restype = ctypes.c_void_p
+            lib.swsim_dev_alloc_noexport.argtypes = [ctypes.c_size_t]
             lib.swsim_dev_free.argtypes = [ctypes.c_void_p]
             cls._lib = lib
         return cls._lib
@@ -68,9 +70,9 @@ class SimDev:
         return b
 
     @classmethod
-    def from_np(cls, a):
+    def from_np(cls, a, exportable=True):
         a = np.ascontiguousarray(a, dtype=np.uint8).reshape(-1)
-        b = cls.Buf(cls.lib(), a.nbytes)
+        b = cls.Buf(cls.lib(), a.nbytes, exportable)
         b.np[:] = a
         return b
 

@@ -32,6 +32,7 @@ struct DevAlloc {
   size_t size;
   std::string name;
   uint64_t id;
+  bool noexport = false;   // stands for memory of the CUDA virtual-memory-management API: ipc_get refuses it
 };
 static std::map<uintptr_t, DevAlloc> g_allocs;       // our "device" allocations (shm backed)
 static std::map<uintptr_t, size_t> g_opened;         // mappings opened through ipc_open
@@ -122,6 +123,10 @@ int ipc_get(const void* alloc_base, uint8_t handle[64]) {
   auto it = g_allocs.find((uintptr_t)alloc_base);
   if (it == g_allocs.end()) {
     g_err = "ipc_get: not the base of a device allocation";
+    return -1;
+  }
+  if (it->second.noexport) {
+    g_err = "ipc_get: invalid argument (allocation cannot be exported)";
     return -1;
   }
   memset(handle, 0, 64);
@@ -737,5 +742,14 @@ int launch_pull(stream_t, SwPullQueue* q, SwPullCtl* ctl, uint64_t launch_seq, u
 // engine's device-buffer paths (zero-copy rendezvous between user buffers, IPC export of user
 // allocations, handle / mapping caches) run on the CPU as well.
 extern "C" void* swsim_dev_alloc(size_t bytes) { return swgpu::dev_alloc(bytes); }
+// a 'device' buffer the IPC export refuses (what cudaIpcGetMemHandle does for cuMemCreate / expandable-segment memory)
+extern "C" void* swsim_dev_alloc_noexport(size_t bytes) {
+  void* p = swgpu::dev_alloc(bytes);
+  if (p) {
+    std::lock_guard<std::mutex> lk(swgpu::g_mu);
+    swgpu::g_allocs[(uintptr_t)p].noexport = true;
+  }
+  return p;
+}
 extern "C" int swsim_dev_free(void* p) { return swgpu::dev_free(p); }
 

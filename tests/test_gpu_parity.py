@@ -54,6 +54,13 @@ def test_two_process_client_send_with_flush_good(cuda_api, port):
     run(cb.case_client_send_with_flush_good(cuda_api, port, "cuda"), timeout=300)
 
 
+def test_two_process_flush_then_exit_multi_gib(cuda_api, port, monkeypatch):
+    """The reference's shape at multi-GiB size (it sends 8 GiB, tests/test_basic.py:280-309): 4 GiB of pageable host
+    memory, the sender flushes, closes and EXITS, the receiver still completes with every byte."""
+    monkeypatch.setenv("STARWAY_FLUSH_BYTES", str(4 << 30))
+    run(cb.case_server_send_with_flush_good(cuda_api, port, "cuda", "flush"), timeout=400)
+
+
 # ------------------------------------------------------------------ golden vectors through the CUDA path
 CASES = load_cases()
 
@@ -571,3 +578,78 @@ def test_bench_cli_loopback_all_scenarios(tmp_path, buffers):
     m = {s["name"]: s["metrics"] for s in report["scenarios"]}
     assert m["large-array"]["avg_gbps"] > 1.0 and m["small-messages"]["messages_per_second"] > 1e4
     assert 0 < m["pingpong-flag"]["median_rtt_us"] < 5000 and m["streaming-duplex"]["aggregate_gbps"] > 1.0
+
+
+# ------------------------------------------------------------------ device memory CUDA IPC cannot export (expandable segments)
+def _proc_expandable_sender(port, sizes):
+    os.environ["PYTORCH_CUDA_ALLOC_CONF"] = "expandable_segments:True"
+    os.environ["STARWAY_QUIET"] = "1"
+    import torch
+
+    import starway_b200 as sw
+
+    async def inner():
+        client = sw.Client()
+        await client.aconnect("127.0.0.1", port)
+        bufs = []
+        for i, n in enumerate(sizes):
+            g = torch.Generator(device="cuda").manual_seed(4242 + i)
+            bufs.append(torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda", generator=g))
+        torch.cuda.synchronize()
+        verdict = torch.zeros(1, dtype=torch.uint8, device="cuda")
+        fv = client.arecv(verdict, 0x77, U64)
+        for rnd in range(2):   # twice: the per-allocation "not exportable" answer is cached
+            for i, b in enumerate(bufs):
+                await client.asend(b, 100 * rnd + i)
+            await client.aflush()
+        assert await asyncio.wait_for(fv, 120) == (0x77, 1)
+        await client.aclose()
+
+    asyncio.run(inner())
+    sw.shutdown()
+
+
+def test_expandable_segment_tensors_two_processes(cuda_api, port):
+    """PyTorch tensors from `expandable_segments:True` live in cuMemCreate / cuMemMap memory, which cudaIpcGetMemHandle
+    refuses.  They must work as send sources (eager and rendezvous) to a peer in another process and as receive
+    targets, bit-exact (the engine stages such sources through an exportable buffer, one HBM copy)."""
+    import multiprocessing as mp
+
+    torch = torch_cuda()
+    sizes = [64, 8128, 8129, (1 << 20) + 16, 48 << 20]
+
+    async def go():
+        server = cuda_api.Server()
+        server.listen("127.0.0.1", port)
+        connected = asyncio.Event()
+        loop = asyncio.get_running_loop()
+        server.set_accept_cb(lambda _: loop.call_soon_threadsafe(connected.set))
+        child = mp.get_context("spawn").Process(target=_proc_expandable_sender, args=(port, sizes))
+        child.start()
+        try:
+            await asyncio.wait_for(connected.wait(), 180)
+            ep = next(iter(server.list_clients()))
+            for rnd in range(2):
+                dsts = [torch.full((n + 32,), 0xEE, dtype=torch.uint8, device="cuda") for n in sizes]
+                torch.cuda.synchronize()
+                futs = [server.arecv(d, 100 * rnd + i, U64) for i, d in enumerate(dsts)]
+                for i, (f, d, n) in enumerate(zip(futs, dsts, sizes)):
+                    assert await asyncio.wait_for(f, 120) == (100 * rnd + i, n)
+                    g = torch.Generator(device="cuda").manual_seed(4242 + i)
+                    want = torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda", generator=g)
+                    torch.cuda.synchronize()
+                    assert torch.equal(d[:n], want) and bool((d[n:] == 0xEE).all()), (rnd, i, n)
+            await server.asend(ep, torch.ones(1, dtype=torch.uint8, device="cuda"), 0x77)
+            await server.aflush()
+            for _ in range(600):
+                if not child.is_alive():
+                    break
+                await asyncio.sleep(0.1)
+            assert child.exitcode == 0
+        finally:
+            if child.is_alive():
+                child.kill()
+            child.join()
+        await server.aclose()
+
+    run(go(), timeout=400)

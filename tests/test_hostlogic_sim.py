@@ -261,10 +261,11 @@ def test_simdev_mixed_host_and_device_buffers(sim_api, port, size):
     run(go())
 
 
-def test_simdev_two_process_device_buffers(sim_api, port):
+@pytest.mark.parametrize("exportable", [True, False], ids=["ipc-exportable", "not-exportable"])
+def test_simdev_two_process_device_buffers(sim_api, port, exportable):
     """Rendezvous pulls straight out of another process's user 'device' allocation (IPC export by
     the sender, mapping cache on the receiver), three rounds over the same allocations."""
-    run(cb.case_simdev_two_process_device_buffers(sim_api, port))
+    run(cb.case_simdev_two_process_device_buffers(sim_api, port, exportable))
 
 
 def test_round_trip_after_a_long_idle_period(sim_api, port):
