@@ -453,6 +453,7 @@ def run_ours(args):
             "timing": "wall clock + CUDA events between device-wide synchronisations, max over ranks",
             "api": "public asyncio API (one Future per message, as the reference)",
             "numa": "rank bound to the GPU-local CPUs" if numa_bound else "no CPU binding applied",
+            "host_cpus_rank0": len(os.sched_getaffinity(0)), "resident": int(ctx.get_option("resident")),
             "payload_check_all_ranks": payload_check,
         },
         "mmsg_per_s": round(world * window * args.steps / (ms * 1e-3) / 1e6, 4),

@@ -232,9 +232,11 @@ def mode_allpairs(args):
         torch.cuda.synchronize()
         el = time.perf_counter() - t0
         assert sorted(counts) == peers and all(v == warm + rounds for v in counts.values()), counts
-        # the last round's payloads: every destination holds one peer's fill pattern
-        vals = sorted(int(d[0]) for d in dst)
-        assert vals == sorted(((p * 16 + rank) & 0xFF) for p in peers), vals
+        # the last round's payloads: every destination holds the fill pattern of the peer its sender_tag names
+        # (ranks drift apart without a barrier per round: a round's seven wildcard receives may well hold two
+        # messages of a fast peer -- the tag says which; tests/test_gpu_multi.py compares full payloads)
+        for d, (tag, _) in zip(dst, res):
+            assert int(d[0]) == ((tag * 16 + rank) & 0xFF) and int(d[-1]) == int(d[0]), (tag, int(d[0]))
         t = torch.tensor([el], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         el = float(t[0])

@@ -921,8 +921,41 @@ async def case_binding_level_callbacks(api, port):
         assert "not running" in str(e)
 
 
+# ------------------------------------------------------------------ a Server outlives more connections than it has rings
+async def case_server_outlives_many_connections(api, port, cycles=70):
+    """A long-lived Server with client churn (round-1 advisor finding: the 65th connect failed with "Out of
+    memory" because endpoints kept their ring index for ever).  Connections that have ended and drained are
+    retired and their ring index is reused; list_clients() still never shrinks (reference tests/test_basic.py:53-56)."""
+    server = api.Server()
+    server.listen(SERVER_ADDR, port)
+    buf = np.zeros(64, dtype=np.uint8)
+    for i in range(cycles):
+        client = api.Client()
+        await asyncio.wait_for(client.aconnect(SERVER_ADDR, port), 30)
+        f = server.arecv(buf, i, (1 << 64) - 1)
+        await client.asend(np.full(64, i & 0xFF, dtype=np.uint8), i)
+        assert await asyncio.wait_for(f, 30) == (i, 64) and (buf == (i & 0xFF)).all()
+        await client.aflush()
+        await client.aclose()
+        if i % 8 == 7:
+            await asyncio.sleep(0.05)   # closed connections drain and are retired
+    assert len(server.list_clients()) == cycles
+    # still fully functional: a rendezvous-size message on a fresh connection
+    client = api.Client()
+    await asyncio.wait_for(client.aconnect(SERVER_ADDR, port), 30)
+    big = np.arange(100000, dtype=np.uint8)
+    dst = np.zeros(100000, dtype=np.uint8)
+    f = server.arecv(dst, 7, 0xFF)
+    await client.asend(big, 7)
+    assert await asyncio.wait_for(f, 30) == (7, 100000)
+    np.testing.assert_array_equal(dst, big)
+    await client.aclose()
+    await server.aclose()
+
+
 SINGLE_PROCESS_CASES = [
     case_server_listen_client_connect_close,
+    case_server_outlives_many_connections,
     case_binding_level_callbacks,
     case_worker_address_connection_roundtrip,
     case_worker_address_accept_callback_invoked,
