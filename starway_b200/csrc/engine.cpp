@@ -258,6 +258,96 @@ struct StagingPool {
   }
 };
 
+// ============================================================================ pageable host buffers
+// cudaMemcpyAsync from / to pageable memory is a synchronous, single-threaded staging loop inside the driver
+// (~6 GB/s on the B200 hosts, and it blocks the progress thread).  Large pageable buffers are moved by a few
+// helper threads between the caller's memory and page-locked staging instead (chunked memcpy), and the copy
+// engine only ever sees page-locked memory.  The payload still travels host -> GPU -> (NVLink) -> GPU -> host.
+struct CopyPool {
+  struct Task {
+    uint8_t* dst;
+    const uint8_t* src;
+    size_t n;
+    std::atomic<int>* pending;
+  };
+  static constexpr size_t CHUNK = 256 << 10;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<Task> q;
+  std::vector<std::thread> threads;
+  bool stop = false;
+  void start(int n, int device) {
+    for (int i = 0; i < n; i++)
+      threads.emplace_back([this, device] {
+        (void)device;
+        for (;;) {
+          Task t;
+          {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return stop || !q.empty(); });
+            if (q.empty()) return;
+            t = q.front();
+            q.pop_front();
+          }
+          memcpy(t.dst, t.src, t.n);
+          t.pending->fetch_sub(1, std::memory_order_acq_rel);
+        }
+      });
+  }
+  // copies n bytes in CHUNK pieces; *pending reaches 0 when every piece is done
+  void submit(void* dst, const void* src, size_t n, std::atomic<int>* pending) {
+    const int pieces = (int)((n + CHUNK - 1) / CHUNK);
+    pending->store(pieces, std::memory_order_release);
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      for (size_t off = 0; off < n; off += CHUNK) q.push_back(Task{(uint8_t*)dst + off, (const uint8_t*)src + off, std::min(CHUNK, n - off), pending});
+    }
+    cv.notify_all();
+  }
+  void shutdown() {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      stop = true;
+    }
+    cv.notify_all();
+    for (auto& t : threads) t.join();
+    threads.clear();
+  }
+};
+
+struct PinnedPool {   // page-locked staging for pageable buffers (cudaHostAlloc costs milliseconds: blocks are kept)
+  std::multimap<size_t, void*> free_blocks;
+  size_t cached = 0;
+  static constexpr size_t MAX_CACHED = 1ull << 30;
+  void* get(size_t n, size_t* got) {
+    const size_t need = (n + 0xFFFFF) & ~(size_t)0xFFFFF;
+    auto it = free_blocks.lower_bound(need);
+    if (it != free_blocks.end() && it->first <= 2 * need) {
+      void* p = it->second;
+      *got = it->first;
+      cached -= it->first;
+      free_blocks.erase(it);
+      return p;
+    }
+    *got = need;
+    return swgpu::host_alloc(need);
+  }
+  void put(void* p, size_t sz) {
+    if (!p) return;
+    if (cached + sz > MAX_CACHED) {
+      swgpu::host_free(p);
+      return;
+    }
+    free_blocks.emplace(sz, p);
+    cached += sz;
+  }
+  void destroy() {
+    for (auto& kv : free_blocks) swgpu::host_free(kv.second);
+    free_blocks.clear();
+    cached = 0;
+  }
+};
+
 // ============================================================================ engine objects
 struct Worker;
 struct Ctx;
@@ -319,6 +409,9 @@ struct SendOp {
   uint64_t rndv_seq = 0;
   // The put block that carries this send's slot still refers to the record until poll_puts retires it: a
   // FIN / close that ends the send earlier only notes the outcome here and poll_puts finishes the record.
+  void* pin_stage = nullptr;           // pageable host source: page-locked copy made by the helper threads
+  size_t pin_stage_size = 0;
+  std::atomic<int> pin_pending{0};     // chunks of that copy still running
   bool stage_d2d = false;   // device source that CUDA IPC cannot export (cuMemCreate / expandable segments):
                             // copied into an exportable staging buffer first
   bool in_put = false;
@@ -342,6 +435,9 @@ struct RecvOp {
   void* dev_staging = nullptr;    // large host receives land here, then D2H
   size_t staging_size = 0;
   bool rndv_capable = false;      // resident path: counted in Worker::rndv_recvs while posted
+  void* pin_stage = nullptr;      // pageable host destination: page-locked landing zone of the device -> host copy
+  size_t pin_stage_size = 0;
+  std::atomic<int> pin_pending{0};
 };
 
 struct FlushOp {
@@ -574,6 +670,7 @@ struct PostCopy {  // device staging -> host user buffer after delivery
   RecvOp* op;
   uint64_t tag, len;
   int32_t status;
+  int phase = 0;   // 0: device -> page-locked copy in flight; 1: helper threads copy page-locked -> caller's memory
 };
 struct Mapping {
   void* base;
@@ -642,6 +739,10 @@ struct Ctx {
   std::deque<PostCopy> post_copies;
   HostPool host_pool;
   StagingPool staging;
+  PinnedPool pinned_pool;
+  CopyPool copy_pool;
+  std::atomic<int64_t> opt_copy_threads{4};   // helper threads for pageable host buffers (0: cudaMemcpyAsync on pageable memory)
+  size_t pin_inflight = 0;                    // bytes of page-locked staging in use by sends
   std::unordered_map<MapKey, Mapping, MapKeyHash> mappings;  // node addresses are stable
   struct HandleEnt {
     uint64_t base;
@@ -796,12 +897,18 @@ void send_finished(Ctx* c, SendOp* op, int32_t status) {
     op->user_done = true;
   }
   if (op->dev_staging) c->staging.put(op->dev_staging, op->staging_size);
+  if (op->pin_stage) {
+    while (op->pin_pending.load(std::memory_order_acquire) > 0) sched_yield();   // (cancelled while the helpers still copy)
+    c->pinned_pool.put(op->pin_stage, op->pin_stage_size);
+    c->pin_inflight -= std::min(c->pin_inflight, op->pin_stage_size);
+  }
   op->ep->out_seqs.erase(op->sseq);
   delete op;
 }
 
 void recv_release(Ctx* c, RecvOp* r) {
   if (r->rndv_capable && r->w && r->w->rndv_recvs) r->w->rndv_recvs--;
+  if (r->pin_stage) c->pinned_pool.put(r->pin_stage, r->pin_stage_size);
   if (r->pinned_bounce) c->host_pool.put(r->pinned_bounce, r->cap);
   if (r->dev_staging) c->staging.put(r->dev_staging, r->staging_size);
   delete r;
@@ -821,7 +928,11 @@ void recv_finish(Ctx* c, Worker* w, uint64_t op_id, int32_t status, uint64_t tag
     // large host receive: bring the bytes down, complete when the copy has finished
     w->recvs.erase(it);
     swgpu::event_t ev = swgpu::event_create(0);
-    swgpu::memcpy_d2h(r->ptr, r->dev_staging, (size_t)len, c->s_bulk);
+    if (!c->copy_pool.threads.empty() && len >= (256u << 10)) {
+      // pageable destination: DMA into page-locked staging, the helper threads finish the job (poll_bulk)
+      r->pin_stage = c->pinned_pool.get((size_t)len, &r->pin_stage_size);
+    }
+    swgpu::memcpy_d2h(r->pin_stage ? r->pin_stage : (void*)r->ptr, r->dev_staging, (size_t)len, c->s_bulk);
     swgpu::event_record(ev, c->s_bulk);
     c->post_copies.push_back(PostCopy{ev, r, tag, len, status});
     std::lock_guard<std::mutex> lk(c->st_mu);
@@ -1452,6 +1563,26 @@ bool pump_sends(Ctx* c) {
               batch_full = true;
               break;
             }
+            if (op->mem == SW_MEM_HOST && !op->stage_d2d && !op->dev_staging && !c->copy_pool.threads.empty()) {
+              // pageable source: helper threads copy it into page-locked staging first (started here, for this
+              // operation and the next few of the queue), the upload then is a plain DMA
+              if (!op->pin_stage) {
+                swgpu::PtrInfo hpi;
+                swgpu::ptr_info(op->ptr, &hpi);
+                if (!hpi.is_pinned) {
+                  size_t ahead = 0;
+                  for (SendOp* o2 : ep->sendq) {
+                    if (ahead++ >= 8 || c->pin_inflight > (512u << 20)) break;
+                    if (o2->pin_stage || o2->mem != SW_MEM_HOST || o2->len <= eager_max || o2->dev_staging) continue;
+                    o2->pin_stage = c->pinned_pool.get(o2->len, &o2->pin_stage_size);
+                    if (!o2->pin_stage) break;
+                    c->pin_inflight += o2->pin_stage_size;
+                    c->copy_pool.submit(o2->pin_stage, o2->ptr, o2->len, &o2->pin_pending);
+                  }
+                }
+              }
+              if (op->pin_stage && op->pin_pending.load(std::memory_order_acquire) > 0) break;   // not copied yet
+            }
             if (!op->dev_staging) staged_bytes += op->len;
             if (!op->dev_staging) {
               op->dev_staging = c->staging.get(op->len, &op->staging_size);
@@ -1481,7 +1612,7 @@ bool pump_sends(Ctx* c) {
                   swgpu::memcpy_h2d((uint8_t*)op->dev_staging + body, op->ptr + body, op->len - body, b.s);
               } else {
                 trace(c, "h2d_enqueue", op->len);
-                swgpu::memcpy_h2d(op->dev_staging, op->ptr, op->len, b.s);
+                swgpu::memcpy_h2d(op->dev_staging, op->pin_stage ? (const uint8_t*)op->pin_stage : op->ptr, op->len, b.s);
                 stream_ordered = true;   // the RTS may only become visible after this copy: needs the put launch behind it
               }
               h2d += op->len;
@@ -2080,14 +2211,35 @@ bool poll_bulk(Ctx* c) {
     c->bulk_head++;
     any = true;
   }
-  while (!c->post_copies.empty()) {
-    PostCopy& pc = c->post_copies.front();
-    int q = swgpu::event_query(pc.ev);
-    if (q == 1) break;
-    complete(c, pc.op->w, pc.op->op_id, SW_OP_RECV, q < 0 ? SW_ERR_IO_ERROR : pc.status, pc.tag, pc.len);
-    swgpu::event_destroy(pc.ev);
+  // host receives: device -> page-locked copies finish in order; the helper threads' second hop may not, so the
+  // queue is scanned (it is short: one entry per large host receive in flight)
+  for (size_t i = 0; i < c->post_copies.size();) {
+    PostCopy& pc = c->post_copies[i];
+    if (pc.phase == 0) {
+      int q = swgpu::event_query(pc.ev);
+      if (q == 1) break;   // later entries' copies are behind this one on the stream
+      swgpu::event_destroy(pc.ev);
+      pc.ev = nullptr;
+      if (q < 0) pc.status = SW_ERR_IO_ERROR;
+      if (pc.op->pin_stage && q == 0) {
+        c->copy_pool.submit(pc.op->ptr, pc.op->pin_stage, (size_t)pc.len, &pc.op->pin_pending);
+        pc.phase = 1;
+        any = true;
+        i++;
+        continue;
+      }
+      pc.phase = 2;
+    }
+    if (pc.phase == 1) {
+      if (pc.op->pin_pending.load(std::memory_order_acquire) > 0) {
+        i++;
+        continue;
+      }
+      pc.phase = 2;
+    }
+    complete(c, pc.op->w, pc.op->op_id, SW_OP_RECV, pc.status, pc.tag, pc.len);
     recv_release(c, pc.op);
-    c->post_copies.pop_front();
+    c->post_copies.erase(c->post_copies.begin() + (long)i);
     any = true;
   }
   return any;
@@ -3139,6 +3291,14 @@ sw_ctx* sw_ctx_create(int device) {
       return nullptr;
     }
   }
+  if (const char* e = getenv("STARWAY_COPY_THREADS")) c->opt_copy_threads = std::max<int64_t>(0, atoll(e));
+  {
+    // helper threads for pageable buffers sit next to the GPU like the progress thread (ScopedAffinity above)
+    int n = (int)c->opt_copy_threads.load();
+    const int hw = (int)std::thread::hardware_concurrency();
+    if (hw > 0 && n > hw / 4) n = std::max(hw >= 4 ? 1 : 0, hw / 4);
+    if (n > 0) c->copy_pool.start(n, device);
+  }
   if (const char* e = getenv("STARWAY_LINGER_US")) c->opt_linger_us = std::max<int64_t>(1, atoll(e));
   if (const char* e = getenv("STARWAY_MAX_LIFE_US")) c->opt_max_life_us = std::max<int64_t>(10, atoll(e));
   if (const char* e = getenv("STARWAY_ARMED_MS")) c->opt_armed_ms = std::max<int64_t>(0, atoll(e));
@@ -3237,6 +3397,8 @@ void sw_ctx_destroy(sw_ctx* ctx) {
   if (c->pq) swgpu::pull_queue_destroy(c->pq);
   if (c->map_tbl) swgpu::map_table_destroy(c->map_tbl);
   swgpu::host_free(c->pull_ctl);
+  c->copy_pool.shutdown();
+  c->pinned_pool.destroy();
   c->host_pool.destroy();
   c->staging.destroy();
   swgpu::stream_destroy(c->s_put);
