@@ -3085,7 +3085,7 @@ void progress_main(Ctx* c) {
   prctl(PR_SET_TIMERSLACK, 1000UL, 0, 0, 0);  // 1 us timer slack: short sleeps stay short
   tls_is_progress = true;
   uint64_t iter = 0;
-  double last_active = now_s();
+  double last_active = now_s(), last_event = last_active;
   while (!c->stop.load(std::memory_order_acquire)) {
     bool active = false;
     drain_sq(c);
@@ -3123,18 +3123,26 @@ void progress_main(Ctx* c) {
     }
     iter++;
     bool inflight = (c->put_head != c->put_tail) || (c->bulk_head != c->bulk_tail) || !c->post_copies.empty();
+    bool resident_only = !inflight;   // nothing but resident kernels on the device
     inflight |= c->pull_running;
     bool expecting = false;  // operations whose completion depends on a peer's doorbell / FIN
     for (Worker* w : c->active) {
       inflight |= w->match_inflight || w->prog_running;
+      resident_only &= !w->match_inflight;
       if (w->close_phase >= 4) continue;
       expecting |= !w->recvs.empty() || !w->flushes.empty() || w->close_phase != 0;
       for (Ep* ep : w->eps) expecting |= !ep->rndv_wait.empty() || !ep->sendq.empty();
     }
+    if (active) last_event = now_s();
     if (active || inflight) {
       last_active = now_s();
-      if (!active)
+      if (!active) {
         for (int k = 0; k < 8; k++) __builtin_ia32_pause();  // polling device events: yield the core's pipeline
+        // Only resident kernels are out and nothing has happened for a while: they may stay for milliseconds
+        // waiting for a peer.  Keep polling their rings, but let other runnable threads (the Python thread of
+        // this rank, other ranks of a crowded host) have the CPU between looks.
+        if (resident_only && last_active - last_event > 30e-6) sched_yield();
+      }
     } else {
       // The reference's worker threads spin at 100 % (main.cpp:361, 1126).  Here: spin while work is
       // outstanding or was seen recently, then back off progressively.
