@@ -138,7 +138,7 @@ async def run_sweep(torch, dev, server, client, rank, world, barrier, allreduce_
     out = []
     for n in sizes:
         window, iters = sweep_plan(n)
-        offs = [(j * n) % (pool_bytes - n + 1) for j in range(window)]
+        offs = [((j * n) % (pool_bytes - n + 1)) & ~255 for j in range(window)]   # 256-byte aligned whatever the pool size
         srcs = [src_pool[o:o + n] for o in offs]
         dsts = [dst_pool[o:o + n] for o in offs]
         dst_pool[: min(pool_bytes, window * n)].fill_(0xEE)
@@ -544,7 +544,7 @@ def cpu_sweep(sizes, budget_s=1.2):
         out = []
         for n in sizes:
             window, _ = sweep_plan(n)
-            offs = [(j * n) % (len(pool) - n + 1) for j in range(window)]
+            offs = [((j * n) % (len(pool) - n + 1)) & ~255 for j in range(window)]
             srcs, dsts = [pool[o:o + n] for o in offs], [dpool[o:o + n] for o in offs]
 
             async def one():

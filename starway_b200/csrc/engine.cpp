@@ -779,6 +779,7 @@ struct Ctx {
   // batches of at most this many sends of ONE worker whose control kernel is resident are executed by that
   // kernel (descriptor ring in pinned memory) instead of a put launch; 0: always launch
   std::atomic<int64_t> opt_resident_puts{24};
+  std::atomic<int64_t> opt_yield_us{30};   // progress thread yields between looks after this much silence with only resident kernels out (0: never)
   SwPullQueue* pq = nullptr;
   SwMapEnt* map_tbl = nullptr;
   SwPullCtl* pull_ctl = nullptr;
@@ -3141,7 +3142,9 @@ void progress_main(Ctx* c) {
         // Only resident kernels are out and nothing has happened for a while: they may stay for milliseconds
         // waiting for a peer.  Keep polling their rings, but let other runnable threads (the Python thread of
         // this rank, other ranks of a crowded host) have the CPU between looks.
-        if (resident_only && last_active - last_event > 30e-6) sched_yield();
+        if (resident_only && c->opt_yield_us.load(std::memory_order_relaxed) > 0 &&
+            last_active - last_event > (double)c->opt_yield_us.load(std::memory_order_relaxed) * 1e-6)
+          sched_yield();
       }
     } else {
       // The reference's worker threads spin at 100 % (main.cpp:361, 1126).  Here: spin while work is
@@ -3453,6 +3456,7 @@ int sw_set_option(sw_ctx* ctx, const char* key, int64_t value) {
   else if (k == "armed_ms") c->opt_armed_ms = std::max<int64_t>(0, value);
   else if (k == "pull_ctas") c->opt_pull_ctas = std::max<int64_t>(0, value);
   else if (k == "resident_puts") c->opt_resident_puts = std::max<int64_t>(0, value);
+  else if (k == "yield_us") c->opt_yield_us = std::max<int64_t>(0, value);
   else {
     set_error("unknown option " + k);
     return -1;
