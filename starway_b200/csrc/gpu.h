@@ -125,5 +125,9 @@ int launch_progress(stream_t s, const ProgressLaunch* a);
 int launch_pull(stream_t s, SwPullQueue* q, SwPullCtl* ctl, uint64_t launch_seq, uint32_t ctas, uint32_t linger_us,
                 uint32_t max_life_us, const BulkTuning* tune);
 int pull_default_ctas();
+// measurement hook (tests/gpu_probe): publishes ONE batch of whole messages (src, dst, len; 16-byte aligned) to the
+// pull queue from the device, the way a matcher does; completion records of the batch are dropped
+int probe_publish_batch(stream_t s, SwPullQueue* q, const SwSeg* msgs_pinned, uint32_t n, uint32_t pull_ctas, void* scratch_dev);
+int pull_queue_read_stats(SwPullQueue* q, uint64_t out[8]);   // bytes, busy_ns, batches, jobs, pickup_ns, copy_ns, fin_ns, alloc
 
 }  // namespace swgpu

@@ -571,6 +571,68 @@ static void map_shadow_reset(SwMapEnt* t) {
     if (kv.first == t) std::fill(kv.second.begin(), kv.second.end(), 0);
 }
 
+// ---- measurement hook: one batch published from the device, like sw_res_flush_pull does
+__global__ void sw_probe_publish_kernel(SwPullQueue* q, const SwSeg* msgs, uint32_t n, uint32_t pull_ctas, uint8_t* scratch) {
+  if (threadIdx.x) return;
+  const uint64_t ticket = atomicAdd(reinterpret_cast<unsigned long long*>(&q->alloc), 1ull);
+  SwPullSlot* s = &q->slot[ticket % SW_PULL_SLOTS];
+  const uint64_t want = ticket >= SW_PULL_SLOTS ? ticket - SW_PULL_SLOTS + 1 : 0;
+  while (sw_ld_acquire_gpu(&s->free_seq) != want) __nanosleep(100);
+  uint64_t total = 0;
+  for (uint32_t j = 0; j < n; j++) {
+    total += msgs[j].len & ~15ull;
+    s->end[j] = total;
+    s->src[j] = msgs[j].src;
+    s->dst[j] = msgs[j].dst;
+    s->meta[j].op_id = j;
+    s->meta[j].tag = 0;
+    s->meta[j].len = msgs[j].len;
+    s->meta[j].fin_addr = 0;
+    s->meta[j].fin_val = 0;
+  }
+  uint64_t chunk = total / (pull_ctas > 1 ? pull_ctas - 1 : 1) + 1023;
+  chunk &= ~1023ull;
+  if (chunk < 8192) chunk = 8192;
+  if (chunk > 262144) chunk = 262144;
+  uint64_t nch = (total + chunk - 1) / chunk;
+  if (!nch) nch = 1;
+  s->njobs = n;
+  s->nchunks = (uint32_t)nch;
+  s->exit = 0;
+  s->chunk_bytes = chunk;
+  s->total = total;
+  s->next_chunk = s->done_chunks = s->retire = 0;
+  s->t_first = 0;
+  s->t_pub = sw_globaltimer();
+  // completion records of the probe go to a scratch ring nobody reads (head words far ahead: never "full")
+  s->cqr_ring = reinterpret_cast<uint64_t>(scratch + 4096);
+  s->cqr_alloc = reinterpret_cast<uint64_t>(scratch);
+  s->cqr_head_dev = reinterpret_cast<uint64_t>(scratch + 8);
+  s->cqr_head_host = reinterpret_cast<uint64_t>(scratch + 8);
+  *reinterpret_cast<volatile uint64_t*>(scratch + 8) = *reinterpret_cast<volatile uint64_t*>(scratch) + (1ull << 40);
+  __threadfence();
+  sw_st_release_gpu(&s->seq, ticket + 1);
+}
+int probe_publish_batch(stream_t s, SwPullQueue* q, const SwSeg* msgs_pinned, uint32_t n, uint32_t pull_ctas, void* scratch_dev) {
+  if (n > SW_PULL_JOBS) return -1;
+  sw_probe_publish_kernel<<<1, 32, 0, (cudaStream_t)s>>>(q, msgs_pinned, n, pull_ctas, (uint8_t*)scratch_dev);
+  SW_CUDA(cudaGetLastError());
+  return 0;
+}
+int pull_queue_read_stats(SwPullQueue* q, uint64_t out[8]) {
+  SwPullQueue h;
+  SW_CUDA(cudaMemcpy(&h, q, offsetof(SwPullQueue, slot), cudaMemcpyDeviceToHost));
+  out[0] = h.bytes;
+  out[1] = h.busy_ns;
+  out[2] = h.batches;
+  out[3] = h.jobs;
+  out[4] = h.pickup_ns;
+  out[5] = h.copy_ns;
+  out[6] = h.fin_ns;
+  out[7] = h.alloc;
+  return 0;
+}
+
 int pull_default_ctas() { return g_sms > 4 ? g_sms - 2 : g_sms; }
 
 int launch_progress(stream_t s, const ProgressLaunch* p) {
@@ -612,7 +674,7 @@ int launch_pull(stream_t s, SwPullQueue* q, SwPullCtl* ctl, uint64_t launch_seq,
   a.max_life_us = max_life_us;
   a.clk_mhz = (uint32_t)g_clk_mhz;
   a.pad = 0;
-  sw_pull_kernel<<<ctas, 32, (size_t)stages * sb, (cudaStream_t)s>>>(a);
+  sw_pull_kernel<<<ctas, 64, (size_t)stages * sb, (cudaStream_t)s>>>(a);
   SW_CUDA(cudaGetLastError());
   return 0;
 }

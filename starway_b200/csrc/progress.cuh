@@ -306,8 +306,9 @@ __device__ __forceinline__ void sw_res_flush_pull(SwMatchState* st, SwProgShared
   }
   if (lane == 0) {
     const uint64_t total = sh.pb_end[n - 1];
-    // chunk: about two per pull CTA, 8 KiB .. 256 KiB, a multiple of 1 KiB
-    uint64_t chunk = total / (2ull * (a.pull_ctas ? a.pull_ctas : 1)) + 1023;
+    // chunk: about one per copy CTA (claims are dynamic: a CTA that is still busy with an earlier batch simply
+    // takes none), 8 KiB .. 256 KiB, a multiple of 1 KiB
+    uint64_t chunk = total / (a.pull_ctas > 1 ? a.pull_ctas - 1 : 1) + 1023;
     chunk &= ~1023ull;
     if (chunk < 8192) chunk = 8192;
     if (chunk > 262144) chunk = 262144;
@@ -1381,10 +1382,16 @@ __device__ __forceinline__ void sw_pull_retire(SwPullSlot* s, uint64_t ticket) {
   if (r == gridDim.x) sw_st_release_gpu(&s->free_seq, ticket + 1);
 }
 
-__global__ void __launch_bounds__(32) sw_pull_kernel(const __grid_constant__ SwPullArgs a) {
+__global__ void __launch_bounds__(64) sw_pull_kernel(const __grid_constant__ SwPullArgs a) {
   extern __shared__ __align__(128) uint8_t sw_smem[];
   __shared__ __align__(8) uint64_t full[SW_BULK_MAX_STAGES];
-  __shared__ uint64_t s_end[SW_PULL_JOBS], s_src[SW_PULL_JOBS], s_dst[SW_PULL_JOBS];
+  // batch descriptors, double-buffered: warp 1 of a copy CTA fetches batch b + 1 (a lane per message) while
+  // thread 0 streams batch b
+  __shared__ uint64_t s_endb[2][SW_PULL_JOBS], s_srcb[2][SW_PULL_JOBS], s_dstb[2][SW_PULL_JOBS];
+  __shared__ uint64_t s_chunk[2], s_total[2];
+  __shared__ uint32_t s_nchunks[2], s_exitb[2];
+  __shared__ volatile uint64_t s_ready;      // descriptors of every ticket below this one are in shared memory
+  __shared__ volatile uint64_t s_released;   // thread 0 has finished with every ticket below this one
   SwPullQueue* q = a.q;
   const uint64_t first = sw_ld_acquire_gpu(&q->start);   // first ticket of this launch
   const long long clk0 = clock64();
@@ -1393,6 +1400,7 @@ __global__ void __launch_bounds__(32) sw_pull_kernel(const __grid_constant__ SwP
 
   if (blockIdx.x == 0) {
     // ================================================================ CTA 0: completions, and when the grid leaves
+    if (threadIdx.x >= 32) return;   // one warp
     const uint32_t lane = threadIdx.x;
     uint64_t finalized = 0;        // batches of this launch completed so far
     uint64_t exit_ticket = 0;
@@ -1488,15 +1496,49 @@ __global__ void __launch_bounds__(32) sw_pull_kernel(const __grid_constant__ SwP
     return;
   }
 
-  // ================================================================ copy CTAs: one elected thread drives the TMA pipeline
+  // ================================================================ copy CTAs
+  // warp 0, thread 0: drives the TMA pipeline.  warp 1: watches the queue and brings the descriptors of the next
+  // batch into shared memory ahead of time (a lane per message: one round trip to L2 instead of 3 x messages).
+  if (threadIdx.x == 0) {
+    s_ready = first;
+    s_released = first;
+  }
+  __syncthreads();
+  if (threadIdx.x >= 32) {
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint64_t t = first;; t++) {
+      SwPullSlot* s = &q->slot[t % SW_PULL_SLOTS];
+      while (t >= s_released + 2) __nanosleep(50);                       // the buffer (t & 1) is still in use
+      while (sw_ld_acquire_gpu(&s->seq) != t + 1) __nanosleep(100);    // not published yet
+      const uint32_t k = t & 1, nj = s->njobs, ex = s->exit;
+      for (uint32_t j = lane; j < nj; j += 32) {
+        s_endb[k][j] = s->end[j];
+        s_srcb[k][j] = s->src[j];
+        s_dstb[k][j] = s->dst[j];
+      }
+      if (lane == 0) {
+        s_chunk[k] = s->chunk_bytes;
+        s_total[k] = s->total;
+        s_nchunks[k] = s->nchunks;
+        s_exitb[k] = ex;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_block();
+        s_ready = t + 1;
+      }
+      if (ex) return;
+    }
+  }
   if (threadIdx.x != 0) return;
   const uint32_t nstages = a.nstages, stage_bytes = a.stage_bytes;
   for (uint32_t i = 0; i < nstages; i++) sw_mbar_init(&full[i], 1);
   sw_fence_mbar_init();
   sw_fence_proxy_async();
 
-  constexpr uint32_t TRK = 16;   // pieces tracked between load issue and accounted completion (> stages + lag)
-  constexpr uint32_t LAG = 2;    // store groups allowed to be outstanding when completions are accounted
+  constexpr uint32_t TRK = 16;   // pieces tracked between load issue and accounted completion (> look-ahead + lag)
+  constexpr uint32_t LAG = 6;    // store groups that may be outstanding when completions are accounted: waiting for
+                                 // fewer would make every iteration wait for a store issued two pieces ago
   uint64_t st_dst[SW_BULK_MAX_STAGES];
   uint32_t st_bytes[SW_BULK_MAX_STAGES];
   SwPullSlot* tr_slot[TRK];      // != nullptr: this piece is the last of a chunk of that slot
@@ -1507,9 +1549,10 @@ __global__ void __launch_bounds__(32) sw_pull_kernel(const __grid_constant__ SwP
   // generator state
   uint64_t b = first;                          // ticket looked at next
   SwPullSlot* cur = nullptr;                   // batch being worked on
-  uint32_t njobs = 0, nchunks = 0, j = 0;
+  uint32_t nchunks = 0, j = 0, kb = 0;
   uint64_t chunk_bytes = 0, total = 0, pos = 0, cend = 0;
   bool have_chunk = false, leave = false;
+  const uint64_t *s_end = s_endb[0], *s_src = s_srcb[0], *s_dst = s_dstb[0];
 
   // a chunk is counted once its bulk stores have completed (cp.async.bulk.wait_group): plain atomic, no fence --
   // CTA 0 fences once per batch before it publishes the completion records
@@ -1535,28 +1578,29 @@ __global__ void __launch_bounds__(32) sw_pull_kernel(const __grid_constant__ SwP
         chunk_done(cur);   // an empty chunk (a batch of tails only)
       }
       if (!cur) {
-        SwPullSlot* s = &q->slot[b % SW_PULL_SLOTS];
-        if (sw_ld_acquire_gpu(&s->seq) != b + 1) return 0;   // not published yet
-        if (s->exit) {
+        if (s_ready <= b) return 0;   // warp 1 has not seen batch b yet
+        __threadfence_block();
+        kb = b & 1;
+        if (s_exitb[kb]) {
           leave = true;
           return 0;
         }
-        cur = s;
-        njobs = s->njobs;
-        nchunks = s->nchunks;
-        chunk_bytes = s->chunk_bytes;
-        total = s->total;
-        for (uint32_t k = 0; k < njobs; k++) {
-          s_end[k] = s->end[k];
-          s_src[k] = s->src[k];
-          s_dst[k] = s->dst[k];
-        }
+        cur = &q->slot[b % SW_PULL_SLOTS];
+        nchunks = s_nchunks[kb];
+        chunk_bytes = s_chunk[kb];
+        total = s_total[kb];
+        s_end = s_endb[kb];
+        s_src = s_srcb[kb];
+        s_dst = s_dstb[kb];
       }
       const uint32_t cidx = atomicAdd(&cur->next_chunk, 1u);
       if (cidx >= nchunks) {
         sw_pull_retire(cur, b);   // nothing left for this CTA in batch b
         cur = nullptr;
         b++;
+        // pieces of batch b - 1 may still be in flight, but their addresses are in st_dst / the TMA unit: the
+        // descriptor buffer can be refilled
+        s_released = b;
         continue;
       }
       if (cidx == 0) cur->t_first = sw_globaltimer();

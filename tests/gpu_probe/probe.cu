@@ -1100,6 +1100,74 @@ static void bench_hostlat(FILE* json) {
   dev_free(dev);
 }
 
+// ------------------------------------------------------------------ pull: the resident pull kernel on its own
+// Publishes batches of whole messages from the device (the way a matcher does) and lets sw_pull_kernel serve them:
+// payload GB/s while a batch is active (first chunk claimed -> records written), per batch shape.  `ncu --set full`
+// of this command profiles the kernel itself (launch = a resident period that serves the published batches).
+static void bench_pull(FILE* json, int nbatches_fixed) {
+  const size_t POOL = 2ull << 30;
+  uint8_t* src = (uint8_t*)dev_alloc_raw(POOL);
+  uint8_t* dst = (uint8_t*)dev_alloc_raw(POOL);
+  uint8_t* scratch = (uint8_t*)dev_alloc(4096 + sizeof(SwCqEnt) * SW_CQ_RING);
+  REQ(src && dst && scratch);
+  CK(cudaMemset(src, 0x5A, POOL));
+  SwPullQueue* q = pull_queue_create();
+  SwPullCtl* ctl = (SwPullCtl*)host_alloc(sizeof(SwPullCtl));
+  SwSeg* msgs = (SwSeg*)host_alloc(sizeof(SwSeg) * SW_PULL_JOBS * 64);
+  stream_t sp = stream_create(), sq = stream_create();
+  BulkTuning tune{0, 8, 24576, 1, 1};
+  const uint32_t ctas = (uint32_t)pull_default_ctas();
+  struct Shape {
+    uint32_t nmsg;
+    uint64_t len;
+    uint32_t nbatch;
+  };
+  const Shape shapes[] = {{1, 1u << 20, 8}, {8, 1u << 20, 8}, {16, 1u << 20, 8}, {64, 1u << 20, 8}, {64, 4u << 20, 6}, {16, 64u << 20, 2}, {1, 1u << 30, 2}, {52, 16384, 8}, {52, 65536, 8}};
+  uint64_t seq = 0;
+  for (const Shape& sh : shapes) {
+    const uint32_t nb = nbatches_fixed ? (uint32_t)nbatches_fixed : sh.nbatch;
+    uint64_t s0[8], s1[8];
+    pull_queue_read_stats(q, s0);
+    // (L2 is 126 MB: batches of a shape use disjoint parts of the 2 GiB pools, wrapping)
+    uint64_t off = 0;
+    for (uint32_t b = 0; b < nb; b++) {
+      SwSeg* m = msgs + (size_t)b * SW_PULL_JOBS;
+      for (uint32_t j = 0; j < sh.nmsg; j++) {
+        if (off + sh.len > POOL) off = 0;
+        m[j] = SwSeg{(uint64_t)(uintptr_t)(src + off), (uint64_t)(uintptr_t)(dst + off), sh.len, 0};
+        off += sh.len;
+      }
+    }
+    ctl->stop = 0;
+    REQ(launch_pull(sp, q, ctl, ++seq, ctas, 20000, 2000000, &tune) == 0);   // stays until told to leave
+    for (uint32_t b = 0; b < nb; b++) {
+      REQ(probe_publish_batch(sq, q, msgs + (size_t)b * SW_PULL_JOBS, sh.nmsg, ctas, scratch) == 0);
+      REQ(stream_sync(sq) == 0);
+      // one batch at a time: wait until it has been completed (alloc counts batches; completed = batches)
+      for (;;) {
+        uint64_t st[8];
+        pull_queue_read_stats(q, st);
+        if (st[2] - s0[2] >= b + 1) break;
+      }
+    }
+    __atomic_store_n(&ctl->stop, (uint64_t)1, __ATOMIC_RELEASE);
+    REQ(stream_sync(sp) == 0);
+    pull_queue_read_stats(q, s1);
+    const double nbat = (double)(s1[2] - s0[2]), bytes = (double)(s1[0] - s0[0]), busy = (double)(s1[1] - s0[1]);
+    printf("pull %2u x %9llu B per batch: %6.1f us per batch, %7.1f GB/s payload while active (x2 = HBM traffic); phases %.1f / %.1f / %.1f us\n",
+           sh.nmsg, (unsigned long long)sh.len, busy / nbat * 1e-3, bytes / busy, (s1[4] - s0[4]) / nbat * 1e-3, (s1[5] - s0[5]) / nbat * 1e-3,
+           (s1[6] - s0[6]) / nbat * 1e-3);
+    if (json)
+      fprintf(json, "{\"probe\":\"pull\",\"msgs\":%u,\"msg_bytes\":%llu,\"us_per_batch\":%.2f,\"payload_gbs\":%.1f,\"pickup_us\":%.2f,\"copy_us\":%.2f,\"records_us\":%.2f}\n",
+              sh.nmsg, (unsigned long long)sh.len, busy / nbat * 1e-3, bytes / busy, (s1[4] - s0[4]) / nbat * 1e-3, (s1[5] - s0[5]) / nbat * 1e-3,
+              (s1[6] - s0[6]) / nbat * 1e-3);
+  }
+  // spot check
+  std::vector<uint8_t> h(4096);
+  CK(cudaMemcpy(h.data(), dst, 4096, cudaMemcpyDeviceToHost));
+  for (auto x : h) REQ(x == 0x5A);
+}
+
 int main(int argc, char** argv) {
   std::string cmd = argc > 1 ? argv[1] : "correctness";
   if (cmd == "ipc-child") return ipc_child(argv[2]);
@@ -1121,6 +1189,7 @@ int main(int argc, char** argv) {
   if (cmd == "balance") bench_balance(json);
   if (cmd == "hostmem") bench_hostmem(json);
   if (cmd == "hostlat") bench_hostlat(json);
+  if (cmd == "pull") bench_pull(json, argc > 3 ? atoi(argv[3]) : 0);
   if (cmd == "tune") bench_tune(json);
   if (cmd == "ipc" || cmd == "all") test_ipc(argv[0]);
   if (cmd == "peer" || cmd == "all") bench_peer(json);

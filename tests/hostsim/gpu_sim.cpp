@@ -530,6 +530,8 @@ int map_table_insert(SwMapEnt* t, stream_t, uint64_t uuid, uint64_t buf_id, uint
   return -1;
 }
 int pull_default_ctas() { return 8; }
+int probe_publish_batch(stream_t, SwPullQueue*, const SwSeg*, uint32_t, uint32_t, void*) { return -1; }
+int pull_queue_read_stats(SwPullQueue*, uint64_t*) { return -1; }
 
 namespace {
 struct Pass {
