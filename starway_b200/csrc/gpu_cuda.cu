@@ -604,12 +604,13 @@ __global__ void sw_probe_publish_kernel(SwPullQueue* q, const SwSeg* msgs, uint3
   s->next_chunk = s->done_chunks = s->retire = 0;
   s->t_first = 0;
   s->t_pub = sw_globaltimer();
-  // completion records of the probe go to a scratch ring nobody reads (head words far ahead: never "full")
+  // completion records of the probe go to a scratch ring nobody reads; its "host cursor" follows the allocation
+  // cursor, so the ring never looks full
   s->cqr_ring = reinterpret_cast<uint64_t>(scratch + 4096);
   s->cqr_alloc = reinterpret_cast<uint64_t>(scratch);
   s->cqr_head_dev = reinterpret_cast<uint64_t>(scratch + 8);
   s->cqr_head_host = reinterpret_cast<uint64_t>(scratch + 8);
-  *reinterpret_cast<volatile uint64_t*>(scratch + 8) = *reinterpret_cast<volatile uint64_t*>(scratch) + (1ull << 40);
+  *reinterpret_cast<volatile uint64_t*>(scratch + 8) = *reinterpret_cast<volatile uint64_t*>(scratch);
   __threadfence();
   sw_st_release_gpu(&s->seq, ticket + 1);
 }

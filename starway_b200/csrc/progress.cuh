@@ -171,6 +171,8 @@ struct SwResCtx {   // warp-uniform state of the matcher, in registers for the l
   uint64_t cq_alloc, hr_alloc, jobs_emitted, pull_jobs, arrivals, post_head;
   uint32_t pend_head, pend_tail, pb_n, err;
   bool stalled;
+  SwPullSlot* last_slot;   // where sw_res_flush_pull published last
+  uint64_t last_ticket;
 };
 
 // ------------------------------------------------------------------ matcher building blocks
@@ -335,6 +337,8 @@ __device__ __forceinline__ void sw_res_flush_pull(SwMatchState* st, SwProgShared
     sw_st_release_gpu(&s->seq, ticket + 1);
     a.ctl->pull_jobs = c.pull_jobs;   // the host keeps the pull kernel alive while jobs are outstanding
   }
+  c.last_slot = s;
+  c.last_ticket = ticket;
   c.pb_n = 0;
   __syncwarp();
 }
@@ -1011,7 +1015,12 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
     c.pend_head = c.pend_tail = 0;
     c.pb_n = 0;
     c.err = 0;
+    c.last_slot = nullptr;
+    c.last_ticket = 0;
     uint64_t echoed = ~0ull, iters = 0;
+    SwPullSlot* pb_prev = nullptr;   // the batch this matcher published last
+    uint64_t pb_prev_ticket = 0;
+    uint32_t pb_wait = 0;
     uint32_t rr = st->rr_ep;
     const uint32_t n_eps = a.n_eps;
     for (;;) {
@@ -1047,7 +1056,28 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
         }
         rr++;
       }
-      if (c.pb_n) sw_res_flush_pull(st, sh, a, c, lane);
+      if (c.pb_n) {
+        // Publish the batch at once when the pull CTAs have nothing of ours to do; while the previous batch is still
+        // being copied, let this one grow (bounded: 32 messages or a few iterations) -- batches then size
+        // themselves to the load, and a lone message never waits.
+        bool go = c.pb_n >= 32 || !pb_prev || ++pb_wait > 6;
+        if (!go) {
+          uint64_t fin = 0, seq = 0;
+          if (lane == 0) {
+            seq = sw_ld_acquire_gpu(&pb_prev->seq);
+            fin = *reinterpret_cast<volatile uint64_t*>(&pb_prev->fin_seq);
+          }
+          seq = sw_shfl64(seq, 0);
+          fin = sw_shfl64(fin, 0);
+          go = seq != pb_prev_ticket + 1 || fin == seq;   // slot reused, or completed
+        }
+        if (go) {
+          sw_res_flush_pull(st, sh, a, c, lane);
+          pb_prev = c.last_slot;
+          pb_prev_ticket = c.last_ticket;
+          pb_wait = 0;
+        }
+      }
       if (c.pend_head != c.pend_tail) sw_retire(st, sh, c, lane, false);
       if (he != echoed) {   // nothing matched under an older dead_mask is left in this warp
         echoed = he;
@@ -1330,7 +1360,6 @@ __device__ __forceinline__ void sw_pull_finalize(SwPullQueue* q, SwPullSlot* sp,
     for (uint64_t k = body; k < len; k++)
       reinterpret_cast<uint8_t*>(s->dst[j])[k] = reinterpret_cast<const volatile uint8_t*>(s->src[j])[k];
   }
-  __threadfence_system();   // the chunks of the batch (complete before their CTAs counted them) and the tails, before the records
   __syncwarp();
   if (n) {
     SwCqEnt* ring = reinterpret_cast<SwCqEnt*>(s->cqr_ring);
@@ -1352,6 +1381,8 @@ __device__ __forceinline__ void sw_pull_finalize(SwPullQueue* q, SwPullSlot* sp,
       e->tag = s->meta[j].tag;
       e->len = s->meta[j].len;
     }
+    // ONE system-scope fence per batch: the chunks (complete before their CTAs counted them), the tails and the
+    // bodies of the records, before the pass words and the FIN words
     __threadfence_system();
     for (uint32_t j = lane; j < n; j += 32) {
       const uint64_t idx = base + j;

@@ -1138,20 +1138,22 @@ static void bench_pull(FILE* json, int nbatches_fixed) {
         off += sh.len;
       }
     }
-    ctl->stop = 0;
-    REQ(launch_pull(sp, q, ctl, ++seq, ctas, 20000, 2000000, &tune) == 0);   // stays until told to leave
+    // one batch per resident period: publish it, start the pull kernel, which serves it and leaves after 40 us of
+    // silence (its statistics count the active interval of the batch only)
     for (uint32_t b = 0; b < nb; b++) {
       REQ(probe_publish_batch(sq, q, msgs + (size_t)b * SW_PULL_JOBS, sh.nmsg, ctas, scratch) == 0);
       REQ(stream_sync(sq) == 0);
-      // one batch at a time: wait until it has been completed (alloc counts batches; completed = batches)
-      for (;;) {
-        uint64_t st[8];
-        pull_queue_read_stats(q, st);
-        if (st[2] - s0[2] >= b + 1) break;
+      ctl->stop = 0;
+      REQ(launch_pull(sp, q, ctl, ++seq, ctas, 40, 100000, &tune) == 0);
+      REQ(stream_sync(sp) == 0);
+      uint64_t st[8];
+      REQ(pull_queue_read_stats(q, st) == 0);
+      if (st[2] - s0[2] != b + 1) {
+        fprintf(stderr, "pull probe: batch %u of shape %u x %llu not completed (batches %llu, alloc %llu, exited %llu)\n", b, sh.nmsg,
+                (unsigned long long)sh.len, (unsigned long long)(st[2] - s0[2]), (unsigned long long)st[7], (unsigned long long)ctl->exited);
+        exit(4);
       }
     }
-    __atomic_store_n(&ctl->stop, (uint64_t)1, __ATOMIC_RELEASE);
-    REQ(stream_sync(sp) == 0);
     pull_queue_read_stats(q, s1);
     const double nbat = (double)(s1[2] - s0[2]), bytes = (double)(s1[0] - s0[0]), busy = (double)(s1[1] - s0[1]);
     printf("pull %2u x %9llu B per batch: %6.1f us per batch, %7.1f GB/s payload while active (x2 = HBM traffic); phases %.1f / %.1f / %.1f us\n",
