@@ -118,7 +118,7 @@ def sweep_plan(n):
     """(window, iterations) of one sweep point: SURVEY 8d shape (window = min(64, max(1, 2^28 / n)) sends in flight,
     then aflush), bounded so that the whole sweep adds a fraction of a second to the run."""
     window = min(64, max(1, (1 << 28) // n))
-    iters = max(3, min(100, (1 << 31) // (window * n)))
+    iters = max(8, min(100, (1 << 31) // (window * n)))
     return window, iters
 
 
@@ -195,7 +195,7 @@ def run_ours(args):
 
     # one process per GPU, bound to the GPU's NUMA node before any host buffer is allocated (the
     # launcher's job -- `numactl --cpunodebind` -- done here because the driver launches us bare)
-    numa_bound = sw.bind_to_device_numa(local_rank)
+    numa_bound = False if os.environ.get("STARWAY_BENCH_NO_BIND") else sw.bind_to_device_numa(local_rank)
 
     dist = None
     if world > 1:
@@ -287,10 +287,14 @@ def run_ours(args):
         dev_ms = e0.elapsed_time(e1)
         wall_ms = (t1 - t0) * 1e3
         ms = max(dev_ms, wall_ms)
+        per_rank = [(round(ms / args.steps, 4), len(os.sched_getaffinity(0)))]
         if dist is not None:
+            per_rank = [None] * world
+            dist.all_gather_object(per_rank, (round(ms / args.steps, 4), len(os.sched_getaffinity(0))))
             t = torch.tensor([ms], dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t[0])
+        st["_per_rank"] = per_rank
         step_bytes = window * msg
         value = world * step_bytes * args.steps / (ms * 1e-3) / 1e9
 
@@ -454,6 +458,7 @@ def run_ours(args):
             "api": "public asyncio API (one Future per message, as the reference)",
             "numa": "rank bound to the GPU-local CPUs" if numa_bound else "no CPU binding applied",
             "host_cpus_rank0": len(os.sched_getaffinity(0)), "resident": int(ctx.get_option("resident")),
+            "per_rank_ms_per_step_and_cpus": st.get("_per_rank"),
             "payload_check_all_ranks": payload_check,
         },
         "mmsg_per_s": round(world * window * args.steps / (ms * 1e-3) / 1e6, 4),
