@@ -1117,6 +1117,8 @@ static void bench_pull(FILE* json, int nbatches_fixed) {
   stream_t sp = stream_create(), sq = stream_create();
   BulkTuning tune{0, 8, 24576, 1, 1};
   const uint32_t ctas = (uint32_t)pull_default_ctas();
+  // SW_PROBE_PULL_LINGER_US=1: the kernel leaves as soon as the batch is done (ncu captures: duration = start-up + batch)
+  const uint32_t linger_us = getenv("SW_PROBE_PULL_LINGER_US") ? (uint32_t)atoi(getenv("SW_PROBE_PULL_LINGER_US")) : 40;
   struct Shape {
     uint32_t nmsg;
     uint64_t len;
@@ -1144,7 +1146,7 @@ static void bench_pull(FILE* json, int nbatches_fixed) {
       REQ(probe_publish_batch(sq, q, msgs + (size_t)b * SW_PULL_JOBS, sh.nmsg, ctas, scratch) == 0);
       REQ(stream_sync(sq) == 0);
       ctl->stop = 0;
-      REQ(launch_pull(sp, q, ctl, ++seq, ctas, 40, 100000, &tune) == 0);
+      REQ(launch_pull(sp, q, ctl, ++seq, ctas, linger_us, 100000, &tune) == 0);
       REQ(stream_sync(sp) == 0);
       uint64_t st[8];
       REQ(pull_queue_read_stats(q, st) == 0);
@@ -1176,7 +1178,7 @@ int main(int argc, char** argv) {
   REQ(init(0) == 0);
   printf("backend %s, %d device(s), %d SMs\n", backend_name(), device_count(), sm_count());
   FILE* json = nullptr;
-  if (argc > 2) json = fopen(argv[2], "a");
+  if (argc > 2 && strcmp(argv[2], "-") != 0) json = fopen(argv[2], "a");
   if (cmd == "correctness" || cmd == "all") {
     test_bulk_correctness();
     test_match_random(1, 300, 4096, 512, true);
