@@ -118,7 +118,10 @@ def sweep_plan(n):
     """(window, iterations) of one sweep point: SURVEY 8d shape (window = min(64, max(1, 2^28 / n)) sends in flight,
     then aflush), bounded so that the whole sweep adds a fraction of a second to the run."""
     window = min(64, max(1, (1 << 28) // n))
-    iters = max(8, min(100, (1 << 31) // (window * n)))
+    # at least 16 GiB per point above 16 MiB: the device-wide synchronisation that ends the timed region also waits
+    # for the resident control kernels to notice the silence and leave (linger_us, 150 us) -- a fixed cost that a
+    # handful of iterations would not amortise
+    iters = max(8, min(100, (1 << 34) // (window * n)))
     return window, iters
 
 

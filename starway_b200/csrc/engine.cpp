@@ -58,6 +58,9 @@
 
 #include "gpu.h"
 #include "sw_device.h"
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 namespace {
 
@@ -521,6 +524,7 @@ struct Ep {
   uint8_t* ring = nullptr;
   uint32_t ring_slots = 0;
   uint8_t* peer_ring = nullptr;
+  bool ring_same_gpu = false;         // the peer's ring is in the memory of this context's GPU (pointer attributes of the mapping)
   void* peer_ring_mapping = nullptr;  // base returned by ipc_open (nullptr when in-process)
   uint32_t peer_ring_slots = 0;
   // control block
@@ -605,7 +609,7 @@ struct Worker {
   SwCqEnt* cq_ring = nullptr;
   SwCqEnt* cqr_ring = nullptr;
   SwHrEnt* hr_ring = nullptr;
-  SwSendEnt* send_ring = nullptr;   // puts executed by the resident kernel (small batches, no launch)
+  SwSendLL* send_ring = nullptr;    // puts executed by the resident kernel (small batches, no launch), stamped units
   uint64_t sends_written = 0;
   swgpu::stream_t s_ctl = nullptr;
   uint64_t prog_seq = 0;          // launches so far
@@ -767,6 +771,7 @@ struct Ctx {
   // 1: same-process pinned host sources are read in place by the receiver's kernel (one host->host
   // kernel, ~37 GB/s); 0: stage them through device memory so upload and download overlap (PCIe duplex)
   std::atomic<int64_t> opt_pinned_send_direct{1};
+  std::atomic<int64_t> opt_pull_keep_us{60};   // the pull kernel stays through gaps between needs up to this long (0: asked to leave at once)
   // 1: upload pinned host sources with the TMA bulk kernel; 0 (default): copy engine (cudaMemcpyAsync).
   // Measured on B200 (profiles/r01_e2e_staging_variants.md): the copy engine leaves the SMs and more of
   // the PCIe duplex budget to the concurrent download kernel (43.8 vs 37.9 GB/s at N=2).
@@ -972,7 +977,8 @@ bool worker_alloc_device(Ctx* c, Worker* w) {
     w->cq_ring = (SwCqEnt*)swgpu::host_alloc(sizeof(SwCqEnt) * SW_CQ_RING);
     w->cqr_ring = (SwCqEnt*)swgpu::host_alloc(sizeof(SwCqEnt) * SW_CQ_RING);
     w->hr_ring = (SwHrEnt*)swgpu::host_alloc(sizeof(SwHrEnt) * SW_HR_RING);
-    w->send_ring = (SwSendEnt*)swgpu::host_alloc(sizeof(SwSendEnt) * SW_SEND_RING);
+    w->send_ring = (SwSendLL*)swgpu::host_alloc(sizeof(SwSendLL) * SW_SEND_RING);
+    if (w->send_ring) memset(w->send_ring, 0, sizeof(SwSendLL) * SW_SEND_RING);   // stamp 0: never an entry
     w->s_ctl = swgpu::stream_create();
     if (!w->pctl || !w->post_ring || !w->cq_ring || !w->cqr_ring || !w->hr_ring || !w->send_ring || !w->s_ctl) {
       set_error(std::string("worker resident-path alloc: ") + swgpu::last_error());
@@ -1234,6 +1240,7 @@ void server_handshake(Ctx* c, Worker* w, int fd, bool tcp) {
     }
     if (ep->in_process) {
       ep->peer_ring = (uint8_t*)(uintptr_t)h.ring_ptr;
+      ep->ring_same_gpu = true;   // same context, same GPU
     } else {
       void* base = nullptr;
       if (swgpu::ipc_open(h.ring_handle, &base) != 0) {
@@ -1243,6 +1250,12 @@ void server_handshake(Ctx* c, Worker* w, int fd, bool tcp) {
       }
       ep->peer_ring_mapping = base;
       ep->peer_ring = (uint8_t*)base;
+      {
+        // CUDA ordinals of two processes need not agree (CUDA_VISIBLE_DEVICES): ask where the mapping lives
+        swgpu::PtrInfo rpi;
+        swgpu::ptr_info(ep->peer_ring, &rpi);
+        ep->ring_same_gpu = rpi.is_device && rpi.device == c->device;
+      }
       if (swgpu::ipc_get(ep->ring, wl.ring_handle) != 0) {
         wl.status = SW_ERR_IO_ERROR;
         break;
@@ -1431,6 +1444,7 @@ void client_connect_thread(Ctx* c, Worker* w, ConnectReq req) {
     ep->peer_ring_slots = wl.ring_slots;
     if (ep->in_process) {
       ep->peer_ring = (uint8_t*)(uintptr_t)wl.ring_ptr;
+      ep->ring_same_gpu = true;   // same context, same GPU
     } else {
       void* base = nullptr;
       if (swgpu::ipc_open(wl.ring_handle, &base) != 0) {
@@ -1440,6 +1454,12 @@ void client_connect_thread(Ctx* c, Worker* w, ConnectReq req) {
       }
       ep->peer_ring_mapping = base;
       ep->peer_ring = (uint8_t*)base;
+      {
+        // CUDA ordinals of two processes need not agree (CUDA_VISIBLE_DEVICES): ask where the mapping lives
+        swgpu::PtrInfo rpi;
+        swgpu::ptr_info(ep->peer_ring, &rpi);
+        ep->ring_same_gpu = rpi.is_device && rpi.device == c->device;
+      }
     }
     snprintf(ep->info.name, sizeof(ep->info.name), "starway-server[pid %u gpu %d]", wl.pid, wl.device);
     describe_transport(c, ep);
@@ -1474,6 +1494,25 @@ void client_connect_thread(Ctx* c, Worker* w, ConnectReq req) {
 }
 
 // ============================================================================ progress: sends
+// One put entry into the stamped ring (SwSendLL, sw_device.h): every 16-byte unit goes out in one store, so the
+// control kernel -- which may read the entry before the cursor announces it -- only ever sees whole units.
+static inline void send_ring_write(SwSendLL* dst, const SwSendEnt& e, uint64_t index) {
+  const uint32_t stamp = sw_send_stamp(index);
+  uint32_t w[SW_SEND_UNITS * 3] = {0};
+  memcpy(w, &e, sizeof e);
+  for (uint32_t k = 0; k < SW_SEND_UNITS; k++) {
+#if defined(__SSE2__)
+    _mm_store_si128(reinterpret_cast<__m128i*>(dst->u[k]),
+                    _mm_set_epi32((int)stamp, (int)w[3 * k + 2], (int)w[3 * k + 1], (int)w[3 * k]));
+#else
+    dst->u[k][0] = w[3 * k];
+    dst->u[k][1] = w[3 * k + 1];
+    dst->u[k][2] = w[3 * k + 2];
+    __atomic_store_n(&dst->u[k][3], stamp, __ATOMIC_RELEASE);
+#endif
+  }
+}
+
 bool pump_sends(Ctx* c) {
   if ((c->put_tail - c->put_head) >= (uint32_t)N_PUT_BLOCKS) return false;
   PutBlock& b = c->put_blocks[c->put_tail % N_PUT_BLOCKS];
@@ -1698,7 +1737,8 @@ bool pump_sends(Ctx* c) {
     one = one && large <= 2;
     if (one) {
       for (uint32_t i = 0; i < n; i++) {
-        SwSendEnt& e = w0->send_ring[(w0->sends_written + i) % SW_SEND_RING];
+        SwSendEnt e;
+        memset(&e, 0, sizeof e);
         e.d = b.descs[i];
         // RTS descriptors and small host payloads travel inside the entry: the kernel fetches descriptor and
         // payload in one PCIe round trip
@@ -1707,6 +1747,8 @@ bool pump_sends(Ctx* c) {
           memcpy(e.inl, (const void*)(uintptr_t)e.d.src, e.d.len);
           e.d.src = 0;
         }
+        if (b.items[i].op->ep && b.items[i].op->ep->ring_same_gpu) e.d.kind |= SW_KIND_SAME_GPU;
+        send_ring_write(&w0->send_ring[(w0->sends_written + i) % SW_SEND_RING], e, w0->sends_written + i);
       }
       w0->sends_written += n;
       __atomic_store_n(&w0->pctl->send_tail, w0->sends_written, __ATOMIC_RELEASE);
@@ -2529,7 +2571,13 @@ bool pump_pull(Ctx* c) {
   if (outstanding || expected) c->pull_last_need = now;
   if (c->pull_running) {
     const bool flush = c->stats_flush.load(std::memory_order_acquire) != 0;
-    if (!c->pull_stop_sent && ((!outstanding && !expected) || flush)) {
+    // No need right now is not a reason to leave: the next receive of a ping-pong or of the next window is
+    // posted a few microseconds later, and a relaunch (old kernel out, new one in: ~15 us) would be paid by
+    // every such message.  The host asks the kernel to leave when nothing has needed it for pull_keep_us
+    // (shorter than the control kernels' linger: a device-wide synchronisation after the last message waits
+    // for those anyway), or when statistics are wanted now; the kernel's own linger is the backstop.
+    const bool unneeded = !outstanding && !expected && now - c->pull_last_need > (double)c->opt_pull_keep_us.load() * 1e-6;
+    if (!c->pull_stop_sent && (unneeded || flush)) {
       __atomic_store_n(&c->pull_ctl->stop, 1, __ATOMIC_RELEASE);
       c->pull_stop_sent = true;
     }
@@ -3323,6 +3371,7 @@ sw_ctx* sw_ctx_create(int device) {
   if (const char* e = getenv("STARWAY_BULK_CTAS")) c->opt_bulk_ctas = atoll(e);
   if (const char* e = getenv("STARWAY_BULK_BALANCE")) c->opt_bulk_balance = atoll(e);
   if (const char* e = getenv("STARWAY_PINNED_SEND_DIRECT")) c->opt_pinned_send_direct = atoll(e);
+  if (const char* e = getenv("STARWAY_PULL_KEEP_US")) c->opt_pull_keep_us = std::max<int64_t>(0, atoll(e));
   if (const char* e = getenv("STARWAY_TRACE")) {
     c->trace_path = std::string(e) + "." + std::to_string((int)getpid());
     c->tracing = true;
@@ -3444,6 +3493,7 @@ int sw_set_option(sw_ctx* ctx, const char* key, int64_t value) {
   else if (k == "heap_big_blocks") c->opt_heap_big = std::max<int64_t>(1, value);
   else if (k == "profile") c->opt_profile = value;
   else if (k == "pinned_send_direct") c->opt_pinned_send_direct = value;
+  else if (k == "pull_keep_us") c->opt_pull_keep_us = std::max<int64_t>(0, value);
   else if (k == "stage_upload_kernel") c->opt_stage_upload_kernel = value;
   else if (k == "coalesce_us") c->opt_coalesce_us = value;
   else if (k == "coalesce_bytes") c->opt_coalesce_bytes = value;
@@ -3480,6 +3530,7 @@ int64_t sw_get_option(sw_ctx* ctx, const char* key) {
   if (k == "max_life_us") return c->opt_max_life_us;
   if (k == "armed_ms") return c->opt_armed_ms;
   if (k == "pull_ctas") return c->opt_pull_ctas;
+  if (k == "pull_keep_us") return c->opt_pull_keep_us;
   if (k == "eager_max") return c->opt_eager_max;
   return -1;
 }

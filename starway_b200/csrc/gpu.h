@@ -115,7 +115,7 @@ struct ProgressLaunch {
   SwCqEnt* cq;
   SwCqEnt* cqr;
   SwHrEnt* hr;
-  SwSendEnt* sends;
+  SwSendLL* sends;
   SwPullQueue* pq;
   SwMapEnt* map;
   uint64_t ctx_uuid, launch_seq;

@@ -143,6 +143,20 @@ __device__ __forceinline__ void sw_put_header(uint8_t* slot, uint64_t tag, uint6
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(slot + 16), "l"(seq) : "memory");
 }
 
+// The same header for a ring in this GPU's own memory: the receiver's acquire load (any scope) runs on this GPU,
+// a device-scope release is enough.
+__device__ __forceinline__ void sw_put_header_same_gpu(uint8_t* slot, uint64_t tag, uint64_t msg_len, uint64_t seq, uint32_t kind) {
+  int4 h0;
+  h0.x = static_cast<int>(tag & 0xffffffffu);
+  h0.y = static_cast<int>(tag >> 32);
+  h0.z = static_cast<int>(msg_len & 0xffffffffu);
+  h0.w = static_cast<int>(msg_len >> 32);
+  sw_st16(slot, h0);
+  const uint64_t km = (static_cast<uint64_t>(SW_SLOT_MAGIC) << 32) | kind;
+  asm volatile("st.global.u64 [%0], %1;" ::"l"(slot + 24), "l"(km) : "memory");
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(slot + 16), "l"(seq) : "memory");
+}
+
 // ------------------------------------------------------------------ K1: eager / RTS put
 // One warp per message.  Payload first (16 B vector stores into the peer ring slot),
 // then a system-scope fence, then the 64 B header whose last word carries the

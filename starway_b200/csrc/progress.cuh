@@ -104,7 +104,7 @@ struct SwProgArgs {
   SwCqEnt* cq;               // pinned host, SW_CQ_RING entries: eager completions (index allocated by the matcher)
   SwCqEnt* cqr;              // pinned host, SW_CQ_RING entries: rendezvous completions (allocated by pull CTAs)
   SwHrEnt* hr;               // pinned host, SW_HR_RING entries
-  const SwSendEnt* sends;    // pinned host, SW_SEND_RING entries
+  const SwSendLL* sends;     // pinned host, SW_SEND_RING stamped entries
   SwPullQueue* pq;           // device memory (nullptr: every rendezvous goes to the host)
   const SwMapEnt* map;       // device memory
   uint64_t ctx_uuid;
@@ -1149,8 +1149,10 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
     for (;;) {
       // units of the two host->kernel lines: 0 {post_tail, cq_head} 1 {cqr_head, hr_head} 2 {send_tail, -}
       //                                      4 {stop, dead_mask} 5 {host_epoch, -}
+      // lanes 6 .. 20: the units of the next put entry the host will write (or has written), speculatively
       int4 v = make_int4(0, 0, 0, 0);
       if (lane < 6) v = sw_ld16_sys(ctl_bytes + 16 * lane);
+      else if (lane < 6 + SW_SEND_UNITS) v = sw_ld16_sys(&a.sends[sstaged % SW_SEND_RING].u[lane - 6][0]);
       auto unit_lo = [&](int u) { return u64of(__shfl_sync(0xffffffffu, v.x, u), __shfl_sync(0xffffffffu, v.y, u)); };
       auto unit_hi = [&](int u) { return u64of(__shfl_sync(0xffffffffu, v.z, u), __shfl_sync(0xffffffffu, v.w, u)); };
       const uint64_t host_tail = unit_lo(0), cq_head = unit_hi(0), cqr_head = unit_lo(1), hr_head = unit_hi(1);
@@ -1204,19 +1206,36 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
           a.ctl->post_head = staged;   // the host may reuse these ring entries
         }
       }
-      // ---- stage puts for the put warp: two entries per load instruction (11 units each)
+      // ---- stage puts for the put warp.  The entry read with the control words is taken when all its units carry
+      //      its stamp (the host's cursor may not have been seen to cover it yet: the entry is complete all the same);
+      //      what the cursor announces beyond it costs one more round trip, two entries per load instruction.
       const uint64_t sdone = sh.send_done;
-      uint64_t ns = host_stail - sstaged;
-      const uint64_t sroom = SW_SSEND_RING - (sstaged - sdone);
-      if (ns > sroom) ns = sroom;
+      uint64_t sroom = SW_SSEND_RING - (sstaged - sdone);
       const long long t_seen = clock64();
-      constexpr uint32_t UNITS = sizeof(SwSendEnt) / 16;
-      for (uint64_t base = 0; base < ns; base += 2) {
-        const uint32_t e = lane / UNITS, u = lane % UNITS;
-        if (e < 2 && base + e < ns) {
-          const int4* src = reinterpret_cast<const int4*>(&a.sends[(sstaged + base + e) % SW_SEND_RING]);
-          reinterpret_cast<int4*>(&sh.sends[(sstaged + base + e) % SW_SSEND_RING])[u] = sw_ld16_sys(src + u);
+      auto stage_unit = [&](uint64_t idx, uint32_t unit, const int4& d) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&sh.sends[idx % SW_SSEND_RING]) + 3 * unit;
+        dst[0] = static_cast<uint32_t>(d.x);
+        dst[1] = static_cast<uint32_t>(d.y);
+        if (3 * unit + 2 < SW_SEND_WORDS) dst[2] = static_cast<uint32_t>(d.z);
+      };
+      const bool is_unit = lane >= 6 && lane < 6 + SW_SEND_UNITS;
+      const bool stamped = !is_unit || static_cast<uint32_t>(v.w) == sw_send_stamp(sstaged);
+      uint64_t ns = 0;
+      if (__all_sync(0xffffffffu, stamped) && sroom) {
+        if (is_unit) stage_unit(sstaged, lane - 6, v);
+        ns = 1;
+      }
+      if (host_stail > sstaged + ns) {
+        uint64_t more = host_stail - (sstaged + ns);
+        if (more > sroom - ns) more = sroom - ns;
+        for (uint64_t base = 0; base < more; base += 2) {
+          const uint32_t e = lane / SW_SEND_UNITS, u = lane % SW_SEND_UNITS;
+          if (e < 2 && base + e < more) {
+            const uint64_t idx = sstaged + ns + base + e;
+            stage_unit(idx, u, sw_ld16_sys(&a.sends[idx % SW_SEND_RING].u[u][0]));
+          }
         }
+        ns += more;
       }
       __syncwarp();
       if (ns) {
@@ -1233,7 +1252,7 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
         }
       }
       const long long now = clock64();
-      const bool idle = n == 0 && ns == 0 && host_tail == staged && staged == sh.post_head && host_stail == sstaged &&
+      const bool idle = n == 0 && ns == 0 && host_tail == staged && staged == sh.post_head && host_stail <= sstaged &&
                         sstaged == sh.send_done && now - sh.active_clk > linger_clk;
       if (stop || idle || now - clk0 > life_clk) {
         if (lane == 0) {
@@ -1271,6 +1290,13 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
       d.src = d.dst = d.tag = d.seq = d.msg_len = 0;
       d.len = d.kind = 0;
       if (lane < n) d = e->d;
+      const bool same_gpu = (d.kind & SW_KIND_SAME_GPU) != 0;
+      d.kind &= ~SW_KIND_SAME_GPU;
+      auto put_header = [&]() {
+        uint8_t* hdr = reinterpret_cast<uint8_t*>(d.dst);
+        if (same_gpu) sw_put_header_same_gpu(hdr, d.tag, d.msg_len, d.seq, d.kind);
+        else sw_put_header(hdr, d.tag, d.msg_len, d.seq, d.kind);
+      };
       const bool mine = lane < n && (d.src == 0 || d.len <= 256);
       if (mine) {
         uint8_t* slot = reinterpret_cast<uint8_t*>(d.dst);
@@ -1279,7 +1305,7 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
         } else {
           for (uint32_t k = 0; k * 16 < d.len; k++) sw_st16(slot + SW_SLOT_HDR + 16 * k, reinterpret_cast<const int4*>(e->inl)[k]);
         }
-        sw_put_header(slot, d.tag, d.msg_len, d.seq, d.kind);
+        put_header();
       }
       const uint32_t big = __ballot_sync(0xffffffffu, lane < n && !mine);
       uint32_t rest = big;
@@ -1290,7 +1316,7 @@ __global__ void __launch_bounds__(SW_PROG_THREADS, 1) sw_progress_kernel(const _
         const uint32_t len = __shfl_sync(0xffffffffu, d.len, L);
         sw_copy(reinterpret_cast<uint8_t*>(dst) + SW_SLOT_HDR, reinterpret_cast<const uint8_t*>(src), len, lane, 32);
         __syncwarp();
-        if (static_cast<int>(lane) == L) sw_put_header(reinterpret_cast<uint8_t*>(dst), d.tag, d.msg_len, d.seq, d.kind);
+        if (static_cast<int>(lane) == L) put_header();
       }
       __syncwarp();
       i += n;

@@ -26,6 +26,9 @@ constexpr uint32_t SW_EAGER_MAX = SW_SLOT_BYTES - SW_SLOT_HDR;  // 8128 B payloa
 constexpr uint32_t SW_RING_SLOTS_DEFAULT = 1024;                // 8 MiB per endpoint
 
 enum : uint32_t { SW_KIND_EAGER = 1, SW_KIND_RTS = 2 };
+// SwSendEnt only (puts executed by the resident control kernel): the destination ring is in the memory of the GPU the
+// kernel runs on, so the arrival flag is released at device scope (~0.3 us) instead of system scope (~1.5 us)
+constexpr uint32_t SW_KIND_SAME_GPU = 0x80000000u;
 
 struct SwSlotHdr {     // 64 B, 16 B aligned, written after the payload by the put kernel
   uint64_t tag;        // sender tag (full uint64)
@@ -267,6 +270,18 @@ struct SwSendEnt {   // pinned host: one put for the resident control kernel of 
   uint8_t inl[128];
 };
 static_assert(sizeof(SwSendEnt) == 176, "SwSendEnt layout");
+
+// The ring itself holds the entry in 16-byte units of 12 data bytes + a 4-byte stamp (the entry's index): the link
+// warp reads the next expected entry in the SAME load instruction as the control words, without waiting for the
+// host's cursor to cover it, and takes it when every unit carries the stamp.  A unit is written with one 16-byte
+// store and read in one piece, so a stamped unit is a whole unit; units of an older entry carry an older stamp.
+constexpr uint32_t SW_SEND_WORDS = sizeof(SwSendEnt) / 4;            // 44
+constexpr uint32_t SW_SEND_UNITS = (SW_SEND_WORDS + 2) / 3;         // 15
+struct alignas(16) SwSendLL {
+  uint32_t u[16][4];   // unit k: words 3k .. 3k+2 of the SwSendEnt, then the stamp; unit 15 is unused
+};
+static_assert(sizeof(SwSendLL) == 256, "SwSendLL layout");
+SW_HD inline uint32_t sw_send_stamp(uint64_t index) { return (static_cast<uint32_t>(index + 1) & 0x7fffffffu) | 0x80000000u; }
 
 struct SwPostEnt {   // pinned host: one posted receive on its way to the control kernel
   uint64_t tag, mask, buf, cap, op_id;

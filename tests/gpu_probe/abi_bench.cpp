@@ -59,7 +59,9 @@ int main(int argc, char** argv) {
   cudaMemset(dst, 0, POOL);
   cudaDeviceSynchronize();
 
+  const size_t n_min = getenv("ABI_MIN") ? (size_t)atoll(getenv("ABI_MIN")) : 64, n_max = getenv("ABI_MAX") ? (size_t)atoll(getenv("ABI_MAX")) : (256u << 20);
   for (size_t n = 64; n <= (256u << 20); n *= 4) {
+    if (n < n_min || n > n_max) continue;
     size_t window = std::min<size_t>(256, std::max<size_t>(1, (512u << 20) / n));
     if (n <= 8192) window = 1024;
     int steps = n >= (16u << 20) ? 8 : 20;
