@@ -368,7 +368,7 @@ def run_ours(args):
             await server.aclose()
             return value, ms, st, clk, float("nan"), step_bytes, {}, payload_check, warm_batches, sweep
         e2e_value, e2e_ms, e2e_steps, st2 = await e2e_leg(True)
-        e2e_pageable, pg_ms, pg_steps, _ = await e2e_leg(False)
+        e2e_pageable, pg_ms, pg_steps, _ = (float("nan"), float("nan"), 1, None) if os.environ.get("STARWAY_BENCH_SKIP_PAGEABLE") else await e2e_leg(False)
         if os.environ.get("STARWAY_TRACE"):
             with open(os.environ["STARWAY_TRACE"] + f".py.{os.getpid()}", "w") as f:
                 for name, t in marks:

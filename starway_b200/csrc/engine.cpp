@@ -454,7 +454,8 @@ struct Mapping;
 
 struct BulkJob {
   double t_enq = 0;
-  bool host_side = false;  // source or destination is pinned host memory: use the SIMT copy
+  bool host_side = false;  // source or destination is pinned host memory
+  bool src_host = false;   // the source is pinned host memory (read over PCIe by the copying kernel)
   Worker* w = nullptr;
   struct Ep* ep = nullptr;
   uint64_t recv_op = 0;
@@ -658,6 +659,10 @@ struct PutBlock {
   // launch), so consecutive batches overlap instead of queueing behind each other; blocks still retire in order
   swgpu::stream_t s = nullptr;
   std::vector<PutItem> items;
+  // host -> staging uploads of this batch, submitted as one copy-engine batch in front of the put
+  std::vector<void*> up_dst;
+  std::vector<const void*> up_src;
+  std::vector<size_t> up_len;
 };
 struct BulkBlock {
   SwSeg* segs = nullptr;
@@ -667,6 +672,9 @@ struct BulkBlock {
   bool busy = false;
   std::vector<BulkJob> jobs;
   std::vector<SwSeg> tma, simt;  // scratch, capacity retained across launches
+  std::vector<void*> ce_dst;     // copies of this block made by the copy engine (device -> pinned host)
+  std::vector<const void*> ce_src;
+  std::vector<size_t> ce_len;
   uint64_t bytes = 0;
 };
 struct PostCopy {  // device staging -> host user buffer after delivery
@@ -776,6 +784,9 @@ struct Ctx {
   // Measured on B200 (profiles/r01_e2e_staging_variants.md): the copy engine leaves the SMs and more of
   // the PCIe duplex budget to the concurrent download kernel (43.8 vs 37.9 GB/s at N=2).
   std::atomic<int64_t> opt_stage_upload_kernel{0};
+  std::atomic<int64_t> opt_stage_batch_bytes{(int64_t)STAGE_BATCH_BYTES};   // staged sends are announced in batches of this size
+  std::atomic<int64_t> opt_hostdst_ce{0};    // device -> pinned-host copies by the copy engine (batched) instead of a kernel
+  std::atomic<int64_t> opt_hostdst_tma{0};   // device -> pinned-host copies by the TMA kernel instead of the SIMT kernel
   // ---- resident path
   // 1: receives are driven by resident control kernels (sw_progress_kernel) and rendezvous copies by the
   // resident pull CTAs (sw_pull_kernel); 0: one match launch per batch, host-launched bulk copies (round 1)
@@ -1523,6 +1534,9 @@ bool pump_sends(Ctx* c) {
   b.items.clear();
   b.nsegs = 0;
   b.res_worker = nullptr;
+  b.up_dst.clear();
+  b.up_src.clear();
+  b.up_len.clear();
   for (Worker* w : c->active) {
     for (Ep* ep : w->eps) {
       while (!ep->sendq.empty() && n < PUT_BATCH) {
@@ -1599,7 +1613,7 @@ bool pump_sends(Ctx* c) {
             // (Host memory; or device memory from the CUDA virtual-memory-management API -- PyTorch's expandable
             // segments -- which cudaIpcGetMemHandle cannot export: one device-to-device copy into an exportable
             // staging buffer, at HBM speed, keeps such tensors usable as rendezvous sources.)
-            if (!op->dev_staging && n > 0 && staged_bytes + op->len > STAGE_BATCH_BYTES) {
+            if (!op->dev_staging && n > 0 && staged_bytes + op->len > (uint64_t)c->opt_stage_batch_bytes.load()) {
               batch_full = true;
               break;
             }
@@ -1651,8 +1665,9 @@ bool pump_sends(Ctx* c) {
                 if (op->len > body)
                   swgpu::memcpy_h2d((uint8_t*)op->dev_staging + body, op->ptr + body, op->len - body, b.s);
               } else {
-                trace(c, "h2d_enqueue", op->len);
-                swgpu::memcpy_h2d(op->dev_staging, op->pin_stage ? (const uint8_t*)op->pin_stage : op->ptr, op->len, b.s);
+                b.up_dst.push_back(op->dev_staging);
+                b.up_src.push_back(op->pin_stage ? (const void*)op->pin_stage : (const void*)op->ptr);
+                b.up_len.push_back((size_t)op->len);
                 stream_ordered = true;   // the RTS may only become visible after this copy: needs the put launch behind it
               }
               h2d += op->len;
@@ -1724,6 +1739,12 @@ bool pump_sends(Ctx* c) {
     if (n >= PUT_BATCH || batch_full) break;
   }
   if (!n) return false;
+  if (!b.up_dst.empty()) {
+    // the uploads of this batch in one copy-engine submission, in front of the put that announces them
+    trace(c, "h2d_batch", b.up_dst.size(), staged_bytes);
+    if (swgpu::memcpy_h2d_batch(b.up_dst.data(), b.up_src.data(), b.up_len.data(), b.up_dst.size(), b.s) != 0)
+      fprintf(stderr, "starway_b200: staging upload failed: %s\n", swgpu::last_error());
+  }
   // ---- small batch of one worker whose control kernel is resident: hand the descriptors to that kernel
   if (n <= (uint32_t)c->opt_resident_puts.load() && !stream_ordered && b.nsegs == 0 && swgpu::resident_lingers()) {
     Worker* w0 = b.items[0].op->w;
@@ -2014,7 +2035,8 @@ bool poll_match(Ctx* c, Worker* w) {
     j.t_enq = now_s();
     {
       auto rit = w->recvs.find(r.op_id);
-      j.host_side = (r.rts.pad[0] & 1) != 0 || (rit != w->recvs.end() && rit->second->mem == MEM_PINNED);
+      j.src_host = (r.rts.pad[0] & 1) != 0;
+      j.host_side = j.src_host || (rit != w->recvs.end() && rit->second->mem == MEM_PINNED);
     }
     if (r.status != SW_OK) {
       j.failed = true;
@@ -2194,10 +2216,22 @@ bool pump_bulk(Ctx* c) {
   std::vector<SwSeg>& simt = b.simt;
   tma.clear();
   simt.clear();
+  b.ce_dst.clear();
+  b.ce_src.clear();
+  b.ce_len.clear();
   for (BulkJob& j : b.jobs) {
     uint64_t src = j.src, dst = j.dst, len = j.len;
+    if (j.host_side && !j.src_host && c->opt_hostdst_ce.load()) {
+      // device (local or peer staging) -> pinned host: the copy engine, one batched submission per launch block --
+      // with the other direction of the PCIe link busy it keeps ~50 GB/s where a copying kernel drops to ~35
+      b.ce_dst.push_back((void*)(uintptr_t)dst);
+      b.ce_src.push_back((const void*)(uintptr_t)src);
+      b.ce_len.push_back((size_t)len);
+      continue;
+    }
     // receives into host memory were redirected to device staging at post time
-    if (tune.mode == 0 && !j.host_side && ((src | dst) & 15) == 0 && len >= 16) {
+    const bool tma_ok = !j.host_side || (!j.src_host && c->opt_hostdst_tma.load());   // device -> pinned host: bulk stores over PCIe
+    if (tune.mode == 0 && tma_ok && ((src | dst) & 15) == 0 && len >= 16) {
       uint64_t body = len & ~15ull;
       for (uint64_t off = 0; off < body; off += seg) tma.push_back(SwSeg{src + off, dst + off, std::min(seg, body - off), 0});
       if (len > body) simt.push_back(SwSeg{src + body, dst + body, len - body, 0});
@@ -2219,6 +2253,7 @@ bool pump_bulk(Ctx* c) {
     t2.ctas_per_sm = 8;
     rc |= swgpu::launch_bulk(c->s_bulk, b.segs + ntma, nsimt, &t2);
   }
+  if (!b.ce_dst.empty()) rc |= swgpu::memcpy_batch(b.ce_dst.data(), b.ce_src.data(), b.ce_len.data(), b.ce_dst.size(), c->s_bulk);
   if (rc) fprintf(stderr, "starway_b200: bulk launch failed: %s\n", swgpu::last_error());
   swgpu::event_record(b.timed ? b.ev : b.ev_fast, c->s_bulk);
   b.busy = true;
@@ -2362,7 +2397,8 @@ bool poll_progress_rings(Ctx* c, Worker* w) {
     j.t_enq = now_s();
     {
       auto rit = w->recvs.find(r.op_id);
-      j.host_side = (r.rts.pad[0] & SW_RTS_PINNED_SRC) != 0 || (rit != w->recvs.end() && rit->second->mem == MEM_PINNED);
+      j.src_host = (r.rts.pad[0] & SW_RTS_PINNED_SRC) != 0;
+      j.host_side = j.src_host || (rit != w->recvs.end() && rit->second->mem == MEM_PINNED);
     }
     if (r.status != SW_OK) {
       j.failed = true;
@@ -3371,7 +3407,21 @@ sw_ctx* sw_ctx_create(int device) {
   if (const char* e = getenv("STARWAY_BULK_CTAS")) c->opt_bulk_ctas = atoll(e);
   if (const char* e = getenv("STARWAY_BULK_BALANCE")) c->opt_bulk_balance = atoll(e);
   if (const char* e = getenv("STARWAY_PINNED_SEND_DIRECT")) c->opt_pinned_send_direct = atoll(e);
+  if (const char* e = getenv("STARWAY_HOSTDST_TMA")) c->opt_hostdst_tma = atoll(e);
   if (const char* e = getenv("STARWAY_PULL_KEEP_US")) c->opt_pull_keep_us = std::max<int64_t>(0, atoll(e));
+  if (const char* e = getenv("STARWAY_OPTS")) {   // "key=value,key=value": any sw_set_option key
+    std::string all(e);
+    size_t pos = 0;
+    while (pos < all.size()) {
+      size_t end = all.find(',', pos);
+      if (end == std::string::npos) end = all.size();
+      const std::string kv = all.substr(pos, end - pos);
+      const size_t eq = kv.find('=');
+      if (eq != std::string::npos && sw_set_option((sw_ctx*)c, kv.substr(0, eq).c_str(), atoll(kv.c_str() + eq + 1)) != 0)
+        fprintf(stderr, "starway_b200: STARWAY_OPTS: unknown option '%s'\n", kv.substr(0, eq).c_str());
+      pos = end + 1;
+    }
+  }
   if (const char* e = getenv("STARWAY_TRACE")) {
     c->trace_path = std::string(e) + "." + std::to_string((int)getpid());
     c->tracing = true;
@@ -3495,6 +3545,9 @@ int sw_set_option(sw_ctx* ctx, const char* key, int64_t value) {
   else if (k == "pinned_send_direct") c->opt_pinned_send_direct = value;
   else if (k == "pull_keep_us") c->opt_pull_keep_us = std::max<int64_t>(0, value);
   else if (k == "stage_upload_kernel") c->opt_stage_upload_kernel = value;
+  else if (k == "hostdst_tma") c->opt_hostdst_tma = value;
+  else if (k == "hostdst_ce") c->opt_hostdst_ce = value;
+  else if (k == "stage_batch_bytes") c->opt_stage_batch_bytes = std::max<int64_t>(65536, value);
   else if (k == "coalesce_us") c->opt_coalesce_us = value;
   else if (k == "coalesce_bytes") c->opt_coalesce_bytes = value;
   else if (k == "done_flags") c->opt_done_flags = value;
@@ -3875,10 +3928,14 @@ double sw_evaluate_perf(sw_ctx* ctx, sw_worker_t wid, sw_ep_t epid, size_t msg_s
   Ep* ep = epid ? find_ep(c, epid) : (w->eps.empty() ? nullptr : w->eps[0]);
   const bool same_gpu = !ep || ep->in_process || ep->peer_device == c->device;
   const bool eager = msg_size <= (size_t)c->opt_eager_max.load();
-  // one-way: put launch + match launch (+ bulk launch and FIN for rendezvous) + asyncio wake-up
-  const double lat = same_gpu ? (eager ? 47e-6 : 62e-6) : (eager ? 49e-6 : 68e-6);
-  // HBM copy (3.1 TB/s payload) on one GPU, NVLink pull (0.74 TB/s) between GPUs
-  const double bw = same_gpu ? 3.1e12 : 7.4e11;
+  // Measured on B200 through the asyncio API (profiles/r02_pingpong_*): one-way 64 B 12.7 us on one GPU, 13.3 us over
+  // NVLink; a rendezvous adds the pull hand-over and the completion records (1 MiB: 25.8 / 26.7 us one-way).  With the
+  // discrete-kernel engine (resident=0) the round-1 figures apply.
+  const bool resident = c->opt_resident.load() != 0;
+  const double lat = resident ? (same_gpu ? (eager ? 12.7e-6 : 25.5e-6) : (eager ? 13.3e-6 : 25.3e-6))
+                              : (same_gpu ? (eager ? 47e-6 : 62e-6) : (eager ? 49e-6 : 68e-6));
+  // copy rate of one large message: HBM copy on one GPU (3.3 TB/s payload), NVLink pull between GPUs (0.65 TB/s)
+  const double bw = same_gpu ? 3.3e12 : 6.5e11;
   return lat + (double)msg_size / bw;
 }
 

@@ -62,6 +62,10 @@ int event_sync(event_t e);
 float event_elapsed_ms(event_t a, event_t b);
 
 int memcpy_h2d(void* dst, const void* src, size_t n, stream_t s);
+// n host -> device copies as ONE copy-engine submission (cudaMemcpyBatchAsync): separate 1 MiB copies reach 28 GB/s while
+// the other direction of the link is busy, the batch 49 GB/s (profiles/r02_probe_duplex_patterns.txt)
+int memcpy_h2d_batch(void* const* dsts, const void* const* srcs, const size_t* sizes, size_t n, stream_t s);
+int memcpy_batch(void* const* dsts, const void* const* srcs, const size_t* sizes, size_t n, stream_t s);   // any direction
 int memcpy_d2h(void* dst, const void* src, size_t n, stream_t s);
 int memcpy_d2d(void* dst, const void* src, size_t n, stream_t s);
 int memset_dev(void* dst, int v, size_t n, stream_t s);

@@ -271,6 +271,26 @@ int memcpy_h2d(void* dst, const void* src, size_t n, stream_t s) {
   SW_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, (cudaStream_t)s));
   return 0;
 }
+int memcpy_batch(void* const* dsts, const void* const* srcs, const size_t* sizes, size_t n, stream_t s) {
+  if (n == 0) return 0;
+#if CUDART_VERSION >= 12080
+  if (n > 1) {
+    cudaMemcpyAttributes at;
+    memset(&at, 0, sizeof at);
+    at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+    size_t attr_idx = 0, fail = 0;
+    cudaError_t e = cudaMemcpyBatchAsync(const_cast<void**>(dsts), (void**)srcs,
+                                         const_cast<size_t*>(sizes), n, &at, &attr_idx, 1, &fail, (cudaStream_t)s);
+    if (e == cudaSuccess) return 0;
+    (void)cudaGetLastError();   // not supported by this driver / for these operands: one copy at a time
+  }
+#endif
+  for (size_t i = 0; i < n; i++) SW_CUDA(cudaMemcpyAsync(dsts[i], srcs[i], sizes[i], cudaMemcpyDefault, (cudaStream_t)s));
+  return 0;
+}
+int memcpy_h2d_batch(void* const* dsts, const void* const* srcs, const size_t* sizes, size_t n, stream_t s) {
+  return memcpy_batch(dsts, srcs, sizes, n, s);
+}
 int memcpy_d2h(void* dst, const void* src, size_t n, stream_t s) {
   SW_CUDA(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, (cudaStream_t)s));
   return 0;

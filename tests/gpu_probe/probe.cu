@@ -717,6 +717,132 @@ static void bench_hostmem(FILE* json) {
   }
 }
 
+
+// ------------------------------------------------------------------ PCIe duplex: host->device and device->host at once
+// What the e2e path (host buffers) can hope for: both directions of the link busy at the same time, by the copy
+// engines, by the bulk kernels (few CTAs each, so that both kernels are resident together), or one of each.
+static void bench_duplex(FILE* json) {
+  const size_t N = 256u << 20;
+  uint8_t *hs = (uint8_t*)host_alloc(N), *hd = (uint8_t*)host_alloc(N);
+  uint8_t *ds = (uint8_t*)dev_alloc(N), *dd = (uint8_t*)dev_alloc(N);
+  REQ(hs && hd && ds && dd);
+  memset(hs, 0x3C, N);
+  CK(cudaMemset(ds, 0x5A, N));
+  stream_t s1 = stream_create(), s2 = stream_create();
+  const uint64_t seg = 1u << 20;
+  auto up = make_segs((uint64_t)hs, (uint64_t)dd, N, seg), down = make_segs((uint64_t)ds, (uint64_t)hd, N, seg);
+  SwSeg* sup = (SwSeg*)host_alloc(sizeof(SwSeg) * up.size());
+  SwSeg* sdown = (SwSeg*)host_alloc(sizeof(SwSeg) * down.size());
+  memcpy(sup, up.data(), sizeof(SwSeg) * up.size());
+  memcpy(sdown, down.data(), sizeof(SwSeg) * down.size());
+  stream_t xs[4] = {stream_create(), stream_create(), stream_create(), stream_create()};
+  auto down64 = make_segs((uint64_t)ds, (uint64_t)hd, N, 65536);
+  SwSeg* small = (SwSeg*)host_alloc(sizeof(SwSeg) * down64.size());
+  memcpy(small, down64.data(), sizeof(SwSeg) * down64.size());
+  const size_t small_n = down64.size();
+  struct Mode {
+    const char* name;
+    int up, down;   // 0: none, 1: copy engine, 2: bulk TMA kernel, 3: SIMT kernel, 4: 1 MiB copies, 5/6: 4 MiB TMA/SIMT kernels
+  } modes[] = {{"H2D copy engine alone", 1, 0},   {"D2H copy engine alone", 0, 1},    {"H2D + D2H copy engines", 1, 1},
+               {"H2D kernel alone", 2, 0},        {"D2H kernel alone", 0, 2},         {"H2D + D2H kernels (TMA)", 2, 2},
+               {"H2D copy engine + D2H kernel", 1, 2}, {"H2D kernel + D2H copy engine", 2, 1}, {"H2D + D2H kernels (SIMT)", 3, 3},
+               // the engine's pattern for host buffers: 1 MiB copies on four streams; 4 MiB kernels of 64 KiB pieces
+               {"H2D 1 MiB copies alone", 4, 0}, {"D2H 4 MiB TMA kernels alone", 0, 5}, {"H2D 1 MiB copies + D2H 4 MiB TMA kernels", 4, 5},
+               {"H2D 1 MiB copies + D2H 4 MiB SIMT kernels", 4, 6}, {"H2D 1 MiB copies + D2H copy engine", 4, 1},
+               {"H2D 1 MiB copies, one stream + D2H 4 MiB TMA kernels", 7, 5},
+               {"H2D 4 MiB copies, one stream + D2H 4 MiB TMA kernels", 9, 5}, {"H2D 16 MiB copies, one stream + D2H 4 MiB TMA kernels", 10, 5},
+               {"H2D kernel 8 CTAs + D2H 4 MiB TMA kernels", 11, 5}, {"H2D kernel 8 CTAs + D2H kernel 8 CTAs", 11, 11},
+               {"H2D 1 MiB copies, batch API alone", 8, 0}, {"H2D 1 MiB copies, batch API + D2H 4 MiB TMA kernels", 8, 5}};
+  for (const Mode& m : modes) {
+    float best = 1e30f, best_up = 0, best_down = 0;
+    for (int it = 0; it < 4; it++) {
+      event_t a = event_create(1), b1 = event_create(1), b2 = event_create(1);
+      CK(cudaDeviceSynchronize());
+      event_record(a, s1);
+      CK(cudaStreamWaitEvent((cudaStream_t)s2, (cudaEvent_t)a, 0));
+      auto go = [&](int how, stream_t st, SwSeg* segs, size_t nseg, void* dst, const void* src) {
+        if (how == 1) CK(cudaMemcpyAsync(dst, src, N, cudaMemcpyDefault, (cudaStream_t)st));
+        if (how == 2) {
+          BulkTuning t{0, 8, 24576, 1, 0};
+          REQ(launch_bulk(st, segs, 32, &t) == 0);   // 32 CTAs ...
+          for (size_t o = 32; o < nseg; o += 32) REQ(launch_bulk(st, segs + o, (uint32_t)std::min<size_t>(32, nseg - o), &t) == 0);
+        }
+        if (how == 3) {
+          BulkTuning t{1, 8, 24576, 1, 0};
+          for (size_t o = 0; o < nseg; o += 64) REQ(launch_bulk(st, segs + o, (uint32_t)std::min<size_t>(64, nseg - o), &t) == 0);
+        }
+        if (how == 4) {   // 1 MiB copies, groups of four per stream, four streams
+          for (size_t o = 0; o < N; o += 1u << 20)
+            CK(cudaMemcpyAsync((uint8_t*)dst + o, (const uint8_t*)src + o, 1u << 20, cudaMemcpyDefault, (cudaStream_t)xs[(o >> 22) & 3]));
+        }
+        if (how == 7 || how == 9 || how == 10) {   // copies of 1 / 4 / 16 MiB on one stream
+          const size_t piece = how == 7 ? (1u << 20) : (how == 9 ? (4u << 20) : (16u << 20));
+          for (size_t o = 0; o < N; o += piece)
+            CK(cudaMemcpyAsync((uint8_t*)dst + o, (const uint8_t*)src + o, piece, cudaMemcpyDefault, (cudaStream_t)st));
+        }
+        if (how == 8) {   // the same 1 MiB copies through cudaMemcpyBatchAsync, 64 per call
+          static std::vector<void*> bd, bs;
+          static std::vector<size_t> bz;
+          bd.clear(); bs.clear(); bz.clear();
+          for (size_t o = 0; o < N; o += 1u << 20) {
+            bd.push_back((uint8_t*)dst + o);
+            bs.push_back((uint8_t*)const_cast<void*>(src) + o);
+            bz.push_back(1u << 20);
+          }
+          cudaMemcpyAttributes at;
+          memset(&at, 0, sizeof at);
+          at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+          size_t ai = 0, fail = 0;
+          for (size_t o = 0; o < bd.size(); o += 64)
+            CK(cudaMemcpyBatchAsync(bd.data() + o, bs.data() + o, bz.data() + o, std::min<size_t>(64, bd.size() - o), &at, &ai, 1, &fail, (cudaStream_t)st));
+        }
+        if (how == 11) {   // bulk TMA kernel on 8 CTAs, 8 MiB per launch
+          BulkTuning t{0, 8, 24576, 1, 0};
+          for (size_t o = 0; o < nseg; o += 8) REQ(launch_bulk(st, segs + o, (uint32_t)std::min<size_t>(8, nseg - o), &t) == 0);
+        }
+        if (how == 5 || how == 6) {   // 4 MiB per launch, 64 KiB pieces
+          BulkTuning t{how == 5 ? 0 : 1, 8, 24576, how == 5 ? 1 : 8, 0};
+          for (size_t o = 0; o < small_n; o += 64) REQ(launch_bulk(st, small + o, (uint32_t)std::min<size_t>(64, small_n - o), &t) == 0);
+        }
+      };
+      if (m.up == 4 || m.down == 4)
+        for (int k = 0; k < 4; k++) CK(cudaStreamWaitEvent((cudaStream_t)xs[k], (cudaEvent_t)a, 0));
+      go(m.up, s1, sup, up.size(), dd, hs);
+      if (m.up == 4)
+        for (int k = 0; k < 4; k++) {
+          event_t j = event_create(0);
+          event_record(j, xs[k]);
+          CK(cudaStreamWaitEvent((cudaStream_t)s1, (cudaEvent_t)j, 0));
+          event_destroy(j);
+        }
+      go(m.down, s2, sdown, down.size(), hd, ds);
+      if (m.down == 4)
+        for (int k = 0; k < 4; k++) {
+          event_t j = event_create(0);
+          event_record(j, xs[k]);
+          CK(cudaStreamWaitEvent((cudaStream_t)s2, (cudaEvent_t)j, 0));
+          event_destroy(j);
+        }
+      event_record(b1, s1);
+      event_record(b2, s2);
+      REQ(event_sync(b1) == 0 && event_sync(b2) == 0);
+      const float ms = std::max(event_elapsed_ms(a, b1), event_elapsed_ms(a, b2));
+      if (it > 0 && ms < best) {
+        best = ms;
+        best_up = event_elapsed_ms(a, b1);
+        best_down = event_elapsed_ms(a, b2);
+      }
+      event_destroy(a);
+      event_destroy(b1);
+      event_destroy(b2);
+    }
+    const double dirs = (m.up ? 1 : 0) + (m.down ? 1 : 0);
+    printf("[duplex] %-44s %8.3f ms  %6.1f GB/s per direction, %6.1f GB/s total  (up %.3f ms, down %.3f ms)\n", m.name, best, N / (best * 1e-3) / 1e9,
+           dirs * N / (best * 1e-3) / 1e9, best_up, best_down);
+    if (json) fprintf(json, "{\"bench\":\"duplex\",\"mode\":\"%s\",\"ms\":%.4f,\"gbs_per_direction\":%.1f}\n", m.name, best, N / (best * 1e-3) / 1e9);
+  }
+}
+
 // ------------------------------------------------------------------ 2-process CUDA IPC
 static int ipc_child(const char* path) {
   int n = device_count();
@@ -1192,6 +1318,7 @@ int main(int argc, char** argv) {
   if (cmd == "floor") bench_floor(json);
   if (cmd == "balance") bench_balance(json);
   if (cmd == "hostmem") bench_hostmem(json);
+  if (cmd == "duplex") bench_duplex(json);
   if (cmd == "hostlat") bench_hostlat(json);
   if (cmd == "pull") bench_pull(json, argc > 3 ? atoi(argv[3]) : 0);
   if (cmd == "tune") bench_tune(json);

@@ -202,6 +202,14 @@ int event_query(event_t) { return 0; }
 int event_sync(event_t) { return 0; }
 float event_elapsed_ms(event_t, event_t) { return 0.001f; }
 int memcpy_h2d(void* d, const void* s, size_t n, stream_t) { memcpy(d, s, n); return 0; }
+int memcpy_batch(void* const* d, const void* const* s, const size_t* z, size_t n, stream_t) {
+  for (size_t i = 0; i < n; i++) memcpy(d[i], s[i], z[i]);
+  return 0;
+}
+int memcpy_h2d_batch(void* const* d, const void* const* s, const size_t* z, size_t n, stream_t) {
+  for (size_t i = 0; i < n; i++) memcpy(d[i], s[i], z[i]);
+  return 0;
+}
 int memcpy_d2h(void* d, const void* s, size_t n, stream_t) { memcpy(d, s, n); return 0; }
 int memcpy_d2d(void* d, const void* s, size_t n, stream_t) { memmove(d, s, n); return 0; }
 int memset_dev(void* d, int v, size_t n, stream_t) { memset(d, v, n); return 0; }

@@ -1,5 +1,8 @@
 mkdir -p gpurun_out; O=gpurun_out
-timeout -k 10 300 python -m pytest tests/test_gpu_multi.py -x -q --timeout 280 2>&1 | tail -3 | tee $O/r02_pytest_gpu_multi_2_v4.log
-timeout -k 10 250 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 100 --warmup 10 > $O/r02_bench_n2_v4.json 2> $O/err2.txt; python -c "
-import json;d=json.load(open('gpurun_out/r02_bench_n2_v4.json'));print(d['value'],d['ms_per_step'],d['e2e']['value'],d['e2e_pageable']['value']);print(d['roofline']['frac'],d['roofline']['batch_phases_us'],d['roofline']['payload_bytes_per_launch']);print([(p['bytes'],p['gbs_per_gpu'],p['mmsg_per_s_per_gpu'],p['frac_of_roofline'],p['bit_exact']) for p in d['sweep']['points']])"
-timeout -k 10 100 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench_scenarios.py pingpong --out $O/r02_pingpong_n2_v4.jsonl > $O/pp2.txt 2>&1; grep -v "^\*\|OMP\|^$" $O/pp2.txt | cut -c1-260 | tail -8
+run() { env STARWAY_OPTS="$1" timeout -k 10 120 python bench.py --steps 20 --warmup 5 --no-sweep --no-cpu-baseline > $O/be.json 2>$O/err.txt; python -c "
+import json;d=json.load(open('gpurun_out/be.json'));e=d['e2e'];print('$1', '->', e['value'], e['rank0_breakdown']['ms_per_step'], e['rank0_breakdown']['copy_kernel_ms_per_step'], e['rank0_breakdown']['bulk_launches_per_step'], 'pageable', d['e2e_pageable']['value'])" || tail -3 $O/err.txt; }
+run "pinned_send_direct=0,hostdst_ce=1"
+run "pinned_send_direct=0,hostdst_ce=1,stage_batch_bytes=8388608"
+run "pinned_send_direct=0,hostdst_ce=1,stage_batch_bytes=2097152"
+run "pinned_send_direct=0,hostdst_ce=1,coalesce_us=10"
+STARWAY_OPTS="pinned_send_direct=0,hostdst_ce=1" timeout -k 10 300 python -m pytest tests -m gpu -x -q --timeout 280 -k "host or pageable or pinned or mixed or numpy or e2e or flush" 2>&1 | tail -2
