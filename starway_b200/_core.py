@@ -248,6 +248,19 @@ def _banner(msg: str) -> None:
         print(msg)
 
 
+def _weak_method(obj, func):
+    """`func` bound to `obj` through a weak reference (the C callable stored on the object must not keep it alive)."""
+    ref = weakref.ref(obj)
+
+    def call(*args, **kwargs):
+        o = ref()
+        if o is None:
+            raise ReferenceError("starway_b200 object is gone")
+        return func(o, *args, **kwargs)
+
+    return call
+
+
 def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_fastpath: bool = True) -> SimpleNamespace:
     """Build Context/Server/Client/ServerEndpoint classes on top of a loaded C-ABI library."""
     declare(lib)
@@ -298,6 +311,7 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
                 addr = lambda f: ctypes.cast(f, ctypes.c_void_p).value  # noqa: E731
                 self._fp = _fastpath.Binding(addr(lib.sw_post_send), addr(lib.sw_post_recv), addr(lib.sw_poll), self._h,
                                              self._ops, as_buffer, self.ensure_reader, self._slow, _err, status_string)
+                self._fp.kick = self._kick
             self._thread = threading.Thread(target=self._poll_loop, name="starway-b200-poller", daemon=True)
             self._thread.start()
 
@@ -454,6 +468,8 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
             if loop not in self._readers or not self._h:
                 return
             self._spin_loop = loop
+            if self._fp is not None:
+                self._fp.spinning = 1
             self._spin_seen = -1
             self._spin_deadline = _monotonic_ns() + self._spin_ns
             lib.sw_set_option(self._h, b"consumer_polling", 1)
@@ -483,6 +499,8 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
 
         def _stop_spin(self, loop) -> None:
             self._spin_loop = None
+            if self._fp is not None:
+                self._fp.spinning = 0
             if self._h:
                 lib.sw_set_option(self._h, b"consumer_polling", 0)
                 if loop is not None:
@@ -531,6 +549,8 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
 
         def close(self):
             if self._h:
+                if self._fp is not None:
+                    self._fp.closed = 1  # objects bound to the fast path (Client.asend ...) fall back to the Python methods
                 self._fp = None  # the C fast path holds the raw context pointer
                 self._stop = True
                 self._wake.set()
@@ -639,6 +659,14 @@ def bind(lib: ctypes.CDLL, default_device: Callable[[], int] | None = None, use_
             self._w = lib.sw_worker_create(self._ctx._h, self._kind)
             if not self._w:
                 raise RuntimeError(_err())
+            fp = self._ctx._fp
+            if fp is not None:
+                # the hot calls as C callables bound to this worker (no Python frame per message); anything but the
+                # plain call shape goes to the Python method of the same name
+                cls = type(self)
+                self.arecv = fp.bound(self._w, 0, True, _weak_method(self, cls.arecv))
+                if self._kind == SW_WORKER_CLIENT:
+                    self.asend = fp.bound(self._w, 0, False, _weak_method(self, cls.asend))
 
         def __del__(self):
             # reference ~Client/~Server: implicit close + join (main.cpp:703-719, 1519-1536)

@@ -10,6 +10,8 @@
  */
 #define PY_SSIZE_T_CLEAN
 #include <Python.h>
+#include <stddef.h>
+#include <structmember.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -65,6 +67,9 @@ typedef struct {
   PyObject* str_create_future;
   PyObject* str_set_result;
   PyObject* str_set_exception;
+  PyObject* kick;           /* kick(): start polling the completion queue from the running loop (None until set) */
+  int spinning;             /* set by the Python shim while the loop polls: a post then needs no kick */
+  int closed;               /* set by the Python shim before the context goes away: Post objects then take the slow path */
 } Binding;
 
 static void tab_clear(Binding* self) {
@@ -77,6 +82,9 @@ static void tab_clear(Binding* self) {
   }
   PyMem_Free(self->tab);
   self->tab = NULL;
+  self->kick = NULL;
+  self->spinning = 0;
+  self->closed = 0;
   self->tab_cap = self->tab_count = 0;
 }
 
@@ -156,6 +164,7 @@ static void Binding_dealloc(Binding* self) {
   Py_XDECREF(self->str_create_future);
   Py_XDECREF(self->str_set_result);
   Py_XDECREF(self->str_set_exception);
+  Py_XDECREF(self->kick);
   Py_TYPE(self)->tp_free((PyObject*)self);
 }
 
@@ -166,6 +175,9 @@ static int Binding_init(Binding* self, PyObject* args, PyObject* kw) {
                         &last_error, &status_string))
     return -1;
   self->tab = NULL;
+  self->kick = NULL;
+  self->spinning = 0;
+  self->closed = 0;
   self->tab_cap = self->tab_count = 0;
   self->tab_shift = 63;
   self->post_send = (post_send_fn)(uintptr_t)ps;
@@ -307,21 +319,12 @@ static PyObject* register_op(Binding* self, uint64_t op, PyObject* loop, PyObjec
   return fut;
 }
 
-/* asend(worker, ep, buffer, tag) -> Future */
-static PyObject* Binding_asend(Binding* self, PyObject* const* args, Py_ssize_t nargs) {
-  if (nargs != 4) {
-    PyErr_SetString(PyExc_TypeError, "asend(worker, ep, buffer, tag)");
-    return NULL;
-  }
-  uint64_t worker = PyLong_AsUnsignedLongLong(args[0]);
-  uint64_t ep = PyLong_AsUnsignedLongLong(args[1]);
-  uint64_t tag = PyLong_AsUnsignedLongLongMask(args[3]);
-  if (PyErr_Occurred()) return NULL;
+static PyObject* post_send_impl(Binding* self, uint64_t worker, uint64_t ep, PyObject* buffer, uint64_t tag) {
   void* ptr;
   size_t n;
   int mem;
   PyObject* keep;
-  if (resolve_buffer(self, args[2], 0, &ptr, &n, &mem, &keep) < 0) return NULL;
+  if (resolve_buffer(self, buffer, 0, &ptr, &n, &mem, &keep) < 0) return NULL;
   PyObject* loop = running_loop(self);
   PyObject* fut = loop ? PyObject_CallMethodNoArgs(loop, self->str_create_future) : NULL;
   if (!fut) {
@@ -337,21 +340,12 @@ static PyObject* Binding_asend(Binding* self, PyObject* const* args, Py_ssize_t 
   return ret;
 }
 
-/* arecv(worker, buffer, tag, mask) -> Future */
-static PyObject* Binding_arecv(Binding* self, PyObject* const* args, Py_ssize_t nargs) {
-  if (nargs != 4) {
-    PyErr_SetString(PyExc_TypeError, "arecv(worker, buffer, tag, tag_mask)");
-    return NULL;
-  }
-  uint64_t worker = PyLong_AsUnsignedLongLong(args[0]);
-  uint64_t tag = PyLong_AsUnsignedLongLongMask(args[2]);
-  uint64_t mask = PyLong_AsUnsignedLongLongMask(args[3]);
-  if (PyErr_Occurred()) return NULL;
+static PyObject* post_recv_impl(Binding* self, uint64_t worker, PyObject* buffer, uint64_t tag, uint64_t mask) {
   void* ptr;
   size_t n;
   int mem;
   PyObject* keep;
-  if (resolve_buffer(self, args[1], 1, &ptr, &n, &mem, &keep) < 0) return NULL;
+  if (resolve_buffer(self, buffer, 1, &ptr, &n, &mem, &keep) < 0) return NULL;
   PyObject* loop = running_loop(self);
   PyObject* fut = loop ? PyObject_CallMethodNoArgs(loop, self->str_create_future) : NULL;
   if (!fut) {
@@ -364,6 +358,107 @@ static PyObject* Binding_arecv(Binding* self, PyObject* const* args, Py_ssize_t 
   Py_DECREF(loop);
   Py_DECREF(keep);
   return ret;
+}
+
+/* asend(worker, ep, buffer, tag) -> Future */
+static PyObject* Binding_asend(Binding* self, PyObject* const* args, Py_ssize_t nargs) {
+  if (nargs != 4) {
+    PyErr_SetString(PyExc_TypeError, "asend(worker, ep, buffer, tag)");
+    return NULL;
+  }
+  uint64_t worker = PyLong_AsUnsignedLongLong(args[0]);
+  uint64_t ep = PyLong_AsUnsignedLongLong(args[1]);
+  uint64_t tag = PyLong_AsUnsignedLongLongMask(args[3]);
+  if (PyErr_Occurred()) return NULL;
+  return post_send_impl(self, worker, ep, args[2], tag);
+}
+
+/* arecv(worker, buffer, tag, mask) -> Future */
+static PyObject* Binding_arecv(Binding* self, PyObject* const* args, Py_ssize_t nargs) {
+  if (nargs != 4) {
+    PyErr_SetString(PyExc_TypeError, "arecv(worker, buffer, tag, tag_mask)");
+    return NULL;
+  }
+  uint64_t worker = PyLong_AsUnsignedLongLong(args[0]);
+  uint64_t tag = PyLong_AsUnsignedLongLongMask(args[2]);
+  uint64_t mask = PyLong_AsUnsignedLongLongMask(args[3]);
+  if (PyErr_Occurred()) return NULL;
+  return post_recv_impl(self, worker, args[1], tag, mask);
+}
+
+/* ---- Post: `Client.asend` / `Client.arecv` / `Server.arecv` of one worker as a C callable.
+ * The Python method did three attribute look-ups, a call into Binding.asend and a test of the polling state per
+ * message; bound once per object, the call goes straight to the post.  Any call shape other than the common one
+ * (an explicit loop, keywords) is handed to `slow`, the Python method it stands in for. */
+typedef struct {
+  PyObject_HEAD
+  vectorcallfunc vc;
+  Binding* b;
+  PyObject* slow;
+  uint64_t worker, ep;
+  int is_recv;
+} Post;
+
+static PyObject* Post_call(PyObject* o, PyObject* const* args, size_t nargsf, PyObject* kwnames) {
+  Post* p = (Post*)o;
+  Py_ssize_t nargs = PyVectorcall_NARGS(nargsf);
+  const Py_ssize_t want = p->is_recv ? 3 : 2;
+  if (p->b->closed || (kwnames && PyTuple_GET_SIZE(kwnames)) || nargs < want || nargs > want + 1 || (nargs == want + 1 && args[want] != Py_None))
+    return PyObject_Vectorcall(p->slow, args, nargsf & ~PY_VECTORCALL_ARGUMENTS_OFFSET, kwnames);
+  PyObject* fut;
+  if (p->is_recv) {
+    uint64_t tag = PyLong_AsUnsignedLongLongMask(args[1]);
+    uint64_t mask = PyLong_AsUnsignedLongLongMask(args[2]);
+    if (PyErr_Occurred()) return NULL;
+    fut = post_recv_impl(p->b, p->worker, args[0], tag, mask);
+  } else {
+    uint64_t tag = PyLong_AsUnsignedLongLongMask(args[1]);
+    if (PyErr_Occurred()) return NULL;
+    fut = post_send_impl(p->b, p->worker, p->ep, args[0], tag);
+  }
+  if (fut && !p->b->spinning && p->b->kick && p->b->kick != Py_None) {
+    PyObject* r = PyObject_CallNoArgs(p->b->kick);
+    if (!r) {
+      Py_DECREF(fut);
+      return NULL;
+    }
+    Py_DECREF(r);
+  }
+  return fut;
+}
+
+static void Post_dealloc(Post* p) {
+  Py_XDECREF((PyObject*)p->b);
+  Py_XDECREF(p->slow);
+  Py_TYPE(p)->tp_free((PyObject*)p);
+}
+
+static PyTypeObject PostType = {
+    PyVarObject_HEAD_INIT(NULL, 0).tp_name = "starway_b200._fastpath.Post",
+    .tp_basicsize = sizeof(Post),
+    .tp_flags = Py_TPFLAGS_DEFAULT | Py_TPFLAGS_HAVE_VECTORCALL,
+    .tp_vectorcall_offset = offsetof(Post, vc),
+    .tp_call = PyVectorcall_Call,
+    .tp_dealloc = (destructor)Post_dealloc,
+};
+
+/* bound(worker, ep, is_recv, slow) -> Post */
+static PyObject* Binding_bound(Binding* self, PyObject* args) {
+  unsigned long long worker, ep;
+  int is_recv;
+  PyObject* slow;
+  if (!PyArg_ParseTuple(args, "KKpO", &worker, &ep, &is_recv, &slow)) return NULL;
+  Post* p = PyObject_New(Post, &PostType);
+  if (!p) return NULL;
+  p->vc = Post_call;
+  Py_INCREF(self);
+  p->b = self;
+  Py_INCREF(slow);
+  p->slow = slow;
+  p->worker = worker;
+  p->ep = ep;
+  p->is_recv = is_recv;
+  return (PyObject*)p;
 }
 
 static void swallow_invalid_state(void) {
@@ -503,7 +598,14 @@ static PyMethodDef Binding_methods[] = {
     {"asend", (PyCFunction)(void (*)(void))Binding_asend, METH_FASTCALL, "asend(worker, ep, buffer, tag) -> Future"},
     {"arecv", (PyCFunction)(void (*)(void))Binding_arecv, METH_FASTCALL, "arecv(worker, buffer, tag, mask) -> Future"},
     {"drain", (PyCFunction)Binding_drain, METH_O, "drain(loop) -> int: resolve pending completions on the loop thread"},
+    {"bound", (PyCFunction)Binding_bound, METH_VARARGS, "bound(worker, ep, is_recv, slow) -> callable posting for that worker"},
     {NULL, NULL, 0, NULL}};
+
+static PyMemberDef Binding_members[] = {
+    {"kick", T_OBJECT, offsetof(Binding, kick), 0, "callable that starts completion polling on the running loop"},
+    {"spinning", T_INT, offsetof(Binding, spinning), 0, "non-zero while the loop polls the completion queue"},
+    {"closed", T_INT, offsetof(Binding, closed), 0, "non-zero once the context is being closed"},
+    {NULL, 0, 0, 0, NULL}};
 
 static PyTypeObject BindingType = {
     PyVarObject_HEAD_INIT(NULL, 0).tp_name = "starway_b200._fastpath.Binding",
@@ -513,6 +615,7 @@ static PyTypeObject BindingType = {
     .tp_init = (initproc)Binding_init,
     .tp_dealloc = (destructor)Binding_dealloc,
     .tp_methods = Binding_methods,
+    .tp_members = Binding_members,
 };
 
 static struct PyModuleDef moddef = {PyModuleDef_HEAD_INIT, "_fastpath",
@@ -520,7 +623,7 @@ static struct PyModuleDef moddef = {PyModuleDef_HEAD_INIT, "_fastpath",
                                     NULL};
 
 PyMODINIT_FUNC PyInit__fastpath(void) {
-  if (PyType_Ready(&BindingType) < 0) return NULL;
+  if (PyType_Ready(&BindingType) < 0 || PyType_Ready(&PostType) < 0) return NULL;
   PyObject* m = PyModule_Create(&moddef);
   if (!m) return NULL;
   Py_INCREF(&BindingType);

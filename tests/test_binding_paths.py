@@ -276,3 +276,44 @@ def test_second_thread_flush_close_and_raw_callbacks(sim_api, ctypes_api, fast):
     t1.join(30)
     assert not errors, errors
     assert not t1.is_alive() and not t2.is_alive()
+
+
+def test_bound_post_callables(sim_api, port):
+    """`Client.asend` / `arecv` and `Server.arecv` are C callables bound to the worker (fastpath.c Post): the plain call
+    shape posts without a Python frame, every other shape (explicit loop, keywords) reaches the Python method, and the
+    callable does not keep its object alive."""
+    import gc
+    import weakref
+
+    from starway_b200 import _core
+
+    post_type = type(sim_api.get_context()._fp.bound(0, 0, False, lambda *a, **k: None))
+
+    async def go():
+        async with cb.gen_server_client(sim_api, port) as (server, client):
+            assert isinstance(client.asend, post_type) and isinstance(client.arecv, post_type) and isinstance(server.arecv, post_type)
+            loop = asyncio.get_running_loop()
+            src, dst = np.arange(64, dtype=np.uint8), np.zeros(64, dtype=np.uint8)
+            f = server.arecv(dst, 7, 0xFFFF)
+            await client.asend(src, 7)
+            assert await f == (7, 64) and np.array_equal(src, dst)
+            dst[:] = 0
+            f = server.arecv(dst, 8, 0xFFFF, loop)            # explicit loop: Python method
+            await client.asend(src, 8, loop=loop)              # keyword: Python method
+            assert await f == (8, 64) and np.array_equal(src, dst)
+            dst[:] = 0
+            f = server.arecv(dst, tag=9, tag_mask=0xFFFF)
+            await client.asend(buffer=src, tag=9)
+            assert await f == (9, 64) and np.array_equal(src, dst)
+            with pytest.raises(TypeError):
+                client.asend(src)                              # wrong arity: the Python method's own error
+            with pytest.raises((TypeError, ValueError, RuntimeError)):
+                client.asend(object(), 1)                      # not a buffer
+
+    run(go())
+    c = sim_api.Client()
+    ref = weakref.ref(c)
+    del c
+    gc.collect()   # (no cycle is needed to free it; collect only makes the assertion independent of frame locals)
+    assert ref() is None
+    assert _core._fastpath is not None
