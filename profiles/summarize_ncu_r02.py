@@ -84,6 +84,18 @@ if os.path.exists(rep):
                    f"{r[col['gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed']]} | {pay / dur:.0f} |")
         traffic[f"{nmsg}x{ln}"] = {"payload_bytes": pay, "dram_read": rd, "dram_write": wr, "duration_ns": dur}
     out.append("")
+    out.append("| batch | instructions executed | warps active % of peak | L2 sector hit rate % | occupancy limit (shared memory) | waves per SM |\n|---|---|---|---|---|---|")
+    for i, r in enumerate(data[: len(SHAPES)]):
+        nmsg, ln = SHAPES[i]
+        g = lambda m: r[col[m]] if m in col else "-"  # noqa: E731
+        out.append(f"| {nmsg} x {ln >> 10} KiB | {g('smsp__inst_executed.sum')} | {g('sm__warps_active.avg.pct_of_peak_sustained_active')} | "
+                   f"{g('lts__t_sector_hit_rate.pct')} | {g('launch__occupancy_limit_shared_mem')} CTA/SM | {g('launch__waves_per_multiprocessor')} |")
+    out.append("")
+    out.append("(One elected thread per CTA drives the TMA pipeline -- `UBLKCP` global->shared->global, 8 x 24 KiB stages -- and a "
+               "second warp prefetches the next batch's descriptors: ~3 % of the warp slots are active by design; the bytes "
+               "move through the TMA unit, not through registers.  76 % of DRAM peak *over the whole launch* at 1 GiB "
+               "includes ~20 us of start-up, descriptor fetch and completion records.)")
+    out.append("")
     out.append("Algorithmic traffic is 2 bytes of DRAM per payload byte (one read, one write); a ratio near 2.0 means no "
                "wasted re-reads. Sources smaller than the 126 MB L2 that were just written by the probe's memset can "
                "read below 1 byte per byte from DRAM.\n")
