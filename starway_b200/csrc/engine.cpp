@@ -32,6 +32,7 @@
 #include <string.h>
 #include <linux/futex.h>
 #include <sys/eventfd.h>
+#include <sys/ioctl.h>
 #include <sys/mman.h>
 #include <sys/prctl.h>
 #include <sys/socket.h>
@@ -591,6 +592,12 @@ struct Worker {
   std::vector<FlushOp*> flushes;
   // listeners
   int tcp_fd = -1, unix_fd = -1;
+  struct PendingHello {   // accepted bootstrap connection whose hello has not arrived yet
+    int fd;
+    bool tcp;
+    double deadline;
+  };
+  std::vector<PendingHello> pending_hello;
   std::string unix_name;
   AddrBlob blob;
   std::atomic<bool> blob_ready{false};
@@ -1341,11 +1348,38 @@ void poll_listeners(Ctx* c, Worker* w) {
   for (int k = 0; k < 2; k++) {
     int lfd = k == 0 ? w->unix_fd : w->tcp_fd;
     if (lfd < 0) continue;
-    for (int n = 0; n < 8; n++) {
+    for (int n = 0; n < 8 && w->pending_hello.size() < 64; n++) {
       int fd = accept4(lfd, nullptr, nullptr, SOCK_CLOEXEC);
       if (fd < 0) break;
-      server_handshake(c, w, fd, k == 1);
+      if (k == 1) {
+        // The bootstrap exchanges CUDA IPC handles and the name of a shared-memory block: it only makes sense within
+        // one host.  A connection made on this host has the same address at both ends.
+        struct sockaddr_in la, ra;
+        socklen_t ll = sizeof(la), rl = sizeof(ra);
+        if (getsockname(fd, (struct sockaddr*)&la, &ll) != 0 || getpeername(fd, (struct sockaddr*)&ra, &rl) != 0 ||
+            la.sin_addr.s_addr != ra.sin_addr.s_addr) {
+          close(fd);
+          continue;
+        }
+      }
+      w->pending_hello.push_back(Worker::PendingHello{fd, k == 1, now_s() + 2.0});
     }
+  }
+  // The handshake runs on this thread (it touches the worker's endpoint tables): start it only once the client's
+  // hello is in the socket buffer, so that a peer that connects and says nothing holds up nobody.
+  for (size_t i = 0; i < w->pending_hello.size();) {
+    Worker::PendingHello ph = w->pending_hello[i];
+    int avail = 0;
+    char probe;
+    bool ready = ioctl(ph.fd, FIONREAD, &avail) == 0 && avail >= (int)sizeof(WireHello);
+    bool dead = !ready && (now_s() > ph.deadline || recv(ph.fd, &probe, 1, MSG_PEEK | MSG_DONTWAIT) == 0);
+    if (!ready && !dead) {
+      i++;
+      continue;
+    }
+    w->pending_hello.erase(w->pending_hello.begin() + (long)i);
+    if (ready) server_handshake(c, w, ph.fd, ph.tcp);
+    else close(ph.fd);
   }
 }
 
@@ -2902,6 +2936,8 @@ void worker_release(Ctx* c, Worker* w, bool leak_rings) {
   if (w->tcp_fd >= 0) close(w->tcp_fd);
   if (w->unix_fd >= 0) close(w->unix_fd);
   w->tcp_fd = w->unix_fd = -1;
+  for (auto& ph : w->pending_hello) close(ph.fd);
+  w->pending_hello.clear();
 }
 
 // reference shutdown sequence: main.cpp:469-550 (client), 1269-1373 (server)

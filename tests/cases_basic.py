@@ -953,9 +953,41 @@ async def case_server_outlives_many_connections(api, port, cycles=70):
     await server.aclose()
 
 
+# ------------------------------------------------------------------ a silent bootstrap peer holds up nobody
+async def case_silent_bootstrap_peer_does_not_stall(api, port):
+    """Round-1 advisor finding: the server's handshake ran blocking reads on the progress thread, so a TCP peer that
+    connected and sent nothing stalled every worker of the context for 2 s.  The hello is now awaited without
+    blocking: with three silent sockets open, a real client connects and exchanges a message promptly, and the silent
+    sockets are dropped after their deadline."""
+    import socket
+    import time
+
+    server = api.Server()
+    server.listen(SERVER_ADDR, port)
+    mutes = [socket.create_connection((SERVER_ADDR, port)) for _ in range(3)]
+    mutes[1].sendall(b"\x00" * 7)   # a partial hello is still no hello
+    t0 = time.monotonic()
+    client = api.Client()
+    await asyncio.wait_for(client.aconnect(SERVER_ADDR, port), 30)
+    dst = np.zeros(32, dtype=np.uint8)
+    f = server.arecv(dst, 5, 0xFF)
+    await client.asend(np.full(32, 9, dtype=np.uint8), 5)
+    assert await asyncio.wait_for(f, 30) == (5, 32) and (dst == 9).all()
+    assert time.monotonic() - t0 < 1.5, "a silent bootstrap connection delayed real traffic"
+    assert len(server.list_clients()) == 1
+    # the silent ones are closed by the server once their 2 s are over
+    mutes[0].settimeout(5)
+    assert mutes[0].recv(1) == b""
+    for m in mutes:
+        m.close()
+    await client.aclose()
+    await server.aclose()
+
+
 SINGLE_PROCESS_CASES = [
     case_server_listen_client_connect_close,
     case_server_outlives_many_connections,
+    case_silent_bootstrap_peer_does_not_stall,
     case_binding_level_callbacks,
     case_worker_address_connection_roundtrip,
     case_worker_address_accept_callback_invoked,
