@@ -93,7 +93,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.05)
 
     def start(self):
         if self._nv is not None:
@@ -257,6 +257,13 @@ def run_ours(args):
             gc.collect()
             gc.freeze()
         # warm-up, then bit-exactness of one full window against the sources of the sending rank
+        # The clock sampler (NVML from a thread, every 50 ms) runs from here to the end of the timed region: its first
+        # query -- the slow one, and NVML queries can hold up kernel launches for milliseconds -- falls into the
+        # warm-up instead of the first timed steps (a K = 20 region lasts 3 ms).
+        late_clocks = bool(os.environ.get("STARWAY_BENCH_CLOCKS_LATE"))
+        clocks = ClockSampler(local_rank)
+        if not late_clocks:
+            clocks.start()
         await timed(max(args.warmup, 3), src, dst, torch.cuda.synchronize)
         # Every rank checks the window it received against the sources of the rank that sent it (rank r-1;
         # its own at N == 1): the sources are a seeded sequence (Philox: seed and offset only), so any rank
@@ -277,8 +284,8 @@ def run_ours(args):
         torch.cuda.synchronize()
         warm_batches = ctx.stats()["pull_batches"]
         ctx.reset_stats()
-        clocks = ClockSampler(local_rank)
-        clocks.start()
+        if late_clocks:
+            clocks.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         t0 = time.perf_counter()
