@@ -297,3 +297,41 @@ def test_round_trip_after_a_long_idle_period(sim_api, port):
                 assert await rtt(100 + i) < 0.05
 
     run(go())
+
+
+@pytest.mark.parametrize("opts", [{"hostdst_ce": 1, "pinned_send_direct": 0}, {"stage_batch_bytes": 65536}, {"pull_keep_us": 0},
+                                  {"hostdst_tma": 1, "stage_upload_kernel": 1}],
+                         ids=["ce_download", "small_stage_batches", "pull_leaves_at_once", "tma_host_legs"])
+def test_host_buffer_and_pull_options(sim_api, port, opts):
+    """The tunables of the host-buffer legs and of the pull kernel's stay keep every message intact:
+    mixed host / device buffers, eager and rendezvous sizes, and a random schedule against the oracle."""
+    from tests.conftest import free_port
+
+    ctx = sim_api.get_context()
+    defaults = {k: ctx.get_option(k) for k in ("pull_keep_us",)}
+    try:
+        for k, v in opts.items():
+            ctx.set_option(k, v)
+        for size in (100, 70000, 3 << 20):
+            run(cb.case_message_integrity(sim_api, free_port(), size))
+        run(cb.case_random_schedule_vs_oracle(sim_api, port, 5))
+    finally:
+        for k, v in {"hostdst_ce": 0, "hostdst_tma": 0, "stage_upload_kernel": 0, "pinned_send_direct": 1,
+                     "stage_batch_bytes": 4 << 20, **defaults}.items():
+            ctx.set_option(k, v)
+
+
+def test_options_from_the_environment(port):
+    """STARWAY_OPTS="key=value,..." is applied when a context is created; unknown keys are reported, not fatal."""
+    import os
+    import subprocess
+    import sys
+
+    code = ("from tests import hostsim; sw = hostsim.load(); c = sw.get_context(); "
+            "print(c.get_option('pull_keep_us'), c.get_option('linger_us')); sw.shutdown()")
+    env = dict(os.environ, STARWAY_OPTS="pull_keep_us=7,linger_us=33,no_such_option=1", STARWAY_QUIET="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split()[-2:] == ["7", "33"], out.stdout
+    assert "no_such_option" in out.stderr
