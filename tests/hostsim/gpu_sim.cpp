@@ -5,7 +5,8 @@
 // connection handshake, credits, rendezvous protocol, flush, close, cancellation,
 // 2-process operation) on a machine without a GPU.  "Device memory" is POSIX shared
 // memory (so the CUDA-IPC exchange has something real to exercise), "kernels" run
-// synchronously on the calling thread, and the match step is a plain sequential
+// synchronously on the calling thread (or, with SWSIM_LINGER=1, the control kernel as a
+// thread that stays for a while: see resident_lingers()), and the match step is a plain sequential
 // restatement of the semantics in oracle/tagmatch.c over the same queue layout the
 // CUDA kernels use.  libstarway_hostsim.so is only ever loaded by tests/.
 #include <fcntl.h>
@@ -16,8 +17,11 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <atomic>
+#include <chrono>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -27,6 +31,12 @@
 namespace swgpu {
 
 static thread_local std::string g_err;
+// shared words of the 'device': relaxed atomic accesses where the host and a lingering 'kernel' thread may meet (on the
+// GPU these are plain loads / cudaMemcpy stores; the protocol does not depend on their order, see Pass::snapshot)
+template <class T>
+static inline void st_rlx(T* p, T v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
+template <class T>
+static inline T ld_rlx(const T* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
 static std::mutex g_mu;
 struct DevAlloc {
   size_t size;
@@ -38,6 +48,8 @@ static std::map<uintptr_t, DevAlloc> g_allocs;       // our "device" allocations
 static std::map<uintptr_t, size_t> g_opened;         // mappings opened through ipc_open
 static int g_counter = 0;
 static int g_device = 0;
+static const bool g_linger = getenv("SWSIM_LINGER") && atoi(getenv("SWSIM_LINGER")) != 0;   // see resident_lingers()
+static std::atomic<int> g_residents{0};   // 'kernels' that are still running (threads)
 
 const char* backend_name() { return "hostsim (test only)"; }
 const char* last_error() { return g_err.c_str(); }
@@ -58,6 +70,7 @@ int sm_count() { return 8; }
 int device_pci_bus_id(int, char*, int) { return -1; }
 
 static void cleanup_all() {
+  for (int i = 0; i < 2000 && g_residents.load() > 0; i++) usleep(100);   // let lingering 'kernels' leave first
   std::lock_guard<std::mutex> lk(g_mu);
   for (auto& kv : g_allocs) shm_unlink(kv.second.name.c_str());
 }
@@ -255,10 +268,10 @@ int match_state_destroy(SwMatchState* st) {
 }
 int match_state_set_ring(SwMatchState* st, uint32_t ep, void* ring_base, uint32_t slots, uint32_t gen) {
   if (ep >= SW_MAX_EPS) return -1;
-  st->ring_base[ep] = (uint64_t)(uintptr_t)ring_base;
-  st->ring_slots[ep] = slots;
-  st->ring_cons[ep] = 0;
-  st->ring_gen[ep] = gen;
+  st_rlx(&st->ring_gen[ep], gen);
+  st_rlx(&st->ring_base[ep], (uint64_t)(uintptr_t)ring_base);
+  st_rlx(&st->ring_slots[ep], slots);
+  st_rlx(&st->ring_cons[ep], (uint64_t)0);
   return 0;
 }
 
@@ -500,13 +513,17 @@ int launch_bulk(stream_t, const SwSeg* segs, uint32_t nseg, const BulkTuning* t)
 // same protocol per launch, synchronously: post ring -> matching -> eager delivery / rendezvous copy through the
 // mapping table -> completion rings, credit words and FIN words -> exit word.  The host engine cannot tell the
 // difference except that nothing happens between launches (resident_lingers() == 0).
-int resident_lingers() { return 0; }
+// SWSIM_LINGER=1: a launch becomes a THREAD that repeats the pass until the host asks it to stop, linger_us of silence or
+// max_life_us have passed -- the resident behaviour of the CUDA kernels (engine.cpp then uses everything that depends on a
+// kernel being there: puts handed over through the stamped send ring, the armed relaunch policy, stop / epoch hand-shakes
+// with a kernel that runs concurrently).  Default: one synchronous pass per launch.
+int resident_lingers() { return g_linger ? 1 : 0; }
 void* host_register(void* p, size_t) { return p; }
 int host_unregister(void*) { return 0; }
 int match_state_set_ep_words(SwMatchState* st, uint32_t ep, void* credit_word, void* fin_words) {
   if (ep >= SW_MAX_EPS) return -1;
-  st->credit_ptr[ep] = (uint64_t)(uintptr_t)credit_word;
-  st->fin_ptr[ep] = (uint64_t)(uintptr_t)fin_words;
+  st_rlx(&st->credit_ptr[ep], (uint64_t)(uintptr_t)credit_word);
+  st_rlx(&st->fin_ptr[ep], (uint64_t)(uintptr_t)fin_words);
   return 0;
 }
 SwPullQueue* pull_queue_create() { return (SwPullQueue*)calloc(1, sizeof(SwPullQueue)); }
@@ -542,13 +559,34 @@ int probe_publish_batch(stream_t, SwPullQueue*, const SwSeg*, uint32_t, uint32_t
 int pull_queue_read_stats(SwPullQueue*, uint64_t*) { return -1; }
 
 namespace {
+template <class T>
+static inline T ld(const volatile T* p) { return __atomic_load_n(const_cast<const T*>(p), __ATOMIC_ACQUIRE); }
+
 struct Pass {
   const ProgressLaunch* a;
   SwMatchState* st;
   SwProgCtl* ctl;
+  // ring geometry and cursors as of the launch (the CUDA kernel keeps them in shared memory): a ring attached while
+  // this launch runs is not seen, and only the cursors of the rings it knew go back to the match state
+  uint64_t ring_base[SW_MAX_EPS], cons[SW_MAX_EPS], credit_ptr[SW_MAX_EPS], fin_ptr[SW_MAX_EPS];
+  uint32_t ring_slots[SW_MAX_EPS], ring_gen[SW_MAX_EPS];
+  void snapshot() {
+    for (uint32_t e = 0; e < SW_MAX_EPS; e++) {
+      ring_base[e] = ld_rlx(&st->ring_base[e]);
+      ring_slots[e] = ld_rlx(&st->ring_slots[e]);
+      ring_gen[e] = ld_rlx(&st->ring_gen[e]);
+      cons[e] = ld_rlx(&st->ring_cons[e]);
+      credit_ptr[e] = ld_rlx(&st->credit_ptr[e]);
+      fin_ptr[e] = ld_rlx(&st->fin_ptr[e]);
+    }
+  }
+  void write_back() {
+    for (uint32_t e = 0; e < SW_MAX_EPS; e++)
+      if (ring_base[e]) st_rlx(&st->ring_cons[e], cons[e]);
+  }
   bool rings_full() const {
-    return st->cq_alloc - ctl->cq_head + 8 > SW_CQ_RING || st->cqr_alloc - ctl->cqr_head + 8 > SW_CQ_RING ||
-           st->hr_alloc - ctl->hr_head + 8 > SW_HR_RING;
+    return st->cq_alloc - ld(&ctl->cq_head) + 8 > SW_CQ_RING || st->cqr_alloc - ld(&ctl->cqr_head) + 8 > SW_CQ_RING ||
+           st->hr_alloc - ld(&ctl->hr_head) + 8 > SW_HR_RING;
   }
   static void cqe(SwCqEnt* ring, uint64_t idx, uint64_t op, uint64_t tag, uint64_t len, int32_t status) {
     SwCqEnt* e = &ring[idx % SW_CQ_RING];
@@ -579,7 +617,7 @@ struct Pass {
     const uint32_t ep = epf & ((1u << SW_EP_IDX_BITS) - 1);
     const bool trunc = msg_len > cap;
     bool device_path = a->pq && a->pull_ctas && !trunc && !(pflags & SW_POST_HOSTPATH) && !(r.pad[0] & SW_RTS_PINNED_SRC) &&
-                       !((ctl->dead_mask >> ep) & 1) && st->fin_ptr[ep] && (epf >> SW_EP_IDX_BITS) == (st->ring_gen[ep] & SW_EP_GEN_MASK);
+                       !((ld(&ctl->dead_mask) >> ep) & 1) && fin_ptr[ep] && (epf >> SW_EP_IDX_BITS) == (ring_gen[ep] & SW_EP_GEN_MASK);
     uint64_t src = 0;
     if (device_path) {
       if (r.ctx_uuid == a->ctx_uuid && r.src_pid == a->pid) {
@@ -594,12 +632,12 @@ struct Pass {
       // what the pull CTAs do: copy, completion record, FIN word of the sender, statistics
       if (msg_len) memcpy((void*)(uintptr_t)buf, (const void*)(uintptr_t)src, msg_len);
       cqe(a->cqr, st->cqr_alloc++, op, stag, msg_len, SW_OK);
-      __atomic_store_n(reinterpret_cast<uint64_t*>(st->fin_ptr[ep] + 8ull * (r.send_seq % SW_FIN_SLOTS)), (r.send_seq << 2) | 1, __ATOMIC_RELEASE);
+      __atomic_store_n(reinterpret_cast<uint64_t*>(fin_ptr[ep] + 8ull * (r.send_seq % SW_FIN_SLOTS)), (r.send_seq << 2) | 1, __ATOMIC_RELEASE);
       st->pull_jobs++;
-      a->pq->bytes += msg_len & ~15ull;
-      a->pq->busy_ns += 1000;
-      a->pq->batches++;
-      a->pq->jobs++;
+      __atomic_fetch_add(&a->pq->bytes, msg_len & ~15ull, __ATOMIC_RELAXED);   // one queue per context: several workers
+      __atomic_fetch_add(&a->pq->busy_ns, (uint64_t)1000, __ATOMIC_RELAXED);
+      __atomic_fetch_add(&a->pq->batches, (uint64_t)1, __ATOMIC_RELAXED);
+      __atomic_fetch_add(&a->pq->jobs, (uint64_t)1, __ATOMIC_RELAXED);
       return;
     }
     SwHrEnt* h = &a->hr[st->hr_alloc % SW_HR_RING];
@@ -618,17 +656,42 @@ struct Pass {
 };
 }  // namespace
 
-int launch_progress(stream_t, const ProgressLaunch* a) {
+namespace {
+// One pass of the control kernel.  Returns whether anything was consumed (receives, arrivals, puts).
+bool run_pass(Pass& p) {
+  const ProgressLaunch* a = p.a;
   const uint64_t PQM = SW_PQ_CAP - 1, UQM = SW_UQ_CAP - 1;
-  Pass p{a, a->st, a->ctl};
-  SwMatchState* st = a->st;
-  SwProgCtl* ctl = a->ctl;
+  SwMatchState* st = p.st;
+  SwProgCtl* ctl = p.ctl;
   const uint64_t epoch = __atomic_load_n(&ctl->host_epoch, __ATOMIC_ACQUIRE);
-  bool stalled = false;
+  bool stalled = false, did = false;
+  // ---- puts handed over by the host (only a kernel that stays gets any): stamped units -> entry -> slot
+  if (g_linger && a->sends) {
+    const uint64_t tail = __atomic_load_n(&ctl->send_tail, __ATOMIC_ACQUIRE);
+    while (st->send_consumed < tail) {
+      const SwSendLL* le = &a->sends[st->send_consumed % SW_SEND_RING];
+      uint32_t w[SW_SEND_UNITS * 3];
+      for (uint32_t k = 0; k < SW_SEND_UNITS; k++) {
+        memcpy(&w[3 * k], le->u[k], 12);
+        if (le->u[k][3] != sw_send_stamp(st->send_consumed)) ctl->err = ctl->err | 2;   // the host's encoding is wrong
+      }
+      SwSendEnt e;
+      memcpy(&e, w, sizeof e);
+      SwPutDesc d = e.d;
+      d.kind &= ~SW_KIND_SAME_GPU;
+      if (d.src == 0) d.src = (uint64_t)(uintptr_t)e.inl;
+      launch_put(nullptr, &d, 1, nullptr);
+      st->send_consumed++;
+      did = true;
+    }
+    ctl->send_head = st->send_consumed;
+    __atomic_store_n(&ctl->send_done, st->send_consumed, __ATOMIC_RELEASE);
+  }
   // ---- new receives, in post order, against the unexpected queue (earliest arrival first)
   while (st->post_consumed < __atomic_load_n(&ctl->post_tail, __ATOMIC_ACQUIRE) && !p.rings_full()) {
     const SwPostEnt e = a->posts[st->post_consumed % SW_POST_RING];
     st->post_consumed++;
+    did = true;
     bool found = false;
     for (uint64_t idx = st->u_head; idx < st->u_tail; idx++) {
       const uint64_t s = idx & UQM;
@@ -667,12 +730,12 @@ int launch_progress(stream_t, const ProgressLaunch* a) {
   // ---- arrivals: a slot has arrived when its header carries the expected sequence number
   for (uint32_t k = 0; k < a->n_eps; k++) {
     const uint32_t ep = (st->rr_ep + k) % a->n_eps;
-    if (!st->ring_base[ep]) continue;
-    const uint32_t epf = ep | ((st->ring_gen[ep] & SW_EP_GEN_MASK) << SW_EP_IDX_BITS);
-    uint64_t cons = st->ring_cons[ep];
+    if (!p.ring_base[ep]) continue;
+    const uint32_t epf = ep | ((p.ring_gen[ep] & SW_EP_GEN_MASK) << SW_EP_IDX_BITS);
+    uint64_t cons = p.cons[ep];
     for (;;) {
       if (p.rings_full()) break;
-      const uint8_t* slot = (const uint8_t*)(uintptr_t)(st->ring_base[ep] + (cons & (st->ring_slots[ep] - 1)) * SW_SLOT_BYTES);
+      const uint8_t* slot = (const uint8_t*)(uintptr_t)(p.ring_base[ep] + (cons & (p.ring_slots[ep] - 1)) * SW_SLOT_BYTES);
       if (__atomic_load_n(reinterpret_cast<const uint64_t*>(slot + 16), __ATOMIC_ACQUIRE) != cons + 1) break;
       SwSlotHdr h;
       memcpy(&h, slot, 32);
@@ -717,31 +780,77 @@ int launch_progress(stream_t, const ProgressLaunch* a) {
       cons++;
       st->arrivals++;
     }
-    if (cons != st->ring_cons[ep]) {
-      st->ring_cons[ep] = cons;
-      if (st->credit_ptr[ep]) __atomic_store_n(reinterpret_cast<uint64_t*>(st->credit_ptr[ep]), cons, __ATOMIC_RELEASE);
+    if (cons != p.cons[ep]) {
+      p.cons[ep] = cons;
+      did = true;
+      if (p.credit_ptr[ep]) __atomic_store_n(reinterpret_cast<uint64_t*>(p.credit_ptr[ep]), cons, __ATOMIC_RELEASE);
     }
   }
   st->rr_ep++;
-  ctl->pull_jobs = st->pull_jobs;
-  ctl->arrivals = st->arrivals;
-  ctl->n_posted = st->p_count;
-  ctl->n_unexp = st->u_count;
-  ctl->stalled = stalled ? 1 : 0;
-  ctl->iterations = ctl->iterations + 1;
-  ctl->exit_reason = 2;
-  ctl->life_us = 1;
+  __atomic_store_n(&ctl->pull_jobs, st->pull_jobs, __ATOMIC_RELEASE);
+  __atomic_store_n(&ctl->arrivals, st->arrivals, __ATOMIC_RELAXED);
+  __atomic_store_n(&ctl->n_posted, st->p_count, __ATOMIC_RELAXED);
+  __atomic_store_n(&ctl->n_unexp, st->u_count, __ATOMIC_RELAXED);
+  __atomic_store_n(&ctl->stalled, (uint64_t)(stalled ? 1 : 0), __ATOMIC_RELAXED);
+  __atomic_store_n(&ctl->iterations, ctl->iterations + 1, __ATOMIC_RELAXED);
   __atomic_store_n(&ctl->dev_epoch, epoch, __ATOMIC_RELEASE);
-  __atomic_store_n(&ctl->exit_seq, a->launch_seq, __ATOMIC_RELEASE);
+  return did;
+}
+
+void finish_launch(Pass& p, uint64_t reason, uint64_t life_us) {
+  p.write_back();
+  p.ctl->exit_reason = reason;
+  p.ctl->life_us = life_us;
+  __atomic_store_n(&p.ctl->exit_seq, p.a->launch_seq, __ATOMIC_RELEASE);   // last: the host may free everything now
+}
+}  // namespace
+
+int launch_progress(stream_t, const ProgressLaunch* a) {
+  if (!g_linger) {
+    Pass p;
+    p.a = a;
+    p.st = a->st;
+    p.ctl = a->ctl;
+    p.snapshot();
+    run_pass(p);
+    finish_launch(p, 2, 1);
+    return 0;
+  }
+  g_residents.fetch_add(1);
+  const ProgressLaunch args = *a;
+  std::thread([args]() {
+    using clock = std::chrono::steady_clock;
+    auto us_since = [](clock::time_point t) { return std::chrono::duration_cast<std::chrono::microseconds>(clock::now() - t).count(); };
+    Pass* p = new Pass;   // (two 512-entry tables: not on a small thread stack)
+    p->a = &args;
+    p->st = args.st;
+    p->ctl = args.ctl;
+    p->snapshot();
+    const auto t0 = clock::now();
+    auto last = t0;
+    uint64_t reason = 0;
+    while (!reason) {
+      const bool did = run_pass(*p);
+      if (did) last = clock::now();
+      if (__atomic_load_n(&args.ctl->stop, __ATOMIC_ACQUIRE)) reason = 1;
+      else if (us_since(last) > (long long)args.linger_us) reason = 2;
+      else if (us_since(t0) > (long long)args.max_life_us) reason = 3;
+      else if (!did) std::this_thread::sleep_for(std::chrono::microseconds(3));
+    }
+    const uint64_t life = (uint64_t)us_since(t0);
+    finish_launch(*p, reason, life ? life : 1);
+    delete p;
+    g_residents.fetch_sub(1);
+  }).detach();
   return 0;
 }
 
 // the copies were made by the pass that matched them: the "pull kernel" only reports and leaves
 int launch_pull(stream_t, SwPullQueue* q, SwPullCtl* ctl, uint64_t launch_seq, uint32_t, uint32_t, uint32_t, const BulkTuning*) {
-  ctl->bytes = q->bytes;
-  ctl->busy_ns = q->busy_ns;
-  ctl->batches = q->batches;
-  ctl->jobs = q->jobs;
+  ctl->bytes = __atomic_load_n(&q->bytes, __ATOMIC_RELAXED);
+  ctl->busy_ns = __atomic_load_n(&q->busy_ns, __ATOMIC_RELAXED);
+  ctl->batches = __atomic_load_n(&q->batches, __ATOMIC_RELAXED);
+  ctl->jobs = __atomic_load_n(&q->jobs, __ATOMIC_RELAXED);
   __atomic_store_n(&ctl->exited, launch_seq, __ATOMIC_RELEASE);
   return 0;
 }
