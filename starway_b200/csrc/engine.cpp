@@ -792,6 +792,7 @@ struct Ctx {
   // the PCIe duplex budget to the concurrent download kernel (43.8 vs 37.9 GB/s at N=2).
   std::atomic<int64_t> opt_stage_upload_kernel{0};
   std::atomic<int64_t> opt_stage_batch_bytes{(int64_t)STAGE_BATCH_BYTES};   // staged sends are announced in batches of this size
+  std::atomic<int64_t> opt_max_mappings{(int64_t)MAX_MAPPINGS};   // peer allocations kept mapped (LRU quarter dropped when full)
   std::atomic<int64_t> opt_hostdst_ce{0};    // device -> pinned-host copies by the copy engine (batched) instead of a kernel
   std::atomic<int64_t> opt_hostdst_tma{0};   // device -> pinned-host copies by the TMA kernel instead of the SIMT kernel
   // ---- resident path
@@ -2103,7 +2104,7 @@ void* resolve_mapping(Ctx* c, BulkJob& j, bool* retry) {
     // Bound the cache (PyTorch's caching allocator hands out many small segments: a few hundred
     // distinct IPC handles are normal).  Opening/closing a mapping costs ~100s of us, so only
     // the least recently used idle quarter is dropped when the bound is hit.
-    if (c->mappings.size() >= MAX_MAPPINGS) {
+    if (c->mappings.size() >= (size_t)std::max<int64_t>(1, c->opt_max_mappings.load())) {
       if (c->map_tbl && mappings_in_use_on_device(c)) {
         // A control kernel may be resolving through the table, a pull may be reading through a mapping:
         // have the control kernels leave (no relaunch while evict_pending), let the pulls drain, come back.
@@ -2119,6 +2120,7 @@ void* resolve_mapping(Ctx* c, BulkJob& j, bool* retry) {
         if (kv.second.refs == 0) idle.emplace_back(kv.second.last_use, kv.first);
       std::sort(idle.begin(), idle.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
       size_t drop = std::max<size_t>(1, idle.size() / 4);
+      trace(c, "map_evict", std::min(drop, idle.size()), c->mappings.size());
       for (size_t i = 0; i < drop && i < idle.size(); i++) {
         auto m = c->mappings.find(idle[i].second);
         swgpu::ipc_close(m->second.base);
@@ -3583,6 +3585,7 @@ int sw_set_option(sw_ctx* ctx, const char* key, int64_t value) {
   else if (k == "stage_upload_kernel") c->opt_stage_upload_kernel = value;
   else if (k == "hostdst_tma") c->opt_hostdst_tma = value;
   else if (k == "hostdst_ce") c->opt_hostdst_ce = value;
+  else if (k == "max_mappings") c->opt_max_mappings = std::max<int64_t>(1, value);
   else if (k == "stage_batch_bytes") c->opt_stage_batch_bytes = std::max<int64_t>(65536, value);
   else if (k == "coalesce_us") c->opt_coalesce_us = value;
   else if (k == "coalesce_bytes") c->opt_coalesce_bytes = value;
@@ -3620,6 +3623,7 @@ int64_t sw_get_option(sw_ctx* ctx, const char* key) {
   if (k == "armed_ms") return c->opt_armed_ms;
   if (k == "pull_ctas") return c->opt_pull_ctas;
   if (k == "pull_keep_us") return c->opt_pull_keep_us;
+  if (k == "max_mappings") return c->opt_max_mappings;
   if (k == "eager_max") return c->opt_eager_max;
   return -1;
 }

@@ -335,3 +335,18 @@ def test_options_from_the_environment(port):
     assert out.returncode == 0, out.stderr
     assert out.stdout.split()[-2:] == ["7", "33"], out.stdout
     assert "no_such_option" in out.stderr
+
+
+@pytest.mark.parametrize("bound", [1, 2])
+def test_mapping_cache_eviction(sim_api, port, bound):
+    """More peer allocations than the receiver keeps mapped (`max_mappings`): the least recently used idle mappings are
+    dropped — after the resident control kernels have left and outstanding pulls have drained — the device table is
+    rebuilt, and an allocation whose mapping was dropped is simply mapped again.  Three rendezvous-size sources, three
+    rounds over them, every payload checked."""
+    ctx = sim_api.get_context()
+    old = ctx.get_option("max_mappings")
+    try:
+        ctx.set_option("max_mappings", bound)
+        run(cb.case_simdev_two_process_device_buffers(sim_api, port, True))
+    finally:
+        ctx.set_option("max_mappings", old)
