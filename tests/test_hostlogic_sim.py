@@ -4,6 +4,7 @@ Covers connection, eager / rendezvous protocol, credits, flush, close, cancellat
 world_size-2 (two processes) operation without a GPU."""
 import asyncio
 
+import numpy as np
 import pytest
 
 from tests import cases_basic as cb
@@ -350,3 +351,56 @@ def test_mapping_cache_eviction(sim_api, port, bound):
         run(cb.case_simdev_two_process_device_buffers(sim_api, port, True))
     finally:
         ctx.set_option("max_mappings", old)
+
+
+class _DevSlice:
+    """A window of a 'device' allocation of the stand-in (one allocation, many messages)."""
+
+    def __init__(self, pool, off, n):
+        self.ptr, self.n, self._pool = pool.ptr + off, n, pool
+        self.np = pool.np[off:off + n]
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (self.n,), "typestr": "|u1", "data": (self.ptr, False), "version": 2}
+
+
+@pytest.mark.parametrize("mem", ["host", "device"])
+@pytest.mark.parametrize("first", ["sends_first", "receives_first"])
+def test_more_rendezvous_in_flight_than_ring_slots_and_fin_words(sim_api, port, first, mem):
+    """2500 rendezvous-size messages on one connection, posted faster than they can complete: more than the 1024 ring
+    slots, the 1023 FIN words per direction and the 64-entry pull batches hold at once.  Credits, the FIN-word window and
+    the unexpected queue's heap (RTS descriptors) have to back-pressure without losing or reordering anything."""
+    n, size = 2500, 9000
+
+    async def go():
+        async with cb.gen_server_client(sim_api, port) as (server, client):
+            if mem == "host":
+                src = [np.full(size, i & 0xFF, dtype=np.uint8) for i in range(n)]
+                dst = [np.zeros(size, dtype=np.uint8) for _ in range(n)]
+            else:   # device buffers: matched, copied and completed (FIN words) by the 'kernels'
+                from tests.hostsim import SimDev
+
+                stride = (size + 255) & ~255
+                spool, dpool = SimDev.alloc(n * stride), SimDev.alloc(n * stride)
+                src = [_DevSlice(spool, i * stride, size) for i in range(n)]
+                dst = [_DevSlice(dpool, i * stride, size) for i in range(n)]
+                for i, s_ in enumerate(src):
+                    s_.np[:] = i & 0xFF
+                dpool.np[:] = 0
+            if first == "sends_first":
+                sends = [client.asend(s, 5) for s in src]
+                await asyncio.sleep(0.05)
+                recvs = [server.arecv(d, 5, 0xFFFF) for d in dst]
+            else:
+                recvs = [server.arecv(d, 5, 0xFFFF) for d in dst]
+                sends = [client.asend(s, 5) for s in src]
+            for f in recvs:
+                assert await asyncio.wait_for(f, 120) == (5, size)
+            await asyncio.wait_for(asyncio.gather(*sends), 120)
+            await client.aflush()
+            for i, d in enumerate(dst):      # per-sender FIFO: message i lands in receive i
+                a = d if mem == "host" else d.np
+                assert a[0] == (i & 0xFF) and a[-1] == (i & 0xFF), i
+
+    run(go())
